@@ -1,0 +1,117 @@
+/* libsaragan_b200 -- C ABI of the B200-native saraGAN 3D-PGAN train-step kernels.
+ *
+ * Drop-in boundary: these entry points replace the third-party torch
+ * operators that the reference's hot path bottoms out in (the reference ships no native
+ * code of its own).  Every function cites the reference call site it replaces
+ * (paths relative to pgan_pytorch/).  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller; nothing is allocated on the
+ *    hot path; all work is enqueued asynchronously on `stream`;
+ *  - return 0 on success, <0 for an invalid/unsupported argument, >0 = cudaError_t;
+ *    sg_last_error() returns the message for the calling thread;
+ *  - dtype: SG_BF16 (bf16 storage, fp32 accumulate) or SG_F32 (fp32 everything);
+ *  - "act" tensors use the channel-blocked layout  T act[N][CC][D][H][W][8],
+ *    CC = 2*ceil(C/16) chunks of 8 channels, pad channels zero;
+ *    "img" tensors are the C == 1 network boundary, float img[N][D][H][W];
+ *    "plain" is torch's float x[N][C][D][H][W].
+ *  - V = D*H*W voxels.
+ */
+#ifndef SARAGAN_B200_H_
+#define SARAGAN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define SG_BF16 0
+#define SG_F32 1
+
+#define SG_IMPL_AUTO 0    /* tcgen05 when the shape is covered, else direct */
+#define SG_IMPL_DIRECT 1  /* CUDA-core kernel (fp32 mode, odd shapes, on-device cross-check) */
+#define SG_IMPL_TCGEN05 2 /* tcgen05/TMEM/TMA implicit GEMM; error if the shape is not covered */
+
+int sg_version(void);
+const char* sg_last_error(void);
+/* number of kernels this library has launched in this process (optionally reset) */
+int64_t sg_launch_count(int reset);
+
+/* ---- layout conversion at the network boundary (network.py:171,271: input.to(device)) */
+int sg_plain_to_act(const float* plain, void* act, int dtype, int N, int C, int64_t V, cudaStream_t stream);
+int sg_act_to_plain(const void* act, float* plain, int dtype, int N, int C, int64_t V, cudaStream_t stream);
+
+/* ---- EqualizedConv3d 3x3x3, stride 1, pad 1 (network.py:54-56 `F.conv3d(input, weight*std, bias, 1, 1)`)
+ * Weights are packed once per optimiser step from the fp32 (Cout,Cin,3,3,3) parameter:
+ *   transpose_flip = 0 -> packing for fprop;  1 -> packing for dgrad (flipped taps,
+ *   swapped channel roles; dgrad is then sg_conv3d_fprop with Cin/Cout swapped).
+ * y = [mask(mask_src) *] [lrelu] (scale * conv(x, wp) + bias)
+ *   scale   = the equalized-LR std of network.py:16-23 (applied to the fp32 accumulator)
+ *   lrelu   = fuse nn.LeakyReLU(0.2) (network.py:89,159,206,251)
+ *   mask_src (nullable, act of y's shape) = multiply by 1 / 0.2 according to its sign:
+ *             LeakyReLU backward fused into the dgrad epilogue. */
+int64_t sg_packed_weight_elems(int Cout, int Cin, int transpose_flip);
+int sg_pack_conv_weight(const float* w, void* dst, int dtype, int Cout, int Cin, int transpose_flip, cudaStream_t stream);
+int sg_conv3d_fprop(const void* x, const void* wp, const float* bias, const void* mask_src, void* y,
+                    int dtype, int N, int Cin, int Cout, int D, int H, int W, float scale, int lrelu,
+                    int impl, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+/* bytes of caller-provided scratch the conv entry points need for this shape (split-K partial
+ * sums); kind 0 = fprop/dgrad, 1 = wgrad.  The library never allocates. */
+int64_t sg_conv3d_workspace_bytes(int kind, int dtype, int N, int Cin, int Cout, int D, int H, int W);
+/* wgrad (autograd of network.py:55): gw[Cout][Cin][27] = scale * sum gy (x) x,  gb[Cout] = sum gy
+ * (gb nullable).  Outputs are fp32 and overwritten. */
+int sg_conv3d_wgrad(const void* x, const void* gy, float* gw, float* gb, int dtype, int N, int Cin,
+                    int Cout, int D, int H, int W, float scale, int impl, void* workspace,
+                    int64_t workspace_bytes, cudaStream_t stream);
+
+/* ---- 1x1x1 EqualizedConv3d with a single image channel
+ * FromRGB (network.py:101-110): y[n][c][v] = lrelu?(scale*w[c]*img[n][v] + bias[c]) */
+int sg_pw_expand(const float* img, const float* w, const float* bias, void* y, int dtype, int N, int C,
+                 int64_t V, float scale, int lrelu, cudaStream_t stream);
+/* ToRGB (network.py:219-225): img[n][v] = scale*sum_c w[c]*x[n][c][v] + bias[0] */
+int sg_pw_reduce(const void* x, const float* w, const float* bias, float* img, int dtype, int N, int C,
+                 int64_t V, float scale, cudaStream_t stream);
+/* their weight/bias gradients: gw[c] = scale*sum g[n][c][v]*img[n][v] (img null: skipped),
+ * gb[c] = sum g[n][c][v]; either output may be null */
+int sg_pw_wgrad(const void* g, const float* img, float* gw, float* gb, int dtype, int N, int C,
+                int64_t V, float scale, cudaStream_t stream);
+
+/* ---- nn.AvgPool3d(2) (network.py:90,154) / nn.Upsample(scale_factor=2) (network.py:203,265)
+ * and their adjoints.  Tensor viewed as [P][D][H][W][vec], vec = 8 (act) or 1 (img);
+ * D,H,W are the INPUT extents.  down2: y = scale*sum(2x2x2);  up2: y[child] = scale*x.
+ * Input and output element types may differ: the 1x4x4 base level of both networks is kept
+ * in fp32 (minibatch-stddev's group centring amplifies bf16 rounding). */
+int sg_down2(const void* x, void* y, int dtype_in, int dtype_out, int vec, int64_t P, int D, int H, int W, float scale, cudaStream_t stream);
+int sg_up2(const void* x, void* y, int dtype_in, int dtype_out, int vec, int64_t P, int D, int H, int W, float scale, cudaStream_t stream);
+
+/* ---- elementwise
+ * y = alpha*a + beta*b (b nullable): fade-in blend (network.py:185,281), instance noise
+ * (train.py:144) and the backward scalings. */
+int sg_lincomb(const void* a, const void* b, void* y, int dtype, int64_t n, float alpha, float beta, cudaStream_t stream);
+/* nn.LeakyReLU(0.2) forward, and y = g * (ref > 0 ? 1 : 0.2) for its backward / double backward */
+int sg_lrelu_fwd(const void* x, void* y, int dtype, int64_t n, cudaStream_t stream);
+int sg_mask_mul(const void* g, const void* ref, void* y, int dtype, int64_t n, cudaStream_t stream);
+
+/* ---- ChannelNormalization (network.py:192-197), optionally followed by LeakyReLU */
+int sg_pixelnorm_fwd(const void* x, void* y, int dtype, int N, int C, int64_t V, float eps, int lrelu_after, cudaStream_t stream);
+int sg_pixelnorm_bwd(const void* x, const void* gy, void* gx, int dtype, int N, int C, int64_t V, float eps, int lrelu_after, cudaStream_t stream);
+
+/* ---- gradient penalty (loss.py:11-13 interpolate, loss.py:25-26 per-sample norm) */
+int sg_interp(const float* real, const float* fake, const float* eps, float* out, int N, int64_t V, cudaStream_t stream);
+int sg_sumsq_rows(const float* x, float* out, int N, int64_t V, cudaStream_t stream);
+int sg_rowscale(const float* x, const float* scale_per_row, float* y, int N, int64_t V, cudaStream_t stream);
+
+/* ---- EqualizedLinear (network.py:76-77 `F.linear(input, weight*std, bias)`), fp32, small batch */
+int sg_linear_fwd(const float* x, const float* w, const float* bias, float* y, int B, int In, int Out, float scale, int lrelu, cudaStream_t stream);
+int sg_linear_dgrad(const float* g, const float* w, float* gx, int B, int In, int Out, float scale, cudaStream_t stream);
+int sg_linear_wgrad(const float* g, const float* x, float* gw, float* gb, int B, int In, int Out, float scale, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SARAGAN_B200_H_ */

@@ -1,0 +1,129 @@
+"""ctypes binding of libsaragan_b200.so (include/saragan_b200.h).
+
+Thin, typed wrappers: torch tensors in, raw device pointers + sizes out.  There is no
+fallback of any kind: if the shared library is missing or a tensor is not on a CUDA
+device the call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsaragan_b200.so")
+
+BF16, F32 = 0, 1
+IMPL_AUTO, IMPL_DIRECT, IMPL_TCGEN05 = 0, 1, 2
+
+_c_int, _c_i64, _c_f, _c_p = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+
+# name -> argtypes (all return int unless listed in _RESTYPES); mirrors include/saragan_b200.h
+SIGNATURES = {
+    "sg_version": [],
+    "sg_last_error": [],
+    "sg_launch_count": [_c_int],
+    "sg_plain_to_act": [_c_p, _c_p, _c_int, _c_int, _c_int, _c_i64, _c_p],
+    "sg_act_to_plain": [_c_p, _c_p, _c_int, _c_int, _c_int, _c_i64, _c_p],
+    "sg_packed_weight_elems": [_c_int, _c_int, _c_int],
+    "sg_pack_conv_weight": [_c_p, _c_p, _c_int, _c_int, _c_int, _c_int, _c_p],
+    "sg_conv3d_fprop": [_c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                        _c_int, _c_f, _c_int, _c_int, _c_p, _c_i64, _c_p],
+    "sg_conv3d_workspace_bytes": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int],
+    "sg_conv3d_wgrad": [_c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                        _c_f, _c_int, _c_p, _c_i64, _c_p],
+    "sg_pw_expand": [_c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_i64, _c_f, _c_int, _c_p],
+    "sg_pw_reduce": [_c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_i64, _c_f, _c_p],
+    "sg_pw_wgrad": [_c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_i64, _c_f, _c_p],
+    "sg_down2": [_c_p, _c_p, _c_int, _c_int, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_f, _c_p],
+    "sg_up2": [_c_p, _c_p, _c_int, _c_int, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_f, _c_p],
+    "sg_lincomb": [_c_p, _c_p, _c_p, _c_int, _c_i64, _c_f, _c_f, _c_p],
+    "sg_lrelu_fwd": [_c_p, _c_p, _c_int, _c_i64, _c_p],
+    "sg_mask_mul": [_c_p, _c_p, _c_p, _c_int, _c_i64, _c_p],
+    "sg_pixelnorm_fwd": [_c_p, _c_p, _c_int, _c_int, _c_int, _c_i64, _c_f, _c_int, _c_p],
+    "sg_pixelnorm_bwd": [_c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_i64, _c_f, _c_int, _c_p],
+    "sg_interp": [_c_p, _c_p, _c_p, _c_p, _c_int, _c_i64, _c_p],
+    "sg_sumsq_rows": [_c_p, _c_p, _c_int, _c_i64, _c_p],
+    "sg_rowscale": [_c_p, _c_p, _c_p, _c_int, _c_i64, _c_p],
+    "sg_linear_fwd": [_c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_f, _c_int, _c_p],
+    "sg_linear_dgrad": [_c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_f, _c_p],
+    "sg_linear_wgrad": [_c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_f, _c_p],
+}
+_RESTYPES = {"sg_last_error": ctypes.c_char_p, "sg_packed_weight_elems": ctypes.c_int64,
+             "sg_conv3d_workspace_bytes": ctypes.c_int64, "sg_launch_count": ctypes.c_int64}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (or `make -C saragan_b200/csrc`). saragan_b200 has no CPU or "
+                "library fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, ctypes.c_int)
+        _lib = lib
+    return _lib
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.bfloat16:
+        return BF16
+    if t.dtype == torch.float32:
+        return F32
+    raise TypeError(f"saragan_b200: unsupported dtype {t.dtype}")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("saragan_b200 kernels need CUDA tensors (no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("saragan_b200 kernels need contiguous tensors")
+    p = t.data_ptr()
+    if p % 16 and t.numel():
+        raise RuntimeError("saragan_b200 kernels need 16-byte aligned tensors")
+    return p
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name: str, *args):
+    """Invoke an ABI function; tensors are turned into device pointers, the current torch
+    stream is appended, a non-zero status raises RuntimeError(sg_last_error())."""
+    lib = load()
+    conv = [(_ptr(a) if (a is None or isinstance(a, torch.Tensor)) else a) for a in args]
+    rc = getattr(lib, name)(*conv, _stream())
+    if rc != 0:
+        msg = lib.sg_last_error()
+        raise RuntimeError(f"{name} failed (status {rc}): {msg.decode() if msg else ''}")
+
+
+def launch_count(reset: bool = False) -> int:
+    """Kernels launched by libsaragan_b200 in this process so far."""
+    return int(load().sg_launch_count(int(reset)))
+
+
+def packed_weight_elems(cout: int, cin: int, flip: int) -> int:
+    return int(load().sg_packed_weight_elems(cout, cin, flip))
+
+
+def conv_workspace_bytes(kind: int, dtype: int, n: int, cin: int, cout: int, d: int, h: int, w: int) -> int:
+    return int(load().sg_conv3d_workspace_bytes(kind, dtype, n, cin, cout, d, h, w))
+
+
+def chunks(c: int) -> int:
+    """Number of 8-channel chunks of the blocked layout (channels padded to 16)."""
+    return 2 * ((c + 15) // 16)

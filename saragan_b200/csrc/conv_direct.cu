@@ -1,0 +1,394 @@
+// 3x3x3 / stride 1 / pad 1 conv3d on the channel-blocked layout: weight packing, the
+// CUDA-core ("direct") fprop / wgrad kernels and the public conv entry points.
+//
+// The direct kernels serve (a) the fp32 precision mode, (b) shapes the tcgen05 kernels in
+// conv_tc.cu do not cover, (c) the on-device cross-check of the tcgen05 kernels in tests/.
+// dgrad is fprop with the flipped/transposed packing: no third kernel.
+#include "../../include/saragan_b200.h"
+#include "common.cuh"
+
+// tcgen05 paths (conv_tc.cu); return 1 when the shape is not covered so the caller can
+// fall through to the direct kernel, 0 on success, <0 / cudaError on failure.
+int sg_tc_fprop(const void* x, const void* wp, const float* bias, const void* mask_src, void* y,
+                int N, int Cin, int Cout, int D, int H, int W, float scale, int lrelu,
+                void* workspace, int64_t workspace_bytes, cudaStream_t s);
+int sg_tc_wgrad(const void* x, const void* gy, float* gw, float* gb, int N, int Cin, int Cout,
+                int D, int H, int W, float scale, void* workspace, int64_t workspace_bytes,
+                cudaStream_t s);
+int64_t sg_tc_workspace_bytes(int kind, int N, int Cin, int Cout, int D, int H, int W);
+
+// ---------------------------------------------------------------------- weight packing
+// src: fp32 [Cout][Cin][27] (torch (Cout,Cin,3,3,3) contiguous).
+// fwd packing  (transpose_flip = 0): dst[tap][CCin ][CoutP][8]: elem(tap, ci, co) = w[co][ci][tap]
+// bwd packing  (transpose_flip = 1): dst[tap][CCout][CinP ][8]: elem(tap, co, ci) = w[co][ci][26-tap]
+// i.e. in both cases dst[tap][kchunk][row][k%8] with (k = contraction channel, row = output
+// channel) of the convolution the packing will be used for.  Pad entries are zero.
+template <typename T>
+__global__ void k_pack_conv_weight(const float* __restrict__ w, T* __restrict__ dst, int Cout,
+                                   int Cin, int transpose_flip) {
+  int K = transpose_flip ? Cout : Cin;     // contraction channels
+  int R = transpose_flip ? Cin : Cout;     // output rows
+  int KC = 2 * ((K + 15) / 16);
+  int RP = 16 * ((R + 15) / 16);
+  int64_t total = (int64_t)27 * KC * RP * 8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int j = (int)(i & 7);
+    int64_t t = i >> 3;
+    int r = (int)(t % RP);
+    t /= RP;
+    int kc = (int)(t % KC);
+    int tap = (int)(t / KC);
+    int k = kc * 8 + j;
+    float v = 0.f;
+    if (k < K && r < R) {
+      int co = transpose_flip ? k : r;
+      int ci = transpose_flip ? r : k;
+      int tp = transpose_flip ? 26 - tap : tap;
+      v = w[((int64_t)co * Cin + ci) * 27 + tp];
+    }
+    st1(dst + i, v);
+  }
+}
+extern "C" int64_t sg_packed_weight_elems(int Cout, int Cin, int transpose_flip) {
+  int K = transpose_flip ? Cout : Cin;
+  int R = transpose_flip ? Cin : Cout;
+  return (int64_t)27 * (2 * ((K + 15) / 16)) * (16 * ((R + 15) / 16)) * 8;
+}
+extern "C" int sg_pack_conv_weight(const float* w, void* dst, int dtype, int Cout, int Cin,
+                                   int transpose_flip, cudaStream_t s) {
+  int64_t total = sg_packed_weight_elems(Cout, Cin, transpose_flip);
+  SG_DISPATCH(dtype, k_pack_conv_weight<T><<<sg_grid(total, 256), 256, 0, s>>>(w, (T*)dst, Cout, Cin, transpose_flip););
+  return sg_check_launch("sg_pack_conv_weight");
+}
+
+// ------------------------------------------------------------------------ direct fprop
+// thread = (voxel, output chunk of 8).  Per (tap, input chunk): one 8-wide x load and eight
+// 8-wide (warp-uniform, L1-broadcast) weight loads feed 64 FMAs.
+template <typename T>
+__global__ void __launch_bounds__(128)
+k_conv_direct(const T* __restrict__ x, const T* __restrict__ wp, const float* __restrict__ bias,
+              const T* __restrict__ mask_src, T* __restrict__ y, int Cout, int CCin, int CCout,
+              int CoutP, int D, int H, int W, float scale, int lrelu) {
+  int64_t V = (int64_t)D * H * W;
+  int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int cco = blockIdx.y;
+  int n = blockIdx.z;
+  if (v >= V) return;
+  int w0 = (int)(v % W);
+  int h0 = (int)((v / W) % H);
+  int d0 = (int)(v / ((int64_t)W * H));
+  float acc[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+  const T* xn = x + (int64_t)n * CCin * V * 8;
+  for (int kd = 0; kd < 3; ++kd) {
+    int d = d0 + kd - 1;
+    if (d < 0 || d >= D) continue;
+    for (int kh = 0; kh < 3; ++kh) {
+      int h = h0 + kh - 1;
+      if (h < 0 || h >= H) continue;
+      for (int kw = 0; kw < 3; ++kw) {
+        int w_ = w0 + kw - 1;
+        if (w_ < 0 || w_ >= W) continue;
+        int tap = (kd * 3 + kh) * 3 + kw;
+        int64_t vin = ((int64_t)d * H + h) * W + w_;
+        const T* wt = wp + (((int64_t)tap * CCin) * CoutP + cco * 8) * 8;
+        for (int cci = 0; cci < CCin; ++cci) {
+          F8 xv = ld8(xn + ((int64_t)cci * V + vin) * 8);
+          const T* wr = wt + (int64_t)cci * CoutP * 8;
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            F8 wv = ld8(wr + r * 8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[r] = fmaf(xv.v[j], wv.v[j], acc[r]);
+          }
+        }
+      }
+    }
+  }
+  int64_t oidx = (((int64_t)n * CCout + cco) * V + v) * 8;
+  F8 o;
+  F8 m;
+  if (mask_src) m = ld8(mask_src + oidx);
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    int co = cco * 8 + r;
+    float t = 0.f;
+    if (co < Cout) {
+      t = acc[r] * scale + (bias ? __ldg(bias + co) : 0.f);
+      if (lrelu) t = lrelu02(t);
+      if (mask_src) t *= lmask02(m.v[r]);
+    }
+    o.v[r] = t;
+  }
+  st8(y + oidx, o);
+}
+
+
+// ------------------------------------------------- small-volume fp32 fprop (base level)
+// The 1x4x4 base level of both networks runs in fp32 (config.py): tiny M = N*V (64 rows at
+// B=4) against K = 27*Cin up to 13851 and Cout = 512 -- a skinny GEMM bound by streaming the
+// 28 MB of fp32 weights.  Implicit-im2col SGEMM: block = 64 rows x 64 output channels x one
+// tap (split-K over the 27 taps -> 8 x 27 blocks for Cout = 512), 4x4 register tile per
+// thread, fp32 atomics into a zeroed [M][CoutP] workspace, then a finishing kernel applies
+// scale / bias / LeakyReLU / mask and writes the blocked layout.
+__global__ void __launch_bounds__(256)
+k_conv_small_f32(const float* __restrict__ x, const float* __restrict__ wp, float* __restrict__ acc,
+                 int N, int CCin, int CoutP, int D, int H, int W) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  int tap = blockIdx.z;
+  int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+  int V = D * H * W;
+  int M = N * V;
+  int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  int t = threadIdx.x;
+  int tx = t & 15, ty = t >> 4;
+  // loader mapping: row/col = t/4, quarter = t%4 (4 consecutive k of the 16-wide k tile)
+  int lrow = t >> 2, lq = t & 3;
+  int m = m0 + lrow;
+  int64_t a_off = -1;   // element offset of (n, chunk 0, vin, 0) or -1 if the tap falls outside
+  if (m < M) {
+    int n = m / V, v = m % V;
+    int w0 = v % W, h0 = (v / W) % H, d0 = v / (W * H);
+    int d = d0 + kd - 1, h = h0 + kh - 1, w_ = w0 + kw - 1;
+    if (d >= 0 && d < D && h >= 0 && h < H && w_ >= 0 && w_ < W)
+      a_off = ((int64_t)n * CCin * V + ((int64_t)d * H + h) * W + w_) * 8;
+  }
+  int co = n0 + lrow;
+  float c[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
+  for (int cc0 = 0; cc0 < CCin; cc0 += 2) {
+    int chunk = cc0 + (lq >> 1), sub = (lq & 1) * 4;
+    float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a_off >= 0) av = *reinterpret_cast<const float4*>(x + a_off + (int64_t)chunk * V * 8 + sub);
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (co < CoutP)
+      bv = *reinterpret_cast<const float4*>(wp + (((int64_t)tap * CCin + chunk) * CoutP + co) * 8 + sub);
+    int k0 = lq * 4;
+    As[k0 + 0][lrow] = av.x; As[k0 + 1][lrow] = av.y; As[k0 + 2][lrow] = av.z; As[k0 + 3][lrow] = av.w;
+    Bs[k0 + 0][lrow] = bv.x; Bs[k0 + 1][lrow] = bv.y; Bs[k0 + 2][lrow] = bv.z; Bs[k0 + 3][lrow] = bv.w;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c[i][j] = fmaf(a[i], b[j], c[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int mm = m0 + ty * 4 + i;
+    if (mm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int nn = n0 + tx * 4 + j;
+      if (nn < CoutP && c[i][j] != 0.f) atomicAdd(acc + (int64_t)mm * CoutP + nn, c[i][j]);
+    }
+  }
+}
+// acc [M][CoutP] fp32 -> y blocked (T), y = [mask][lrelu](scale*acc + bias)
+template <typename T>
+__global__ void k_conv_finish(const float* __restrict__ acc, const float* __restrict__ bias,
+                              const T* __restrict__ mask_src, T* __restrict__ y, int N, int Cout,
+                              int CCout, int CoutP, int64_t V, float scale, int lrelu) {
+  int64_t total = (int64_t)N * CCout * V;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t v = i % V;
+    int64_t t = i / V;
+    int cc = (int)(t % CCout);
+    int64_t n = t / CCout;
+    const float* a = acc + (n * V + v) * CoutP + cc * 8;
+    F8 o, m;
+    if (mask_src) m = ld8(mask_src + i * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int co = cc * 8 + j;
+      float r = 0.f;
+      if (co < Cout) {
+        r = a[j] * scale + (bias ? __ldg(bias + co) : 0.f);
+        if (lrelu) r = lrelu02(r);
+        if (mask_src) r *= lmask02(m.v[j]);
+      }
+      o.v[j] = r;
+    }
+    st8(y + i * 8, o);
+  }
+}
+int sg_conv_finish_bf16(const float* acc, const float* bias, const void* mask_src, void* y, int N,
+                        int Cout, int64_t V, float scale, int lrelu, cudaStream_t s) {
+  int CCout = sg_chunks(Cout), CoutP = 16 * ((Cout + 15) / 16);
+  int64_t total = (int64_t)N * CCout * V;
+  k_conv_finish<__nv_bfloat16><<<sg_grid(total, 256), 256, 0, s>>>(
+      acc, bias, (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)y, N, Cout, CCout, CoutP, V, scale, lrelu);
+  return sg_check_launch("sg_conv_finish");
+}
+
+static bool small_f32_applies(int dtype, int N, int D, int H, int W) {
+  return dtype == SG_DTYPE_F32 && (int64_t)D * H * W <= 128 && (int64_t)N * D * H * W <= 8192;
+}
+static int launch_small_f32(const void* x, const void* wp, const float* bias, const void* mask_src,
+                            void* y, int N, int Cin, int Cout, int D, int H, int W, float scale,
+                            int lrelu, void* ws, int64_t ws_bytes, cudaStream_t s) {
+  int CCin = sg_chunks(Cin), CCout = sg_chunks(Cout), CoutP = 16 * ((Cout + 15) / 16);
+  int64_t V = (int64_t)D * H * W, M = (int64_t)N * V;
+  int64_t need = M * CoutP * (int64_t)sizeof(float);
+  SG_REQUIRE(ws != nullptr && ws_bytes >= need, "sg_conv3d_fprop: workspace too small (%lld < %lld)",
+             (long long)ws_bytes, (long long)need);
+  cudaMemsetAsync(ws, 0, (size_t)need, s);
+  dim3 grid((unsigned)((M + 63) / 64), (unsigned)((CoutP + 63) / 64), 27);
+  k_conv_small_f32<<<grid, 256, 0, s>>>((const float*)x, (const float*)wp, (float*)ws, N, CCin, CoutP, D, H, W);
+  int rc = sg_check_launch("sg_conv3d_fprop(small f32)");
+  if (rc) return rc;
+  int64_t total = (int64_t)N * CCout * V;
+  k_conv_finish<float><<<sg_grid(total, 256), 256, 0, s>>>((const float*)ws, bias, (const float*)mask_src,
+                                                          (float*)y, N, Cout, CCout, CoutP, V, scale, lrelu);
+  return sg_check_launch("sg_conv3d_fprop(small f32 finish)");
+}
+
+extern "C" int64_t sg_conv3d_workspace_bytes(int kind, int dtype, int N, int Cin, int Cout, int D,
+                                             int H, int W) {
+  int64_t need = 0;
+  if (kind == 0 && small_f32_applies(dtype, N, D, H, W))
+    need = (int64_t)N * D * H * W * (16 * ((Cout + 15) / 16)) * (int64_t)sizeof(float);
+  if (dtype == SG_DTYPE_BF16) {
+    int64_t t = sg_tc_workspace_bytes(kind, N, Cin, Cout, D, H, W);
+    if (t > need) need = t;
+  }
+  return need;
+}
+
+template <typename T>
+static int launch_direct_fprop(const void* x, const void* wp, const float* bias,
+                               const void* mask_src, void* y, int N, int Cin, int Cout, int D,
+                               int H, int W, float scale, int lrelu, cudaStream_t s) {
+  int CCin = sg_chunks(Cin), CCout = sg_chunks(Cout);
+  int CoutP = 16 * ((Cout + 15) / 16);
+  int64_t V = (int64_t)D * H * W;
+  dim3 grid((unsigned)((V + 127) / 128), (unsigned)CCout, (unsigned)N);
+  k_conv_direct<T><<<grid, 128, 0, s>>>((const T*)x, (const T*)wp, bias, (const T*)mask_src, (T*)y,
+                                        Cout, CCin, CCout, CoutP, D, H, W, scale, lrelu);
+  return sg_check_launch("sg_conv3d_fprop(direct)");
+}
+
+extern "C" int sg_conv3d_fprop(const void* x, const void* wp, const float* bias,
+                               const void* mask_src, void* y, int dtype, int N, int Cin, int Cout,
+                               int D, int H, int W, float scale, int lrelu, int impl, void* ws,
+                               int64_t ws_bytes, cudaStream_t s) {
+  SG_REQUIRE(N >= 0 && Cin > 0 && Cout > 0 && D > 0 && H > 0 && W > 0, "sg_conv3d_fprop: bad shape");
+  SG_REQUIRE(impl >= 0 && impl <= 2, "sg_conv3d_fprop: impl must be 0 (auto), 1 (direct), 2 (tcgen05)");
+  if (N == 0) return 0;
+  if (impl != SG_IMPL_DIRECT && dtype == SG_DTYPE_BF16) {
+    int rc = sg_tc_fprop(x, wp, bias, mask_src, y, N, Cin, Cout, D, H, W, scale, lrelu, ws, ws_bytes, s);
+    if (rc != 1) return rc;
+    SG_REQUIRE(impl != SG_IMPL_TCGEN05, "sg_conv3d_fprop: shape not covered by the tcgen05 kernel");
+  } else {
+    SG_REQUIRE(impl != SG_IMPL_TCGEN05, "sg_conv3d_fprop: tcgen05 path needs bf16 activations");
+  }
+  if (impl == SG_IMPL_AUTO && small_f32_applies(dtype, N, D, H, W))
+    return launch_small_f32(x, wp, bias, mask_src, y, N, Cin, Cout, D, H, W, scale, lrelu, ws, ws_bytes, s);
+  SG_DISPATCH(dtype, return launch_direct_fprop<T>(x, wp, bias, mask_src, y, N, Cin, Cout, D, H, W, scale, lrelu, s););
+}
+
+// ------------------------------------------------------------------------ direct wgrad
+// gw[co][ci][tap] = scale * sum_{n,v} gy[n][co][v] * x[n][ci][v + tap - 1]
+// block = (voxel slab, (cco, cci) chunk pair, tap); thread accumulates an 8x8 register tile
+// over its voxels, warp-shuffle reduce, one atomic per output per warp.
+template <typename T>
+__global__ void __launch_bounds__(128)
+k_wgrad_direct(const T* __restrict__ x, const T* __restrict__ gy, float* __restrict__ gw, int N,
+               int Cin, int Cout, int CCin, int CCout, int D, int H, int W, float scale,
+               int64_t per_slab) {
+  int tap = blockIdx.z;
+  int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+  int cco = blockIdx.y / CCin;
+  int cci = blockIdx.y % CCin;
+  int64_t V = (int64_t)D * H * W;
+  int64_t total = (int64_t)N * V;
+  int64_t lo = blockIdx.x * per_slab;
+  int64_t hi = lo + per_slab < total ? lo + per_slab : total;
+  float acc[8][8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[r][j] = 0.f;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    int64_t v = i % V;
+    int64_t n = i / V;
+    int w0 = (int)(v % W);
+    int h0 = (int)((v / W) % H);
+    int d0 = (int)(v / ((int64_t)W * H));
+    int d = d0 + kd - 1, h = h0 + kh - 1, w_ = w0 + kw - 1;
+    if (d < 0 || d >= D || h < 0 || h >= H || w_ < 0 || w_ >= W) continue;
+    int64_t vin = ((int64_t)d * H + h) * W + w_;
+    F8 g = ld8(gy + ((n * CCout + cco) * V + v) * 8);
+    F8 a = ld8(x + ((n * CCin + cci) * V + vin) * 8);
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[r][j] = fmaf(g.v[r], a.v[j], acc[r][j]);
+  }
+  int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = warp_sum(acc[r][j]);
+      int co = cco * 8 + r, ci = cci * 8 + j;
+      if (lane == 0 && co < Cout && ci < Cin && t != 0.f)
+        atomicAdd(gw + ((int64_t)co * Cin + ci) * 27 + tap, t * scale);
+    }
+}
+
+template <typename T>
+static int launch_direct_wgrad(const void* x, const void* gy, float* gw, int N, int Cin, int Cout,
+                               int D, int H, int W, float scale, cudaStream_t s) {
+  int CCin = sg_chunks(Cin), CCout = sg_chunks(Cout);
+  int64_t total = (int64_t)N * D * H * W;
+  int64_t pairs = (int64_t)CCin * CCout * 27;
+  int64_t want = ((int64_t)sg_num_sms() * 16 + pairs - 1) / pairs;
+  int64_t slabs = (total + 1023) / 1024;
+  if (slabs > want) slabs = want;
+  if (slabs < 1) slabs = 1;
+  int64_t per = (total + slabs - 1) / slabs;
+  slabs = (total + per - 1) / per;
+  SG_REQUIRE((int64_t)CCin * CCout <= 65535, "sg_conv3d_wgrad(direct): too many channel chunks");
+  dim3 grid((unsigned)slabs, (unsigned)(CCin * CCout), 27);
+  k_wgrad_direct<T><<<grid, 128, 0, s>>>((const T*)x, (const T*)gy, gw, N, Cin, Cout, CCin, CCout,
+                                         D, H, W, scale, per);
+  return sg_check_launch("sg_conv3d_wgrad(direct)");
+}
+
+// gb[co] = sum_{n,v} gy[n][co][v]
+extern "C" int sg_conv3d_wgrad(const void* x, const void* gy, float* gw, float* gb, int dtype,
+                               int N, int Cin, int Cout, int D, int H, int W, float scale, int impl,
+                               void* ws, int64_t ws_bytes, cudaStream_t s) {
+  SG_REQUIRE(N >= 0 && Cin > 0 && Cout > 0 && D > 0 && H > 0 && W > 0, "sg_conv3d_wgrad: bad shape");
+  SG_REQUIRE(impl >= 0 && impl <= 2, "sg_conv3d_wgrad: impl must be 0 (auto), 1 (direct), 2 (tcgen05)");
+  if (impl != SG_IMPL_DIRECT && dtype == SG_DTYPE_BF16 && N > 0) {
+    int rc = sg_tc_wgrad(x, gy, gw, gb, N, Cin, Cout, D, H, W, scale, ws, ws_bytes, s);
+    if (rc != 1) return rc;
+    SG_REQUIRE(impl != SG_IMPL_TCGEN05, "sg_conv3d_wgrad: shape not covered by the tcgen05 kernel");
+  } else {
+    SG_REQUIRE(impl != SG_IMPL_TCGEN05 || N == 0, "sg_conv3d_wgrad: tcgen05 path needs bf16 activations");
+  }
+  cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)Cout * Cin * 27, s);
+  if (gb) {
+    int rc = sg_pw_wgrad(gy, nullptr, nullptr, gb, dtype, N, Cout, (int64_t)D * H * W, 1.f, s);
+    if (rc) return rc;
+  }
+  if (N == 0) return 0;
+  SG_DISPATCH(dtype, return launch_direct_wgrad<T>(x, gy, gw, N, Cin, Cout, D, H, W, scale, s););
+}

@@ -1,0 +1,681 @@
+// Memory-bound kernels of the PGAN step: layout conversion, resampling, fade-in blend,
+// LeakyReLU mask, pixel-norm, 1x1x1 to/from-RGB, gradient-penalty reductions, tiny linears.
+// All are HBM-bound: 16/32-byte vector accesses, consecutive threads on consecutive vectors,
+// grid-stride loops sized in whole waves of the SM count, warp-shuffle reductions.
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/saragan_b200.h"
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+
+void sg_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+static unsigned long long g_launches = 0;
+extern "C" int64_t sg_launch_count(int reset) {
+  unsigned long long v = g_launches;
+  if (reset) g_launches = 0;
+  return (int64_t)v;
+}
+int sg_check_launch(const char* what) {
+  ++g_launches;   // called exactly once after every kernel launch of this library
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    sg_set_error("%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+extern "C" const char* sg_last_error(void) { return g_err; }
+extern "C" int sg_version(void) { return 100; }
+
+// -------------------------------------------------------------------- layout conversion
+// plain [N][C][V] fp32 -> act [N][CC][V][8] (pad channels zero)
+template <typename T>
+__global__ void k_plain_to_act(const float* __restrict__ src, T* __restrict__ dst, int N, int C,
+                               int CC, int64_t V) {
+  int64_t total = (int64_t)N * CC * V;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t v = i % V;
+    int64_t t = i / V;
+    int cc = (int)(t % CC);
+    int n = (int)(t / CC);
+    F8 r;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int c = cc * 8 + j;
+      r.v[j] = c < C ? src[((int64_t)n * C + c) * V + v] : 0.f;
+    }
+    st8(dst + i * 8, r);
+  }
+}
+template <typename T>
+__global__ void k_act_to_plain(const T* __restrict__ src, float* __restrict__ dst, int N, int C,
+                               int CC, int64_t V) {
+  int64_t total = (int64_t)N * CC * V;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t v = i % V;
+    int64_t t = i / V;
+    int cc = (int)(t % CC);
+    int n = (int)(t / CC);
+    F8 r = ld8(src + i * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int c = cc * 8 + j;
+      if (c < C) dst[((int64_t)n * C + c) * V + v] = r.v[j];
+    }
+  }
+}
+
+extern "C" int sg_plain_to_act(const float* plain, void* act, int dtype, int N, int C, int64_t V,
+                               cudaStream_t s) {
+  int CC = sg_chunks(C);
+  int64_t total = (int64_t)N * CC * V;
+  if (total == 0) return 0;
+  SG_DISPATCH(dtype, k_plain_to_act<T><<<sg_grid(total, 256), 256, 0, s>>>(plain, (T*)act, N, C, CC, V););
+  return sg_check_launch("sg_plain_to_act");
+}
+extern "C" int sg_act_to_plain(const void* act, float* plain, int dtype, int N, int C, int64_t V,
+                               cudaStream_t s) {
+  int CC = sg_chunks(C);
+  int64_t total = (int64_t)N * CC * V;
+  if (total == 0) return 0;
+  SG_DISPATCH(dtype, k_act_to_plain<T><<<sg_grid(total, 256), 256, 0, s>>>((const T*)act, plain, N, C, CC, V););
+  return sg_check_launch("sg_act_to_plain");
+}
+
+// ----------------------------------------------------------------------- elementwise
+// y = alpha*a + beta*b   (b may be null).  Fade-in blend (network.py:185,281) and its
+// backward, instance noise (train.py:144), gradient scaling.
+template <typename T>
+__global__ void k_lincomb(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y,
+                          int64_t nvec, int64_t n, float alpha, float beta) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    F8 x = ld8(a + i * 8);
+    if (b) {
+      F8 z = ld8(b + i * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x.v[j] = alpha * x.v[j] + beta * z.v[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x.v[j] = alpha * x.v[j];
+    }
+    st8(y + i * 8, x);
+  }
+  // scalar tail (n not a multiple of 8): handled by the first threads of block 0
+  int64_t tail0 = nvec * 8;
+  if (blockIdx.x == 0) {
+    for (int64_t i = tail0 + threadIdx.x; i < n; i += blockDim.x) {
+      float x = alpha * ld1(a + i) + (b ? beta * ld1(b + i) : 0.f);
+      st1(y + i, x);
+    }
+  }
+}
+extern "C" int sg_lincomb(const void* a, const void* b, void* y, int dtype, int64_t n, float alpha,
+                          float beta, cudaStream_t s) {
+  if (n == 0) return 0;
+  int64_t nvec = n / 8;
+  SG_DISPATCH(dtype, k_lincomb<T><<<sg_grid(nvec > 0 ? nvec : 1, 256), 256, 0, s>>>(
+                         (const T*)a, (const T*)b, (T*)y, nvec, n, alpha, beta););
+  return sg_check_launch("sg_lincomb");
+}
+
+// mode 0: y = lrelu(x)            (network.py:89 etc.)
+// mode 1: y = x * m(ref), m = 1 if ref > 0 else 0.2   (LeakyReLU backward and its double
+//         backward, SURVEY Appendix B: the mask is recovered from the layer OUTPUT's sign)
+template <typename T>
+__global__ void k_lrelu(const T* __restrict__ x, const T* __restrict__ ref, T* __restrict__ y,
+                        int64_t nvec, int mode) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    F8 a = ld8(x + i * 8);
+    if (mode == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a.v[j] = lrelu02(a.v[j]);
+    } else {
+      F8 r = ld8(ref + i * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a.v[j] *= lmask02(r.v[j]);
+    }
+    st8(y + i * 8, a);
+  }
+}
+extern "C" int sg_lrelu_fwd(const void* x, void* y, int dtype, int64_t n, cudaStream_t s) {
+  SG_REQUIRE(n % 8 == 0, "sg_lrelu_fwd: n must be a multiple of 8");
+  if (n == 0) return 0;
+  SG_DISPATCH(dtype, k_lrelu<T><<<sg_grid(n / 8, 256), 256, 0, s>>>((const T*)x, (const T*)nullptr, (T*)y, n / 8, 0););
+  return sg_check_launch("sg_lrelu_fwd");
+}
+extern "C" int sg_mask_mul(const void* g, const void* ref, void* y, int dtype, int64_t n,
+                           cudaStream_t s) {
+  SG_REQUIRE(n % 8 == 0, "sg_mask_mul: n must be a multiple of 8");
+  if (n == 0) return 0;
+  SG_DISPATCH(dtype, k_lrelu<T><<<sg_grid(n / 8, 256), 256, 0, s>>>((const T*)g, (const T*)ref, (T*)y, n / 8, 1););
+  return sg_check_launch("sg_mask_mul");
+}
+
+// ----------------------------------------------------------------------- resampling
+// x: [P][D][H][W][VEC] -> y: [P][D/2][H/2][W/2][VEC], y = scale * sum over the 2x2x2 block.
+// avg-pool (network.py:90,154) = scale 1/8; backward of nearest-upsample = scale 1.
+template <typename T, typename TO, int VEC>
+__global__ void k_down2(const T* __restrict__ x, TO* __restrict__ y, int64_t P, int D, int H, int W,
+                        float scale) {
+  int Do = D / 2, Ho = H / 2, Wo = W / 2;
+  int64_t total = P * Do * Ho * Wo;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int wo = (int)(i % Wo);
+    int64_t t = i / Wo;
+    int ho = (int)(t % Ho);
+    t /= Ho;
+    int d_o = (int)(t % Do);
+    int64_t p = t / Do;
+    const T* base = x + ((((p * D + 2 * d_o) * H + 2 * ho) * (int64_t)W) + 2 * wo) * VEC;
+    float acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const T* q = base + (((int64_t)dz * H + dy) * W + dx) * VEC;
+          if (VEC == 8) {
+            F8 r = ld8(q);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) acc[j] += r.v[j];
+          } else {
+            acc[0] += ld1(q);
+          }
+        }
+    if (VEC == 8) {
+      F8 r;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r.v[j] = acc[j % VEC] * scale;
+      st8(y + i * 8, r);
+    } else {
+      st1(y + i, acc[0] * scale);
+    }
+  }
+}
+// x: [P][D][H][W][VEC] -> y: [P][2D][2H][2W][VEC], y[child] = scale * x[parent].
+// nearest upsample (network.py:203,265) = scale 1; backward of avg-pool = scale 1/8.
+template <typename T, typename TO, int VEC>
+__global__ void k_up2(const T* __restrict__ x, TO* __restrict__ y, int64_t P, int D, int H, int W,
+                      float scale) {
+  int64_t total = P * D * H * W;
+  int H2 = 2 * H, W2 = 2 * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int w = (int)(i % W);
+    int64_t t = i / W;
+    int h = (int)(t % H);
+    t /= H;
+    int d = (int)(t % D);
+    int64_t p = t / D;
+    TO* base = y + ((((p * 2 * D + 2 * d) * H2 + 2 * h) * (int64_t)W2) + 2 * w) * VEC;
+    if (VEC == 8) {
+      F8 r = ld8(x + i * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r.v[j] *= scale;
+#pragma unroll
+      for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) st8(base + (((int64_t)dz * H2 + dy) * W2 + dx) * 8, r);
+    } else {
+      float r = ld1(x + i) * scale;
+#pragma unroll
+      for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) st1(base + (((int64_t)dz * H2 + dy) * W2 + dx), r);
+    }
+  }
+}
+// in/out element types may differ (the 1x4x4 base level is kept in fp32, config.py)
+#define SG_DISPATCH2(din, dout, ...)                                         \
+  do {                                                                       \
+    if ((din) == SG_DTYPE_BF16 && (dout) == SG_DTYPE_BF16) {                 \
+      typedef __nv_bfloat16 T; typedef __nv_bfloat16 TO; __VA_ARGS__         \
+    } else if ((din) == SG_DTYPE_BF16 && (dout) == SG_DTYPE_F32) {           \
+      typedef __nv_bfloat16 T; typedef float TO; __VA_ARGS__                 \
+    } else if ((din) == SG_DTYPE_F32 && (dout) == SG_DTYPE_BF16) {           \
+      typedef float T; typedef __nv_bfloat16 TO; __VA_ARGS__                 \
+    } else if ((din) == SG_DTYPE_F32 && (dout) == SG_DTYPE_F32) {            \
+      typedef float T; typedef float TO; __VA_ARGS__                         \
+    } else {                                                                 \
+      sg_set_error("unsupported dtype pair %d/%d", (int)(din), (int)(dout)); \
+      return -1;                                                             \
+    }                                                                        \
+  } while (0)
+
+extern "C" int sg_down2(const void* x, void* y, int dtype_in, int dtype_out, int vec, int64_t P,
+                        int D, int H, int W, float scale, cudaStream_t s) {
+  SG_REQUIRE(D % 2 == 0 && H % 2 == 0 && W % 2 == 0, "sg_down2: odd extent %dx%dx%d", D, H, W);
+  SG_REQUIRE(vec == 8 || vec == 1, "sg_down2: vec must be 1 or 8");
+  int64_t total = P * (D / 2) * (H / 2) * (W / 2);
+  if (total == 0) return 0;
+  unsigned g = sg_grid(total, 256);
+  if (vec == 8) {
+    SG_DISPATCH2(dtype_in, dtype_out, k_down2<T, TO, 8><<<g, 256, 0, s>>>((const T*)x, (TO*)y, P, D, H, W, scale););
+  } else {
+    SG_DISPATCH2(dtype_in, dtype_out, k_down2<T, TO, 1><<<g, 256, 0, s>>>((const T*)x, (TO*)y, P, D, H, W, scale););
+  }
+  return sg_check_launch("sg_down2");
+}
+extern "C" int sg_up2(const void* x, void* y, int dtype_in, int dtype_out, int vec, int64_t P, int D,
+                      int H, int W, float scale, cudaStream_t s) {
+  SG_REQUIRE(vec == 8 || vec == 1, "sg_up2: vec must be 1 or 8");
+  int64_t total = P * D * H * W;
+  if (total == 0) return 0;
+  unsigned g = sg_grid(total, 256);
+  if (vec == 8) {
+    SG_DISPATCH2(dtype_in, dtype_out, k_up2<T, TO, 8><<<g, 256, 0, s>>>((const T*)x, (TO*)y, P, D, H, W, scale););
+  } else {
+    SG_DISPATCH2(dtype_in, dtype_out, k_up2<T, TO, 1><<<g, 256, 0, s>>>((const T*)x, (TO*)y, P, D, H, W, scale););
+  }
+  return sg_check_launch("sg_up2");
+}
+
+// ------------------------------------------------------------------------ pixel-norm
+// y = x * rsqrt(mean_c(x^2) + eps)   (network.py:196-197), optionally followed by LeakyReLU
+// (GeneratorBlock's second conv: conv -> pixel-norm -> lrelu, network.py:214-216).
+template <typename T>
+__global__ void k_pixelnorm_fwd(const T* __restrict__ x, T* __restrict__ y, int N, int C, int CC,
+                                int64_t V, float eps, int lrelu_after) {
+  int64_t total = (int64_t)N * V;
+  float invC = 1.f / (float)C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t v = i % V;
+    int64_t n = i / V;
+    const T* px = x + (n * CC * V + v) * 8;
+    T* py = y + (n * CC * V + v) * 8;
+    float ss = 0.f;
+    for (int cc = 0; cc < CC; ++cc) {
+      F8 r = ld8(px + (int64_t)cc * V * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss += r.v[j] * r.v[j];
+    }
+    float r_ = rsqrtf(ss * invC + eps);
+    for (int cc = 0; cc < CC; ++cc) {
+      F8 r = ld8(px + (int64_t)cc * V * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float o = r.v[j] * r_;
+        r.v[j] = lrelu_after ? lrelu02(o) : o;
+      }
+      st8(py + (int64_t)cc * V * 8, r);
+    }
+  }
+}
+// g' = gy * m(x) if lrelu_after;  gx = r*g' - x * r^3 * mean_c(x*g')   
+template <typename T>
+__global__ void k_pixelnorm_bwd(const T* __restrict__ x, const T* __restrict__ gy,
+                                T* __restrict__ gx, int N, int C, int CC, int64_t V, float eps,
+                                int lrelu_after) {
+  int64_t total = (int64_t)N * V;
+  float invC = 1.f / (float)C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t v = i % V;
+    int64_t n = i / V;
+    int64_t off = (n * CC * V + v) * 8;
+    float ss = 0.f, xg = 0.f;
+    for (int cc = 0; cc < CC; ++cc) {
+      F8 a = ld8(x + off + (int64_t)cc * V * 8);
+      F8 g = ld8(gy + off + (int64_t)cc * V * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float gj = lrelu_after ? g.v[j] * lmask02(a.v[j]) : g.v[j];
+        ss += a.v[j] * a.v[j];
+        xg += a.v[j] * gj;
+      }
+    }
+    float r_ = rsqrtf(ss * invC + eps);
+    float k = r_ * r_ * r_ * xg * invC;
+    for (int cc = 0; cc < CC; ++cc) {
+      F8 a = ld8(x + off + (int64_t)cc * V * 8);
+      F8 g = ld8(gy + off + (int64_t)cc * V * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float gj = lrelu_after ? g.v[j] * lmask02(a.v[j]) : g.v[j];
+        a.v[j] = r_ * gj - a.v[j] * k;
+      }
+      st8(gx + off + (int64_t)cc * V * 8, a);
+    }
+  }
+}
+extern "C" int sg_pixelnorm_fwd(const void* x, void* y, int dtype, int N, int C, int64_t V,
+                                float eps, int lrelu_after, cudaStream_t s) {
+  int64_t total = (int64_t)N * V;
+  if (total == 0) return 0;
+  int CC = sg_chunks(C);
+  SG_DISPATCH(dtype, k_pixelnorm_fwd<T><<<sg_grid(total, 256), 256, 0, s>>>((const T*)x, (T*)y, N, C, CC, V, eps, lrelu_after););
+  return sg_check_launch("sg_pixelnorm_fwd");
+}
+extern "C" int sg_pixelnorm_bwd(const void* x, const void* gy, void* gx, int dtype, int N, int C,
+                                int64_t V, float eps, int lrelu_after, cudaStream_t s) {
+  int64_t total = (int64_t)N * V;
+  if (total == 0) return 0;
+  int CC = sg_chunks(C);
+  SG_DISPATCH(dtype, k_pixelnorm_bwd<T><<<sg_grid(total, 256), 256, 0, s>>>((const T*)x, (const T*)gy, (T*)gx, N, C, CC, V, eps, lrelu_after););
+  return sg_check_launch("sg_pixelnorm_bwd");
+}
+
+// ------------------------------------------------------------------ 1x1x1 to/from RGB
+// FromRGB (network.py:101-110): y[n][c][v] = act(scale*w[c]*img[n][v] + bias[c])
+template <typename T>
+__global__ void k_pw_expand(const float* __restrict__ img, const float* __restrict__ w,
+                            const float* __restrict__ bias, T* __restrict__ y, int N, int C, int CC,
+                            int64_t V, float scale, int lrelu) {
+  int64_t total = (int64_t)N * CC * V;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t v = i % V;
+    int64_t t = i / V;
+    int cc = (int)(t % CC);
+    int64_t n = t / CC;
+    float p = img[n * V + v];
+    F8 r;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int c = cc * 8 + j;
+      float o = 0.f;
+      if (c < C) {
+        o = scale * __ldg(w + c) * p + (bias ? __ldg(bias + c) : 0.f);
+        if (lrelu) o = lrelu02(o);
+      }
+      r.v[j] = o;
+    }
+    st8(y + i * 8, r);
+  }
+}
+// ToRGB (network.py:219-225): img[n][v] = scale*sum_c w[c]*x[n][c][v] + bias[0]
+template <typename T>
+__global__ void k_pw_reduce(const T* __restrict__ x, const float* __restrict__ w,
+                            const float* __restrict__ bias, float* __restrict__ img, int N, int C,
+                            int CC, int64_t V, float scale) {
+  int64_t total = (int64_t)N * V;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t v = i % V;
+    int64_t n = i / V;
+    const T* px = x + (n * CC * V + v) * 8;
+    float acc = 0.f;
+    for (int cc = 0; cc < CC; ++cc) {
+      F8 r = ld8(px + (int64_t)cc * V * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int c = cc * 8 + j;
+        if (c < C) acc += __ldg(w + c) * r.v[j];
+      }
+    }
+    img[i] = scale * acc + (bias ? __ldg(bias) : 0.f);
+  }
+}
+// gw[c] = scale * sum_{n,v} g[n][c][v]*img[n][v]  (img == null: plain channel sum),
+// gb[c] = sum_{n,v} g[n][c][v].  One block per (chunk, slab); warp-shuffle + one atomic
+// per channel per block.  Outputs must be zeroed by the caller (the entry point does).
+template <typename T>
+__global__ void k_pw_wgrad(const T* __restrict__ g, const float* __restrict__ img,
+                           float* __restrict__ gw, float* __restrict__ gb, int N, int C, int CC,
+                           int64_t V, float scale, int64_t per_slab) {
+  int cc = blockIdx.y;
+  int64_t total = (int64_t)N * V;
+  int64_t lo = blockIdx.x * per_slab;
+  int64_t hi = lo + per_slab < total ? lo + per_slab : total;
+  float aw[8], ab[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) aw[j] = ab[j] = 0.f;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    int64_t v = i % V;
+    int64_t n = i / V;
+    F8 r = ld8(g + ((n * CC + cc) * V + v) * 8);
+    float p = img ? img[i] : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      aw[j] += r.v[j] * p;
+      ab[j] += r.v[j];
+    }
+  }
+  __shared__ float sm[2][8][8];  // [w|b][warp][j]
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float a = warp_sum(aw[j]);
+    float b = warp_sum(ab[j]);
+    if (lane == 0) {
+      sm[0][warp][j] = a;
+      sm[1][warp][j] = b;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    int which = threadIdx.x >> 3, j = threadIdx.x & 7;
+    float tot = 0.f;
+    for (int wp = 0; wp < (int)(blockDim.x >> 5); ++wp) tot += sm[which][wp][j];
+    int c = cc * 8 + j;
+    if (c < C) {
+      if (which == 0 && gw) atomicAdd(gw + c, tot * scale);
+      if (which == 1 && gb) atomicAdd(gb + c, tot);
+    }
+  }
+}
+extern "C" int sg_pw_expand(const float* img, const float* w, const float* bias, void* y, int dtype,
+                            int N, int C, int64_t V, float scale, int lrelu, cudaStream_t s) {
+  int CC = sg_chunks(C);
+  int64_t total = (int64_t)N * CC * V;
+  if (total == 0) return 0;
+  SG_DISPATCH(dtype, k_pw_expand<T><<<sg_grid(total, 256), 256, 0, s>>>(img, w, bias, (T*)y, N, C, CC, V, scale, lrelu););
+  return sg_check_launch("sg_pw_expand");
+}
+extern "C" int sg_pw_reduce(const void* x, const float* w, const float* bias, float* img, int dtype,
+                            int N, int C, int64_t V, float scale, cudaStream_t s) {
+  int CC = sg_chunks(C);
+  int64_t total = (int64_t)N * V;
+  if (total == 0) return 0;
+  SG_DISPATCH(dtype, k_pw_reduce<T><<<sg_grid(total, 256), 256, 0, s>>>((const T*)x, w, bias, img, N, C, CC, V, scale););
+  return sg_check_launch("sg_pw_reduce");
+}
+extern "C" int sg_pw_wgrad(const void* g, const float* img, float* gw, float* gb, int dtype, int N,
+                           int C, int64_t V, float scale, cudaStream_t s) {
+  int CC = sg_chunks(C);
+  int64_t total = (int64_t)N * V;
+  if (gw) cudaMemsetAsync(gw, 0, sizeof(float) * C, s);
+  if (gb) cudaMemsetAsync(gb, 0, sizeof(float) * C, s);
+  if (total == 0) return 0;
+  // slabs: enough blocks for ~4 waves, at least 2048 voxels per block
+  int64_t want = ((int64_t)sg_num_sms() * 4 + CC - 1) / CC;
+  int64_t slabs = (total + 2047) / 2048;
+  if (slabs > want) slabs = want;
+  if (slabs < 1) slabs = 1;
+  int64_t per = (total + slabs - 1) / slabs;
+  slabs = (total + per - 1) / per;
+  dim3 grid((unsigned)slabs, (unsigned)CC);
+  SG_DISPATCH(dtype, k_pw_wgrad<T><<<grid, 256, 0, s>>>((const T*)g, img, gw, gb, N, C, CC, V, scale, per););
+  return sg_check_launch("sg_pw_wgrad");
+}
+
+// ------------------------------------------------------------ gradient-penalty helpers
+// out[n] = sum_v x[n][v]^2   (loss.py:25-26: per-sample squared L2 norm of the input gradient)
+__global__ void k_sumsq_rows(const float* __restrict__ x, float* __restrict__ out, int64_t V,
+                             int64_t per_slab) {
+  int n = blockIdx.y;
+  int64_t lo = blockIdx.x * per_slab;
+  int64_t hi = lo + per_slab < V ? lo + per_slab : V;
+  const float* p = x + (int64_t)n * V;
+  float acc = 0.f;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    float a = p[i];
+    acc += a * a;
+  }
+  acc = warp_sum(acc);
+  __shared__ float sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sm[w];
+    atomicAdd(out + n, t);
+  }
+}
+extern "C" int sg_sumsq_rows(const float* x, float* out, int N, int64_t V, cudaStream_t s) {
+  if (N == 0) return 0;
+  cudaMemsetAsync(out, 0, sizeof(float) * N, s);
+  if (V == 0) return 0;
+  int64_t slabs = (V + 8191) / 8192;
+  int64_t want = ((int64_t)sg_num_sms() * 4 + N - 1) / N;
+  if (slabs > want) slabs = want;
+  int64_t per = (V + slabs - 1) / slabs;
+  slabs = (V + per - 1) / per;
+  k_sumsq_rows<<<dim3((unsigned)slabs, (unsigned)N), 256, 0, s>>>(x, out, V, per);
+  return sg_check_launch("sg_sumsq_rows");
+}
+// y[n][v] = s[n] * x[n][v]
+__global__ void k_rowscale(const float* __restrict__ x, const float* __restrict__ sc,
+                           float* __restrict__ y, int64_t V, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = x[i] * __ldg(sc + i / V);
+}
+extern "C" int sg_rowscale(const float* x, const float* sc, float* y, int N, int64_t V,
+                           cudaStream_t s) {
+  int64_t total = (int64_t)N * V;
+  if (total == 0) return 0;
+  k_rowscale<<<sg_grid(total, 256), 256, 0, s>>>(x, sc, y, V, total);
+  return sg_check_launch("sg_rowscale");
+}
+// out = eps[n]*real + (1-eps[n])*fake   (loss.py:13)
+__global__ void k_interp(const float* __restrict__ real, const float* __restrict__ fake,
+                         const float* __restrict__ eps, float* __restrict__ out, int64_t V,
+                         int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float e = __ldg(eps + i / V);
+    out[i] = e * real[i] + (1.f - e) * fake[i];
+  }
+}
+extern "C" int sg_interp(const float* real, const float* fake, const float* eps, float* out, int N,
+                         int64_t V, cudaStream_t s) {
+  int64_t total = (int64_t)N * V;
+  if (total == 0) return 0;
+  k_interp<<<sg_grid(total, 256), 256, 0, s>>>(real, fake, eps, out, V, total);
+  return sg_check_launch("sg_interp");
+}
+
+// -------------------------------------------------------------- tiny-batch linears (fp32)
+// EqualizedLinear (network.py:59-77) with batch <= a few dozen rows: weight-bandwidth bound.
+// y[b][o] = act(scale * sum_i x[b][i]*w[o][i] + bias[o]);  one warp per output feature.
+#define LIN_BT 8
+__global__ void k_linear_fwd(const float* __restrict__ x, const float* __restrict__ w,
+                             const float* __restrict__ bias, float* __restrict__ y, int B, int In,
+                             int Out, float scale, int lrelu) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= Out) return;
+  const float* wr = w + (int64_t)warp * In;
+  for (int b0 = 0; b0 < B; b0 += LIN_BT) {
+    float acc[LIN_BT];
+#pragma unroll
+    for (int k = 0; k < LIN_BT; ++k) acc[k] = 0.f;
+    for (int i = lane; i < In; i += 32) {
+      float wv = wr[i];
+#pragma unroll
+      for (int k = 0; k < LIN_BT; ++k)
+        if (b0 + k < B) acc[k] += wv * x[(int64_t)(b0 + k) * In + i];
+    }
+#pragma unroll
+    for (int k = 0; k < LIN_BT; ++k) {
+      float t = warp_sum(acc[k]);
+      if (lane == 0 && b0 + k < B) {
+        float o = scale * t + (bias ? bias[warp] : 0.f);
+        y[(int64_t)(b0 + k) * Out + warp] = lrelu ? lrelu02(o) : o;
+      }
+    }
+  }
+}
+// gx[b][i] = scale * sum_o g[b][o]*w[o][i];  thread per input feature, outputs split over
+// gridDim.y slices with atomics (gx zeroed by the entry point).
+__global__ void k_linear_dgrad(const float* __restrict__ g, const float* __restrict__ w,
+                               float* __restrict__ gx, int B, int In, int Out, float scale,
+                               int o_per) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= In) return;
+  int o_lo = blockIdx.y * o_per;
+  int o_hi = o_lo + o_per < Out ? o_lo + o_per : Out;
+  for (int b0 = 0; b0 < B; b0 += LIN_BT) {
+    float acc[LIN_BT];
+#pragma unroll
+    for (int k = 0; k < LIN_BT; ++k) acc[k] = 0.f;
+    for (int o = o_lo; o < o_hi; ++o) {
+      float wv = w[(int64_t)o * In + i];
+#pragma unroll
+      for (int k = 0; k < LIN_BT; ++k)
+        if (b0 + k < B) acc[k] += wv * __ldg(g + (int64_t)(b0 + k) * Out + o);
+    }
+#pragma unroll
+    for (int k = 0; k < LIN_BT; ++k)
+      if (b0 + k < B) atomicAdd(gx + (int64_t)(b0 + k) * In + i, scale * acc[k]);
+  }
+}
+// gw[o][i] = scale * sum_b g[b][o]*x[b][i];  gb[o] = sum_b g[b][o]
+__global__ void k_linear_wgrad(const float* __restrict__ g, const float* __restrict__ x,
+                               float* __restrict__ gw, float* __restrict__ gb, int B, int In,
+                               int Out, float scale) {
+  int64_t total = (int64_t)Out * In;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    int i = (int)(e % In);
+    int o = (int)(e / In);
+    float acc = 0.f, sb = 0.f;
+    for (int b = 0; b < B; ++b) {
+      float gv = __ldg(g + (int64_t)b * Out + o);
+      acc += gv * __ldg(x + (int64_t)b * In + i);
+      sb += gv;
+    }
+    gw[e] = scale * acc;
+    if (gb && i == 0) gb[o] = sb;
+  }
+}
+extern "C" int sg_linear_fwd(const float* x, const float* w, const float* bias, float* y, int B,
+                             int In, int Out, float scale, int lrelu, cudaStream_t s) {
+  if (B == 0 || Out == 0) return 0;
+  int threads = 256;
+  int64_t blocks = ((int64_t)Out * 32 + threads - 1) / threads;
+  k_linear_fwd<<<(unsigned)blocks, threads, 0, s>>>(x, w, bias, y, B, In, Out, scale, lrelu);
+  return sg_check_launch("sg_linear_fwd");
+}
+extern "C" int sg_linear_dgrad(const float* g, const float* w, float* gx, int B, int In, int Out,
+                               float scale, cudaStream_t s) {
+  if (B == 0 || In == 0) return 0;
+  cudaMemsetAsync(gx, 0, sizeof(float) * (size_t)B * In, s);
+  int bx = (In + 127) / 128;
+  int splits = (sg_num_sms() * 2 + bx - 1) / bx;
+  if (splits > Out) splits = Out;
+  if (splits < 1) splits = 1;
+  int o_per = (Out + splits - 1) / splits;
+  splits = (Out + o_per - 1) / o_per;
+  k_linear_dgrad<<<dim3(bx, splits), 128, 0, s>>>(g, w, gx, B, In, Out, scale, o_per);
+  return sg_check_launch("sg_linear_dgrad");
+}
+extern "C" int sg_linear_wgrad(const float* g, const float* x, float* gw, float* gb, int B, int In,
+                               int Out, float scale, cudaStream_t s) {
+  int64_t total = (int64_t)Out * In;
+  if (total == 0) return 0;
+  k_linear_wgrad<<<sg_grid(total, 256), 256, 0, s>>>(g, x, gw, gb, B, In, Out, scale);
+  return sg_check_launch("sg_linear_wgrad");
+}

@@ -1,0 +1,247 @@
+"""Tensor-level wrappers over the C ABI: allocate outputs, launch, return.
+
+Every function here maps 1:1 onto an entry point of include/saragan_b200.h.  Shapes:
+  act   (N, CC, D, H, W, 8)  bf16 | fp32, CC = 2*ceil(C/16)
+  img   (N, 1, D, H, W)      fp32
+  plain (N, C, D, H, W)      fp32
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import call, chunks
+
+EPS_PN = 1e-8
+
+# Optional per-launch timing of the convolution kernels (bench.py installs a ConvProbe to time the
+# dominant kernel with CUDA events on the launching stream inside the timed region).
+conv_probe = None
+
+
+class ConvProbe:
+    """Records CUDA-event pairs around the conv launches whose (kind, N, Cin, Cout, D, H, W)
+    matches `select`; `durations_ms()` after a synchronize."""
+
+    def __init__(self, select):
+        self.select = tuple(select)
+        self.pairs = []
+
+    def start(self, kind, n, cin, cout, d, h, w):
+        if (kind, n, cin, cout, d, h, w) != self.select:
+            return None
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream())
+        return e0
+
+    def stop(self, e0):
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record(torch.cuda.current_stream())
+        self.pairs.append((e0, e1))
+
+    def durations_ms(self):
+        return [a.elapsed_time(b) for a, b in self.pairs]
+
+
+def _vox(t: torch.Tensor) -> int:
+    return t.shape[2] * t.shape[3] * t.shape[4]
+
+
+# ----------------------------------------------------------------------------- layout
+def plain_to_act(plain: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    n, c, d, h, w = plain.shape
+    out = torch.empty((n, chunks(c), d, h, w, 8), dtype=dtype, device=plain.device)
+    call("sg_plain_to_act", plain, out, _lib.dtype_code(out), n, c, d * h * w)
+    return out
+
+
+def act_to_plain(act: torch.Tensor, c: int) -> torch.Tensor:
+    n, cc, d, h, w, _ = act.shape
+    out = torch.empty((n, c, d, h, w), dtype=torch.float32, device=act.device)
+    call("sg_act_to_plain", act, out, _lib.dtype_code(act), n, c, d * h * w)
+    return out
+
+
+# ------------------------------------------------------------------------------- conv
+def pack_conv_weight(w: torch.Tensor, dtype: torch.dtype, flip: bool) -> torch.Tensor:
+    cout, cin = w.shape[0], w.shape[1]
+    out = torch.empty(_lib.packed_weight_elems(cout, cin, int(flip)), dtype=dtype, device=w.device)
+    call("sg_pack_conv_weight", w, out, _lib.dtype_code(out), cout, cin, int(flip))
+    return out
+
+
+def _workspace(kind: int, x: torch.Tensor, n, cin, cout, d, h, w):
+    """Caller-owned scratch for the conv entry points (the library never allocates)."""
+    nbytes = _lib.conv_workspace_bytes(kind, _lib.dtype_code(x), n, cin, cout, d, h, w)
+    if nbytes == 0:
+        return None, 0
+    return torch.empty((nbytes,), dtype=torch.uint8, device=x.device), nbytes
+
+
+def conv3d_fprop(x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor],
+                 mask_src: Optional[torch.Tensor], cin: int, cout: int, scale: float, lrelu: bool,
+                 impl: int = _lib.IMPL_AUTO) -> torch.Tensor:
+    n, cc, d, h, w, _ = x.shape
+    assert cc == chunks(cin), (cc, cin)
+    y = torch.empty((n, chunks(cout), d, h, w, 8), dtype=x.dtype, device=x.device)
+    ws, nbytes = _workspace(0, x, n, cin, cout, d, h, w)
+    probe = conv_probe
+    tok = probe.start("fprop", n, cin, cout, d, h, w) if probe is not None else None
+    call("sg_conv3d_fprop", x, wp, bias, mask_src, y, _lib.dtype_code(x), n, cin, cout, d, h, w,
+         float(scale), int(lrelu), impl, ws, nbytes)
+    if tok is not None:
+        probe.stop(tok)
+    return y
+
+
+def conv3d_wgrad(x: torch.Tensor, gy: torch.Tensor, cin: int, cout: int, scale: float,
+                 want_bias: bool, impl: int = _lib.IMPL_AUTO
+                 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    n, cc, d, h, w, _ = x.shape
+    assert cc == chunks(cin) and gy.shape[1] == chunks(cout)
+    gw = torch.empty((cout, cin, 3, 3, 3), dtype=torch.float32, device=x.device)
+    gb = torch.empty((cout,), dtype=torch.float32, device=x.device) if want_bias else None
+    ws, nbytes = _workspace(1, x, n, cin, cout, d, h, w)
+    probe = conv_probe
+    tok = probe.start("wgrad", n, cin, cout, d, h, w) if probe is not None else None
+    call("sg_conv3d_wgrad", x, gy, gw, gb, _lib.dtype_code(x), n, cin, cout, d, h, w, float(scale), impl,
+         ws, nbytes)
+    if tok is not None:
+        probe.stop(tok)
+    return gw, gb
+
+
+# ----------------------------------------------------------------------------- 1x1x1
+def pw_expand(img: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], dtype: torch.dtype,
+              c: int, scale: float, lrelu: bool) -> torch.Tensor:
+    n, _, d, h, wd = img.shape
+    y = torch.empty((n, chunks(c), d, h, wd, 8), dtype=dtype, device=img.device)
+    call("sg_pw_expand", img, w, bias, y, _lib.dtype_code(y), n, c, d * h * wd, float(scale), int(lrelu))
+    return y
+
+
+def pw_reduce(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], c: int,
+              scale: float) -> torch.Tensor:
+    n, cc, d, h, wd, _ = x.shape
+    img = torch.empty((n, 1, d, h, wd), dtype=torch.float32, device=x.device)
+    call("sg_pw_reduce", x, w, bias, img, _lib.dtype_code(x), n, c, d * h * wd, float(scale))
+    return img
+
+
+def pw_wgrad(g: torch.Tensor, img: Optional[torch.Tensor], c: int, scale: float, want_w: bool,
+             want_b: bool) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    n, cc, d, h, wd, _ = g.shape
+    gw = torch.empty((c,), dtype=torch.float32, device=g.device) if want_w else None
+    gb = torch.empty((c,), dtype=torch.float32, device=g.device) if want_b else None
+    call("sg_pw_wgrad", g, img if want_w else None, gw, gb, _lib.dtype_code(g), n, c, d * h * wd,
+         float(scale))
+    return gw, gb
+
+
+# ------------------------------------------------------------------------- resampling
+def _resample(name: str, x: torch.Tensor, scale: float, factor_num: int, factor_den: int,
+              out_dtype: Optional[torch.dtype] = None):
+    if x.dim() == 6:
+        n, cc, d, h, w, _ = x.shape
+        shape = (n, cc, d * factor_num // factor_den, h * factor_num // factor_den,
+                 w * factor_num // factor_den, 8)
+        vec, planes = 8, n * cc
+    else:
+        n, c1, d, h, w = x.shape
+        assert x.dtype == torch.float32
+        shape = (n, c1, d * factor_num // factor_den, h * factor_num // factor_den,
+                 w * factor_num // factor_den)
+        vec, planes = 1, n * c1
+    y = torch.empty(shape, dtype=out_dtype or x.dtype, device=x.device)
+    call(name, x, y, _lib.dtype_code(x), _lib.dtype_code(y), vec, planes, d, h, w, float(scale))
+    return y
+
+
+def down2(x: torch.Tensor, scale: float, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    return _resample("sg_down2", x, scale, 1, 2, out_dtype)
+
+
+def up2(x: torch.Tensor, scale: float, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    return _resample("sg_up2", x, scale, 2, 1, out_dtype)
+
+
+# ------------------------------------------------------------------------ elementwise
+def lincomb(a: torch.Tensor, b: Optional[torch.Tensor], alpha: float, beta: float) -> torch.Tensor:
+    y = torch.empty_like(a)
+    call("sg_lincomb", a, b, y, _lib.dtype_code(a), a.numel(), float(alpha), float(beta))
+    return y
+
+
+def lrelu_fwd(x: torch.Tensor) -> torch.Tensor:
+    y = torch.empty_like(x)
+    call("sg_lrelu_fwd", x, y, _lib.dtype_code(x), x.numel())
+    return y
+
+
+def mask_mul(g: torch.Tensor, ref: torch.Tensor) -> torch.Tensor:
+    y = torch.empty_like(g)
+    call("sg_mask_mul", g, ref, y, _lib.dtype_code(g), g.numel())
+    return y
+
+
+def pixelnorm_fwd(x: torch.Tensor, c: int, lrelu_after: bool) -> torch.Tensor:
+    y = torch.empty_like(x)
+    call("sg_pixelnorm_fwd", x, y, _lib.dtype_code(x), x.shape[0], c, _vox(x), EPS_PN, int(lrelu_after))
+    return y
+
+
+def pixelnorm_bwd(x: torch.Tensor, gy: torch.Tensor, c: int, lrelu_after: bool) -> torch.Tensor:
+    gx = torch.empty_like(x)
+    call("sg_pixelnorm_bwd", x, gy, gx, _lib.dtype_code(x), x.shape[0], c, _vox(x), EPS_PN,
+         int(lrelu_after))
+    return gx
+
+
+# ------------------------------------------------------------------- gradient penalty
+def interp(real: torch.Tensor, fake: torch.Tensor, eps: torch.Tensor) -> torch.Tensor:
+    out = torch.empty_like(real)
+    n = real.shape[0]
+    call("sg_interp", real, fake, eps, out, n, real.numel() // max(n, 1))
+    return out
+
+
+def sumsq_rows(x: torch.Tensor) -> torch.Tensor:
+    n = x.shape[0]
+    out = torch.empty((n,), dtype=torch.float32, device=x.device)
+    call("sg_sumsq_rows", x, out, n, x.numel() // max(n, 1))
+    return out
+
+
+def rowscale(x: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
+    y = torch.empty_like(x)
+    n = x.shape[0]
+    call("sg_rowscale", x, s, y, n, x.numel() // max(n, 1))
+    return y
+
+
+# ----------------------------------------------------------------------------- linear
+def linear_fwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], scale: float,
+               lrelu: bool) -> torch.Tensor:
+    b, fin = x.shape
+    y = torch.empty((b, w.shape[0]), dtype=torch.float32, device=x.device)
+    call("sg_linear_fwd", x, w, bias, y, b, fin, w.shape[0], float(scale), int(lrelu))
+    return y
+
+
+def linear_dgrad(g: torch.Tensor, w: torch.Tensor, scale: float) -> torch.Tensor:
+    b, fout = g.shape
+    gx = torch.empty((b, w.shape[1]), dtype=torch.float32, device=g.device)
+    call("sg_linear_dgrad", g, w, gx, b, w.shape[1], fout, float(scale))
+    return gx
+
+
+def linear_wgrad(g: torch.Tensor, x: torch.Tensor, scale: float, want_bias: bool
+                 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    b, fout = g.shape
+    fin = x.shape[1]
+    gw = torch.empty((fout, fin), dtype=torch.float32, device=g.device)
+    gb = torch.empty((fout,), dtype=torch.float32, device=g.device) if want_bias else None
+    call("sg_linear_wgrad", g, x, gw, gb, b, fin, fout, float(scale))
+    return gw, gb

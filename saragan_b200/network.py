@@ -1,0 +1,366 @@
+"""Drop-in for the reference's ``pgan_pytorch/network.py``: same classes, constructor
+arguments, attribute / sub-module / parameter names, ``state_dict`` layout, RNG consumption at
+construction, ``phase`` / ``alpha`` semantics and return types -- with every operator running in
+libsaragan_b200.so (hand-written sm_100a CUDA) on the channel-blocked activation layout.
+
+Deliberate differences from the reference file:
+  * the five debug ``print(x.sum())`` host syncs of ``Discriminator.forward``
+    (network.py:176-188) and the constructor banner (network.py:259) are not reproduced;
+  * ``MinibatchStandardDeviation`` does not mutate its argument; it returns the same values
+    the reference's in-place version produces (the concatenated features are the
+    group-centred ones, network.py:127-133).
+
+Building blocks accept either plain ``(N,C,D,H,W)`` fp32 tensors (converted on entry and
+exit, for stand-alone use) or blocked activations (zero-copy between blocks inside
+``Generator`` / ``Discriminator``).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from torch import nn
+from torch.nn.modules.utils import _triple
+
+from . import config, ops
+
+
+def num_filters(phase, num_phases, base_dim):
+    """network.py:10-13."""
+    num_downscales = int(np.log2(base_dim / 16))
+    return min(base_dim // (2 ** (phase - num_phases + num_downscales)), base_dim)
+
+
+def _fan_in(weight: torch.Tensor) -> int:
+    return int(weight[0].numel())
+
+
+def _voxels(x: torch.Tensor) -> int:
+    return int(x.shape[2] * x.shape[3] * x.shape[4])
+
+
+def _as_float(alpha) -> float:
+    return float(alpha.item()) if isinstance(alpha, torch.Tensor) else float(alpha)
+
+
+class _Blocked:
+    """Marker mixin: helpers to enter/leave the blocked layout at module boundaries."""
+
+    @staticmethod
+    def is_act(x: torch.Tensor) -> bool:
+        return x.dim() == 6
+
+    @staticmethod
+    def enter(x: torch.Tensor) -> torch.Tensor:
+        return ops.ToAct.apply(x.float(), config.act_dtype(_voxels(x)))
+
+    @staticmethod
+    def leave(x: torch.Tensor, c: int) -> torch.Tensor:
+        return ops.ToPlain.apply(x, c)
+
+
+class EqualizedConv3d(nn.Module, _Blocked):
+    """network.py:26-56.  Weight ~ N(0,1) with the He constant applied at run time
+    (``std = 1/sqrt(fan_in)``), bias ~ U(+-1/sqrt(fan_in)).  Supported kernels: 3x3x3/pad 1
+    (tcgen05 implicit GEMM) and 1x1x1/pad 0 with a single image channel on one side
+    (To/FromRGB)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_size = _triple(kernel_size)
+        self.stride = _triple(stride)
+        self.padding = _triple(padding)
+        self.weight = nn.Parameter(torch.Tensor(out_channels, in_channels, *self.kernel_size))
+        self.bias = nn.Parameter(torch.Tensor(out_channels))
+        self.std = None
+        self.reset_parameters()
+        self._packed = ops.PackedWeight(self.weight)
+
+    def reset_parameters(self):
+        fan_in = _fan_in(self.weight)
+        self.std = 1.0 / np.sqrt(fan_in)
+        with torch.no_grad():
+            self.weight.normal_(0, 1)
+            bound = 1 / np.sqrt(fan_in)
+            self.bias.uniform_(-bound, bound)
+
+    def _kind(self) -> str:
+        if self.kernel_size == (3, 3, 3) and self.padding == (1, 1, 1) and self.stride == (1, 1, 1):
+            return "3x3x3"
+        if self.kernel_size == (1, 1, 1) and self.padding == (0, 0, 0) and self.stride == (1, 1, 1):
+            if self.in_channels == 1:
+                return "from_rgb"
+            if self.out_channels == 1:
+                return "to_rgb"
+        raise NotImplementedError(
+            "saragan_b200.EqualizedConv3d covers the PGAN hot path only: 3x3x3/stride 1/pad 1, "
+            "and 1x1x1 with one image channel")
+
+    def forward(self, input, lrelu: bool = False):
+        kind = self._kind()
+        if kind == "3x3x3":
+            plain = not self.is_act(input)
+            x = self.enter(input) if plain else input
+            if self._packed.weight is not self.weight:  # parameter was re-bound (.to(), load)
+                self._packed = ops.PackedWeight(self.weight)
+            y = ops.Conv3x3.apply(x, self.weight, self.bias, self._packed, float(self.std), lrelu)
+            return self.leave(y, self.out_channels) if plain else y
+        if kind == "from_rgb":
+            return ops.PwExpand.apply(input.float().contiguous(), self.weight.reshape(-1), self.bias,
+                                      float(self.std), lrelu, self.out_channels,
+                                      config.act_dtype(_voxels(input)))
+        plain = not self.is_act(input)
+        x = self.enter(input) if plain else input
+        img = ops.PwReduce.apply(x, self.weight.reshape(-1), self.bias, float(self.std),
+                                 self.in_channels)
+        return ops.LeakyRelu.apply(img) if lrelu else img
+
+
+class EqualizedLinear(nn.Module):
+    """network.py:59-77 (including its double RNG draw for the weight)."""
+
+    def __init__(self, in_features, out_features):
+        super().__init__()
+        self.in_features = in_features
+        self.out_features = out_features
+        self.weight = nn.Parameter(torch.randn(out_features, in_features))
+        self.bias = nn.Parameter(torch.zeros(out_features))
+        self.std = None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        fan_in = self.weight.shape[1]
+        self.std = 1.0 / np.sqrt(fan_in)
+        with torch.no_grad():
+            self.weight.normal_(0, 1)
+            bound = 1 / np.sqrt(fan_in)
+            self.bias.uniform_(-bound, bound)
+
+    def forward(self, input, lrelu: bool = False):
+        return ops.Linear.apply(input.float().contiguous(), self.weight, self.bias, float(self.std),
+                                lrelu)
+
+
+class DiscriminatorBlock(nn.Sequential, _Blocked):
+    """network.py:80-98: conv1 -> lrelu -> conv2 -> lrelu -> AvgPool3d(2) (lrelu fused into
+    the conv epilogues)."""
+
+    def __init__(self, filters_in, filters_out):
+        super().__init__()
+        self.filters_in = filters_in
+        self.filters_out = filters_out
+        self.conv1 = EqualizedConv3d(filters_in, filters_in, 3, padding=1)
+        self.conv2 = EqualizedConv3d(filters_in, filters_out, 3, padding=1)
+        self.lrelu = nn.LeakyReLU(negative_slope=0.2)
+        self.downsampling = nn.AvgPool3d(2)
+
+    def forward(self, input):
+        plain = not self.is_act(input)
+        x = self.enter(input) if plain else input
+        x = self.conv1(x, lrelu=True)
+        x = self.conv2(x, lrelu=True)
+        x = ops.Down2.apply(x, 0.125, config.act_dtype(_voxels(x) // 8))
+        return self.leave(x, self.filters_out) if plain else x
+
+
+class FromRGB(nn.Sequential):
+    """network.py:101-110: 1x1x1 conv (1 -> filters) + lrelu; takes the fp32 image, returns a
+    blocked activation."""
+
+    def __init__(self, channels_in, filters):
+        super().__init__()
+        self.fromrgb = nn.Sequential(
+            EqualizedConv3d(channels_in, filters, 1),
+            nn.LeakyReLU(negative_slope=0.2),
+        )
+
+    def forward(self, input):
+        return self.fromrgb[0](input, lrelu=True)
+
+
+class MinibatchStandardDeviation(nn.Module):
+    """network.py:113-133 on the plain fp32 (B,C,1,4,4) base-level tensor.  Tiny (B*C*16
+    elements): composed of torch tensor ops so that autograd supplies its exact second
+    derivative for the gradient penalty (the only non-piecewise-linear op of D)."""
+
+    def __init__(self, group_size=4):
+        super().__init__()
+        self.group_size = group_size
+
+    def forward(self, input):
+        group_size = min(self.group_size, input.shape[0])
+        if group_size < len(input):
+            for i in range(group_size, len(input) + 1):
+                if len(input) % i == 0:
+                    group_size = i
+                    break
+        s = input.shape
+        y = input.reshape(group_size, -1, s[1], s[2], s[3], s[4])
+        yc = y - torch.mean(y, dim=0, keepdim=True)
+        sd = torch.sqrt(torch.mean(yc ** 2, dim=0) + 1e-8)
+        t = torch.mean(sd, dim=[1, 2, 3, 4], keepdim=True)
+        t = t.repeat([group_size, 1, s[2], s[3], s[4]])
+        return torch.cat([yc.reshape(s), t], dim=1)
+
+
+class Discriminator(nn.Module):
+    """network.py:136-189."""
+
+    def __init__(self, phase, num_phases, base_dim, latent_dim, base_shape):
+        super().__init__()
+        self.channels = base_shape[0]
+        self.base_shape = base_shape[1:]
+        self.phase = phase
+        if self.channels != 1:
+            raise NotImplementedError("saragan_b200 covers single-channel volumes (CT), as the reference's data does")
+
+        self.fromrgbs = nn.ModuleList()
+        self.blocks = nn.ModuleList()
+        filters_out = base_dim
+        for i in reversed(range(2, num_phases + 1)):
+            filters_in = num_filters(i, num_phases, base_dim)
+            filters_out = num_filters(i - 1, num_phases, base_dim)
+            self.blocks.append(DiscriminatorBlock(filters_in, filters_out))
+            self.fromrgbs.append(FromRGB(self.channels, filters_in))
+        self.fromrgbs.append(FromRGB(self.channels, base_dim))
+        self.downscale = nn.AvgPool3d(2)
+        self.discriminator_out = nn.Sequential(
+            MinibatchStandardDeviation(),
+            EqualizedConv3d(filters_out + 1, base_dim, 3, padding=1),
+            nn.LeakyReLU(negative_slope=0.2),
+            nn.Flatten(),
+            EqualizedLinear(int(np.prod(self.base_shape)) * base_dim, latent_dim),
+            nn.LeakyReLU(negative_slope=0.2),
+            EqualizedLinear(latent_dim, 1),
+        )
+        self._trunk_channels = filters_out
+        self.device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
+        self.to(self.device)
+
+    def forward(self, input, alpha):
+        alpha = _as_float(alpha)
+        img = input.to(self.device).float().contiguous()
+        x = self.fromrgbs[-self.phase](img)
+        for i in reversed(range(1, self.phase)):
+            x = self.blocks[-i](x)
+            img = ops.Down2.apply(img, 0.125)
+            prev = self.fromrgbs[-i](img)
+            x = ops.Lincomb.apply(prev, x, alpha, 1.0 - alpha)
+        out = self.discriminator_out
+        c = out[1].in_channels - 1
+        x = out[0](ops.ToPlain.apply(x, c))
+        x = out[1](ops.ToAct.apply(x, config.act_dtype(_voxels(x))), lrelu=True)
+        x = torch.flatten(ops.ToPlain.apply(x, out[1].out_channels), 1)
+        x = out[4](x, lrelu=True)
+        return out[6](x)
+
+
+class ChannelNormalization(nn.Module, _Blocked):
+    """network.py:192-197."""
+
+    def __init__(self):
+        super().__init__()
+
+    def forward(self, input, lrelu_after: bool = False, channels: int = None):
+        if self.is_act(input):
+            assert channels is not None
+            return ops.PixelNorm.apply(input, channels, lrelu_after)
+        c = input.shape[1]
+        return self.leave(ops.PixelNorm.apply(self.enter(input), c, lrelu_after), c)
+
+
+class GeneratorBlock(nn.Sequential, _Blocked):
+    """network.py:200-217: up x2 -> conv1 -> lrelu -> pixel-norm -> conv2 -> pixel-norm ->
+    lrelu (note the swapped order after the second conv)."""
+
+    def __init__(self, filters_in, filters_out):
+        super().__init__()
+        self.upsampling = nn.Upsample(scale_factor=2)
+        self.conv1 = EqualizedConv3d(filters_in, filters_out, 3, padding=1)
+        self.conv2 = EqualizedConv3d(filters_out, filters_out, 3, padding=1)
+        self.lrelu = nn.LeakyReLU(negative_slope=0.2)
+        self.cn = ChannelNormalization()
+
+    def forward(self, input):
+        plain = not self.is_act(input)
+        x = self.enter(input) if plain else input
+        c = self.conv1.out_channels
+        x = ops.Up2.apply(x, 1.0, config.act_dtype(_voxels(x) * 8))
+        x = self.conv1(x, lrelu=True)
+        x = self.cn(x, channels=c)
+        x = self.conv2(x)
+        x = self.cn(x, lrelu_after=True, channels=c)
+        return self.leave(x, c) if plain else x
+
+
+class ToRGB(nn.Sequential):
+    """network.py:219-225: 1x1x1 conv to the single image channel; returns the fp32 image."""
+
+    def __init__(self, filters_in, channels):
+        super().__init__()
+        self.conv = EqualizedConv3d(filters_in, channels, 1)
+
+    def forward(self, input):
+        return self.conv(input)
+
+
+class Reshape(nn.Module):
+    def __init__(self, shape):
+        super().__init__()
+        self.shape = shape
+
+    def forward(self, input):
+        return torch.reshape(input, self.shape)
+
+
+class Generator(nn.Module):
+    """network.py:237-284.  ``forward`` returns the LIST of images at every resolution up to
+    ``phase`` (network.py:274-284), each fp32 (N,1,D,H,W)."""
+
+    def __init__(self, phase, num_phases, base_dim, latent_dim, base_shape):
+        super().__init__()
+        self.channels = base_shape[0]
+        self.base_shape = base_shape[1:]
+        self.phase = phase
+        self.latent_dim = latent_dim
+        if self.channels != 1:
+            raise NotImplementedError("saragan_b200 covers single-channel volumes (CT), as the reference's data does")
+        filters_out = base_dim
+        self.generator_in = nn.Sequential(
+            EqualizedLinear(latent_dim, int(np.prod(self.base_shape)) * filters_out),
+            nn.LeakyReLU(negative_slope=0.2),
+            Reshape([-1, filters_out] + list(self.base_shape)),
+            EqualizedConv3d(filters_out, filters_out, 3, padding=1),
+            nn.LeakyReLU(negative_slope=0.2),
+            ChannelNormalization(),
+        )
+        self.blocks = nn.ModuleList()
+        self.to_rgbs = nn.ModuleList([ToRGB(filters_out, self.channels)])
+        for i in range(2, num_phases + 1):
+            filters_in = num_filters(i, num_phases, base_dim)
+            filters_out = num_filters(i + 1, num_phases, base_dim)
+            self.blocks.append(GeneratorBlock(filters_in, filters_out))
+            self.to_rgbs.append(ToRGB(filters_out, self.channels))
+        self.upsample = nn.Upsample(scale_factor=2)
+        self.device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
+        self.to(self.device)
+
+    def forward(self, input, alpha):
+        alpha = _as_float(alpha)
+        gin = self.generator_in
+        x = gin[0](input.to(self.device), lrelu=True)
+        x = gin[2](x)
+        x = ops.ToAct.apply(x, config.act_dtype(_voxels(x)))
+        x = gin[3](x, lrelu=True)
+        x = gin[5](x, channels=gin[3].out_channels)
+
+        all_out = []
+        images_out = self.to_rgbs[0](x)
+        all_out.append(images_out)
+        for i in range(0, self.phase - 1):
+            x = self.blocks[i](x)
+            img_gen = self.to_rgbs[i + 1](x)
+            images_out = ops.Lincomb.apply(ops.Up2.apply(images_out, 1.0), img_gen, alpha, 1.0 - alpha)
+            all_out.append(images_out)
+        return all_out

@@ -1,0 +1,442 @@
+"""Autograd wiring of the CUDA kernels.
+
+Every differentiable op of the PGAN step is a ``torch.autograd.Function`` whose
+``backward`` is itself written in terms of these Functions (the closed set
+fprop <-> dgrad <-> wgrad, avg-pool <-> nearest-upsample, expand <-> reduce), so
+``torch.autograd.grad(..., create_graph=True)`` -- the WGAN-GP double backward of
+loss.py:17-24 -- differentiates through them to any order.
+
+torch is the tensor/stream/autograd host only; all arithmetic on activations happens in
+libsaragan_b200.so.
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import Optional
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import kernels as K
+from ._lib import IMPL_AUTO
+
+_weight_grads_enabled = True
+
+
+@contextlib.contextmanager
+def no_weight_gradients():
+    """Skip wgrad work inside the block.  Used around the gradient penalty's
+    ``autograd.grad(outputs, inputs=interpolates, only_inputs=True)`` (loss.py:17-24): custom
+    Functions cannot see that only the input gradient is wanted, and computing every layer's
+    weight gradient there would cost a full extra wgrad pass."""
+    global _weight_grads_enabled
+    old = _weight_grads_enabled
+    _weight_grads_enabled = False
+    try:
+        yield
+    finally:
+        _weight_grads_enabled = old
+
+
+def _c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    return None if t is None else t.contiguous()
+
+
+class PackedWeight:
+    """Per-parameter cache of the two bf16/fp32 packings of a (Cout,Cin,3,3,3) weight; refreshed
+    when the optimiser bumps the parameter's version counter."""
+
+    def __init__(self, weight: torch.Tensor, cache: bool = True):
+        self.weight = weight
+        self.cache = cache
+        self._key = None
+        self._packs = {}
+
+    def get(self, dtype: torch.dtype, flip: bool) -> torch.Tensor:
+        w = self.weight
+        key = (w._version, w.data_ptr(), w.device)
+        if key != self._key:
+            self._key, self._packs = key, {}
+        k = (dtype, flip)
+        if k not in self._packs:
+            self._packs[k] = K.pack_conv_weight(w.detach().contiguous(), dtype, flip)
+        return self._packs[k]
+
+
+# ================================================================================ conv
+class Conv3x3(Function):
+    """y = [lrelu](std * conv3d(x, w, pad=1) + b)   -- network.py:54-56 (+ :89 etc. fused)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, pw: Optional[PackedWeight], std: float, lrelu: bool):
+        cout, cin = weight.shape[0], weight.shape[1]
+        pw = pw if pw is not None else PackedWeight(weight, cache=False)
+        y = K.conv3d_fprop(x, pw.get(x.dtype, False), bias, None, cin, cout, std, lrelu, IMPL_AUTO)
+        ctx.save_for_backward(x, weight, y if lrelu else None)
+        ctx.pw, ctx.std, ctx.lrelu, ctx.has_bias = pw, std, lrelu, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight, y = ctx.saved_tensors
+        g = _c(gy)
+        if ctx.lrelu:
+            g = MaskMul.apply(g, y)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = ConvDgrad.apply(g, weight, ctx.pw, ctx.std)
+        want_w = ctx.needs_input_grad[1] and _weight_grads_enabled
+        want_b = ctx.has_bias and ctx.needs_input_grad[2] and _weight_grads_enabled
+        if want_w:
+            gw, gb_ = ConvWgrad.apply(x, g, ctx.std, weight.shape[1], weight.shape[0], want_b)
+            gb = gb_ if want_b else None
+        elif want_b:
+            gb = ChanSum.apply(g, weight.shape[0])
+        return gx, gw, gb, None, None, None
+
+
+class ConvDgrad(Function):
+    """gx = std * dgrad(g, w): the same implicit GEMM on the flipped/transposed packing."""
+
+    @staticmethod
+    def forward(ctx, g, weight, pw: Optional[PackedWeight], std: float):
+        cout, cin = weight.shape[0], weight.shape[1]
+        pw = pw if pw is not None else PackedWeight(weight, cache=False)
+        gx = K.conv3d_fprop(g, pw.get(g.dtype, True), None, None, cout, cin, std, False, IMPL_AUTO)
+        ctx.save_for_backward(g, weight)
+        ctx.pw, ctx.std = pw, std
+        return gx
+
+    @staticmethod
+    def backward(ctx, ggx):
+        g, weight = ctx.saved_tensors
+        ggx = _c(ggx)
+        gg = gw = None
+        if ctx.needs_input_grad[0]:
+            gg = Conv3x3.apply(ggx, weight, None, ctx.pw, ctx.std, False)
+        if ctx.needs_input_grad[1] and _weight_grads_enabled:
+            gw, _ = ConvWgrad.apply(ggx, g, ctx.std, weight.shape[1], weight.shape[0], False)
+        return gg, gw, None, None
+
+
+class ConvWgrad(Function):
+    """gw = std * sum_p g (x) x,  gb = sum_p g   (fp32)."""
+
+    @staticmethod
+    def forward(ctx, x, g, std: float, cin: int, cout: int, want_bias: bool):
+        gw, gb = K.conv3d_wgrad(x, g, cin, cout, std, want_bias, IMPL_AUTO)
+        ctx.save_for_backward(x, g)
+        ctx.std, ctx.cin, ctx.cout = std, cin, cout
+        if gb is None:
+            gb = gw.new_zeros(())
+            ctx.mark_non_differentiable(gb)
+        return gw, gb
+
+    @staticmethod
+    def backward(ctx, ggw, ggb):
+        x, g = ctx.saved_tensors
+        ggw = _c(ggw)
+        gx = gg = None
+        if ctx.needs_input_grad[0]:
+            gx = ConvDgrad.apply(g, ggw, None, ctx.std)
+        if ctx.needs_input_grad[1]:
+            gg = Conv3x3.apply(x, ggw, _c(ggb) if ggb is not None and ggb.dim() == 1 else None, None,
+                               ctx.std, False)
+        return gx, gg, None, None, None, None
+
+
+class ChanSum(Function):
+    """out[c] = sum over batch and voxels (bias gradient)."""
+
+    @staticmethod
+    def forward(ctx, g, c: int):
+        ctx.shape, ctx.dtype, ctx.c = g.shape, g.dtype, c
+        return K.pw_wgrad(g, None, c, 1.0, False, True)[1]
+
+    @staticmethod
+    def backward(ctx, gb):
+        n, cc, d, h, w, _ = ctx.shape
+        ones = torch.ones((n, 1, d, h, w), dtype=torch.float32, device=gb.device)
+        return PwExpand.apply(ones, _c(gb), None, 1.0, False, ctx.c, ctx.dtype), None
+
+
+class MaskMul(Function):
+    """y = g * (ref > 0 ? 1 : 0.2): LeakyReLU backward from the sign of the layer OUTPUT; linear
+    in g, so its own backward is the same op (LeakyReluBackwardBackward)."""
+
+    @staticmethod
+    def forward(ctx, g, ref):
+        ctx.save_for_backward(ref)
+        return K.mask_mul(g, ref)
+
+    @staticmethod
+    def backward(ctx, gg):
+        (ref,) = ctx.saved_tensors
+        return MaskMul.apply(_c(gg), ref), None
+
+
+class LeakyRelu(Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = K.lrelu_fwd(x)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        return MaskMul.apply(_c(gy), y)
+
+
+# ========================================================================== resampling
+class Down2(Function):
+    """y = scale * (2x2x2 block sum): AvgPool3d(2) with scale 1/8 (network.py:90,154)."""
+
+    @staticmethod
+    def forward(ctx, x, scale: float, out_dtype: Optional[torch.dtype] = None):
+        ctx.scale, ctx.in_dtype = scale, x.dtype
+        return K.down2(x, scale, out_dtype)
+
+    @staticmethod
+    def backward(ctx, gy):
+        return Up2.apply(_c(gy), ctx.scale, ctx.in_dtype), None, None
+
+
+class Up2(Function):
+    """y[child] = scale * x[parent]: nearest Upsample(2) with scale 1 (network.py:203,265)."""
+
+    @staticmethod
+    def forward(ctx, x, scale: float, out_dtype: Optional[torch.dtype] = None):
+        ctx.scale, ctx.in_dtype = scale, x.dtype
+        return K.up2(x, scale, out_dtype)
+
+    @staticmethod
+    def backward(ctx, gy):
+        return Down2.apply(_c(gy), ctx.scale, ctx.in_dtype), None, None
+
+
+class Lincomb(Function):
+    """y = alpha*a + beta*b: the fade-in blend (network.py:185,281)."""
+
+    @staticmethod
+    def forward(ctx, a, b, alpha: float, beta: float):
+        ctx.alpha, ctx.beta, ctx.has_b = alpha, beta, b is not None
+        return K.lincomb(a, b, alpha, beta)
+
+    @staticmethod
+    def backward(ctx, gy):
+        gy = _c(gy)
+        ga = Lincomb.apply(gy, None, ctx.alpha, 0.0) if ctx.needs_input_grad[0] else None
+        gb = Lincomb.apply(gy, None, ctx.beta, 0.0) if ctx.has_b and ctx.needs_input_grad[1] else None
+        return ga, gb, None, None
+
+
+# =============================================================================== 1x1x1
+class PwExpand(Function):
+    """FromRGB (network.py:101-110): y[n,c,v] = [lrelu](std*w[c]*img[n,v] + b[c])."""
+
+    @staticmethod
+    def forward(ctx, img, w, bias, std: float, lrelu: bool, c: int, dtype: torch.dtype):
+        y = K.pw_expand(img, w, bias, dtype, c, std, lrelu)
+        ctx.save_for_backward(img, w, y if lrelu else None)
+        ctx.std, ctx.lrelu, ctx.c, ctx.has_bias = std, lrelu, c, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        img, w, y = ctx.saved_tensors
+        g = _c(gy)
+        if ctx.lrelu:
+            g = MaskMul.apply(g, y)
+        gimg = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gimg = PwReduce.apply(g, w, None, ctx.std, ctx.c)
+        want_w = ctx.needs_input_grad[1] and _weight_grads_enabled
+        want_b = ctx.has_bias and ctx.needs_input_grad[2] and _weight_grads_enabled
+        if want_w or want_b:
+            gw_, gb_ = PwWgrad.apply(g, img, ctx.std, ctx.c)
+            gw = gw_ if want_w else None
+            gb = gb_ if want_b else None
+        return gimg, gw, gb, None, None, None, None
+
+
+class PwReduce(Function):
+    """ToRGB (network.py:219-225): img[n,v] = std*sum_c w[c]*x[n,c,v] + b."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, std: float, c: int):
+        img = K.pw_reduce(x, w, bias, c, std)
+        ctx.save_for_backward(x, w)
+        ctx.std, ctx.c, ctx.has_bias = std, c, bias is not None
+        return img
+
+    @staticmethod
+    def backward(ctx, gimg):
+        x, w = ctx.saved_tensors
+        gimg = _c(gimg)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = PwExpand.apply(gimg, w, None, ctx.std, False, ctx.c, x.dtype)
+        if ctx.needs_input_grad[1] and _weight_grads_enabled:
+            gw, _ = PwWgrad.apply(x, gimg, ctx.std, ctx.c)
+        if ctx.has_bias and ctx.needs_input_grad[2] and _weight_grads_enabled:
+            gb = gimg.sum().reshape(1)
+        return gx, gw, gb, None, None
+
+
+class PwWgrad(Function):
+    """gw[c] = std*sum g[n,c,v]*img[n,v],  gb[c] = sum g[n,c,v]."""
+
+    @staticmethod
+    def forward(ctx, g, img, std: float, c: int):
+        gw, gb = K.pw_wgrad(g, img, c, std, True, True)
+        ctx.save_for_backward(g, img)
+        ctx.std, ctx.c = std, c
+        return gw, gb
+
+    @staticmethod
+    def backward(ctx, ggw, ggb):
+        g, img = ctx.saved_tensors
+        gg = gimg = None
+        if ctx.needs_input_grad[0]:
+            gg = PwExpand.apply(img, _c(ggw), _c(ggb), ctx.std, False, ctx.c, g.dtype)
+        if ctx.needs_input_grad[1]:
+            gimg = PwReduce.apply(g, _c(ggw), None, ctx.std, ctx.c)
+        return gg, gimg, None, None
+
+
+# ========================================================================== pixel-norm
+class PixelNorm(Function):
+    """ChannelNormalization (network.py:192-197) [+ LeakyReLU]; generator only, first order."""
+
+    @staticmethod
+    def forward(ctx, x, c: int, lrelu_after: bool):
+        ctx.save_for_backward(x)
+        ctx.c, ctx.lrelu_after = c, lrelu_after
+        return K.pixelnorm_fwd(x, c, lrelu_after)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        return K.pixelnorm_bwd(x, _c(gy), ctx.c, ctx.lrelu_after), None, None
+
+
+# ============================================================================== layout
+class ToAct(Function):
+    """plain fp32 NCDHW -> blocked activation layout."""
+
+    @staticmethod
+    def forward(ctx, plain, dtype: torch.dtype):
+        ctx.c = plain.shape[1]
+        return K.plain_to_act(_c(plain), dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ToPlain.apply(_c(g), ctx.c), None
+
+
+class ToPlain(Function):
+    """blocked activation layout -> plain fp32 NCDHW."""
+
+    @staticmethod
+    def forward(ctx, act, c: int):
+        ctx.dtype = act.dtype
+        return K.act_to_plain(act, c)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ToAct.apply(_c(g), ctx.dtype), None
+
+
+# ============================================================================== linear
+class Linear(Function):
+    """y = [lrelu](std * x @ w.T + b)   -- network.py:76-77."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, std: float, lrelu: bool):
+        y = K.linear_fwd(x, w, bias, std, lrelu)
+        ctx.save_for_backward(x, w, y if lrelu else None)
+        ctx.std, ctx.lrelu, ctx.has_bias = std, lrelu, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        g = _c(gy)
+        if ctx.lrelu:
+            g = MaskMul.apply(g, y)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = LinearDgrad.apply(g, w, ctx.std)
+        want_w = ctx.needs_input_grad[1] and _weight_grads_enabled
+        want_b = ctx.has_bias and ctx.needs_input_grad[2] and _weight_grads_enabled
+        if want_w or want_b:
+            gw_, gb_ = LinearWgrad.apply(g, x, ctx.std)
+            gw = gw_ if want_w else None
+            gb = gb_ if want_b else None
+        return gx, gw, gb, None, None
+
+
+class LinearDgrad(Function):
+    @staticmethod
+    def forward(ctx, g, w, std: float):
+        ctx.save_for_backward(g, w)
+        ctx.std = std
+        return K.linear_dgrad(g, w, std)
+
+    @staticmethod
+    def backward(ctx, ggx):
+        g, w = ctx.saved_tensors
+        ggx = _c(ggx)
+        gg = gw = None
+        if ctx.needs_input_grad[0]:
+            gg = Linear.apply(ggx, w, None, ctx.std, False)
+        if ctx.needs_input_grad[1] and _weight_grads_enabled:
+            gw, _ = LinearWgrad.apply(g, ggx, ctx.std)
+        return gg, gw, None
+
+
+class LinearWgrad(Function):
+    @staticmethod
+    def forward(ctx, g, x, std: float):
+        ctx.save_for_backward(g, x)
+        ctx.std = std
+        return K.linear_wgrad(g, x, std, True)
+
+    @staticmethod
+    def backward(ctx, ggw, ggb):
+        g, x = ctx.saved_tensors
+        gg = gx = None
+        if ctx.needs_input_grad[0]:
+            gg = Linear.apply(x, _c(ggw), _c(ggb), ctx.std, False)
+        if ctx.needs_input_grad[1]:
+            gx = LinearDgrad.apply(g, _c(ggw), ctx.std)
+        return gg, gx, None
+
+
+# ==================================================================== gradient penalty
+class RowNorm(Function):
+    """norm[n] = ||x[n].flatten()||_2   (loss.py:25-26 `gradients.norm(2, dim=1)`).  The
+    backward seeds the double-backward chain: g_hat[n] = gn[n] * x[n] / norm[n] (0 at norm 0,
+    like torch's norm backward)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        norm = torch.sqrt(K.sumsq_rows(x))
+        ctx.save_for_backward(x, norm)
+        return norm
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gn):
+        x, norm = ctx.saved_tensors
+        coef = torch.where(norm > 0, gn / norm, torch.zeros_like(norm)).contiguous()
+        return K.rowscale(x, coef)
+
+
+def interpolate(real: torch.Tensor, fake: torch.Tensor, eps: torch.Tensor) -> torch.Tensor:
+    """eps*real + (1-eps)*fake  (loss.py:13); not differentiated (the result is the leaf)."""
+    return K.interp(_c(real), _c(fake), _c(eps.reshape(-1).float()))

@@ -1,0 +1,129 @@
+"""The train step of the reference's ``pgan_pytorch/train.py:126-198`` on the CUDA path.
+
+``train_epoch`` keeps the reference's signature and return value.  ``train_step`` is one
+iteration of its loop body (train.py:133-190); it takes optional pre-drawn random tensors so a
+parity test can replay the oracle's exact draws, and returns the scalars as 0-dim device
+tensors (the reference's five ``.item()`` host syncs per step, train.py:163-164,187-188, are
+left to the caller).
+
+Differences from the reference file as written: ``G(z, alpha)[-1]`` replaces
+``G(z, alpha)`` because network.py's generator returns the list of images at every resolution
+and ``.detach()`` on a list raises (train.py:146).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import kernels as K
+from .loss import compute_gradient_penalty, wasserstein_loss
+
+
+def _set_requires_grad(module, flag: bool) -> None:
+    for p in module.parameters():
+        p.requires_grad = flag
+
+
+def train_step(x_real: torch.Tensor, generator, discriminator, generator_optim, discriminator_optim,
+               alpha, *, noise: Optional[torch.Tensor] = None, z_d: Optional[torch.Tensor] = None,
+               z_g: Optional[torch.Tensor] = None, eps: Optional[torch.Tensor] = None,
+               apply: bool = True, grad_sync=None) -> Dict[str, torch.Tensor]:
+    """One D update followed by one G update (train.py:133-190).
+
+    grad_sync: optional ``comm.DataParallel``; ``arm(module)`` is called before ``backward()``
+    and ``finish(module)`` before ``optim.step()`` (the data-parallel gradient all-reduce,
+    reference: hvd.DistributedOptimizer, main.py:153-160)."""
+    dev = discriminator.device
+    batch = x_real.shape[0]
+
+    # ---- discriminator (train.py:134-161)
+    generator.eval()
+    discriminator.train()
+    _set_requires_grad(generator, False)
+    _set_requires_grad(discriminator, True)
+
+    x_real = x_real.to(dev, non_blocking=True).float().contiguous()
+    if noise is None:
+        noise = torch.randn_like(x_real)
+    x_real = K.lincomb(x_real, noise.to(dev).float().contiguous(), 1.0, 1e-2)
+    if z_d is None:
+        z_d = torch.randn(batch, generator.latent_dim)
+    with torch.no_grad():
+        x_fake = generator(z_d, alpha)[-1].detach()
+
+    d_real = discriminator(x_real, alpha)
+    d_fake = discriminator(x_fake, alpha)
+    gp_loss = compute_gradient_penalty(discriminator, x_real, x_fake, alpha, random_uniform=eps)
+    real_loss = wasserstein_loss(d_real)
+    fake_loss = wasserstein_loss(d_fake)
+    drift_loss = 1e-3 * (d_real ** 2).mean()
+    d_loss = -real_loss + fake_loss + gp_loss + drift_loss
+
+    discriminator_optim.zero_grad()
+    if grad_sync is not None:
+        grad_sync.arm(discriminator)
+    d_loss.backward()
+    if grad_sync is not None:
+        grad_sync.finish(discriminator)
+    if apply:
+        discriminator_optim.step()
+    out = {"d_loss": d_loss.detach(), "gp": gp_loss.detach(), "d_real_mean": real_loss.detach()}
+    del z_d, d_fake, gp_loss, real_loss, fake_loss, d_loss
+
+    # ---- generator (train.py:166-185)
+    generator.train()
+    discriminator.eval()
+    _set_requires_grad(generator, True)
+    _set_requires_grad(discriminator, False)
+
+    if z_g is None:
+        z_g = torch.randn(batch, generator.latent_dim)
+    x_fake = generator(z_g, alpha)[-1]
+    d_fake = discriminator(x_fake, alpha)
+    g_loss = -wasserstein_loss(d_fake)
+
+    generator_optim.zero_grad()
+    if grad_sync is not None:
+        grad_sync.arm(generator)
+    g_loss.backward()
+    if grad_sync is not None:
+        grad_sync.finish(generator)
+    if apply:
+        generator_optim.step()
+
+    out["g_loss"] = g_loss.detach()
+    out["distance"] = out["d_real_mean"] - d_fake.detach().mean()
+    out["x_fake"] = x_fake.detach()
+    out["x_real"] = x_real
+    _set_requires_grad(generator, True)
+    _set_requires_grad(discriminator, True)
+    return out
+
+
+def train_epoch(data_loader, generator, discriminator, generator_optim, discriminator_optim, alpha):
+    """train.py:126-198, same signature and return tuple."""
+    d_losses, g_losses, distances, gradient_penalties = [], [], [], []
+    out = None
+    for x_real in data_loader:
+        out = train_step(x_real, generator, discriminator, generator_optim, discriminator_optim, alpha)
+        d_losses.append(out["d_loss"])
+        g_losses.append(out["g_loss"])
+        distances.append(out["distance"])
+        gradient_penalties.append(out["gp"])
+    if out is None:
+        raise ValueError("empty data_loader")
+    # one host sync per epoch instead of five per step
+    stats = torch.stack([torch.stack(v).mean() for v in (d_losses, g_losses, distances,
+                                                         gradient_penalties)]).cpu().numpy()
+    return (out["x_fake"].cpu(), out["x_real"].cpu(), np.float64(stats[0]), np.float64(stats[1]),
+            np.float64(stats[2]), np.float64(stats[3]))
+
+
+def make_optimizers(generator, discriminator, lr: float = 1e-3, world_size: int = 1):
+    """main.py:138-145: Adam(lr * sqrt(world), betas=(0, 0.99)) for both nets."""
+    lr = lr * float(np.sqrt(world_size))
+    d_optim = torch.optim.Adam(discriminator.parameters(), lr=lr, betas=(0.0, 0.99))
+    g_optim = torch.optim.Adam(generator.parameters(), lr=lr, betas=(0.0, 0.99))
+    return g_optim, d_optim

@@ -1,0 +1,180 @@
+"""CPU emulation of saragan_b200.kernels for the `not gpu` tests (TEST INFRASTRUCTURE).
+
+Each function restates one C-ABI entry point with torch CPU ops on the same blocked layout, so
+that the host logic above the ABI -- the autograd wiring, the double backward of the gradient
+penalty, the module plumbing, the gradient bucketing -- can be checked against the oracle on a
+box without a GPU.  It is injected with monkeypatch by tests/conftest.py's `cpu_kernels`
+fixture; nothing under saragan_b200/ knows it exists.
+"""
+import torch
+import torch.nn.functional as F
+
+
+def chunks(c):
+    return 2 * ((c + 15) // 16)
+
+
+def plain_to_act(plain, dtype):
+    n, c, d, h, w = plain.shape
+    cc = chunks(c)
+    pad = torch.zeros((n, cc * 8, d, h, w), dtype=torch.float32)
+    pad[:, :c] = plain
+    return pad.view(n, cc, 8, d, h, w).permute(0, 1, 3, 4, 5, 2).contiguous().to(dtype)
+
+
+def act_to_plain(act, c):
+    n, cc, d, h, w, _ = act.shape
+    return act.float().permute(0, 1, 5, 2, 3, 4).reshape(n, cc * 8, d, h, w)[:, :c].contiguous()
+
+
+class _Packed:
+    """stand-in for the packed weight buffer: keeps the logical (Cout,Cin,3,3,3) tensor"""
+
+    def __init__(self, w, dtype, flip):
+        self.w = w.detach().to(dtype).float()
+        self.flip = flip
+
+
+def pack_conv_weight(w, dtype, flip):
+    return _Packed(w, dtype, flip)
+
+
+def _mask(ref):
+    return torch.where(ref.float() > 0, 1.0, 0.2)
+
+
+def conv3d_fprop(x, wp, bias, mask_src, cin, cout, scale, lrelu, impl=0):
+    xp = act_to_plain(x, cin)
+    if wp.flip:   # dgrad packing: contraction over the weight's Cout, flipped taps
+        w = wp.w.flip(2, 3, 4).transpose(0, 1)
+    else:
+        w = wp.w
+    y = F.conv3d(xp, w, None, 1, 1) * scale
+    if bias is not None:
+        y = y + bias.view(1, -1, 1, 1, 1)
+    if lrelu:
+        y = F.leaky_relu(y, 0.2)
+    out = plain_to_act(y, x.dtype)
+    if mask_src is not None:
+        out = (out.float() * _mask(mask_src)).to(x.dtype)
+    return out
+
+
+def conv3d_wgrad(x, gy, cin, cout, scale, want_bias, impl=0):
+    xp = act_to_plain(x, cin)
+    gp = act_to_plain(gy, cout)
+    gw = torch.nn.grad.conv3d_weight(xp, (cout, cin, 3, 3, 3), gp, stride=1, padding=1) * scale
+    gb = gp.sum(dim=(0, 2, 3, 4)) if want_bias else None
+    return gw.contiguous(), gb
+
+
+def pw_expand(img, w, bias, dtype, c, scale, lrelu):
+    y = img * (w.view(1, -1, 1, 1, 1) * scale)
+    if bias is not None:
+        y = y + bias.view(1, -1, 1, 1, 1)
+    if lrelu:
+        y = F.leaky_relu(y, 0.2)
+    return plain_to_act(y, dtype)
+
+
+def pw_reduce(x, w, bias, c, scale):
+    xp = act_to_plain(x, c)
+    img = (xp * w.view(1, -1, 1, 1, 1)).sum(1, keepdim=True) * scale
+    if bias is not None:
+        img = img + bias.view(1, 1, 1, 1, 1)
+    return img.contiguous()
+
+
+def pw_wgrad(g, img, c, scale, want_w, want_b):
+    gp = act_to_plain(g, c)
+    gw = (gp * img).sum(dim=(0, 2, 3, 4)) * scale if want_w else None
+    gb = gp.sum(dim=(0, 2, 3, 4)) if want_b else None
+    return gw, gb
+
+
+def _to5(x):
+    if x.dim() == 6:
+        n, cc, d, h, w, _ = x.shape
+        return x.float().permute(0, 1, 5, 2, 3, 4).reshape(n, cc * 8, d, h, w), True
+    return x, False
+
+
+def _from5(y, blocked, dtype):
+    if blocked:
+        n, c8, d, h, w = y.shape
+        return y.view(n, c8 // 8, 8, d, h, w).permute(0, 1, 3, 4, 5, 2).contiguous().to(dtype)
+    return y.contiguous()
+
+
+def down2(x, scale, out_dtype=None):
+    y, blocked = _to5(x)
+    return _from5(F.avg_pool3d(y, 2) * (8.0 * scale), blocked, out_dtype or x.dtype)
+
+
+def up2(x, scale, out_dtype=None):
+    y, blocked = _to5(x)
+    return _from5(F.interpolate(y, scale_factor=2, mode="nearest") * scale, blocked, out_dtype or x.dtype)
+
+
+def lincomb(a, b, alpha, beta):
+    y = a.float() * alpha
+    if b is not None:
+        y = y + b.float() * beta
+    return y.to(a.dtype)
+
+
+def lrelu_fwd(x):
+    return F.leaky_relu(x.float(), 0.2).to(x.dtype)
+
+
+def mask_mul(g, ref):
+    return (g.float() * _mask(ref)).to(g.dtype)
+
+
+def pixelnorm_fwd(x, c, lrelu_after):
+    xp = act_to_plain(x, c)
+    y = xp * torch.rsqrt(torch.mean(xp ** 2, dim=1, keepdim=True) + 1e-8)
+    if lrelu_after:
+        y = F.leaky_relu(y, 0.2)
+    return plain_to_act(y, x.dtype)
+
+
+def pixelnorm_bwd(x, gy, c, lrelu_after):
+    xp = act_to_plain(x, c).requires_grad_(True)
+    with torch.enable_grad():
+        y = xp * torch.rsqrt(torch.mean(xp ** 2, dim=1, keepdim=True) + 1e-8)
+        if lrelu_after:
+            y = F.leaky_relu(y, 0.2)
+        (gx,) = torch.autograd.grad(y, xp, act_to_plain(gy, c))
+    return plain_to_act(gx, x.dtype)
+
+
+def interp(real, fake, eps):
+    e = eps.view(-1, 1, 1, 1, 1)
+    return e * real + (1 - e) * fake
+
+
+def sumsq_rows(x):
+    return (x.reshape(x.shape[0], -1) ** 2).sum(1)
+
+
+def rowscale(x, s):
+    return x * s.view(-1, *([1] * (x.dim() - 1)))
+
+
+def linear_fwd(x, w, bias, scale, lrelu):
+    y = F.linear(x, w) * scale
+    if bias is not None:
+        y = y + bias
+    return F.leaky_relu(y, 0.2) if lrelu else y
+
+
+def linear_dgrad(g, w, scale):
+    return (g @ w) * scale
+
+
+def linear_wgrad(g, x, scale, want_bias):
+    return (g.t() @ x) * scale, (g.sum(0) if want_bias else None)
+
+
+ALL = [n for n in dir() if not n.startswith("_") and n not in ("torch", "F", "chunks", "ALL")]
