@@ -63,6 +63,9 @@ int sg_conv3d_fprop(const void* x, const void* wp, const float* bias, const void
 /* bytes of caller-provided scratch the conv entry points need for this shape (split-K partial
  * sums); kind 0 = fprop/dgrad, 1 = wgrad.  The library never allocates. */
 int64_t sg_conv3d_workspace_bytes(int kind, int dtype, int N, int Cin, int Cout, int D, int H, int W);
+/* introspection: tiling of the tcgen05 path for a shape; out[16] = ok, NT, tn, td, th, n_sub,
+ * kb_chunks, w_stages, splits, kblocks_per_split, grid.x, grid.y, grid.z, smem bytes, tmem cols, a_bytes */
+int sg_tc_plan_debug(int N, int Cin, int Cout, int D, int H, int W, int* out);
 /* wgrad (autograd of network.py:55): gw[Cout][Cin][27] = scale * sum gy (x) x,  gb[Cout] = sum gy
  * (gb nullable).  Outputs are fp32 and overwritten. */
 int sg_conv3d_wgrad(const void* x, const void* gy, float* gw, float* gb, int dtype, int N, int Cin,

@@ -1,6 +1,514 @@
-// placeholder until the tcgen05 kernels land
+// tcgen05 / TMEM / TMA implicit-GEMM 3x3x3 convolution (fprop; dgrad through the flipped
+// packing) for sm_100a, bf16 operands, fp32 accumulation in tensor memory.
+//
+// Design (DESIGN.md "conv3d"):
+//  * activations live in the channel-blocked layout [N][C/8][D][H][W][8]; one TMA tiled load
+//    per 8-channel chunk brings a HALO block (tn x (td+2) x (th+2) x (tw+2) voxels, out-of-
+//    bounds = zero = the conv padding) into shared memory as [line][w][8ch], i.e. 16 bytes per
+//    voxel and one "line" per (n,d,h);
+//  * that block is exactly a K-major, un-swizzled UMMA operand: 8 consecutive voxels of a line
+//    are one 8x16B core matrix, lines are SBO apart, channel chunks LBO apart.  The A operand
+//    of tap (kd,kh,kw) is the SAME block with the descriptor start address shifted by
+//    ((kd-1)*(th+2) + (kh-1)) lines + kw voxels -- the 27 taps re-use one halo load instead of
+//    27 im2col loads (L2->SMEM traffic /9);
+//  * an MMA covers 16 consecutive lines x 8 voxels = 128 rows (M=128) and N = NT output
+//    channels; rows that fall on halo lines/columns are computed and discarded;
+//  * weights [tap][C/8][CoutP][8] stream through a ring of bulk-copy stages;
+//  * warp roles: warp 0 = TMA/bulk producer, warp 1 = TMEM allocator + single-thread MMA
+//    issuer, warps 2-5 = epilogue (tcgen05.ld -> scale, bias, LeakyReLU, mask -> 16-byte stores,
+//    or fp32 atomics into the split-K workspace).
+#include <cuda.h>
+
 #include "../../include/saragan_b200.h"
 #include "common.cuh"
-int sg_tc_fprop(const void*, const void*, const float*, const void*, void*, int, int, int, int, int, int, float, int, void*, int64_t, cudaStream_t) { return 1; }
-int sg_tc_wgrad(const void*, const void*, float*, float*, int, int, int, int, int, int, float, void*, int64_t, cudaStream_t) { return 1; }
-int64_t sg_tc_workspace_bytes(int, int, int, int, int, int, int) { return 0; }
+
+int sg_conv_finish_bf16(const float* acc, const float* bias, const void* mask_src, void* y, int N,
+                        int Cout, int64_t V, float scale, int lrelu, cudaStream_t s);
+
+#ifndef SG_TC_WATCHDOG
+#define SG_TC_WATCHDOG 1
+#endif
+
+namespace {
+
+constexpr int kMaxSub = 8;
+constexpr int kThreads = 192;
+
+struct TcParams {
+  const __nv_bfloat16* wp;   // packed weights [27][CCin][CoutP][8]
+  const float* bias;         // nullable
+  const __nv_bfloat16* mask; // nullable
+  __nv_bfloat16* y;          // output act (splits == 1)
+  float* ws;                 // fp32 [N*V][CoutP] (splits > 1)
+  int N, D, H, W;
+  int CCin, Cout, CoutP, CCout;
+  int td, th, tn;            // tile extents in output voxels (tw == 8)
+  int tiles_w, tiles_h, tiles_d, tiles_n;
+  int halo_w, halo_h, halo_d;
+  int chunk_bytes;           // bytes of one 8-channel halo block
+  int n_sub;
+  int sub_line[kMaxSub];     // first halo line (centre coordinates) of each 16-line MMA tile
+  int kb_chunks;             // 8-channel chunks per K block (2 or 4)
+  int kblocks_per_split;
+  int splits;
+  int sw;                    // weight ring stages
+  int a_bytes, w_stage_bytes;
+  int tmem_cols;
+  float scale;
+  int lrelu;
+};
+
+// ----------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#if SG_TC_WATCHDOG
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {   // ~2 s: a protocol bug must fault, not hang the GPU
+      printf("conv_tc: mbarrier timeout (block %d,%d,%d thread %d bar %u parity %u)\n", blockIdx.x,
+             blockIdx.y, blockIdx.z, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+#else
+  while (!mbar_try_wait(bar, parity)) {
+  }
+#endif
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                            int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+      "%5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 x bf16 -> fp32, M = 128, N from idesc, K = 16
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, no swizzle: 8 rows x 16 B core matrices; LBO = byte distance between the two core
+// matrices along K, SBO = byte distance between 8-row groups along M/N (cute::UMMA::SmemDescriptor).
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version 1 (Blackwell)
+  return d;                 // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+      "%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// --------------------------------------------------------------------------------- kernel
+template <int NT>
+__global__ void __launch_bounds__(kThreads)
+k_conv_tc(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ TcParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  // carve-up: [A halo block][weight ring][barriers][tmem base]
+  uint8_t* a_smem = smem;
+  uint8_t* w_smem = smem + p.a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + p.sw * p.w_stage_bytes);
+  // bars: [0] full_a, [1] empty_a, [2] acc_full, [3 .. 3+sw) full_w, [3+sw .. 3+2sw) empty_w
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 + 2 * kMaxSub + 2);
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  const int FULL_A = 0, EMPTY_A = 1, ACC_FULL = 2, FULL_W = 3, EMPTY_W = 3 + p.sw;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // tile coordinates
+  int t = blockIdx.x;
+  const int tile_w = t % p.tiles_w; t /= p.tiles_w;
+  const int tile_h = t % p.tiles_h; t /= p.tiles_h;
+  const int tile_d = t % p.tiles_d; t /= p.tiles_d;
+  const int tile_n = t;
+  const int w0 = tile_w * 8, h0 = tile_h * p.th, d0 = tile_d * p.td, n0 = tile_n * p.tn;
+  const int co0 = blockIdx.y * NT;
+  const int kb0 = blockIdx.z * p.kblocks_per_split;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+    mbar_init(BAR(FULL_A), 1);
+    mbar_init(BAR(EMPTY_A), 1);
+    mbar_init(BAR(ACC_FULL), 1);
+    for (int i = 0; i < p.sw; ++i) {
+      mbar_init(BAR(FULL_W + i), 1);
+      mbar_init(BAR(EMPTY_W + i), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ producer ================================
+    if (lane == 0) {
+      const uint32_t a_addr = smem_u32(a_smem);
+      const uint32_t w_addr = smem_u32(w_smem);
+      const uint32_t a_tx = (uint32_t)p.kb_chunks * (uint32_t)p.chunk_bytes;
+      const uint32_t w_tx = (uint32_t)p.kb_chunks * NT * 16u;
+      int it = 0;
+      for (int kb = 0; kb < p.kblocks_per_split; ++kb) {
+        mbar_wait(BAR(EMPTY_A), (kb & 1) ^ 1);
+        mbar_expect_tx(BAR(FULL_A), a_tx);
+        const int chunk0 = (kb0 + kb) * p.kb_chunks;
+        for (int c = 0; c < p.kb_chunks; ++c)
+          tma_load_5d(a_addr + c * p.chunk_bytes, &xmap, BAR(FULL_A), (w0 - 1) * 8, h0 - 1, d0 - 1, chunk0 + c, n0);
+        for (int tap = 0; tap < 27; ++tap, ++it) {
+          const int s = it % p.sw;
+          mbar_wait(BAR(EMPTY_W + s), ((it / p.sw) & 1) ^ 1);
+          mbar_expect_tx(BAR(FULL_W + s), w_tx);
+          for (int c = 0; c < p.kb_chunks; ++c) {
+            const __nv_bfloat16* src = p.wp + (((int64_t)tap * p.CCin + chunk0 + c) * p.CoutP + co0) * 8;
+            bulk_load(w_addr + s * p.w_stage_bytes + c * NT * 16, src, NT * 16u, BAR(FULL_W + s));
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N = NT, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t a_addr = smem_u32(a_smem);
+      const uint32_t w_addr = smem_u32(w_smem);
+      const uint32_t line_pitch = (uint32_t)p.halo_w * 16u;
+      int it = 0;
+      for (int kb = 0; kb < p.kblocks_per_split; ++kb) {
+        mbar_wait(BAR(FULL_A), kb & 1);
+        for (int tap = 0; tap < 27; ++tap, ++it) {
+          const int s = it % p.sw;
+          mbar_wait(BAR(FULL_W + s), (it / p.sw) & 1);
+          tc_fence_after();
+          const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+          const int line_off = (kd - 1) * p.halo_h + (kh - 1);
+          for (int kk = 0; kk < p.kb_chunks / 2; ++kk) {
+            const uint64_t bdesc = make_desc(w_addr + s * p.w_stage_bytes + kk * 2 * NT * 16, NT * 16u, 128u);
+            for (int sub = 0; sub < p.n_sub; ++sub) {
+              const uint32_t a0 = a_addr + kk * 2 * p.chunk_bytes +
+                                  ((uint32_t)(p.sub_line[sub] + line_off) * p.halo_w + kw) * 16u;
+              const uint64_t adesc = make_desc(a0, (uint32_t)p.chunk_bytes, line_pitch);
+              tc_mma(tmem_base + sub * NT, adesc, bdesc, idesc, (kb | tap | kk) != 0);
+            }
+          }
+          tc_commit(BAR(EMPTY_W + s));
+        }
+        tc_commit(BAR(EMPTY_A));
+      }
+      tc_commit(BAR(ACC_FULL));
+    }
+  } else {
+    // ================================ epilogue ================================
+    const int quad = warp & 3;              // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;       // accumulator row == TMEM lane
+    mbar_wait(BAR(ACC_FULL), 0);
+    tc_fence_after();
+    const int64_t V = (int64_t)p.D * p.H * p.W;
+    const int plane_lines = p.halo_d * p.halo_h;
+    for (int sub = 0; sub < p.n_sub; ++sub) {
+      const int line = p.sub_line[sub] + (row >> 3);
+      const int wl = row & 7;
+      const int nl = line / plane_lines;
+      const int rem = line - nl * plane_lines;
+      const int dh = rem / p.halo_h, hh = rem - dh * p.halo_h;
+      const int n = n0 + nl, d = d0 + dh - 1, h = h0 + hh - 1, w = w0 + wl;
+      const bool valid = nl < p.tn && dh >= 1 && dh <= p.td && hh >= 1 && hh <= p.th && n < p.N && d < p.D &&
+                         h < p.H && w < p.W;
+      const int64_t vox = ((int64_t)d * p.H + h) * p.W + w;
+      for (int c0 = 0; c0 < NT; c0 += 16) {
+        float v[16];
+        __syncwarp();   // tcgen05.ld is .sync.aligned: the warp must be converged here
+        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(sub * NT + c0), v);
+        if (!valid) {
+          // row lies on a halo line / column or outside the volume: computed, discarded
+        } else if (p.splits > 1) {
+          float* dst = p.ws + ((int64_t)n * V + vox) * p.CoutP + co0 + c0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) atomicAdd(dst + j, v[j]);
+        } else {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int cc = (co0 + c0) / 8 + half;
+            const int64_t oidx = (((int64_t)n * p.CCout + cc) * V + vox) * 8;
+            F8 o, m;
+            if (p.mask) m = ld8(p.mask + oidx);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int co = cc * 8 + j;
+              float r = 0.f;
+              if (co < p.Cout) {
+                r = v[half * 8 + j] * p.scale + (p.bias ? __ldg(p.bias + co) : 0.f);
+                if (p.lrelu) r = lrelu02(r);
+                if (p.mask) r *= lmask02(m.v[j]);
+              }
+              o.v[j] = r;
+            }
+            st8(p.y + oidx, o);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+struct Plan {
+  bool ok = false;
+  int NT = 0;
+  TcParams p{};
+  size_t smem = 0;
+  dim3 grid;
+};
+
+int round_pow2_cols(int c) {
+  int r = 32;
+  while (r < c) r <<= 1;
+  return r;
+}
+
+// greedy cover of the tile's valid output lines with 16-line MMA tiles; returns the count
+int cover_lines(int tn, int td, int th, int halo_d, int halo_h, int* out) {
+  int n_sub = 0, covered_to = -1;
+  for (int nl = 0; nl < tn; ++nl)
+    for (int dl = 0; dl < td; ++dl)
+      for (int hl = 0; hl < th; ++hl) {
+        int line = (nl * halo_d + dl + 1) * halo_h + hl + 1;
+        if (line <= covered_to) continue;
+        if (n_sub == kMaxSub) return kMaxSub + 1;
+        out[n_sub++] = line;
+        covered_to = line + 15;
+      }
+  return n_sub;
+}
+
+Plan make_plan(int N, int Cin, int Cout, int D, int H, int W) {
+  Plan pl;
+  TcParams& p = pl.p;
+  if (W % 8 != 0 || H < 8) return pl;
+  const int CCin = sg_chunks(Cin), CoutP = 16 * ((Cout + 15) / 16);
+  int NT = CoutP % 128 == 0 ? 128 : CoutP % 64 == 0 ? 64 : CoutP % 32 == 0 ? 32 : 16;
+  const int max_sub = 256 / NT < kMaxSub ? 256 / NT : kMaxSub;
+  int th = H < 16 ? H : 16;
+  if (H % th != 0) return pl;
+  // largest (tn, td) whose MMA tiles fit the TMEM budget of two co-resident CTAs
+  int best_tn = 0, best_td = 0, best_sub = 0, best_lines[kMaxSub];
+  for (int td = 1; td <= D && td <= 8; ++td) {
+    if (D % td) continue;
+    for (int tn = 1; tn <= N && tn <= 8; ++tn) {
+      if (td < D && tn > 1) continue;   // span samples only when a tile already holds a whole volume
+      int lines[kMaxSub];
+      int ns = cover_lines(tn, td, th, td + 2, th + 2, lines);
+      if (ns > max_sub) continue;
+      if (tn * td > best_tn * best_td) {
+        best_tn = tn; best_td = td; best_sub = ns;
+        for (int i = 0; i < ns; ++i) best_lines[i] = lines[i];
+      }
+    }
+  }
+  if (best_sub == 0) return pl;
+  p.td = best_td; p.th = th; p.tn = best_tn;
+  p.n_sub = best_sub;
+  for (int i = 0; i < best_sub; ++i) p.sub_line[i] = best_lines[i];
+  p.halo_w = 10; p.halo_h = th + 2; p.halo_d = p.td + 2;
+  p.chunk_bytes = p.tn * p.halo_d * p.halo_h * p.halo_w * 16;
+  p.kb_chunks = (CCin % 4 == 0 && 4 * p.chunk_bytes <= 72 * 1024) ? 4 : 2;
+  p.a_bytes = p.kb_chunks * p.chunk_bytes;
+  // garbage rows of the last MMA tile may read past the block: keep those reads inside the allocation
+  int last_line = p.sub_line[p.n_sub - 1] + 15 + p.halo_h + 1;
+  int over = (last_line + 1) * p.halo_w * 16 + 8 * 16 + (p.kb_chunks - 1) * p.chunk_bytes - p.a_bytes;
+  p.w_stage_bytes = p.kb_chunks * NT * 16;
+  p.a_bytes = (p.a_bytes + 127) / 128 * 128;
+  int budget = 110 * 1024 - p.a_bytes - 256;
+  int sw = budget / p.w_stage_bytes;
+  if (sw > 8) sw = 8;
+  if (sw < 2) return pl;
+  if (over > sw * p.w_stage_bytes) return pl;
+  p.sw = sw;
+  p.tiles_w = W / 8; p.tiles_h = H / th; p.tiles_d = D / p.td; p.tiles_n = (N + p.tn - 1) / p.tn;
+  p.N = N; p.D = D; p.H = H; p.W = W;
+  p.CCin = CCin; p.Cout = Cout; p.CoutP = CoutP; p.CCout = sg_chunks(Cout);
+  p.tmem_cols = round_pow2_cols(p.n_sub * NT);
+  const int n_kblocks = CCin / p.kb_chunks;
+  const int64_t ctas = (int64_t)p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n * (CoutP / NT);
+  int splits = 1;
+  if (ctas < sg_num_sms()) {
+    int want = (int)((2 * sg_num_sms() + ctas - 1) / ctas);
+    for (int s = 1; s <= n_kblocks; ++s)
+      if (n_kblocks % s == 0 && s <= want) splits = s;
+  }
+  p.splits = splits;
+  p.kblocks_per_split = n_kblocks / splits;
+  pl.NT = NT;
+  pl.smem = (size_t)p.a_bytes + (size_t)p.sw * p.w_stage_bytes + 8 * (3 + 2 * kMaxSub + 2) + 16;
+  pl.grid = dim3((unsigned)(p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n), (unsigned)(CoutP / NT), (unsigned)splits);
+  pl.ok = true;
+  return pl;
+}
+
+template <int NT>
+int launch(const Plan& pl, const CUtensorMap& map, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_conv_tc<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) {
+      sg_set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  k_conv_tc<NT><<<pl.grid, kThreads, pl.smem, s>>>(map, pl.p);
+  return sg_check_launch("sg_conv3d_fprop(tcgen05)");
+}
+
+}  // namespace
+
+int64_t sg_tc_workspace_bytes(int kind, int N, int Cin, int Cout, int D, int H, int W) {
+  if (kind != 0) return 0;
+  Plan pl = make_plan(N, Cin, Cout, D, H, W);
+  if (!pl.ok || pl.p.splits == 1) return 0;
+  return (int64_t)N * D * H * W * pl.p.CoutP * (int64_t)sizeof(float);
+}
+
+int sg_tc_fprop(const void* x, const void* wp, const float* bias, const void* mask_src, void* y, int N, int Cin,
+                int Cout, int D, int H, int W, float scale, int lrelu, void* ws, int64_t ws_bytes, cudaStream_t s) {
+  Plan pl = make_plan(N, Cin, Cout, D, H, W);
+  if (!pl.ok) return 1;
+  EncodeTiledFn encode = get_encode();
+  if (!encode) {
+    sg_set_error("conv_tc: cuTensorMapEncodeTiled not available");
+    return -2;
+  }
+  TcParams& p = pl.p;
+  p.wp = (const __nv_bfloat16*)wp;
+  p.bias = bias;
+  p.mask = (const __nv_bfloat16*)mask_src;
+  p.y = (__nv_bfloat16*)y;
+  p.ws = (float*)ws;
+  p.scale = scale;
+  p.lrelu = lrelu;
+  if (p.splits > 1) {
+    int64_t need = (int64_t)N * D * H * W * p.CoutP * (int64_t)sizeof(float);
+    SG_REQUIRE(ws != nullptr && ws_bytes >= need, "sg_conv3d_fprop(tcgen05): workspace too small (%lld < %lld)",
+               (long long)ws_bytes, (long long)need);
+    cudaMemsetAsync(ws, 0, (size_t)need, s);
+  }
+  // activations as a 5-D tensor [W*8 | H | D | CC | N] of bf16; box = one 8-channel halo block
+  CUtensorMap map;
+  cuuint64_t dims[5] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)p.CCin, (cuuint64_t)N};
+  cuuint64_t strides[4] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16,
+                           (cuuint64_t)p.CCin * D * H * W * 16};
+  cuuint32_t box[5] = {(cuuint32_t)p.halo_w * 8, (cuuint32_t)p.halo_h, (cuuint32_t)p.halo_d, 1, (cuuint32_t)p.tn};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    sg_set_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return -3;
+  }
+  int rc;
+  switch (pl.NT) {
+    case 16: rc = launch<16>(pl, map, s); break;
+    case 32: rc = launch<32>(pl, map, s); break;
+    case 64: rc = launch<64>(pl, map, s); break;
+    default: rc = launch<128>(pl, map, s); break;
+  }
+  if (rc) return rc;
+  if (p.splits > 1)
+    return sg_conv_finish_bf16((const float*)ws, bias, mask_src, y, N, Cout, (int64_t)D * H * W, scale, lrelu, s);
+  return 0;
+}
+
+int sg_tc_wgrad(const void*, const void*, float*, float*, int, int, int, int, int, int, float, void*, int64_t,
+                cudaStream_t) {
+  return 1;   // tcgen05 wgrad: next milestone; the caller falls through to the direct kernel
+}
+
+// Introspection for tests / DESIGN.md: the tiling the tcgen05 path would use for a shape.
+// out[0..15] = ok, NT, tn, td, th, n_sub, kb_chunks, sw, splits, kblocks_per_split, grid.x, grid.y,
+//              grid.z, smem bytes, tmem columns, a_bytes
+extern "C" int sg_tc_plan_debug(int N, int Cin, int Cout, int D, int H, int W, int* out) {
+  Plan pl = make_plan(N, Cin, Cout, D, H, W);
+  const TcParams& p = pl.p;
+  int v[16] = {pl.ok, pl.NT, p.tn, p.td, p.th, p.n_sub, p.kb_chunks, p.sw, p.splits, p.kblocks_per_split,
+               (int)pl.grid.x, (int)pl.grid.y, (int)pl.grid.z, (int)pl.smem, p.tmem_cols, p.a_bytes};
+  for (int i = 0; i < 16; ++i) out[i] = v[i];
+  return 0;
+}

@@ -1,0 +1,75 @@
+"""tcgen05 implicit-GEMM convolution (SG_IMPL_TCGEN05) against the CUDA-core direct kernel
+(SG_IMPL_DIRECT) and the torch-CPU restatement, through the C ABI, bf16 in / fp32 accumulate.
+Both GPU arms read identical bf16 inputs and packed weights, so they may differ only by fp32
+summation order and the final bf16 rounding (tolerance 3e-3 norm-wise)."""
+import pytest
+import torch
+
+from saragan_b200 import _lib
+from saragan_b200 import kernels as K
+from tests import cpu_emul as E
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+SHAPES = [
+    # n, cin, cout, d, h, w                     what it exercises
+    (1, 16, 16, 4, 16, 8),     # one tile, NT=16, 4 MMA tiles, single K block of 2 chunks
+    (1, 32, 64, 4, 16, 16),    # the D.b6 shape class: kb_chunks=4, NT=64, two tiles along w
+    (2, 32, 32, 8, 32, 32),    # several tiles in every direction
+    (2, 64, 128, 2, 16, 16),   # NT=128, two K blocks (A stage reuse / EMPTY_A handshake)
+    (1, 128, 256, 4, 16, 16),  # two N tiles, four K blocks
+    (4, 64, 64, 2, 8, 8),      # H=8: MMA tiles straddle halo lines, tiles span samples, split-K
+    (3, 256, 128, 2, 8, 8),    # ragged batch vs tn, deep K, split-K workspace
+    (2, 16, 8, 4, 16, 16),     # Cout=8 padded to 16
+    (1, 24, 48, 2, 16, 8),     # Cin padded (24 -> 32), CoutP=48 -> NT=16 x 3
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("flip", [False, True])
+def test_tcgen05_fprop_matches_direct(shape, flip):
+    n, cin, cout, d, h, w = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    wt = torch.randn(cout, cin, 3, 3, 3, generator=g)
+    kin, kout = (cout, cin) if flip else (cin, cout)
+    xa = E.plain_to_act(torch.randn(n, kin, d, h, w, generator=g), BF)
+    ma = E.plain_to_act(torch.randn(n, kout, d, h, w, generator=g), BF)
+    bias = torch.randn(kout, generator=g)
+    xg, mg, wp = xa.cuda(), ma.cuda(), K.pack_conv_weight(wt.cuda(), BF, flip)
+    for (b, lrelu, mask) in [(None, False, False), (bias, True, False), (bias, False, True)]:
+        args = (xg, wp, None if b is None else b.cuda(), mg if mask else None, kin, kout, 0.05, lrelu)
+        ref = K.conv3d_fprop(*args, _lib.IMPL_DIRECT)
+        got = K.conv3d_fprop(*args, _lib.IMPL_TCGEN05)
+        torch.cuda.synchronize()
+        e = rel_err(got.float(), ref.float())
+        assert e < 3e-3, f"{shape} flip={flip} lrelu={lrelu} mask={mask}: tcgen05 vs direct {e:.3e}"
+    want = E.conv3d_fprop(xa, E.pack_conv_weight(wt, BF, flip), bias, None, kin, kout, 0.05, True)
+    got = K.conv3d_fprop(xg, wp, bias.cuda(), None, kin, kout, 0.05, True, _lib.IMPL_TCGEN05)
+    assert rel_err(got.float().cpu(), want.float()) < 3e-3
+
+
+def test_tcgen05_pad_channels_are_zero():
+    """pad channels of the output chunk must be written as zeros (the next layer contracts over them)"""
+    n, cin, cout, d, h, w = 1, 16, 8, 4, 16, 8
+    wt = torch.randn(cout, cin, 3, 3, 3)
+    x = E.plain_to_act(torch.randn(n, cin, d, h, w), BF).cuda()
+    y = K.conv3d_fprop(x, K.pack_conv_weight(wt.cuda(), BF, False), torch.ones(cout).cuda(), None, cin, cout,
+                       1.0, False, _lib.IMPL_TCGEN05)
+    assert float(y[:, 1].abs().max()) == 0.0
+
+
+def test_tcgen05_adjoint_property_full_size():
+    """Size-independent property at the BASELINE cfg3 top-level shape (32->64 @32x128x128):
+    <conv(x), g> == <x, dgrad(g)> for the tcgen05 fprop and its flipped-packing dgrad."""
+    n, cin, cout, d, h, w = 1, 32, 64, 32, 128, 128
+    g = torch.Generator(device="cuda").manual_seed(0)
+    wt = torch.randn(cout, cin, 3, 3, 3, device="cuda", generator=g)
+    x = K.plain_to_act(torch.randn(n, cin, d, h, w, device="cuda", generator=g), BF)
+    gy = K.plain_to_act(torch.randn(n, cout, d, h, w, device="cuda", generator=g), BF)
+    y = K.conv3d_fprop(x, K.pack_conv_weight(wt, BF, False), None, None, cin, cout, 0.03, False, _lib.IMPL_TCGEN05)
+    gx = K.conv3d_fprop(gy, K.pack_conv_weight(wt, BF, True), None, None, cout, cin, 0.03, False, _lib.IMPL_TCGEN05)
+    lhs = float((y.double() * gy.double()).sum())
+    rhs = float((x.double() * gx.double()).sum())
+    assert abs(lhs - rhs) < 5e-3 * max(abs(lhs), abs(rhs)), (lhs, rhs)
