@@ -101,12 +101,24 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# tools/profile_step.py sets this to a list to collect (name, int-args, start event, end event)
+# for every ABI call (CUDA events on the launching stream; no effect when None).
+PROFILE = None
+
+
 def call(name: str, *args):
     """Invoke an ABI function; tensors are turned into device pointers, the current torch
     stream is appended, a non-zero status raises RuntimeError(sg_last_error())."""
     lib = load()
     conv = [(_ptr(a) if (a is None or isinstance(a, torch.Tensor)) else a) for a in args]
-    rc = getattr(lib, name)(*conv, _stream())
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream())
+        rc = getattr(lib, name)(*conv, _stream())
+        e1.record(torch.cuda.current_stream())
+        PROFILE.append((name, tuple(a for a in args if isinstance(a, (int, bool))), e0, e1))
+    else:
+        rc = getattr(lib, name)(*conv, _stream())
     if rc != 0:
         msg = lib.sg_last_error()
         raise RuntimeError(f"{name} failed (status {rc}): {msg.decode() if msg else ''}")

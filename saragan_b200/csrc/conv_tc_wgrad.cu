@@ -1,0 +1,284 @@
+// tcgen05 / TMEM / TMA weight-gradient of the 3x3x3 convolution for sm_100a:
+//   gw[co][ci][tap] = scale * sum_{n,p} gy[n][co][p] * x[n][ci][p + tap - 1]     (fp32 out)
+//
+// GEMM view per tap: D[M = co][N = ci] += A[co][K = voxel] * B[ci][K = voxel]^T with K running
+// over the voxels of a tile.  In the channel-blocked layout a voxel is a 16-byte vector of 8
+// channels, i.e. both operands are "MN-major" UMMA operands straight out of the TMA tiles:
+//   element (channel c, voxel k) at (c/8)*SBO + (k/8)*LBO + (k%8)*16 + (c%8)*2
+// with SBO = the 8-channel chunk stride and LBO = the line pitch (one K=16 MMA step = two
+// consecutive lines x 8 voxels).  As in the fprop kernel the 9 in-plane taps (kh,kw) of x re-use
+// one halo tile through the descriptor start address; the three kd planes are separate CTAs
+// (blockIdx.y), each keeping its 9 accumulators [128 x NT] in tensor memory while it streams
+// through its share of the voxel tiles (persistent, multi-stage TMA pipeline), then adds them
+// to gw with fp32 atomics.
+#include "../../include/saragan_b200.h"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int kThreadsW = 192;
+
+struct WgParams {
+  float* gw;               // [Cout][Cin][27]
+  int N, D, H, W;
+  int Cin, Cout, CCin, CCout;
+  int td, th;              // tile = td x th x 8 voxels
+  int tiles_w, tiles_h, tiles_d;
+  int n_tiles;             // tiles_w * tiles_h * tiles_d * N
+  int g_chunk_bytes;       // td*th*8*16
+  int x_chunk_bytes;       // td*(th+2)*10*16 rounded up to 128 (TMA destinations are 128-byte aligned)
+  int x_box_bytes;         // td*(th+2)*10*16
+  int g_chunks;            // 8-channel chunks of gy loaded per tile (<= 16)
+  int stage_bytes;
+  int stages;
+  int slack_bytes;         // room after the last stage for the garbage-row reads of the M = 128 operand
+  int ci_tiles;            // CinP / NT
+  int tmem_cols;
+  float scale;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(kThreadsW)
+k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUtensorMap xmap,
+           const __grid_constant__ WgParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  // carve-up: stages x [gy tile (g_chunks chunks) | x halo tile (NT/8 chunks)], then barriers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes + p.slack_bytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * 8 + 1);
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  const int FULL = 0, EMPTY = p.stages, ACC_FULL = 2 * p.stages;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kd = blockIdx.y;
+  const int co_tile = blockIdx.z / p.ci_tiles, ci_tile = blockIdx.z % p.ci_tiles;
+  const int x_chunks = NT / 8;
+  const int halo_h = p.th + 2;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&gmap) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(BAR(FULL + i), 1);
+      mbar_init(BAR(EMPTY + i), 1);
+    }
+    mbar_init(BAR(ACC_FULL), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t smem_base = smem_u32(smem);
+
+  if (warp == 0) {
+    // ================================ producer ================================
+    if (lane == 0) {
+      const uint32_t tx = (uint32_t)(p.g_chunks * p.g_chunk_bytes + x_chunks * p.x_box_bytes);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        int t = tile;
+        const int tw_ = t % p.tiles_w; t /= p.tiles_w;
+        const int th_ = t % p.tiles_h; t /= p.tiles_h;
+        const int td_ = t % p.tiles_d; t /= p.tiles_d;
+        const int n = t;
+        const int w0 = tw_ * 8, h0 = th_ * p.th, d0 = td_ * p.td;
+        const int s = it % p.stages;
+        mbar_wait(BAR(EMPTY + s), ((it / p.stages) & 1) ^ 1);
+        mbar_expect_tx(BAR(FULL + s), tx);
+        const uint32_t g_dst = smem_base + s * p.stage_bytes;
+        const uint32_t x_dst = g_dst + p.g_chunks * p.g_chunk_bytes;
+        for (int c = 0; c < p.g_chunks; ++c)
+          tma_load_5d(g_dst + c * p.g_chunk_bytes, &gmap, BAR(FULL + s), w0 * 8, h0, d0, co_tile * 16 + c, n);
+        for (int c = 0; c < x_chunks; ++c)
+          tma_load_5d(x_dst + c * p.x_chunk_bytes, &xmap, BAR(FULL + s), (w0 - 1) * 8, h0 - 1, d0 + kd - 1,
+                      ci_tile * x_chunks + c, n);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      // D=f32, A=B=bf16, both MN-major (bits 15,16), N = NT, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+      int it = 0;
+      const int ksteps_per_plane = p.th / 2;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        const int s = it % p.stages;
+        mbar_wait(BAR(FULL + s), (it / p.stages) & 1);
+        tc_fence_after();
+        const uint32_t g_addr = smem_base + s * p.stage_bytes;
+        const uint32_t x_addr = g_addr + p.g_chunks * p.g_chunk_bytes;
+        for (int dl = 0; dl < p.td; ++dl) {
+          for (int j = 0; j < ksteps_per_plane; ++j) {
+            const uint32_t a0 = g_addr + (uint32_t)((dl * p.th + 2 * j) * 8) * 16u;
+            const uint64_t adesc = make_desc(a0, 128u, (uint32_t)p.g_chunk_bytes);
+#pragma unroll
+            for (int t9 = 0; t9 < 9; ++t9) {
+              const int kh = t9 / 3, kw = t9 % 3;
+              const uint32_t b0 = x_addr + (uint32_t)((dl * halo_h + 2 * j + kh) * 10 + kw) * 16u;
+              const uint64_t bdesc = make_desc(b0, 160u, (uint32_t)p.x_chunk_bytes);
+              tc_mma(tmem_base + t9 * NT, adesc, bdesc, idesc, (it | dl | j) != 0);
+            }
+          }
+        }
+        tc_commit(BAR(EMPTY + s));
+      }
+      tc_commit(BAR(ACC_FULL));
+    }
+  } else {
+    // ================================ epilogue ================================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int co = co_tile * 128 + row;
+    mbar_wait(BAR(ACC_FULL), 0);
+    tc_fence_after();
+    const bool any_tile = blockIdx.x < p.n_tiles;
+    for (int t9 = 0; t9 < 9; ++t9) {
+      const int tap = kd * 9 + t9;
+      for (int c0 = 0; c0 < NT; c0 += 16) {
+        float v[16];
+        __syncwarp();
+        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(t9 * NT + c0), v);
+        if (any_tile && co < p.Cout) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int ci = ci_tile * NT + c0 + j;
+            if (ci < p.Cin && v[j] != 0.f) atomicAdd(p.gw + ((int64_t)co * p.Cin + ci) * 27 + tap, v[j] * p.scale);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+struct WgPlan {
+  bool ok = false;
+  int NT = 0;
+  WgParams p{};
+  size_t smem = 0;
+  dim3 grid;
+};
+
+WgPlan make_wgrad_plan(int N, int Cin, int Cout, int D, int H, int W) {
+  WgPlan pl;
+  WgParams& p = pl.p;
+  if (W % 8 != 0 || H % 2 != 0 || H < 2) return pl;
+  const int CinP = 16 * ((Cin + 15) / 16), CoutP = 16 * ((Cout + 15) / 16);
+  const int NT = CinP % 32 == 0 ? 32 : 16;
+  int th = H < 16 ? H : 16;
+  if (H % th) return pl;
+  p.th = th;
+  p.g_chunks = CoutP / 8 < 16 ? CoutP / 8 : 16;
+  // td: as many planes per tile as keep a stage <= ~56 KB
+  int td = 1;
+  for (int cand = 1; cand <= D && cand <= 4; ++cand) {
+    if (D % cand) continue;
+    int gb = cand * th * 8 * 16, xb = (cand * (th + 2) * 10 * 16 + 127) / 128 * 128;
+    if (p.g_chunks * gb + (NT / 8) * xb <= 56 * 1024) td = cand;
+  }
+  p.td = td;
+  p.g_chunk_bytes = td * th * 8 * 16;
+  p.x_box_bytes = td * (th + 2) * 10 * 16;
+  p.x_chunk_bytes = (p.x_box_bytes + 127) / 128 * 128;
+  p.stage_bytes = (p.g_chunks * p.g_chunk_bytes + (NT / 8) * p.x_chunk_bytes + 127) / 128 * 128;
+  // the M = 128 operand reads 16 chunk strides of gy: with fewer real chunks the rest are
+  // garbage rows (discarded) read from the following bytes -- keep them inside the allocation
+  int over = 16 * p.g_chunk_bytes - p.stage_bytes;
+  p.slack_bytes = over > 0 ? (over + 255) / 128 * 128 : 128;
+  int stages = (int)((200 * 1024 - p.slack_bytes) / p.stage_bytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) return pl;
+  size_t total = (size_t)stages * p.stage_bytes;
+  p.stages = stages;
+  p.N = N; p.D = D; p.H = H; p.W = W;
+  p.Cin = Cin; p.Cout = Cout; p.CCin = sg_chunks(Cin); p.CCout = sg_chunks(Cout);
+  p.tiles_w = W / 8; p.tiles_h = H / th; p.tiles_d = D / td;
+  p.n_tiles = p.tiles_w * p.tiles_h * p.tiles_d * N;
+  p.ci_tiles = CinP / NT;
+  p.tmem_cols = 9 * NT <= 256 ? 256 : 512;
+  const int co_tiles = (CoutP + 127) / 128;
+  const int groups = 3 * co_tiles * p.ci_tiles;
+  int per_group = sg_num_sms() / groups;   // one CTA per SM (smem-limited): never more than one wave
+  if (per_group > p.n_tiles) per_group = p.n_tiles;
+  if (per_group < 1) per_group = 1;
+  pl.grid = dim3((unsigned)per_group, 3, (unsigned)(co_tiles * p.ci_tiles));
+  pl.smem = total + p.slack_bytes + 8 * (2 * 8 + 1) + 16;
+  pl.NT = NT;
+  pl.ok = true;
+  return pl;
+}
+
+template <int NT>
+int launch_wgrad(const WgPlan& pl, const CUtensorMap& gmap, const CUtensorMap& xmap, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+    if (e != cudaSuccess) {
+      sg_set_error("conv_tc_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  k_wgrad_tc<NT><<<pl.grid, kThreadsW, pl.smem, s>>>(gmap, xmap, pl.p);
+  return sg_check_launch("sg_conv3d_wgrad(tcgen05)");
+}
+
+int encode_act_map(CUtensorMap* map, const void* base, int N, int CC, int D, int H, int W, int box_w_vox, int box_h,
+                   int box_d) {
+  EncodeTiledFn encode = get_encode();
+  if (!encode) {
+    sg_set_error("conv_tc: cuTensorMapEncodeTiled not available");
+    return -2;
+  }
+  cuuint64_t dims[5] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)CC, (cuuint64_t)N};
+  cuuint64_t strides[4] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16,
+                           (cuuint64_t)CC * D * H * W * 16};
+  cuuint32_t box[5] = {(cuuint32_t)box_w_vox * 8, (cuuint32_t)box_h, (cuuint32_t)box_d, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    sg_set_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return -3;
+  }
+  return 0;
+}
+
+}  // namespace
+
+// returns 1 if the shape is not covered (caller falls through to the direct kernel)
+int sg_tc_wgrad(const void* x, const void* gy, float* gw, float* gb, int N, int Cin, int Cout, int D, int H, int W,
+                float scale, void* ws, int64_t ws_bytes, cudaStream_t s) {
+  (void)ws; (void)ws_bytes;
+  WgPlan pl = make_wgrad_plan(N, Cin, Cout, D, H, W);
+  if (!pl.ok) return 1;
+  WgParams& p = pl.p;
+  p.gw = gw;
+  p.scale = scale;
+  CUtensorMap gmap, xmap;
+  int rc = encode_act_map(&gmap, gy, N, p.CCout, D, H, W, 8, p.th, p.td);
+  if (rc) return rc;
+  rc = encode_act_map(&xmap, x, N, p.CCin, D, H, W, 10, p.th + 2, p.td);
+  if (rc) return rc;
+  cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)Cout * Cin * 27, s);
+  if (gb) {
+    rc = sg_pw_wgrad(gy, nullptr, nullptr, gb, SG_DTYPE_BF16, N, Cout, (int64_t)D * H * W, 1.f, s);
+    if (rc) return rc;
+  }
+  return pl.NT == 32 ? launch_wgrad<32>(pl, gmap, xmap, s) : launch_wgrad<16>(pl, gmap, xmap, s);
+}

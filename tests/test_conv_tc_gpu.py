@@ -50,6 +50,52 @@ def test_tcgen05_fprop_matches_direct(shape, flip):
     assert rel_err(got.float().cpu(), want.float()) < 3e-3
 
 
+WGRAD_SHAPES = [
+    (1, 16, 16, 2, 16, 8),     # one tile, NT=16, 2 gy chunks (14 garbage row-chunks)
+    (1, 32, 64, 4, 16, 16),    # D.b6 class: NT=32, td=2, several tiles, 3-stage ring wraps
+    (2, 64, 128, 2, 16, 16),   # two ci tiles, full M=128
+    (1, 128, 256, 4, 16, 16),  # two co tiles x four ci tiles
+    (4, 64, 64, 2, 8, 8),      # H=8 planes
+    (3, 256, 128, 2, 8, 8),    # ragged batch, many channel tiles
+    (2, 16, 8, 4, 16, 16),     # Cout=8 padded
+    (1, 24, 48, 2, 16, 8),     # padded Cin/Cout
+    (2, 32, 32, 8, 32, 32),    # persistent CTAs loop over many tiles
+]
+
+
+@pytest.mark.parametrize("shape", WGRAD_SHAPES)
+def test_tcgen05_wgrad_matches_direct(shape):
+    n, cin, cout, d, h, w = shape
+    g = torch.Generator().manual_seed(sum(shape) + 1)
+    xa = E.plain_to_act(torch.randn(n, cin, d, h, w, generator=g), BF)
+    ga = E.plain_to_act(torch.randn(n, cout, d, h, w, generator=g), BF)
+    xg, gg = xa.cuda(), ga.cuda()
+    ref_w, ref_b = K.conv3d_wgrad(xg, gg, cin, cout, 0.07, True, _lib.IMPL_DIRECT)
+    got_w, got_b = K.conv3d_wgrad(xg, gg, cin, cout, 0.07, True, _lib.IMPL_TCGEN05)
+    torch.cuda.synchronize()
+    e = rel_err(got_w, ref_w)
+    assert e < 1e-3, f"{shape}: tcgen05 wgrad vs direct {e:.3e}"
+    assert rel_err(got_b, ref_b) < 1e-4
+    want_w, _ = E.conv3d_wgrad(xa, ga, cin, cout, 0.07, False)
+    assert rel_err(got_w.cpu(), want_w) < 1e-3
+
+
+def test_tcgen05_wgrad_linearity_full_size():
+    """Size-independent property at the cfg3 top-level shape (32->64 @32x128x128):
+    <wgrad(x, g), w> == <conv(x, w), g> ties the tcgen05 wgrad to the tcgen05 fprop."""
+    n, cin, cout, d, h, w = 1, 32, 64, 32, 128, 128
+    g = torch.Generator(device="cuda").manual_seed(1)
+    wt = torch.randn(cout, cin, 3, 3, 3, device="cuda", generator=g).bfloat16().float()
+    x = K.plain_to_act(torch.randn(n, cin, d, h, w, device="cuda", generator=g), BF)
+    gy = K.plain_to_act(torch.randn(n, cout, d, h, w, device="cuda", generator=g), BF)
+    gw, _ = K.conv3d_wgrad(x, gy, cin, cout, 1.0, False, _lib.IMPL_TCGEN05)
+    y = K.conv3d_fprop(x, K.pack_conv_weight(wt, BF, False), None, None, cin, cout, 1.0, False,
+                       _lib.IMPL_TCGEN05)
+    lhs = float((gw.double() * wt.double()).sum())
+    rhs = float((y.double() * gy.double()).sum())
+    assert abs(lhs - rhs) < 5e-3 * max(abs(lhs), abs(rhs)), (lhs, rhs)
+
+
 def test_tcgen05_pad_channels_are_zero():
     """pad channels of the output chunk must be written as zeros (the next layer contracts over them)"""
     n, cin, cout, d, h, w = 1, 16, 8, 4, 16, 8

@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""Per-entry-point time breakdown of one train step, measured in situ with CUDA events around
+every C-ABI call (no profiler attached).  Usage: python tools/profile_step.py [--config cfg3]"""
+import argparse
+import collections
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import saragan_b200 as sg  # noqa: E402
+from saragan_b200 import _lib, costmodel as C  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="cfg3")
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--top", type=int, default=40)
+    args = ap.parse_args()
+    cfg = dict(C.CONFIGS[args.config])
+    B = args.batch or cfg["batch"]
+    vol = C.volume(cfg["phase"])
+    torch.manual_seed(0)
+    g = sg.Generator(cfg["phase"], cfg["num_phases"], cfg["base_dim"], cfg["latent_dim"], C.BASE_SHAPE)
+    d = sg.Discriminator(cfg["phase"], cfg["num_phases"], cfg["base_dim"], cfg["latent_dim"], C.BASE_SHAPE)
+    g_opt, d_opt = sg.make_optimizers(g, d)
+    x = torch.rand(B, 1, *vol, device="cuda") * 2
+    for _ in range(2):
+        sg.train_step(x, g, d, g_opt, d_opt, 0.5)
+    torch.cuda.synchronize()
+    _lib.PROFILE = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        sg.train_step(x, g, d, g_opt, d_opt, 0.5)
+    e1.record()
+    torch.cuda.synchronize()
+    total = e0.elapsed_time(e1) / args.steps
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    byname = collections.defaultdict(lambda: [0, 0.0])
+    for name, key, a, b in _lib.PROFILE:
+        ms = a.elapsed_time(b) / args.steps
+        agg[(name, key)][0] += 1
+        agg[(name, key)][1] += ms
+        byname[name][0] += 1
+        byname[name][1] += ms
+    _lib.PROFILE = None
+    covered = sum(v[1] for v in byname.values())
+    print(f"config {args.config} B={B}: {total:.2f} ms/step; ABI calls cover {covered:.2f} ms "
+          f"({100 * covered / total:.1f} %); {len(agg)} distinct (entry point, shape) pairs")
+    print("\n-- by entry point")
+    for name, (n, ms) in sorted(byname.items(), key=lambda kv: -kv[1][1]):
+        print(f"{ms:9.3f} ms {100 * ms / total:5.1f} %  n/step={n / args.steps:6.1f}  {name}")
+    print("\n-- by (entry point, integer args)")
+    for (name, key), (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:args.top]:
+        print(f"{ms:9.3f} ms {100 * ms / total:5.1f} %  n/step={n / args.steps:5.1f}  {ms / n * args.steps * 1e3:9.1f} us/call  {name} {key}")
+
+
+if __name__ == "__main__":
+    main()
