@@ -31,6 +31,7 @@ SIGNATURES = {
     "sg_pack_conv_weight": [_c_p, _c_p, _c_int, _c_int, _c_int, _c_int, _c_p],
     "sg_conv3d_fprop": [_c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                         _c_int, _c_f, _c_int, _c_int, _c_p, _c_i64, _c_p],
+    "sg_tc_force_streaming": [_c_int],
     "sg_tc_plan_debug": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, ctypes.POINTER(ctypes.c_int)],
     "sg_conv3d_workspace_bytes": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int],
     "sg_conv3d_wgrad": [_c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
@@ -53,7 +54,8 @@ SIGNATURES = {
     "sg_linear_wgrad": [_c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_f, _c_p],
 }
 _RESTYPES = {"sg_last_error": ctypes.c_char_p, "sg_packed_weight_elems": ctypes.c_int64,
-             "sg_conv3d_workspace_bytes": ctypes.c_int64, "sg_launch_count": ctypes.c_int64}
+             "sg_conv3d_workspace_bytes": ctypes.c_int64, "sg_launch_count": ctypes.c_int64,
+             "sg_tc_force_streaming": None}
 
 _lib = None
 

@@ -352,6 +352,71 @@ k_wgrad_direct(const T* __restrict__ x, const T* __restrict__ gy, float* __restr
     }
 }
 
+
+// ------------------------------------------------- small-volume fp32 wgrad (base level)
+// gw[co][ci][tap] = scale * sum_m gy[m][co] * x[m + tap][ci] with only M = N*V rows (64 at B=4)
+// but Cout*Cin*27 = 7 M outputs: an SGEMM with a tiny K.  block = 64 co x 64 ci x one tap,
+// 4x4 register tile per thread, K = M streamed through shared memory in steps of 16; every
+// output is owned by exactly one thread (no atomics, deterministic).
+__global__ void __launch_bounds__(256)
+k_wgrad_small_f32(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gw,
+                  int N, int Cin, int Cout, int CCin, int CCout, int D, int H, int W, float scale) {
+  __shared__ float As[16][64 + 4];   // [m][co]
+  __shared__ float Bs[16][64 + 4];   // [m][ci]
+  const int tap = blockIdx.z;
+  const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+  const int V = D * H * W, M = N * V;
+  const int co0 = blockIdx.x * 64, ci0 = blockIdx.y * 64;
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const int lm = t >> 4, l4 = (t & 15) * 4;     // loader: row m (0..15), 4 consecutive channels
+  float c[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
+  for (int m0 = 0; m0 < M; m0 += 16) {
+    const int m = m0 + lm;
+    float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m < M) {
+      const int n = m / V, v = m % V;
+      const int co = co0 + l4, ci = ci0 + l4;
+      if (co < CCout * 8)
+        av = *reinterpret_cast<const float4*>(gy + (((int64_t)n * CCout + (co >> 3)) * V + v) * 8 + (co & 7));
+      const int w0 = v % W, h0 = (v / W) % H, d0 = v / (W * H);
+      const int d = d0 + kd - 1, h = h0 + kh - 1, w_ = w0 + kw - 1;
+      if (ci < CCin * 8 && d >= 0 && d < D && h >= 0 && h < H && w_ >= 0 && w_ < W)
+        bv = *reinterpret_cast<const float4*>(
+            x + (((int64_t)n * CCin + (ci >> 3)) * V + ((int64_t)d * H + h) * W + w_) * 8 + (ci & 7));
+    }
+    As[lm][l4 + 0] = av.x; As[lm][l4 + 1] = av.y; As[lm][l4 + 2] = av.z; As[lm][l4 + 3] = av.w;
+    Bs[lm][l4 + 0] = bv.x; Bs[lm][l4 + 1] = bv.y; Bs[lm][l4 + 2] = bv.z; Bs[lm][l4 + 3] = bv.w;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c[i][j] = fmaf(a[i], b[j], c[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = co0 + ty * 4 + i;
+    if (co >= Cout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ci = ci0 + tx * 4 + j;
+      if (ci < Cin) gw[((int64_t)co * Cin + ci) * 27 + tap] = c[i][j] * scale;
+    }
+  }
+}
+
 template <typename T>
 static int launch_direct_wgrad(const void* x, const void* gy, float* gw, int N, int Cin, int Cout,
                                int D, int H, int W, float scale, cudaStream_t s) {
@@ -384,11 +449,18 @@ extern "C" int sg_conv3d_wgrad(const void* x, const void* gy, float* gw, float* 
   } else {
     SG_REQUIRE(impl != SG_IMPL_TCGEN05 || N == 0, "sg_conv3d_wgrad: tcgen05 path needs bf16 activations");
   }
-  cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)Cout * Cin * 27, s);
   if (gb) {
     int rc = sg_pw_wgrad(gy, nullptr, nullptr, gb, dtype, N, Cout, (int64_t)D * H * W, 1.f, s);
     if (rc) return rc;
   }
+  if (impl == SG_IMPL_AUTO && N > 0 && small_f32_applies(dtype, N, D, H, W)) {
+    int CCin = sg_chunks(Cin), CCout = sg_chunks(Cout);
+    dim3 grid((unsigned)((Cout + 63) / 64), (unsigned)((Cin + 63) / 64), 27);
+    k_wgrad_small_f32<<<grid, 256, 0, s>>>((const float*)x, (const float*)gy, gw, N, Cin, Cout, CCin, CCout, D, H,
+                                           W, scale);
+    return sg_check_launch("sg_conv3d_wgrad(small f32)");
+  }
+  cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)Cout * Cin * 27, s);
   if (N == 0) return 0;
   SG_DISPATCH(dtype, return launch_direct_wgrad<T>(x, gy, gw, N, Cin, Cout, D, H, W, scale, s););
 }

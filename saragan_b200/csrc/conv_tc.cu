@@ -29,7 +29,6 @@ int sg_conv_finish_bf16(const float* acc, const float* bias, const void* mask_sr
 
 namespace {
 
-constexpr int kMaxSub = 8;
 constexpr int kThreads = 192;
 
 struct TcParams {
@@ -133,40 +132,53 @@ k_conv_tc(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ TcPa
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    {
+      const uint32_t leader = elect_one();   // all lanes run the loops; one issues
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N = NT, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t a_addr = smem_u32(a_smem);
-      const uint32_t w_addr = smem_u32(w_smem);
       const uint32_t line_pitch = (uint32_t)p.halo_w * 16u;
-      int it = 0;
+      // hoisted descriptor pieces (16-byte units): the first valid line sits (halo_h + 1) lines into
+      // the block, which is also the most negative tap offset, so both offset families are >= 0
+      const int bias_vox = (p.halo_h + 1) * p.halo_w;
+      uint32_t sub_off[kMaxSub];
+#pragma unroll
+      for (int i = 0; i < kMaxSub; ++i) sub_off[i] = i < p.n_sub ? (uint32_t)(p.sub_line[i] * p.halo_w - bias_vox) : 0u;
+      const uint64_t a_desc0 = make_desc(smem_u32(a_smem), (uint32_t)p.chunk_bytes, line_pitch);
+      const uint64_t w_desc0 = make_desc(smem_u32(w_smem), NT * 16u, 128u);
+      const uint32_t kk_a = (uint32_t)(2 * p.chunk_bytes) >> 4;
+      const uint32_t w_stage16 = (uint32_t)p.w_stage_bytes >> 4;
+      const int kpairs = p.kb_chunks / 2, n_sub = p.n_sub, halo_w = p.halo_w, halo_h = p.halo_h, sw = p.sw;
+      int s = 0, ph = 0;
       for (int kb = 0; kb < p.kblocks_per_split; ++kb) {
         mbar_wait(BAR(FULL_A), kb & 1);
-        for (int tap = 0; tap < 27; ++tap, ++it) {
-          const int s = it % p.sw;
-          mbar_wait(BAR(FULL_W + s), (it / p.sw) & 1);
-          tc_fence_after();
-          const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-          const int line_off = (kd - 1) * p.halo_h + (kh - 1);
-          for (int kk = 0; kk < p.kb_chunks / 2; ++kk) {
-            const uint64_t bdesc = make_desc(w_addr + s * p.w_stage_bytes + kk * 2 * NT * 16, NT * 16u, 128u);
-            for (int sub = 0; sub < p.n_sub; ++sub) {
-              const uint32_t a0 = a_addr + kk * 2 * p.chunk_bytes +
-                                  ((uint32_t)(p.sub_line[sub] + line_off) * p.halo_w + kw) * 16u;
-              const uint64_t adesc = make_desc(a0, (uint32_t)p.chunk_bytes, line_pitch);
-              tc_mma(tmem_base + sub * NT, adesc, bdesc, idesc, (kb | tap | kk) != 0);
+        int tap = 0;
+        for (int kd = 0; kd < 3; ++kd)
+          for (int kh = 0; kh < 3; ++kh) {
+            const int row_off = ((kd - 1) * halo_h + (kh - 1)) * halo_w + bias_vox;
+            for (int kw = 0; kw < 3; ++kw, ++tap) {
+              mbar_wait(BAR(FULL_W + s), ph);
+              tc_fence_after();
+              issue_tap<NT>(tmem_base, a_desc0 + (uint64_t)(uint32_t)(row_off + kw), w_desc0 + (uint64_t)(s * w_stage16),
+                            sub_off, n_sub, kpairs, kk_a, idesc, (kb | tap) != 0, leader);
+              tc_commit(BAR(EMPTY_W + s), leader);
+              if (++s == sw) { s = 0; ph ^= 1; }
             }
           }
-          tc_commit(BAR(EMPTY_W + s));
-        }
-        tc_commit(BAR(EMPTY_A));
+        tc_commit(BAR(EMPTY_A), leader);
       }
-      tc_commit(BAR(ACC_FULL));
+      tc_commit(BAR(ACC_FULL), leader);
     }
   } else {
     // ================================ epilogue ================================
     const int quad = warp & 3;              // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;       // accumulator row == TMEM lane
+    const float scale = p.scale;
+    const int lrelu = p.lrelu;
+    const __nv_bfloat16* mask = p.mask;
+    __nv_bfloat16* yout = p.y;
+    float* s_bias = reinterpret_cast<float*>(bars + 24);   // NT floats, 16-byte aligned, after the barriers
+    for (int i = row; i < NT; i += 128) s_bias[i] = (p.bias && co0 + i < p.Cout) ? p.bias[co0 + i] : 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
     mbar_wait(BAR(ACC_FULL), 0);
     tc_fence_after();
     const int64_t V = (int64_t)p.D * p.H * p.W;
@@ -192,25 +204,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ TcPa
 #pragma unroll
           for (int j = 0; j < 16; ++j) atomicAdd(dst + j, v[j]);
         } else {
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const int cc = (co0 + c0) / 8 + half;
-            const int64_t oidx = (((int64_t)n * p.CCout + cc) * V + vox) * 8;
-            F8 o, m;
-            if (p.mask) m = ld8(p.mask + oidx);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int co = cc * 8 + j;
-              float r = 0.f;
-              if (co < p.Cout) {
-                r = v[half * 8 + j] * p.scale + (p.bias ? __ldg(p.bias + co) : 0.f);
-                if (p.lrelu) r = lrelu02(r);
-                if (p.mask) r *= lmask02(m.v[j]);
-              }
-              o.v[j] = r;
-            }
-            st8(p.y + oidx, o);
-          }
+          const int64_t o = (((int64_t)n * p.CCout + (co0 + c0) / 8) * V + vox) * 8;
+          epilogue16(v, s_bias + c0, scale, lrelu, mask ? mask + o : nullptr, yout + o, V * 8);
         }
       }
     }
@@ -313,7 +308,7 @@ Plan make_plan(int N, int Cin, int Cout, int D, int H, int W) {
   p.splits = splits;
   p.kblocks_per_split = n_kblocks / splits;
   pl.NT = NT;
-  pl.smem = (size_t)p.a_bytes + (size_t)p.sw * p.w_stage_bytes + 8 * (3 + 2 * kMaxSub + 2) + 16;
+  pl.smem = (size_t)p.a_bytes + (size_t)p.sw * p.w_stage_bytes + 8 * 24 + 4 * 128 + 16;
   pl.grid = dim3((unsigned)(p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n), (unsigned)(CoutP / NT), (unsigned)splits);
   pl.ok = true;
   return pl;
@@ -336,8 +331,42 @@ int launch(const Plan& pl, const CUtensorMap& map, cudaStream_t s) {
 
 }  // namespace
 
+#include "conv_tc_res.cuh"
+
+namespace {
+// tests: 0 = auto, 1 = always the streaming kernel, 2 = the weight-resident kernel whenever the
+// geometry allows (ignoring the "enough tiles to amortise the weight load" heuristic)
+int g_force_streaming = 0;
+
+int encode_halo_map(CUtensorMap* map, const void* x, int N, int CC, int D, int H, int W, int halo_w, int halo_h,
+                    int halo_d, int tn) {
+  EncodeTiledFn encode = get_encode();
+  if (!encode) {
+    sg_set_error("conv_tc: cuTensorMapEncodeTiled not available");
+    return -2;
+  }
+  // activations as a 5-D tensor [W*8 | H | D | CC | N] of bf16; box = one 8-channel halo block
+  cuuint64_t dims[5] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)CC, (cuuint64_t)N};
+  cuuint64_t strides[4] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16,
+                           (cuuint64_t)CC * D * H * W * 16};
+  cuuint32_t box[5] = {(cuuint32_t)halo_w * 8, (cuuint32_t)halo_h, (cuuint32_t)halo_d, 1, (cuuint32_t)tn};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    sg_set_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return -3;
+  }
+  return 0;
+}
+}  // namespace
+
+extern "C" void sg_tc_force_streaming(int on) { g_force_streaming = on; }
+
 int64_t sg_tc_workspace_bytes(int kind, int N, int Cin, int Cout, int D, int H, int W) {
   if (kind != 0) return 0;
+  if (g_force_streaming != 1 && make_res_plan(N, Cin, Cout, D, H, W, g_force_streaming == 2).ok) return 0;
   Plan pl = make_plan(N, Cin, Cout, D, H, W);
   if (!pl.ok || pl.p.splits == 1) return 0;
   return (int64_t)N * D * H * W * pl.p.CoutP * (int64_t)sizeof(float);
@@ -345,6 +374,26 @@ int64_t sg_tc_workspace_bytes(int kind, int N, int Cin, int Cout, int D, int H, 
 
 int sg_tc_fprop(const void* x, const void* wp, const float* bias, const void* mask_src, void* y, int N, int Cin,
                 int Cout, int D, int H, int W, float scale, int lrelu, void* ws, int64_t ws_bytes, cudaStream_t s) {
+  if (g_force_streaming != 1) {
+    ResPlan rp = make_res_plan(N, Cin, Cout, D, H, W, g_force_streaming == 2);
+    if (rp.ok) {
+      ResParams& q = rp.p;
+      q.wp = (const __nv_bfloat16*)wp;
+      q.bias = bias;
+      q.mask = (const __nv_bfloat16*)mask_src;
+      q.y = (__nv_bfloat16*)y;
+      q.scale = scale;
+      q.lrelu = lrelu;
+      CUtensorMap rmap;
+      int rc = encode_halo_map(&rmap, x, N, q.CCin, D, H, W, q.halo_w, q.halo_h, q.halo_d, 1);
+      if (rc) return rc;
+      switch (rp.NT) {
+        case 16: return launch_res<16>(rp, rmap, s);
+        case 32: return launch_res<32>(rp, rmap, s);
+        default: return launch_res<64>(rp, rmap, s);
+      }
+    }
+  }
   Plan pl = make_plan(N, Cin, Cout, D, H, W);
   if (!pl.ok) return 1;
   EncodeTiledFn encode = get_encode();

@@ -1,0 +1,321 @@
+// Persistent, weight-resident variant of the tcgen05 implicit-GEMM convolution (included by
+// conv_tc.cu).  For the high-resolution, small-channel layers that hold ~85 % of the step's
+// FLOPs the whole packed weight slice of a CTA's N tile (27 taps x Cin x NT <= ~110 KB) fits in
+// shared memory next to a double-buffered halo tile:
+//   * one CTA per SM, weights loaded ONCE per launch (the streaming kernel re-fetched them per
+//     tile: 60 % of its L2->SMEM bytes, and its MMA issuer starved on the 1 KB bulk copies);
+//   * static tile schedule tile = blockIdx.x + i*gridDim.x; the producer runs ahead across
+//     tile boundaries through a ring of halo stages;
+//   * two TMEM accumulator sets: the epilogue of tile i overlaps the MMAs of tile i+1.
+// Geometry, operand descriptors and epilogue are those of k_conv_tc.
+#pragma once
+
+namespace {
+
+constexpr int kResStages = 4;   // upper bound of halo stages
+
+struct ResParams {
+  const __nv_bfloat16* wp;
+  const float* bias;
+  const __nv_bfloat16* mask;
+  __nv_bfloat16* y;
+  int N, D, H, W;
+  int CCin, Cout, CoutP, CCout;
+  int td, th;
+  int tiles_w, tiles_h, tiles_d, n_tiles;
+  int halo_w, halo_h, halo_d;
+  int chunk_bytes, chunk_tx_bytes;
+  int n_sub;
+  int sub_line[kMaxSub];
+  int kb_chunks, n_kblocks;
+  int stages, stage_bytes;
+  int w_bytes;               // resident weights: 27 * CCin * NT * 16
+  int tmem_cols;
+  float scale;
+  int lrelu;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// NT = output-channel tile, TD = depth planes per tile (= MMA tiles per accumulator set),
+// KBC = 8-channel chunks per K block.  With th = 16 and tw = 8 fixed, every descriptor offset of
+// the 27 x KBC/2 x TD MMAs of a K block is a compile-time constant: the fully unrolled issue
+// loop costs one uniform-datapath add per MMA.
+template <int NT, int TD, int KBC>
+__global__ void __launch_bounds__(kThreads, 1)
+k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ ResParams p) {
+  constexpr int HALO_H = 18, HALO_W = 10;
+  constexpr int CHUNK_BYTES = ((TD + 2) * HALO_H * HALO_W * 16 + 127) / 128 * 128;
+  constexpr uint32_t KK_A = (2u * CHUNK_BYTES) >> 4;
+  constexpr uint32_t PLANE = HALO_H * HALO_W;   // voxels (16-byte units) per halo plane
+  extern __shared__ __align__(128) uint8_t smem[];
+  // carve-up: [weights][halo stages][slack for garbage-row reads][barriers][tmem slot]
+  uint8_t* w_smem = smem;
+  uint8_t* a_smem = smem + p.w_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_smem + p.stages * p.stage_bytes + 4096);
+  // bars: [0] w_full, [1..1+S) a_full, [1+S..1+2S) a_empty, then acc_full[2], acc_empty[2]
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  const int W_FULL = 0, A_FULL = 1, A_EMPTY = 1 + p.stages, ACC_FULL = 1 + 2 * p.stages, ACC_EMPTY = ACC_FULL + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * kResStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int co0 = blockIdx.y * NT;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+    mbar_init(BAR(W_FULL), 1);
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(BAR(A_FULL + i), 1);
+      mbar_init(BAR(A_EMPTY + i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(BAR(ACC_FULL + i), 1);
+      mbar_init(BAR(ACC_EMPTY + i), 4);   // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int acc_cols = p.n_sub * NT;      // columns of one accumulator set
+  float* s_bias = reinterpret_cast<float*>(bars + 16);   // NT floats, 16-byte aligned, after the barriers
+
+  if (warp == 0) {
+    // ================================ producer ================================
+    if (lane == 0) {
+      // resident weights: 27*CCin pieces of NT rows x 16 B, contiguous in the packed tensor
+      const uint32_t w_addr = smem_u32(w_smem);
+      mbar_expect_tx(BAR(W_FULL), (uint32_t)p.w_bytes);
+      for (int i = 0; i < 27 * p.CCin; ++i)
+        bulk_load(w_addr + i * NT * 16, p.wp + ((int64_t)i * p.CoutP + co0) * 8, NT * 16u, BAR(W_FULL));
+      const uint32_t a_addr = smem_u32(a_smem);
+      const uint32_t a_tx = (uint32_t)p.kb_chunks * (uint32_t)p.chunk_tx_bytes;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int tile_w = t % p.tiles_w; t /= p.tiles_w;
+        const int tile_h = t % p.tiles_h; t /= p.tiles_h;
+        const int tile_d = t % p.tiles_d; t /= p.tiles_d;
+        const int n = t;
+        const int w0 = tile_w * 8, h0 = tile_h * p.th, d0 = tile_d * p.td;
+        for (int kb = 0; kb < p.n_kblocks; ++kb, ++it) {
+          const int s = it % p.stages;
+          mbar_wait(BAR(A_EMPTY + s), ((it / p.stages) & 1) ^ 1);
+          mbar_expect_tx(BAR(A_FULL + s), a_tx);
+          for (int c = 0; c < p.kb_chunks; ++c)
+            tma_load_5d(a_addr + s * p.stage_bytes + c * p.chunk_bytes, &xmap, BAR(A_FULL + s), (w0 - 1) * 8, h0 - 1,
+                        d0 - 1, kb * p.kb_chunks + c, n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    {
+      const uint32_t leader = elect_one();   // all lanes run the loops; one issues
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+      const uint64_t a_desc0 = make_desc(smem_u32(a_smem), (uint32_t)CHUNK_BYTES, HALO_W * 16u);
+      const uint64_t w_desc0 = make_desc(smem_u32(w_smem), NT * 16u, 128u);
+      const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4;
+      const int stages = p.stages, n_kblocks = p.n_kblocks;
+      const uint32_t w_tap16 = (uint32_t)(p.CCin * NT);
+      mbar_wait(BAR(W_FULL), 0);
+      int s = 0, ph = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
+        const int buf = ti & 1;
+        mbar_wait(BAR(ACC_EMPTY + buf), ((ti >> 1) & 1) ^ 1);   // epilogue has drained this set
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * acc_cols;
+        for (int kb = 0; kb < n_kblocks; ++kb) {
+          mbar_wait(BAR(A_FULL + s), ph);
+          tc_fence_after();
+          const uint64_t a_stage = a_desc0 + (uint64_t)(s * stage16);
+          uint64_t b_tap = w_desc0 + (uint64_t)(kb * (KBC * NT));
+          const uint32_t acc0 = kb != 0;
+#pragma unroll
+          for (int tap = 0; tap < 27; ++tap) {
+            // output voxel (d,h,w) of MMA tile `sub` reads halo voxel (sub+kd, h+kh, w+kw)
+            const uint32_t a_off = (uint32_t)(((tap / 9) * HALO_H + (tap / 3) % 3) * HALO_W + tap % 3);
+#pragma unroll
+            for (int kk = 0; kk < KBC / 2; ++kk)
+#pragma unroll
+              for (int sub = 0; sub < TD; ++sub)
+                tc_mma(d_tmem + sub * NT, a_stage + (uint64_t)(a_off + sub * PLANE + kk * KK_A),
+                       b_tap + (uint64_t)(kk * 2 * NT), idesc, (tap | kk) ? 1u : acc0, leader);
+            b_tap += w_tap16;
+          }
+          tc_commit(BAR(A_EMPTY + s), leader);
+          if (++s == stages) { s = 0; ph ^= 1; }
+        }
+        tc_commit(BAR(ACC_FULL + buf), leader);
+      }
+    }
+  } else {
+    // ================================ epilogue ================================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int64_t V = (int64_t)p.D * p.H * p.W;
+    const float scale = p.scale;
+    const int lrelu = p.lrelu;
+    const __nv_bfloat16* mask = p.mask;
+    __nv_bfloat16* yout = p.y;
+    for (int i = row; i < NT; i += 128) s_bias[i] = (p.bias && co0 + i < p.Cout) ? p.bias[co0 + i] : 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
+      int t = tile;
+      const int tile_w = t % p.tiles_w; t /= p.tiles_w;
+      const int tile_h = t % p.tiles_h; t /= p.tiles_h;
+      const int tile_d = t % p.tiles_d; t /= p.tiles_d;
+      const int n = t;
+      const int w0 = tile_w * 8, h0 = tile_h * p.th, d0 = tile_d * p.td;
+      const int buf = ti & 1;
+      mbar_wait(BAR(ACC_FULL + buf), (ti >> 1) & 1);
+      tc_fence_after();
+      for (int sub = 0; sub < p.n_sub; ++sub) {
+        const int line = p.sub_line[sub] + (row >> 3);
+        const int wl = row & 7;
+        const int dh = line / p.halo_h, hh = line - dh * p.halo_h;
+        const int d = d0 + dh - 1, h = h0 + hh - 1, w = w0 + wl;
+        const bool valid = dh >= 1 && dh <= p.td && hh >= 1 && hh <= p.th && d < p.D && h < p.H && w < p.W;
+        const int64_t vox = ((int64_t)d * p.H + h) * p.W + w;
+        const int64_t obase = (((int64_t)n * p.CCout + co0 / 8) * V + vox) * 8;
+#pragma unroll
+        for (int c0 = 0; c0 < NT; c0 += 16) {
+          float v[16];
+          __syncwarp();
+          tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * acc_cols + sub * NT + c0), v);
+          if (valid) {
+            const int64_t o = obase + (int64_t)(c0 / 8) * V * 8;
+            epilogue16(v, s_bias + c0, scale, lrelu, mask ? mask + o : nullptr, yout + o, V * 8);
+          }
+        }
+      }
+      // this warp is done reading the accumulator set: hand it back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(ACC_EMPTY + buf));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+struct ResPlan {
+  bool ok = false;
+  int NT = 0;
+  ResParams p{};
+  size_t smem = 0;
+  dim3 grid;
+};
+
+// Applies when H >= 16, W % 8 == 0 and the weight slice of one N tile fits next to >= 2 halo stages.
+ResPlan make_res_plan(int N, int Cin, int Cout, int D, int H, int W, bool for_test = false) {
+  ResPlan pl;
+  ResParams& p = pl.p;
+  if (W % 8 != 0 || H % 16 != 0) return pl;
+  const int CCin = sg_chunks(Cin), CoutP = 16 * ((Cout + 15) / 16);
+  const int budget = 222 * 1024;
+  // N tile: the largest of {64, 32, 16} dividing CoutP whose resident weights leave room for the halo ring
+  int NT = 0;
+  for (int cand : {64, 32, 16}) {
+    if (CoutP % cand) continue;
+    if (27 * CCin * cand * 16 <= 120 * 1024) { NT = cand; break; }
+  }
+  if (NT == 0) return pl;
+  if (CoutP / NT > 2) return pl;           // more N tiles would re-read the halo too often: stream instead
+  p.w_bytes = 27 * CCin * NT * 16;
+  p.th = 16;
+  p.halo_w = 10; p.halo_h = 18;
+  p.kb_chunks = CCin % 4 == 0 ? 4 : 2;
+  p.n_kblocks = CCin / p.kb_chunks;
+  // td: two accumulator sets of td MMA tiles must fit TMEM; >= 2 stages must fit shared memory
+  int best_td = 0;
+  for (int td = 1; td <= D && td <= 4; td *= 2) {
+    if (D % td) continue;
+    if (2 * td * NT > 512) continue;
+    int chunk = ((td + 2) * 18 * 10 * 16 + 127) / 128 * 128;
+    int stage = p.kb_chunks * chunk;
+    if (p.w_bytes + 2 * stage + 4096 + 512 > budget) continue;
+    best_td = td;
+  }
+  if (best_td == 0) return pl;
+  p.td = best_td;
+  p.halo_d = p.td + 2;
+  p.chunk_tx_bytes = p.halo_d * p.halo_h * p.halo_w * 16;
+  p.chunk_bytes = (p.chunk_tx_bytes + 127) / 128 * 128;
+  p.stage_bytes = p.kb_chunks * p.chunk_bytes;
+  int stages = (budget - p.w_bytes - 4096 - 512) / p.stage_bytes;
+  if (stages > kResStages) stages = kResStages;
+  p.stages = stages;
+  p.n_sub = p.td;
+  for (int i = 0; i < p.td; ++i) p.sub_line[i] = (i + 1) * p.halo_h + 1;
+  p.tiles_w = W / 8; p.tiles_h = H / 16; p.tiles_d = D / p.td;
+  p.n_tiles = p.tiles_w * p.tiles_h * p.tiles_d * N;
+  p.N = N; p.D = D; p.H = H; p.W = W;
+  p.CCin = CCin; p.Cout = Cout; p.CoutP = CoutP; p.CCout = sg_chunks(Cout);
+  p.tmem_cols = round_pow2_cols(2 * p.n_sub * NT);
+  const int n_ntiles = CoutP / NT;
+  int ctas = sg_num_sms() / n_ntiles;
+  if (ctas > p.n_tiles) ctas = p.n_tiles;
+  if (ctas < 1) return pl;
+  if (for_test) {
+    ctas = p.n_tiles >= 3 ? p.n_tiles / 3 : 1;   // tests: every CTA walks ~3 tiles (both accumulator sets, ring wrap)
+    if (ctas > sg_num_sms() / n_ntiles) ctas = sg_num_sms() / n_ntiles;
+  } else if (p.n_tiles < 2 * ctas) {
+    return pl;                                   // too few tiles to amortise the weight load: stream instead
+  }
+  pl.grid = dim3((unsigned)ctas, (unsigned)n_ntiles, 1);
+  pl.smem = (size_t)p.w_bytes + (size_t)p.stages * p.stage_bytes + 4096 + 8 * 16 + 4 * 64 + 16;
+  pl.NT = NT;
+  pl.ok = true;
+  return pl;
+}
+
+template <int NT, int TD, int KBC>
+int launch_res_inst(const ResPlan& pl, const CUtensorMap& map, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e =
+        cudaFuncSetAttribute(k_conv_tc_res<NT, TD, KBC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      sg_set_error("conv_tc_res: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  k_conv_tc_res<NT, TD, KBC><<<pl.grid, kThreads, pl.smem, s>>>(map, pl.p);
+  return sg_check_launch("sg_conv3d_fprop(tcgen05 resident)");
+}
+
+template <int NT>
+int launch_res(const ResPlan& pl, const CUtensorMap& map, cudaStream_t s) {
+  const int td = pl.p.td, kbc = pl.p.kb_chunks;
+  if (kbc == 4) {
+    if (td == 1) return launch_res_inst<NT, 1, 4>(pl, map, s);
+    if (td == 2) return launch_res_inst<NT, 2, 4>(pl, map, s);
+    if (td == 4) return launch_res_inst<NT, 4, 4>(pl, map, s);
+  } else {
+    if (td == 1) return launch_res_inst<NT, 1, 2>(pl, map, s);
+    if (td == 2) return launch_res_inst<NT, 2, 2>(pl, map, s);
+    if (td == 4) return launch_res_inst<NT, 4, 2>(pl, map, s);
+  }
+  sg_set_error("conv_tc_res: no instantiation for td=%d kb_chunks=%d", td, kbc);
+  return -4;
+}
+
+}  // namespace

@@ -103,34 +103,39 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    {
+      const uint32_t leader = elect_one();   // all lanes run the loops; one issues
       // D=f32, A=B=bf16, both MN-major (bits 15,16), N = NT, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
-      int it = 0;
-      const int ksteps_per_plane = p.th / 2;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-        const int s = it % p.stages;
-        mbar_wait(BAR(FULL + s), (it / p.stages) & 1);
+      // descriptors: bases hoisted, per-MMA cost = one 64-bit add (offsets in 16-byte units = voxels)
+      const uint64_t g_desc0 = make_desc(smem_base, 128u, (uint32_t)p.g_chunk_bytes);
+      const uint64_t x_desc0 = make_desc(smem_base + p.g_chunks * p.g_chunk_bytes, 160u, (uint32_t)p.x_chunk_bytes);
+      const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4;
+      const int ksteps_per_plane = p.th / 2, td = p.td, th = p.th, stages = p.stages;
+      int s = 0, ph = 0;
+      uint32_t acc = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        mbar_wait(BAR(FULL + s), ph);
         tc_fence_after();
-        const uint32_t g_addr = smem_base + s * p.stage_bytes;
-        const uint32_t x_addr = g_addr + p.g_chunks * p.g_chunk_bytes;
-        for (int dl = 0; dl < p.td; ++dl) {
+        const uint64_t g_stage = g_desc0 + (uint64_t)(s * stage16);
+        const uint64_t x_stage = x_desc0 + (uint64_t)(s * stage16);
+        for (int dl = 0; dl < td; ++dl) {
+          uint64_t a_k = g_stage + (uint64_t)(dl * th * 8);
+          uint64_t b_k = x_stage + (uint64_t)(dl * halo_h * 10);
           for (int j = 0; j < ksteps_per_plane; ++j) {
-            const uint32_t a0 = g_addr + (uint32_t)((dl * p.th + 2 * j) * 8) * 16u;
-            const uint64_t adesc = make_desc(a0, 128u, (uint32_t)p.g_chunk_bytes);
 #pragma unroll
-            for (int t9 = 0; t9 < 9; ++t9) {
-              const int kh = t9 / 3, kw = t9 % 3;
-              const uint32_t b0 = x_addr + (uint32_t)((dl * halo_h + 2 * j + kh) * 10 + kw) * 16u;
-              const uint64_t bdesc = make_desc(b0, 160u, (uint32_t)p.x_chunk_bytes);
-              tc_mma(tmem_base + t9 * NT, adesc, bdesc, idesc, (it | dl | j) != 0);
-            }
+            for (int t9 = 0; t9 < 9; ++t9)
+              tc_mma(tmem_base + t9 * NT, a_k, b_k + (uint64_t)((t9 / 3) * 10 + (t9 % 3)), idesc, acc, leader);
+            acc = 1;
+            a_k += 16;   // two lines of 8 voxels
+            b_k += 20;   // two halo lines of 10 voxels
           }
         }
-        tc_commit(BAR(EMPTY + s));
+        tc_commit(BAR(EMPTY + s), leader);
+        if (++s == stages) { s = 0; ph ^= 1; }
       }
-      tc_commit(BAR(ACC_FULL));
+      tc_commit(BAR(ACC_FULL), leader);
     }
   } else {
     // ================================ epilogue ================================

@@ -61,17 +61,31 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+// The MMA warp runs its loops with all 32 lanes (warp-uniform control flow and operands, so ptxas
+// keeps descriptors in uniform registers) and predicates only the tcgen05 instructions on the
+// elected lane.  Issuing from inside an `if (lane == 0)` region instead costs ~10 extra SASS
+// instructions per MMA (R2UR moves and an ELECT/BRA.U.ANY loop around every UTCHMMA).
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar, uint32_t leader = 1) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar),
+      "r"(leader)
+      : "memory");
 }
 // D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 x bf16 -> fp32, M = 128, N from idesc, K = 16
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                       uint32_t accumulate) {
+                                       uint32_t accumulate, uint32_t leader = 1) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, q;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
       : "memory");
 }
 // K-major, no swizzle: 8 rows x 16 B core matrices; LBO = byte distance between the two core
@@ -95,6 +109,64 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+constexpr int kMaxSub = 8;   // MMA tiles (128 rows each) per CTA tile
+
+// Epilogue of 16 accumulator columns (= two 8-channel chunks) of one output voxel:
+// y = [mask] [lrelu] (acc*scale + bias) -> two 16-byte stores.  `sb` points at the 16 biases in
+// SHARED memory (broadcast float4 reads; the first version fetched them with per-element __ldg
+// and the four epilogue warps became the kernel's bottleneck).  Pad output channels need no
+// special case: their packed weight rows and biases are zero, so they come out as exact zeros.
+__device__ __forceinline__ void epilogue16(const float (&v)[16], const float* sb, float scale, int lrelu,
+                                           const __nv_bfloat16* mask, __nv_bfloat16* y, int64_t chunk_stride) {
+  float r[16];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 b = *reinterpret_cast<const float4*>(sb + 4 * q);
+    r[4 * q + 0] = fmaf(v[4 * q + 0], scale, b.x);
+    r[4 * q + 1] = fmaf(v[4 * q + 1], scale, b.y);
+    r[4 * q + 2] = fmaf(v[4 * q + 2], scale, b.z);
+    r[4 * q + 3] = fmaf(v[4 * q + 3], scale, b.w);
+  }
+  if (lrelu) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) r[j] = fmaxf(r[j], 0.2f * r[j]);
+  }
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    F8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.v[j] = r[half * 8 + j];
+    if (mask) {
+      const F8 m = ld8(mask + half * chunk_stride);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o.v[j] *= lmask02(m.v[j]);
+    }
+    st8(y + half * chunk_stride, o);
+  }
+}
+
+// One tap of one K block: (kpairs <= 2) x (n_sub <= kMaxSub) MMAs.  The issuing thread is a
+// single lane, so the per-MMA instruction count is what bounds the tensor pipe for small N
+// (an MMA with N = 64 lasts ~32-48 cycles): descriptors are formed with one 64-bit add each
+// from bases and offsets hoisted out of the loops (all offsets in 16-byte units, i.e. added to
+// the descriptors' start-address field).
+template <int NT>
+__device__ __forceinline__ void issue_tap(uint32_t tmem_acc, uint64_t a_desc, uint64_t b_desc,
+                                          const uint32_t (&sub_off)[kMaxSub], int n_sub, int kpairs, uint32_t kk_a,
+                                          uint32_t idesc, uint32_t acc_first, uint32_t leader) {
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk) {
+    if (kk < kpairs) {
+      const uint64_t b = b_desc + (uint64_t)(kk * 2 * NT);
+      const uint64_t a_k = a_desc + (uint64_t)(kk * kk_a);
+      const uint32_t acc = kk == 0 ? acc_first : 1u;
+#pragma unroll
+      for (int sub = 0; sub < kMaxSub; ++sub)
+        if (sub < n_sub) tc_mma(tmem_acc + sub * NT, a_k + sub_off[sub], b, idesc, acc, leader);
+    }
+  }
 }
 
 // MN-major, no swizzle (operand element (mn, k) at (mn/8)*SBO + (k/8)*LBO + (k%8)*16 + (mn%8)*2):

@@ -50,6 +50,45 @@ def test_tcgen05_fprop_matches_direct(shape, flip):
     assert rel_err(got.float().cpu(), want.float()) < 3e-3
 
 
+RES_SHAPES = [
+    (1, 32, 64, 8, 32, 16),    # D.b6.conv2 class: NT=64, td=2, one K block, 16 tiles
+    (2, 64, 32, 4, 16, 32),    # its dgrad class: two K blocks per tile through the halo ring
+    (2, 32, 32, 8, 16, 16),    # td=4 accumulator sets
+    (1, 16, 16, 8, 32, 32),    # kb_chunks=2, 4 halo stages
+    (2, 64, 64, 4, 16, 16),    # two N tiles (blockIdx.y)
+    (3, 16, 8, 4, 16, 8),      # Cout padded, ragged tile count per CTA
+]
+
+
+@pytest.mark.parametrize("shape", RES_SHAPES)
+@pytest.mark.parametrize("flip", [False, True])
+def test_tcgen05_resident_kernel_matches_direct(shape, flip):
+    """The persistent weight-resident kernel (forced via the test hook so that small shapes take it
+    and every CTA walks several tiles) against the direct kernel and the streaming tcgen05 kernel."""
+    n, cin, cout, d, h, w = shape
+    g = torch.Generator().manual_seed(sum(shape) + 7)
+    wt = torch.randn(cout, cin, 3, 3, 3, generator=g)
+    kin, kout = (cout, cin) if flip else (cin, cout)
+    xg = E.plain_to_act(torch.randn(n, kin, d, h, w, generator=g), BF).cuda()
+    mg = E.plain_to_act(torch.randn(n, kout, d, h, w, generator=g), BF).cuda()
+    bias = torch.randn(kout, generator=g).cuda()
+    wp = K.pack_conv_weight(wt.cuda(), BF, flip)
+    lib = _lib.load()
+    try:
+        for (b, lrelu, mask) in [(None, False, False), (bias, True, True)]:
+            args = (xg, wp, b, mg if mask else None, kin, kout, 0.05, lrelu)
+            ref = K.conv3d_fprop(*args, _lib.IMPL_DIRECT)
+            lib.sg_tc_force_streaming(2)
+            res = K.conv3d_fprop(*args, _lib.IMPL_TCGEN05)
+            lib.sg_tc_force_streaming(1)
+            stream = K.conv3d_fprop(*args, _lib.IMPL_TCGEN05)
+            torch.cuda.synchronize()
+            assert rel_err(res.float(), ref.float()) < 3e-3, (shape, flip, "resident vs direct")
+            assert rel_err(res.float(), stream.float()) < 3e-3, (shape, flip, "resident vs streaming")
+    finally:
+        lib.sg_tc_force_streaming(0)
+
+
 WGRAD_SHAPES = [
     (1, 16, 16, 2, 16, 8),     # one tile, NT=16, 2 gy chunks (14 garbage row-chunks)
     (1, 32, 64, 4, 16, 16),    # D.b6 class: NT=32, td=2, several tiles, 3-stage ring wraps
