@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--alpha", type=float, default=0.5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=2)
+    ap.add_argument("--graph", type=int, default=-1, help="1: replay the step as a CUDA graph; 0: eager; "
+                    "-1: graph on one GPU, eager with the overlapped all-reduce on several")
     return ap.parse_args()
 
 
@@ -172,7 +174,12 @@ def main():
     torch.manual_seed(0)
     g = sg.Generator(cfg["phase"], cfg["num_phases"], cfg["base_dim"], cfg["latent_dim"], C.BASE_SHAPE)
     d = sg.Discriminator(cfg["phase"], cfg["num_phases"], cfg["base_dim"], cfg["latent_dim"], C.BASE_SHAPE)
-    g_opt, d_opt = sg.make_optimizers(g, d, world_size=world)
+    use_graph = args.graph == 1 or (args.graph == -1 and world == 1)
+    if use_graph:
+        from saragan_b200.graph import GraphedTrainStep, make_capturable_optimizers
+        g_opt, d_opt = make_capturable_optimizers(g, d, world_size=world)
+    else:
+        g_opt, d_opt = sg.make_optimizers(g, d, world_size=world)
     dp = comm.DataParallel(g, d) if world > 1 else None
 
     n_pool = 4
@@ -186,8 +193,14 @@ def main():
                     z_g=torch.randn((B, cfg["latent_dim"]), device=dev, generator=rng),
                     eps=torch.rand((B, 1, 1, 1, 1), device=dev, generator=rng))
 
-    def step(x):
-        return sg.train_step(x, g, d, g_opt, d_opt, alpha, grad_sync=dp, **draws())
+    if use_graph:
+        graphed = GraphedTrainStep(g, d, g_opt, d_opt, B, vol, alpha, warmup=2, seed=1000 + rank)
+
+        def step(x):
+            return graphed(x)
+    else:
+        def step(x):
+            return sg.train_step(x, g, d, g_opt, d_opt, alpha, grad_sync=dp, **draws())
 
     def barrier():
         if world > 1:
@@ -213,7 +226,15 @@ def main():
         e1.record()
         barrier()
     kernels.conv_probe = None
-    launches = _lib.launch_count() - launches0
+    if use_graph:
+        # a graph replay cannot carry per-kernel events: time the dominant kernel in two eager
+        # passes of the same step (same shapes, same in-step cache state) right after the timed region
+        kernels.conv_probe = probe
+        for i in range(2):
+            sg.train_step(dev_pool[i % n_pool], g, d, g_opt, d_opt, alpha, grad_sync=dp, **draws())
+        barrier()
+        kernels.conv_probe = None
+    launches = graphed.launches_per_step * args.steps if use_graph else _lib.launch_count() - launches0
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -222,14 +243,17 @@ def main():
     kd = probe.durations_ms()
 
     # end-to-end: pinned host batch -> H2D -> step -> D2H of the three losses, every step
+    def e2e_step(i):
+        # graph mode copies the pinned host batch straight into the graph's static input buffer
+        return step(host_pool[i % n_pool] if use_graph else host_pool[i % n_pool].to(dev, non_blocking=True))
+
     for i in range(2):
-        step(host_pool[i % n_pool].to(dev, non_blocking=True))
+        e2e_step(i)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for i in range(args.steps):
-        x = host_pool[i % n_pool].to(dev, non_blocking=True)
-        o = step(x)
+        o = e2e_step(i)
         losses = torch.stack([o["d_loss"], o["g_loss"], o["gp"]]).cpu()
     f1.record()
     barrier()
@@ -247,6 +271,7 @@ def main():
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": cfg["desc"], "name": args.config, "per_gpu_batch": B, "global_batch": B * world,
                        "alpha": alpha, "parallelism": f"dp{world}",
+                       "launch": "cuda-graph replay of the whole step" if use_graph else "eager",
                        "l2": "per-step working set (GBs of activations) >> 126 MB L2; 4 rotating input batches",
                        "step_gflop_per_image": step_flops / 1e9,
                        "step_tensor_frac": step_flops * value / world / (pk["bf16"] * 1e12)},

@@ -6,11 +6,17 @@
 // channels, i.e. both operands are "MN-major" UMMA operands straight out of the TMA tiles:
 //   element (channel c, voxel k) at (c/8)*SBO + (k/8)*LBO + (k%8)*16 + (c%8)*2
 // with SBO = the 8-channel chunk stride and LBO = the line pitch (one K=16 MMA step = two
-// consecutive lines x 8 voxels).  As in the fprop kernel the 9 in-plane taps (kh,kw) of x re-use
-// one halo tile through the descriptor start address; the three kd planes are separate CTAs
-// (blockIdx.y), each keeping its 9 accumulators [128 x NT] in tensor memory while it streams
-// through its share of the voxel tiles (persistent, multi-stage TMA pipeline), then adds them
-// to gw with fp32 atomics.
+// consecutive lines x 8 voxels).
+//
+// A tap's output is only [Cout x NT] -- far too small for the tensor core, whose M=128 MMA costs
+// ~45 cycles whatever N <= 64 is (tools/mma_bench.cu).  So the three kw taps are STACKED ALONG N:
+// the x tile is loaded three times, shifted by one voxel in w each (3 TMA boxes of 8 w-voxels
+// instead of one of 10), into consecutive chunk slots; one B descriptor then spans
+// 3 x NT/8 slots = the N = 3*NT columns [kw][ci] and one MMA does three taps.  The three kh taps
+// shift the descriptor start by one line; the three kd planes are separate CTAs (blockIdx.y).
+// Each CTA keeps its 3 accumulators [128 x 3*NT] in tensor memory while it streams through its
+// share of the voxel tiles (persistent, multi-stage TMA pipeline), then adds them to gw with
+// fp32 atomics.
 #include "../../include/saragan_b200.h"
 #include "tc_common.cuh"
 
@@ -26,8 +32,7 @@ struct WgParams {
   int tiles_w, tiles_h, tiles_d;
   int n_tiles;             // tiles_w * tiles_h * tiles_d * N
   int g_chunk_bytes;       // td*th*8*16
-  int x_chunk_bytes;       // td*(th+2)*10*16 rounded up to 128 (TMA destinations are 128-byte aligned)
-  int x_box_bytes;         // td*(th+2)*10*16
+  int x_chunk_bytes;       // td*(th+2)*8*16: one (kw copy, 8-channel chunk) slot of the x tile
   int g_chunks;            // 8-channel chunks of gy loaded per tile (<= 16)
   int stage_bytes;
   int stages;
@@ -80,7 +85,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
   if (warp == 0) {
     // ================================ producer ================================
     if (lane == 0) {
-      const uint32_t tx = (uint32_t)(p.g_chunks * p.g_chunk_bytes + x_chunks * p.x_box_bytes);
+      const uint32_t tx = (uint32_t)(p.g_chunks * p.g_chunk_bytes + 3 * x_chunks * p.x_chunk_bytes);
       int it = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
         int t = tile;
@@ -96,21 +101,22 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
         const uint32_t x_dst = g_dst + p.g_chunks * p.g_chunk_bytes;
         for (int c = 0; c < p.g_chunks; ++c)
           tma_load_5d(g_dst + c * p.g_chunk_bytes, &gmap, BAR(FULL + s), w0 * 8, h0, d0, co_tile * 16 + c, n);
-        for (int c = 0; c < x_chunks; ++c)
-          tma_load_5d(x_dst + c * p.x_chunk_bytes, &xmap, BAR(FULL + s), (w0 - 1) * 8, h0 - 1, d0 + kd - 1,
-                      ci_tile * x_chunks + c, n);
+        for (int k = 0; k < 3; ++k)        // kw copy k = the tile shifted by k - 1 voxels in w
+          for (int c = 0; c < x_chunks; ++c)
+            tma_load_5d(x_dst + (k * x_chunks + c) * p.x_chunk_bytes, &xmap, BAR(FULL + s), (w0 - 1 + k) * 8, h0 - 1,
+                        d0 + kd - 1, ci_tile * x_chunks + c, n);
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     {
       const uint32_t leader = elect_one();   // all lanes run the loops; one issues
-      // D=f32, A=B=bf16, both MN-major (bits 15,16), N = NT, M = 128
+      // D=f32, A=B=bf16, both MN-major (bits 15,16), N = 3*NT ([kw][ci]), M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                             ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+                             ((uint32_t)((3 * NT) >> 3) << 17) | ((128u >> 4) << 24);
       // descriptors: bases hoisted, per-MMA cost = one 64-bit add (offsets in 16-byte units = voxels)
       const uint64_t g_desc0 = make_desc(smem_base, 128u, (uint32_t)p.g_chunk_bytes);
-      const uint64_t x_desc0 = make_desc(smem_base + p.g_chunks * p.g_chunk_bytes, 160u, (uint32_t)p.x_chunk_bytes);
+      const uint64_t x_desc0 = make_desc(smem_base + p.g_chunks * p.g_chunk_bytes, 128u, (uint32_t)p.x_chunk_bytes);
       const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4;
       const int ksteps_per_plane = p.th / 2, td = p.td, th = p.th, stages = p.stages;
       int s = 0, ph = 0;
@@ -122,14 +128,14 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
         const uint64_t x_stage = x_desc0 + (uint64_t)(s * stage16);
         for (int dl = 0; dl < td; ++dl) {
           uint64_t a_k = g_stage + (uint64_t)(dl * th * 8);
-          uint64_t b_k = x_stage + (uint64_t)(dl * halo_h * 10);
+          uint64_t b_k = x_stage + (uint64_t)(dl * halo_h * 8);
           for (int j = 0; j < ksteps_per_plane; ++j) {
 #pragma unroll
-            for (int t9 = 0; t9 < 9; ++t9)
-              tc_mma(tmem_base + t9 * NT, a_k, b_k + (uint64_t)((t9 / 3) * 10 + (t9 % 3)), idesc, acc, leader);
+            for (int kh = 0; kh < 3; ++kh)
+              tc_mma(tmem_base + kh * 3 * NT, a_k, b_k + (uint64_t)(kh * 8), idesc, acc, leader);
             acc = 1;
-            a_k += 16;   // two lines of 8 voxels
-            b_k += 20;   // two halo lines of 10 voxels
+            a_k += 16;   // two lines of 8 voxels (gy tile and x copies alike)
+            b_k += 16;
           }
         }
         tc_commit(BAR(EMPTY + s), leader);
@@ -188,18 +194,18 @@ WgPlan make_wgrad_plan(int N, int Cin, int Cout, int D, int H, int W) {
   if (H % th) return pl;
   p.th = th;
   p.g_chunks = CoutP / 8 < 16 ? CoutP / 8 : 16;
-  // td: as many planes per tile as keep a stage <= ~56 KB
-  int td = 1;
-  for (int cand = 1; cand <= D && cand <= 4; ++cand) {
+  // td: as many planes per tile (1, 2, 4) as leave room for two pipeline stages
+  int td = 0;
+  for (int cand = 1; cand <= D && cand <= 4; cand *= 2) {
     if (D % cand) continue;
-    int gb = cand * th * 8 * 16, xb = (cand * (th + 2) * 10 * 16 + 127) / 128 * 128;
-    if (p.g_chunks * gb + (NT / 8) * xb <= 56 * 1024) td = cand;
+    int gb = cand * th * 8 * 16, xb = cand * (th + 2) * 8 * 16;
+    if (p.g_chunks * gb + 3 * (NT / 8) * xb <= 100 * 1024) td = cand;
   }
+  if (td == 0) return pl;
   p.td = td;
   p.g_chunk_bytes = td * th * 8 * 16;
-  p.x_box_bytes = td * (th + 2) * 10 * 16;
-  p.x_chunk_bytes = (p.x_box_bytes + 127) / 128 * 128;
-  p.stage_bytes = (p.g_chunks * p.g_chunk_bytes + (NT / 8) * p.x_chunk_bytes + 127) / 128 * 128;
+  p.x_chunk_bytes = td * (th + 2) * 8 * 16;
+  p.stage_bytes = p.g_chunks * p.g_chunk_bytes + 3 * (NT / 8) * p.x_chunk_bytes;
   // the M = 128 operand reads 16 chunk strides of gy: with fewer real chunks the rest are
   // garbage rows (discarded) read from the following bytes -- keep them inside the allocation
   int over = 16 * p.g_chunk_bytes - p.stage_bytes;
@@ -278,7 +284,7 @@ int sg_tc_wgrad(const void* x, const void* gy, float* gw, float* gb, int N, int 
   CUtensorMap gmap, xmap;
   int rc = encode_act_map(&gmap, gy, N, p.CCout, D, H, W, 8, p.th, p.td);
   if (rc) return rc;
-  rc = encode_act_map(&xmap, x, N, p.CCin, D, H, W, 10, p.th + 2, p.td);
+  rc = encode_act_map(&xmap, x, N, p.CCin, D, H, W, 8, p.th + 2, p.td);
   if (rc) return rc;
   cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)Cout * Cin * 27, s);
   if (gb) {

@@ -581,31 +581,37 @@ extern "C" int sg_interp(const float* real, const float* fake, const float* eps,
 // EqualizedLinear (network.py:59-77) with batch <= a few dozen rows: weight-bandwidth bound.
 // y[b][o] = act(scale * sum_i x[b][i]*w[o][i] + bias[o]);  one warp per output feature.
 #define LIN_BT 8
-__global__ void k_linear_fwd(const float* __restrict__ x, const float* __restrict__ w,
-                             const float* __restrict__ bias, float* __restrict__ y, int B, int In,
-                             int Out, float scale, int lrelu) {
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (warp >= Out) return;
-  const float* wr = w + (int64_t)warp * In;
+// one 128-thread block per output feature: 512-8192 blocks keep every SM streaming weight rows
+__global__ void __launch_bounds__(128)
+k_linear_fwd(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+             float* __restrict__ y, int B, int In, int Out, float scale, int lrelu) {
+  const int o = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* wr = w + (int64_t)o * In;
+  __shared__ float red[4][LIN_BT];
   for (int b0 = 0; b0 < B; b0 += LIN_BT) {
     float acc[LIN_BT];
 #pragma unroll
     for (int k = 0; k < LIN_BT; ++k) acc[k] = 0.f;
-    for (int i = lane; i < In; i += 32) {
-      float wv = wr[i];
+    for (int i = threadIdx.x; i < In; i += 128) {
+      const float wv = wr[i];
 #pragma unroll
       for (int k = 0; k < LIN_BT; ++k)
-        if (b0 + k < B) acc[k] += wv * x[(int64_t)(b0 + k) * In + i];
+        if (b0 + k < B) acc[k] = fmaf(wv, __ldg(x + (int64_t)(b0 + k) * In + i), acc[k]);
     }
 #pragma unroll
     for (int k = 0; k < LIN_BT; ++k) {
-      float t = warp_sum(acc[k]);
-      if (lane == 0 && b0 + k < B) {
-        float o = scale * t + (bias ? bias[warp] : 0.f);
-        y[(int64_t)(b0 + k) * Out + warp] = lrelu ? lrelu02(o) : o;
-      }
+      const float t = warp_sum(acc[k]);
+      if (lane == 0) red[warp][k] = t;
     }
+    __syncthreads();
+    if (threadIdx.x < LIN_BT && b0 + threadIdx.x < B) {
+      const int k = threadIdx.x;
+      const float t = red[0][k] + red[1][k] + red[2][k] + red[3][k];
+      const float r = scale * t + (bias ? bias[o] : 0.f);
+      y[(int64_t)(b0 + k) * Out + o] = lrelu ? lrelu02(r) : r;
+    }
+    __syncthreads();
   }
 }
 // gx[b][i] = scale * sum_o g[b][o]*w[o][i];  thread per input feature, outputs split over
@@ -654,9 +660,7 @@ __global__ void k_linear_wgrad(const float* __restrict__ g, const float* __restr
 extern "C" int sg_linear_fwd(const float* x, const float* w, const float* bias, float* y, int B,
                              int In, int Out, float scale, int lrelu, cudaStream_t s) {
   if (B == 0 || Out == 0) return 0;
-  int threads = 256;
-  int64_t blocks = ((int64_t)Out * 32 + threads - 1) / threads;
-  k_linear_fwd<<<(unsigned)blocks, threads, 0, s>>>(x, w, bias, y, B, In, Out, scale, lrelu);
+  k_linear_fwd<<<(unsigned)Out, 128, 0, s>>>(x, w, bias, y, B, In, Out, scale, lrelu);
   return sg_check_launch("sg_linear_fwd");
 }
 extern "C" int sg_linear_dgrad(const float* g, const float* w, float* gx, int B, int In, int Out,

@@ -1,0 +1,90 @@
+"""Whole-step CUDA graph: one D update (with the WGAN-GP double backward) + one G update +
+both Adam steps captured once and replayed per batch.
+
+The step launches ~900 of our kernels plus a few hundred tiny torch ops (autograd bookkeeping,
+minibatch-stddev, Adam); issued one by one from Python they cost more host time than the GPU
+needs to execute them once the convolutions run on tcgen05.  Capturing the step removes the
+host from the loop (the north-star's "CUDA streams and graphs instead of a tracing compiler").
+
+Inputs live in static buffers: the real batch, the instance-noise draw, the two latent draws and
+the GP interpolation draw are refreshed outside the graph (`draw()`), then `replay()` runs the
+captured work.  `alpha` is a Python float baked into the kernels' arguments, so a graph is
+captured per alpha value (it changes once per epoch in the reference, train.py:33,63).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from .train import train_step
+
+
+def make_capturable_optimizers(generator, discriminator, lr: float = 1e-3, world_size: int = 1):
+    """main.py:138-145's Adam(lr*sqrt(world), betas=(0, .99)) with device-side step counters
+    (capturable=True) so `optim.step()` can live inside a CUDA graph."""
+    lr = lr * float(world_size) ** 0.5
+    d_optim = torch.optim.Adam(discriminator.parameters(), lr=lr, betas=(0.0, 0.99), capturable=True)
+    g_optim = torch.optim.Adam(generator.parameters(), lr=lr, betas=(0.0, 0.99), capturable=True)
+    return g_optim, d_optim
+
+
+class GraphedTrainStep:
+    def __init__(self, generator, discriminator, g_optim, d_optim, batch: int, volume, alpha: float,
+                 warmup: int = 3, seed: Optional[int] = None):
+        self.g, self.d, self.g_optim, self.d_optim = generator, discriminator, g_optim, d_optim
+        self.alpha = float(alpha)
+        dev = discriminator.device
+        self.dev = dev
+        latent = generator.latent_dim
+        self.x = torch.zeros((batch, 1, *volume), device=dev)
+        self.noise = torch.zeros_like(self.x)
+        self.z_d = torch.zeros((batch, latent), device=dev)
+        self.z_g = torch.zeros((batch, latent), device=dev)
+        self.eps = torch.zeros((batch, 1, 1, 1, 1), device=dev)
+        self.rng = torch.Generator(device=dev)
+        if seed is not None:
+            self.rng.manual_seed(seed)
+        self.out: Dict[str, torch.Tensor] = {}
+        self.graph = torch.cuda.CUDAGraph()
+        # warm-up on a side stream (lazy inits, kernel attributes, allocator state), then capture
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.draw()
+                self._step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        # the packed-weight caches hold buffers packed OUTSIDE the graph: drop them so that the
+        # first use of every weight inside the capture re-packs (and the pack kernel is captured)
+        for net in (generator, discriminator):
+            for m in net.modules():
+                if hasattr(m, "_packed"):
+                    m._packed = type(m._packed)(m.weight)
+        self.draw()
+        from . import _lib
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.out = self._step()
+        self.launches_per_step = _lib.launch_count() - n0   # our kernels inside one replay
+
+    def _step(self):
+        o = train_step(self.x, self.g, self.d, self.g_optim, self.d_optim, self.alpha, noise=self.noise,
+                       z_d=self.z_d, z_g=self.z_g, eps=self.eps)
+        return {k: o[k] for k in ("d_loss", "gp", "g_loss", "distance", "x_fake")}
+
+    def draw(self) -> None:
+        """Fresh random draws of train.py:144-145,178 and loss.py:11 into the static buffers."""
+        self.noise.normal_(generator=self.rng)
+        self.z_d.normal_(generator=self.rng)
+        self.z_g.normal_(generator=self.rng)
+        self.eps.uniform_(generator=self.rng)
+
+    def __call__(self, x_real: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """x_real: host (pinned) or device batch.  Returns the step's scalars as device tensors
+        (valid until the next call)."""
+        self.x.copy_(x_real, non_blocking=True)
+        self.draw()
+        self.graph.replay()
+        return self.out
