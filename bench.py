@@ -180,7 +180,10 @@ def main():
         g_opt, d_opt = make_capturable_optimizers(g, d, world_size=world)
     else:
         g_opt, d_opt = sg.make_optimizers(g, d, world_size=world)
-    dp = comm.DataParallel(g, d) if world > 1 else None
+    if world > 1:
+        dp = comm.CapturableAllReduce(g, d) if use_graph else comm.DataParallel(g, d)
+    else:
+        dp = None
 
     n_pool = 4
     host_pool = [smooth_volumes(B, vol, seed=1234 + 17 * rank + i).pin_memory() for i in range(n_pool)]
@@ -194,7 +197,7 @@ def main():
                     eps=torch.rand((B, 1, 1, 1, 1), device=dev, generator=rng))
 
     if use_graph:
-        graphed = GraphedTrainStep(g, d, g_opt, d_opt, B, vol, alpha, warmup=2, seed=1000 + rank)
+        graphed = GraphedTrainStep(g, d, g_opt, d_opt, B, vol, alpha, warmup=2, seed=1000 + rank, grad_sync=dp)
 
         def step(x):
             return graphed(x)

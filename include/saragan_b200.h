@@ -93,7 +93,9 @@ int sg_pw_wgrad(const void* g, const float* img, float* gw, float* gb, int dtype
  * Input and output element types may differ: the 1x4x4 base level of both networks is kept
  * in fp32 (minibatch-stddev's group centring amplifies bf16 rounding). */
 int sg_down2(const void* x, void* y, int dtype_in, int dtype_out, int vec, int64_t P, int D, int H, int W, float scale, cudaStream_t stream);
-int sg_up2(const void* x, void* y, int dtype_in, int dtype_out, int vec, int64_t P, int D, int H, int W, float scale, cudaStream_t stream);
+/* mask_ref (nullable, act shaped like y): y *= (mask_ref > 0 ? 1 : 0.2) -- LeakyReLU backward fused
+ * into the avg-pool backward */
+int sg_up2(const void* x, void* y, const void* mask_ref, int dtype_in, int dtype_out, int vec, int64_t P, int D, int H, int W, float scale, cudaStream_t stream);
 
 /* ---- elementwise
  * y = alpha*a + beta*b (b nullable): fade-in blend (network.py:185,281), instance noise
@@ -105,7 +107,8 @@ int sg_mask_mul(const void* g, const void* ref, void* y, int dtype, int64_t n, c
 
 /* ---- ChannelNormalization (network.py:192-197), optionally followed by LeakyReLU */
 int sg_pixelnorm_fwd(const void* x, void* y, int dtype, int N, int C, int64_t V, float eps, int lrelu_after, cudaStream_t stream);
-int sg_pixelnorm_bwd(const void* x, const void* gy, void* gx, int dtype, int N, int C, int64_t V, float eps, int lrelu_after, cudaStream_t stream);
+/* mask_input: x is itself a LeakyReLU output; also multiply gx by (x > 0 ? 1 : 0.2) */
+int sg_pixelnorm_bwd(const void* x, const void* gy, void* gx, int dtype, int N, int C, int64_t V, float eps, int lrelu_after, int mask_input, cudaStream_t stream);
 
 /* ---- gradient penalty (loss.py:11-13 interpolate, loss.py:25-26 per-sample norm) */
 int sg_interp(const float* real, const float* fake, const float* eps, float* out, int N, int64_t V, cudaStream_t stream);

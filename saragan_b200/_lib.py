@@ -40,12 +40,12 @@ SIGNATURES = {
     "sg_pw_reduce": [_c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_i64, _c_f, _c_p],
     "sg_pw_wgrad": [_c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_i64, _c_f, _c_p],
     "sg_down2": [_c_p, _c_p, _c_int, _c_int, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_f, _c_p],
-    "sg_up2": [_c_p, _c_p, _c_int, _c_int, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_f, _c_p],
+    "sg_up2": [_c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_f, _c_p],
     "sg_lincomb": [_c_p, _c_p, _c_p, _c_int, _c_i64, _c_f, _c_f, _c_p],
     "sg_lrelu_fwd": [_c_p, _c_p, _c_int, _c_i64, _c_p],
     "sg_mask_mul": [_c_p, _c_p, _c_p, _c_int, _c_i64, _c_p],
     "sg_pixelnorm_fwd": [_c_p, _c_p, _c_int, _c_int, _c_int, _c_i64, _c_f, _c_int, _c_p],
-    "sg_pixelnorm_bwd": [_c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_i64, _c_f, _c_int, _c_p],
+    "sg_pixelnorm_bwd": [_c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_i64, _c_f, _c_int, _c_int, _c_p],
     "sg_interp": [_c_p, _c_p, _c_p, _c_p, _c_int, _c_i64, _c_p],
     "sg_sumsq_rows": [_c_p, _c_p, _c_int, _c_i64, _c_p],
     "sg_rowscale": [_c_p, _c_p, _c_p, _c_int, _c_i64, _c_p],

@@ -178,3 +178,27 @@ class DataParallel:
 
     def finish(self, module) -> None:
         self._b[id(module)].finish()
+
+
+class CapturableAllReduce:
+    """Gradient averaging that can be captured in a CUDA graph: one flat all-reduce per module on
+    the capturing stream (no side stream, no hooks).  Used by graph.GraphedTrainStep on several
+    GPUs; the <= 0.5 GB of gradients cost ~1 ms un-overlapped on NVLink 5 against a ~30 ms step,
+    less than the host launch overhead the graph removes."""
+
+    def __init__(self, generator, discriminator):
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        broadcast_parameters(generator)
+        broadcast_parameters(discriminator)
+
+    def arm(self, module) -> None:
+        pass
+
+    def finish(self, module) -> None:
+        if self.world == 1:
+            return
+        grads = [p.grad for p in module.parameters() if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        flat.mul_(1.0 / self.world)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        GradBucketer._scatter(flat, grads)

@@ -210,9 +210,11 @@ __global__ void k_down2(const T* __restrict__ x, TO* __restrict__ y, int64_t P, 
 }
 // x: [P][D][H][W][VEC] -> y: [P][2D][2H][2W][VEC], y[child] = scale * x[parent].
 // nearest upsample (network.py:203,265) = scale 1; backward of avg-pool = scale 1/8.
+// mask_ref (nullable, shaped like y): y *= 1 / 0.2 by its sign -- the LeakyReLU backward of the
+// conv that fed an avg-pool, fused into the pool's backward.
 template <typename T, typename TO, int VEC>
-__global__ void k_up2(const T* __restrict__ x, TO* __restrict__ y, int64_t P, int D, int H, int W,
-                      float scale) {
+__global__ void k_up2(const T* __restrict__ x, TO* __restrict__ y, const TO* __restrict__ mask_ref, int64_t P,
+                      int D, int H, int W, float scale) {
   int64_t total = P * D * H * W;
   int H2 = 2 * H, W2 = 2 * W;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
@@ -233,7 +235,18 @@ __global__ void k_up2(const T* __restrict__ x, TO* __restrict__ y, int64_t P, in
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-          for (int dx = 0; dx < 2; ++dx) st8(base + (((int64_t)dz * H2 + dy) * W2 + dx) * 8, r);
+          for (int dx = 0; dx < 2; ++dx) {
+            const int64_t off = (((int64_t)dz * H2 + dy) * W2 + dx) * 8;
+            if (mask_ref) {
+              const F8 m = ld8(mask_ref + (base - y) + off);
+              F8 o;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o.v[j] = r.v[j] * lmask02(m.v[j]);
+              st8(base + off, o);
+            } else {
+              st8(base + off, r);
+            }
+          }
     } else {
       float r = ld1(x + i) * scale;
 #pragma unroll
@@ -276,16 +289,17 @@ extern "C" int sg_down2(const void* x, void* y, int dtype_in, int dtype_out, int
   }
   return sg_check_launch("sg_down2");
 }
-extern "C" int sg_up2(const void* x, void* y, int dtype_in, int dtype_out, int vec, int64_t P, int D,
-                      int H, int W, float scale, cudaStream_t s) {
+extern "C" int sg_up2(const void* x, void* y, const void* mask_ref, int dtype_in, int dtype_out, int vec,
+                      int64_t P, int D, int H, int W, float scale, cudaStream_t s) {
   SG_REQUIRE(vec == 8 || vec == 1, "sg_up2: vec must be 1 or 8");
+  SG_REQUIRE(mask_ref == nullptr || vec == 8, "sg_up2: mask_ref needs an activation tensor (vec 8)");
   int64_t total = P * D * H * W;
   if (total == 0) return 0;
   unsigned g = sg_grid(total, 256);
   if (vec == 8) {
-    SG_DISPATCH2(dtype_in, dtype_out, k_up2<T, TO, 8><<<g, 256, 0, s>>>((const T*)x, (TO*)y, P, D, H, W, scale););
+    SG_DISPATCH2(dtype_in, dtype_out, k_up2<T, TO, 8><<<g, 256, 0, s>>>((const T*)x, (TO*)y, (const TO*)mask_ref, P, D, H, W, scale););
   } else {
-    SG_DISPATCH2(dtype_in, dtype_out, k_up2<T, TO, 1><<<g, 256, 0, s>>>((const T*)x, (TO*)y, P, D, H, W, scale););
+    SG_DISPATCH2(dtype_in, dtype_out, k_up2<T, TO, 1><<<g, 256, 0, s>>>((const T*)x, (TO*)y, (const TO*)nullptr, P, D, H, W, scale););
   }
   return sg_check_launch("sg_up2");
 }
@@ -326,7 +340,7 @@ __global__ void k_pixelnorm_fwd(const T* __restrict__ x, T* __restrict__ y, int 
 template <typename T>
 __global__ void k_pixelnorm_bwd(const T* __restrict__ x, const T* __restrict__ gy,
                                 T* __restrict__ gx, int N, int C, int CC, int64_t V, float eps,
-                                int lrelu_after) {
+                                int lrelu_after, int mask_input) {
   int64_t total = (int64_t)N * V;
   float invC = 1.f / (float)C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
@@ -353,7 +367,9 @@ __global__ void k_pixelnorm_bwd(const T* __restrict__ x, const T* __restrict__ g
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float gj = lrelu_after ? g.v[j] * lmask02(a.v[j]) : g.v[j];
-        a.v[j] = r_ * gj - a.v[j] * k;
+        float o = r_ * gj - a.v[j] * k;
+        // mask_input: x is the LeakyReLU output of the producing conv; fold that conv's mask in
+        a.v[j] = mask_input ? o * lmask02(a.v[j]) : o;
       }
       st8(gx + off + (int64_t)cc * V * 8, a);
     }
@@ -368,11 +384,11 @@ extern "C" int sg_pixelnorm_fwd(const void* x, void* y, int dtype, int N, int C,
   return sg_check_launch("sg_pixelnorm_fwd");
 }
 extern "C" int sg_pixelnorm_bwd(const void* x, const void* gy, void* gx, int dtype, int N, int C,
-                                int64_t V, float eps, int lrelu_after, cudaStream_t s) {
+                                int64_t V, float eps, int lrelu_after, int mask_input, cudaStream_t s) {
   int64_t total = (int64_t)N * V;
   if (total == 0) return 0;
   int CC = sg_chunks(C);
-  SG_DISPATCH(dtype, k_pixelnorm_bwd<T><<<sg_grid(total, 256), 256, 0, s>>>((const T*)x, (const T*)gy, (T*)gx, N, C, CC, V, eps, lrelu_after););
+  SG_DISPATCH(dtype, k_pixelnorm_bwd<T><<<sg_grid(total, 256), 256, 0, s>>>((const T*)x, (const T*)gy, (T*)gx, N, C, CC, V, eps, lrelu_after, mask_input););
   return sg_check_launch("sg_pixelnorm_bwd");
 }
 

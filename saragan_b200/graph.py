@@ -31,7 +31,8 @@ def make_capturable_optimizers(generator, discriminator, lr: float = 1e-3, world
 
 class GraphedTrainStep:
     def __init__(self, generator, discriminator, g_optim, d_optim, batch: int, volume, alpha: float,
-                 warmup: int = 3, seed: Optional[int] = None):
+                 warmup: int = 3, seed: Optional[int] = None, grad_sync=None):
+        self.grad_sync = grad_sync    # e.g. comm.CapturableAllReduce on several GPUs
         self.g, self.d, self.g_optim, self.d_optim = generator, discriminator, g_optim, d_optim
         self.alpha = float(alpha)
         dev = discriminator.device
@@ -71,7 +72,7 @@ class GraphedTrainStep:
 
     def _step(self):
         o = train_step(self.x, self.g, self.d, self.g_optim, self.d_optim, self.alpha, noise=self.noise,
-                       z_d=self.z_d, z_g=self.z_g, eps=self.eps)
+                       z_d=self.z_d, z_g=self.z_g, eps=self.eps, grad_sync=self.grad_sync)
         return {k: o[k] for k in ("d_loss", "gp", "g_loss", "distance", "x_fake")}
 
     def draw(self) -> None:

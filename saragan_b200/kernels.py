@@ -142,7 +142,7 @@ def pw_wgrad(g: torch.Tensor, img: Optional[torch.Tensor], c: int, scale: float,
 
 # ------------------------------------------------------------------------- resampling
 def _resample(name: str, x: torch.Tensor, scale: float, factor_num: int, factor_den: int,
-              out_dtype: Optional[torch.dtype] = None):
+              out_dtype: Optional[torch.dtype] = None, mask_ref: Optional[torch.Tensor] = None):
     if x.dim() == 6:
         n, cc, d, h, w, _ = x.shape
         shape = (n, cc, d * factor_num // factor_den, h * factor_num // factor_den,
@@ -155,7 +155,11 @@ def _resample(name: str, x: torch.Tensor, scale: float, factor_num: int, factor_
                  w * factor_num // factor_den)
         vec, planes = 1, n * c1
     y = torch.empty(shape, dtype=out_dtype or x.dtype, device=x.device)
-    call(name, x, y, _lib.dtype_code(x), _lib.dtype_code(y), vec, planes, d, h, w, float(scale))
+    if name == "sg_up2":
+        assert mask_ref is None or (mask_ref.shape == y.shape and mask_ref.dtype == y.dtype)
+        call(name, x, y, mask_ref, _lib.dtype_code(x), _lib.dtype_code(y), vec, planes, d, h, w, float(scale))
+    else:
+        call(name, x, y, _lib.dtype_code(x), _lib.dtype_code(y), vec, planes, d, h, w, float(scale))
     return y
 
 
@@ -163,8 +167,9 @@ def down2(x: torch.Tensor, scale: float, out_dtype: Optional[torch.dtype] = None
     return _resample("sg_down2", x, scale, 1, 2, out_dtype)
 
 
-def up2(x: torch.Tensor, scale: float, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
-    return _resample("sg_up2", x, scale, 2, 1, out_dtype)
+def up2(x: torch.Tensor, scale: float, out_dtype: Optional[torch.dtype] = None,
+        mask_ref: Optional[torch.Tensor] = None) -> torch.Tensor:
+    return _resample("sg_up2", x, scale, 2, 1, out_dtype, mask_ref)
 
 
 # ------------------------------------------------------------------------ elementwise
@@ -192,10 +197,11 @@ def pixelnorm_fwd(x: torch.Tensor, c: int, lrelu_after: bool) -> torch.Tensor:
     return y
 
 
-def pixelnorm_bwd(x: torch.Tensor, gy: torch.Tensor, c: int, lrelu_after: bool) -> torch.Tensor:
+def pixelnorm_bwd(x: torch.Tensor, gy: torch.Tensor, c: int, lrelu_after: bool,
+                  mask_input: bool = False) -> torch.Tensor:
     gx = torch.empty_like(x)
     call("sg_pixelnorm_bwd", x, gy, gx, _lib.dtype_code(x), x.shape[0], c, _vox(x), EPS_PN,
-         int(lrelu_after))
+         int(lrelu_after), int(mask_input))
     return gx
 
 

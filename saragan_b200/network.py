@@ -97,19 +97,22 @@ class EqualizedConv3d(nn.Module, _Blocked):
             "saragan_b200.EqualizedConv3d covers the PGAN hot path only: 3x3x3/stride 1/pad 1, "
             "and 1x1x1 with one image channel")
 
-    def forward(self, input, lrelu: bool = False):
+    def forward(self, input, lrelu: bool = False, premasked: bool = False, mask_input_grad: bool = False):
+        """lrelu fuses the following LeakyReLU(0.2); premasked / mask_input_grad are the
+        LeakyReLU-backward fusion flags of ops.Conv3x3 (internal wiring of the blocks)."""
         kind = self._kind()
         if kind == "3x3x3":
             plain = not self.is_act(input)
             x = self.enter(input) if plain else input
             if self._packed.weight is not self.weight:  # parameter was re-bound (.to(), load)
                 self._packed = ops.PackedWeight(self.weight)
-            y = ops.Conv3x3.apply(x, self.weight, self.bias, self._packed, float(self.std), lrelu)
+            y = ops.Conv3x3.apply(x, self.weight, self.bias, self._packed, float(self.std), lrelu,
+                                  premasked and not plain, mask_input_grad and not plain)
             return self.leave(y, self.out_channels) if plain else y
         if kind == "from_rgb":
             return ops.PwExpand.apply(input.float().contiguous(), self.weight.reshape(-1), self.bias,
                                       float(self.std), lrelu, self.out_channels,
-                                      config.act_dtype(_voxels(input)))
+                                      config.act_dtype(_voxels(input)), premasked)
         plain = not self.is_act(input)
         x = self.enter(input) if plain else input
         img = ops.PwReduce.apply(x, self.weight.reshape(-1), self.bias, float(self.std),
@@ -155,12 +158,16 @@ class DiscriminatorBlock(nn.Sequential, _Blocked):
         self.lrelu = nn.LeakyReLU(negative_slope=0.2)
         self.downsampling = nn.AvgPool3d(2)
 
-    def forward(self, input):
+    def forward(self, input, input_is_lrelu: bool = False):
+        """input_is_lrelu: `input` is the LeakyReLU output of a premasked producer (the top-level
+        FromRGB) whose only consumer is this block."""
         plain = not self.is_act(input)
         x = self.enter(input) if plain else input
-        x = self.conv1(x, lrelu=True)
-        x = self.conv2(x, lrelu=True)
-        x = ops.Down2.apply(x, 0.125, config.act_dtype(_voxels(x) // 8))
+        # LeakyReLU backward masks ride in the consumers' kernels: conv2's dgrad epilogue masks
+        # for conv1, the avg-pool backward masks for conv2
+        x = self.conv1(x, lrelu=True, premasked=True, mask_input_grad=input_is_lrelu and not plain)
+        x = self.conv2(x, lrelu=True, premasked=True, mask_input_grad=True)
+        x = ops.Down2.apply(x, 0.125, config.act_dtype(_voxels(x) // 8), True)
         return self.leave(x, self.filters_out) if plain else x
 
 
@@ -175,8 +182,8 @@ class FromRGB(nn.Sequential):
             nn.LeakyReLU(negative_slope=0.2),
         )
 
-    def forward(self, input):
-        return self.fromrgb[0](input, lrelu=True)
+    def forward(self, input, premasked: bool = False):
+        return self.fromrgb[0](input, lrelu=True, premasked=premasked)
 
 
 class MinibatchStandardDeviation(nn.Module):
@@ -241,9 +248,11 @@ class Discriminator(nn.Module):
     def forward(self, input, alpha):
         alpha = _as_float(alpha)
         img = input.to(self.device).float().contiguous()
-        x = self.fromrgbs[-self.phase](img)
+        # at phase > 1 the top FromRGB feeds only the first block's conv1, whose dgrad epilogue
+        # then applies FromRGB's LeakyReLU mask
+        x = self.fromrgbs[-self.phase](img, premasked=self.phase > 1)
         for i in reversed(range(1, self.phase)):
-            x = self.blocks[-i](x)
+            x = self.blocks[-i](x, input_is_lrelu=(i == self.phase - 1))
             img = ops.Down2.apply(img, 0.125)
             prev = self.fromrgbs[-i](img)
             x = ops.Lincomb.apply(prev, x, alpha, 1.0 - alpha)
@@ -262,10 +271,10 @@ class ChannelNormalization(nn.Module, _Blocked):
     def __init__(self):
         super().__init__()
 
-    def forward(self, input, lrelu_after: bool = False, channels: int = None):
+    def forward(self, input, lrelu_after: bool = False, channels: int = None, mask_input: bool = False):
         if self.is_act(input):
             assert channels is not None
-            return ops.PixelNorm.apply(input, channels, lrelu_after)
+            return ops.PixelNorm.apply(input, channels, lrelu_after, mask_input)
         c = input.shape[1]
         return self.leave(ops.PixelNorm.apply(self.enter(input), c, lrelu_after), c)
 
@@ -287,8 +296,8 @@ class GeneratorBlock(nn.Sequential, _Blocked):
         x = self.enter(input) if plain else input
         c = self.conv1.out_channels
         x = ops.Up2.apply(x, 1.0, config.act_dtype(_voxels(x) * 8))
-        x = self.conv1(x, lrelu=True)
-        x = self.cn(x, channels=c)
+        x = self.conv1(x, lrelu=True, premasked=True)          # pixel-norm's backward applies the mask
+        x = self.cn(x, channels=c, mask_input=True)
         x = self.conv2(x)
         x = self.cn(x, lrelu_after=True, channels=c)
         return self.leave(x, c) if plain else x
@@ -352,8 +361,8 @@ class Generator(nn.Module):
         x = gin[0](input.to(self.device), lrelu=True)
         x = gin[2](x)
         x = ops.ToAct.apply(x, config.act_dtype(_voxels(x)))
-        x = gin[3](x, lrelu=True)
-        x = gin[5](x, channels=gin[3].out_channels)
+        x = gin[3](x, lrelu=True, premasked=True)
+        x = gin[5](x, channels=gin[3].out_channels, mask_input=True)
 
         all_out = []
         images_out = self.to_rgbs[0](x)

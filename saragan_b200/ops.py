@@ -66,26 +66,35 @@ class PackedWeight:
 
 # ================================================================================ conv
 class Conv3x3(Function):
-    """y = [lrelu](std * conv3d(x, w, pad=1) + b)   -- network.py:54-56 (+ :89 etc. fused)."""
+    """y = [lrelu](std * conv3d(x, w, pad=1) + b)   -- network.py:54-56 (+ :89 etc. fused).
+
+    LeakyReLU-mask fusion (the mask of a layer is the sign of its OUTPUT):
+      premasked       -- the consumer of y already multiplied the incoming gradient by m(y)
+                         (a following conv's dgrad epilogue, an avg-pool backward, a pixel-norm
+                         backward), so this op must not do it again;
+      mask_input_grad -- x is the LeakyReLU output of the producing op: multiply the returned
+                         input gradient by m(x) in the dgrad epilogue (the producer is premasked)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, pw: Optional[PackedWeight], std: float, lrelu: bool):
+    def forward(ctx, x, weight, bias, pw: Optional[PackedWeight], std: float, lrelu: bool,
+                premasked: bool = False, mask_input_grad: bool = False):
         cout, cin = weight.shape[0], weight.shape[1]
         pw = pw if pw is not None else PackedWeight(weight, cache=False)
         y = K.conv3d_fprop(x, pw.get(x.dtype, False), bias, None, cin, cout, std, lrelu, IMPL_AUTO)
-        ctx.save_for_backward(x, weight, y if lrelu else None)
+        ctx.save_for_backward(x, weight, y if (lrelu and not premasked) else None)
         ctx.pw, ctx.std, ctx.lrelu, ctx.has_bias = pw, std, lrelu, bias is not None
+        ctx.premasked, ctx.mask_input_grad = premasked, mask_input_grad
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, weight, y = ctx.saved_tensors
         g = _c(gy)
-        if ctx.lrelu:
+        if ctx.lrelu and not ctx.premasked:
             g = MaskMul.apply(g, y)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = ConvDgrad.apply(g, weight, ctx.pw, ctx.std)
+            gx = ConvDgrad.apply(g, weight, ctx.pw, ctx.std, x if ctx.mask_input_grad else None)
         want_w = ctx.needs_input_grad[1] and _weight_grads_enabled
         want_b = ctx.has_bias and ctx.needs_input_grad[2] and _weight_grads_enabled
         if want_w:
@@ -93,31 +102,34 @@ class Conv3x3(Function):
             gb = gb_ if want_b else None
         elif want_b:
             gb = ChanSum.apply(g, weight.shape[0])
-        return gx, gw, gb, None, None, None
+        return gx, gw, gb, None, None, None, None, None
 
 
 class ConvDgrad(Function):
-    """gx = std * dgrad(g, w): the same implicit GEMM on the flipped/transposed packing."""
+    """gx = [m(mask_ref) *] std * dgrad(g, w): the same implicit GEMM on the flipped/transposed
+    packing; mask_ref fuses the producing layer's LeakyReLU backward into the epilogue."""
 
     @staticmethod
-    def forward(ctx, g, weight, pw: Optional[PackedWeight], std: float):
+    def forward(ctx, g, weight, pw: Optional[PackedWeight], std: float, mask_ref=None):
         cout, cin = weight.shape[0], weight.shape[1]
         pw = pw if pw is not None else PackedWeight(weight, cache=False)
-        gx = K.conv3d_fprop(g, pw.get(g.dtype, True), None, None, cout, cin, std, False, IMPL_AUTO)
-        ctx.save_for_backward(g, weight)
+        gx = K.conv3d_fprop(g, pw.get(g.dtype, True), None, mask_ref, cout, cin, std, False, IMPL_AUTO)
+        ctx.save_for_backward(g, weight, mask_ref)
         ctx.pw, ctx.std = pw, std
         return gx
 
     @staticmethod
     def backward(ctx, ggx):
-        g, weight = ctx.saved_tensors
+        g, weight, mask_ref = ctx.saved_tensors
         ggx = _c(ggx)
+        if mask_ref is not None:
+            ggx = MaskMul.apply(ggx, mask_ref)
         gg = gw = None
         if ctx.needs_input_grad[0]:
             gg = Conv3x3.apply(ggx, weight, None, ctx.pw, ctx.std, False)
         if ctx.needs_input_grad[1] and _weight_grads_enabled:
             gw, _ = ConvWgrad.apply(ggx, g, ctx.std, weight.shape[1], weight.shape[0], False)
-        return gg, gw, None, None
+        return gg, gw, None, None, None
 
 
 class ConvWgrad(Function):
@@ -194,26 +206,35 @@ class Down2(Function):
     """y = scale * (2x2x2 block sum): AvgPool3d(2) with scale 1/8 (network.py:90,154)."""
 
     @staticmethod
-    def forward(ctx, x, scale: float, out_dtype: Optional[torch.dtype] = None):
+    def forward(ctx, x, scale: float, out_dtype: Optional[torch.dtype] = None, premask: bool = False):
+        """premask: x is the LeakyReLU output of a (premasked) conv; fold that conv's mask into
+        this op's backward (the up-sampling kernel multiplies by m(x))."""
         ctx.scale, ctx.in_dtype = scale, x.dtype
+        ctx.save_for_backward(x if premask else None)
         return K.down2(x, scale, out_dtype)
 
     @staticmethod
     def backward(ctx, gy):
-        return Up2.apply(_c(gy), ctx.scale, ctx.in_dtype), None, None
+        (ref,) = ctx.saved_tensors
+        return Up2.apply(_c(gy), ctx.scale, ctx.in_dtype, ref), None, None, None
 
 
 class Up2(Function):
     """y[child] = scale * x[parent]: nearest Upsample(2) with scale 1 (network.py:203,265)."""
 
     @staticmethod
-    def forward(ctx, x, scale: float, out_dtype: Optional[torch.dtype] = None):
+    def forward(ctx, x, scale: float, out_dtype: Optional[torch.dtype] = None, mask_ref=None):
         ctx.scale, ctx.in_dtype = scale, x.dtype
-        return K.up2(x, scale, out_dtype)
+        ctx.save_for_backward(mask_ref)
+        return K.up2(x, scale, out_dtype, mask_ref)
 
     @staticmethod
     def backward(ctx, gy):
-        return Down2.apply(_c(gy), ctx.scale, ctx.in_dtype), None, None
+        (ref,) = ctx.saved_tensors
+        gy = _c(gy)
+        if ref is not None:
+            gy = MaskMul.apply(gy, ref)
+        return Down2.apply(gy, ctx.scale, ctx.in_dtype), None, None, None
 
 
 class Lincomb(Function):
@@ -237,17 +258,18 @@ class PwExpand(Function):
     """FromRGB (network.py:101-110): y[n,c,v] = [lrelu](std*w[c]*img[n,v] + b[c])."""
 
     @staticmethod
-    def forward(ctx, img, w, bias, std: float, lrelu: bool, c: int, dtype: torch.dtype):
+    def forward(ctx, img, w, bias, std: float, lrelu: bool, c: int, dtype: torch.dtype,
+                premasked: bool = False):
         y = K.pw_expand(img, w, bias, dtype, c, std, lrelu)
-        ctx.save_for_backward(img, w, y if lrelu else None)
-        ctx.std, ctx.lrelu, ctx.c, ctx.has_bias = std, lrelu, c, bias is not None
+        ctx.save_for_backward(img, w, y if (lrelu and not premasked) else None)
+        ctx.std, ctx.lrelu, ctx.c, ctx.has_bias, ctx.premasked = std, lrelu, c, bias is not None, premasked
         return y
 
     @staticmethod
     def backward(ctx, gy):
         img, w, y = ctx.saved_tensors
         g = _c(gy)
-        if ctx.lrelu:
+        if ctx.lrelu and not ctx.premasked:
             g = MaskMul.apply(g, y)
         gimg = gw = gb = None
         if ctx.needs_input_grad[0]:
@@ -258,7 +280,7 @@ class PwExpand(Function):
             gw_, gb_ = PwWgrad.apply(g, img, ctx.std, ctx.c)
             gw = gw_ if want_w else None
             gb = gb_ if want_b else None
-        return gimg, gw, gb, None, None, None, None
+        return gimg, gw, gb, None, None, None, None, None
 
 
 class PwReduce(Function):
@@ -311,16 +333,18 @@ class PixelNorm(Function):
     """ChannelNormalization (network.py:192-197) [+ LeakyReLU]; generator only, first order."""
 
     @staticmethod
-    def forward(ctx, x, c: int, lrelu_after: bool):
+    def forward(ctx, x, c: int, lrelu_after: bool, mask_input: bool = False):
+        """mask_input: x is the LeakyReLU output of a (premasked) conv; the backward kernel also
+        applies that conv's mask m(x)."""
         ctx.save_for_backward(x)
-        ctx.c, ctx.lrelu_after = c, lrelu_after
+        ctx.c, ctx.lrelu_after, ctx.mask_input = c, lrelu_after, mask_input
         return K.pixelnorm_fwd(x, c, lrelu_after)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
         (x,) = ctx.saved_tensors
-        return K.pixelnorm_bwd(x, _c(gy), ctx.c, ctx.lrelu_after), None, None
+        return K.pixelnorm_bwd(x, _c(gy), ctx.c, ctx.lrelu_after, ctx.mask_input), None, None, None
 
 
 # ============================================================================== layout

@@ -111,9 +111,12 @@ def down2(x, scale, out_dtype=None):
     return _from5(F.avg_pool3d(y, 2) * (8.0 * scale), blocked, out_dtype or x.dtype)
 
 
-def up2(x, scale, out_dtype=None):
+def up2(x, scale, out_dtype=None, mask_ref=None):
     y, blocked = _to5(x)
-    return _from5(F.interpolate(y, scale_factor=2, mode="nearest") * scale, blocked, out_dtype or x.dtype)
+    out = _from5(F.interpolate(y, scale_factor=2, mode="nearest") * scale, blocked, out_dtype or x.dtype)
+    if mask_ref is not None:
+        out = (out.float() * _mask(mask_ref)).to(out.dtype)
+    return out
 
 
 def lincomb(a, b, alpha, beta):
@@ -139,13 +142,15 @@ def pixelnorm_fwd(x, c, lrelu_after):
     return plain_to_act(y, x.dtype)
 
 
-def pixelnorm_bwd(x, gy, c, lrelu_after):
+def pixelnorm_bwd(x, gy, c, lrelu_after, mask_input=False):
     xp = act_to_plain(x, c).requires_grad_(True)
     with torch.enable_grad():
         y = xp * torch.rsqrt(torch.mean(xp ** 2, dim=1, keepdim=True) + 1e-8)
         if lrelu_after:
             y = F.leaky_relu(y, 0.2)
         (gx,) = torch.autograd.grad(y, xp, act_to_plain(gy, c))
+    if mask_input:
+        gx = gx * _mask(xp.detach())
     return plain_to_act(gx, x.dtype)
 
 
