@@ -179,25 +179,30 @@ k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
       const int n = t;
       const int w0 = tile_w * 8, h0 = tile_h * p.th, d0 = tile_d * p.td;
       const int buf = ti & 1;
+      // resident geometry: tiles divide the volume exactly, every accumulator row is a real voxel
+      const int64_t plane8 = (int64_t)p.H * p.W * 8;
+      const int64_t obase0 =
+          (((int64_t)n * p.CCout + co0 / 8) * V + ((int64_t)d0 * p.H + h0 + (row >> 3)) * p.W + w0 + (row & 7)) * 8;
+      // prefetch the LeakyReLU-mask vectors of the whole tile before waiting for the MMAs
+      uint4 mk[TD][NT / 8];
+      if (mask) {
+#pragma unroll
+        for (int sub = 0; sub < TD; ++sub)
+#pragma unroll
+          for (int c = 0; c < NT / 8; ++c)
+            mk[sub][c] = __ldg(reinterpret_cast<const uint4*>(mask + obase0 + sub * plane8 + (int64_t)c * V * 8));
+      }
       mbar_wait(BAR(ACC_FULL + buf), (ti >> 1) & 1);
       tc_fence_after();
-      for (int sub = 0; sub < p.n_sub; ++sub) {
-        const int line = p.sub_line[sub] + (row >> 3);
-        const int wl = row & 7;
-        const int dh = line / p.halo_h, hh = line - dh * p.halo_h;
-        const int d = d0 + dh - 1, h = h0 + hh - 1, w = w0 + wl;
-        const bool valid = dh >= 1 && dh <= p.td && hh >= 1 && hh <= p.th && d < p.D && h < p.H && w < p.W;
-        const int64_t vox = ((int64_t)d * p.H + h) * p.W + w;
-        const int64_t obase = (((int64_t)n * p.CCout + co0 / 8) * V + vox) * 8;
+#pragma unroll
+      for (int sub = 0; sub < TD; ++sub) {
 #pragma unroll
         for (int c0 = 0; c0 < NT; c0 += 16) {
           float v[16];
           __syncwarp();
           tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * acc_cols + sub * NT + c0), v);
-          if (valid) {
-            const int64_t o = obase + (int64_t)(c0 / 8) * V * 8;
-            epilogue16(v, s_bias + c0, scale, lrelu, mask ? mask + o : nullptr, yout + o, V * 8);
-          }
+          epilogue16_regmask(v, s_bias + c0, scale, lrelu, mask != nullptr, mk[sub][c0 / 8], mk[sub][c0 / 8 + 1],
+                             yout + obase0 + sub * plane8 + (int64_t)(c0 / 8) * V * 8, V * 8);
         }
       }
       // this warp is done reading the accumulator set: hand it back to the MMA issuer

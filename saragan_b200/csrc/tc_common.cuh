@@ -113,6 +113,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 
 constexpr int kMaxSub = 8;   // MMA tiles (128 rows each) per CTA tile
 
+__device__ __forceinline__ F8 unpack8(const uint4& u) {
+  F8 r;
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    r.v[2 * i] = f.x;
+    r.v[2 * i + 1] = f.y;
+  }
+  return r;
+}
+
 // Epilogue of 16 accumulator columns (= two 8-channel chunks) of one output voxel:
 // y = [mask] [lrelu] (acc*scale + bias) -> two 16-byte stores.  `sb` points at the 16 biases in
 // SHARED memory (broadcast float4 reads; the first version fetched them with per-element __ldg
@@ -166,6 +178,41 @@ __device__ __forceinline__ void issue_tap(uint32_t tmem_acc, uint64_t a_desc, ui
       for (int sub = 0; sub < kMaxSub; ++sub)
         if (sub < n_sub) tc_mma(tmem_acc + sub * NT, a_k + sub_off[sub], b, idesc, acc, leader);
     }
+  }
+}
+
+// Same as epilogue16 with the two mask vectors already in registers (prefetched while the MMAs of
+// the tile were still running, so their global-load latency is off the epilogue's critical path).
+__device__ __forceinline__ void epilogue16_regmask(const float (&v)[16], const float* sb, float scale, int lrelu,
+                                                   bool has_mask, const uint4& m0, const uint4& m1, __nv_bfloat16* y,
+                                                   int64_t chunk_stride) {
+  float r[16];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 b = *reinterpret_cast<const float4*>(sb + 4 * q);
+    r[4 * q + 0] = fmaf(v[4 * q + 0], scale, b.x);
+    r[4 * q + 1] = fmaf(v[4 * q + 1], scale, b.y);
+    r[4 * q + 2] = fmaf(v[4 * q + 2], scale, b.z);
+    r[4 * q + 3] = fmaf(v[4 * q + 3], scale, b.w);
+  }
+  if (lrelu) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) r[j] = fmaxf(r[j], 0.2f * r[j]);
+  }
+  if (has_mask) {
+    const F8 a = unpack8(m0), b = unpack8(m1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      r[j] *= lmask02(a.v[j]);
+      r[8 + j] *= lmask02(b.v[j]);
+    }
+  }
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    F8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.v[j] = r[half * 8 + j];
+    st8(y + half * chunk_stride, o);
   }
 }
 

@@ -32,6 +32,10 @@ def make_capturable_optimizers(generator, discriminator, lr: float = 1e-3, world
 class GraphedTrainStep:
     def __init__(self, generator, discriminator, g_optim, d_optim, batch: int, volume, alpha: float,
                  warmup: int = 3, seed: Optional[int] = None, grad_sync=None):
+        if warmup < 1:
+            # the first optim.step() creates the Adam state; inside a capture that initialisation
+            # would be replayed (state reset to zero) on every step
+            raise ValueError("GraphedTrainStep needs at least one eager warm-up step before the capture")
         self.grad_sync = grad_sync    # e.g. comm.CapturableAllReduce on several GPUs
         self.g, self.d, self.g_optim, self.d_optim = generator, discriminator, g_optim, d_optim
         self.alpha = float(alpha)

@@ -10,33 +10,38 @@ from tests.util import build_pair
 pytestmark = pytest.mark.gpu
 
 
+class _Recording(GraphedTrainStep):
+    """records every random draw (the warm-up steps of __init__ included)"""
+
+    def draw(self):
+        super().draw()
+        if not hasattr(self, "draws"):
+            self.draws = []
+        self.draws.append({k: getattr(self, k).clone() for k in ("noise", "z_d", "z_g", "eps")})
+
+
 def test_graph_replay_matches_eager():
     cfg = dict(phase=3, num_phases=4, base_dim=64, latent_dim=64, base_shape=(1, 1, 4, 4))
-    vol, b, alpha = (4, 16, 16), 4, 0.5
+    vol, b, alpha, warm = (4, 16, 16), 4, 0.5, 2
     x = [torch.rand(b, 1, *vol, device="cuda") for _ in range(3)]
 
     g1, d1 = build_pair(cfg, seed=5)
     g_opt, d_opt = make_capturable_optimizers(g1, d1)
-    graphed = GraphedTrainStep(g1, d1, g_opt, d_opt, b, vol, alpha, warmup=0, seed=7)
-    draws = []
-    orig_draw = graphed.draw
-
-    def recording_draw():
-        orig_draw()
-        draws.append({k: getattr(graphed, k).clone() for k in ("noise", "z_d", "z_g", "eps")})
-    graphed.draw = recording_draw
+    # warm-up steps run eagerly on the (zero) static input buffer and initialise the Adam state
+    # outside the graph; the draw made right before the capture is consumed by no executed step
+    graphed = _Recording(g1, d1, g_opt, d_opt, b, vol, alpha, warmup=warm, seed=7)
     losses = []
     for xi in x:
         o = graphed(xi)
         losses.append([float(o[k]) for k in ("d_loss", "gp", "g_loss")])
+    draws = graphed.draws
+    assert len(draws) == warm + 1 + len(x)
 
     g2, d2 = build_pair(cfg, seed=5)
     g_opt2, d_opt2 = make_capturable_optimizers(g2, d2)
-    # the capture itself applied one (un-replayed) update with the draw made just before it:
-    # replay that history eagerly -- capture-time step first, then the three recorded steps
-    # (warmup=0, so nothing else touched the weights)
-    # NOTE: torch.cuda.graph capture does not execute kernels, so the weights are only updated by replays.
-    for xi, dr in zip(x, draws):
+    history = [(torch.zeros_like(x[0]), draws[i]) for i in range(warm)] + \
+              [(xi, draws[warm + 1 + i]) for i, xi in enumerate(x)]
+    for xi, dr in history:
         o = sg.train_step(xi, g2, d2, g_opt2, d_opt2, alpha, noise=dr["noise"], z_d=dr["z_d"], z_g=dr["z_g"],
                           eps=dr["eps"])
     torch.cuda.synchronize()
@@ -44,4 +49,9 @@ def test_graph_replay_matches_eager():
     for (n1, p1), (n2, p2) in zip(list(g1.named_parameters()) + list(d1.named_parameters()),
                                   list(g2.named_parameters()) + list(d2.named_parameters())):
         assert n1 == n2
-        assert float((p1 - p2).abs().max()) < 5e-3, n1      # 3 Adam steps of lr 1e-3 each at most 3e-3 apart
+        # Adam with beta1 = 0 moves a weight by ~lr*sign(g) per step: a weight whose tiny gradient
+        # flips sign between the two runs (atomics order) ends up to 2*lr apart per step -- bound
+        # the maximum by that and require the bulk to agree closely
+        diff = (p1.detach() - p2.detach()).abs()
+        assert float(diff.max()) < 1.1e-2, n1
+        assert float(diff.mean()) < 3e-4, (n1, float(diff.mean()))
