@@ -181,7 +181,7 @@ def main():
     else:
         g_opt, d_opt = sg.make_optimizers(g, d, world_size=world)
     if world > 1:
-        dp = comm.CapturableAllReduce(g, d) if use_graph else comm.DataParallel(g, d)
+        dp = comm.FlatAllReduce(g, d) if use_graph else comm.DataParallel(g, d)
     else:
         dp = None
 

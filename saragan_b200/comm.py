@@ -180,11 +180,11 @@ class DataParallel:
         self._b[id(module)].finish()
 
 
-class CapturableAllReduce:
-    """Gradient averaging that can be captured in a CUDA graph: one flat all-reduce per module on
-    the capturing stream (no side stream, no hooks).  Used by graph.GraphedTrainStep on several
-    GPUs; the <= 0.5 GB of gradients cost ~1 ms un-overlapped on NVLink 5 against a ~30 ms step,
-    less than the host launch overhead the graph removes."""
+class FlatAllReduce:
+    """Gradient averaging for the CUDA-graph step: one flat all-reduce per module on the current
+    stream, run eagerly between the graph segments of graph.GraphedTrainStep (no hooks: hooks do
+    not fire during a graph replay).  The <= 0.5 GB of gradients cost ~1 ms un-overlapped on
+    NVLink 5 against a ~30 ms step -- less than the host launch overhead the graph removes."""
 
     def __init__(self, generator, discriminator):
         self.world = dist.get_world_size() if dist.is_initialized() else 1

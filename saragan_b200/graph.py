@@ -6,6 +6,9 @@ minibatch-stddev, Adam); issued one by one from Python they cost more host time 
 needs to execute them once the convolutions run on tcgen05.  Capturing the step removes the
 host from the loop (the north-star's "CUDA streams and graphs instead of a tracing compiler").
 
+On several GPUs the step is captured as three segments with the (eager) NCCL gradient all-reduce
+between them -- see __init__.
+
 Inputs live in static buffers: the real batch, the instance-noise draw, the two latent draws and
 the GP interpolation draw are refreshed outside the graph (`draw()`), then `replay()` runs the
 captured work.  `alpha` is a Python float baked into the kernels' arguments, so a graph is
@@ -17,7 +20,7 @@ from typing import Dict, Optional
 
 import torch
 
-from .train import train_step
+from .train import d_phase, g_phase, train_step
 
 
 def make_capturable_optimizers(generator, discriminator, lr: float = 1e-3, world_size: int = 1):
@@ -70,8 +73,27 @@ class GraphedTrainStep:
         self.draw()
         from . import _lib
         n0 = _lib.launch_count()
-        with torch.cuda.graph(self.graph):
-            self.out = self._step()
+        if grad_sync is None:
+            with torch.cuda.graph(self.graph):
+                self.out = self._step()
+            self.segments = None
+        else:
+            # several GPUs: the gradient all-reduce runs EAGERLY between three graph segments
+            # (D forward/backward | D update + G forward/backward | G update) that share one memory
+            # pool, so NCCL never has to be captured; the gradients are static buffers of the pool
+            g1, g2, g3 = self.graph, torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                od = d_phase(self.x, self.g, self.d, self.d_optim, self.alpha, noise=self.noise, z_d=self.z_d,
+                             eps=self.eps)
+            with torch.cuda.graph(g2, pool=g1.pool()):
+                self.d_optim.step()
+                og = g_phase(self.x.shape[0], self.g, self.d, self.g_optim, self.alpha, z_g=self.z_g)
+                dist_ = od["d_real_mean"] - og["d_fake_mean"]
+            with torch.cuda.graph(g3, pool=g1.pool()):
+                self.g_optim.step()
+            self.segments = (g1, g2, g3)
+            self.out = {"d_loss": od["d_loss"], "gp": od["gp"], "g_loss": og["g_loss"], "distance": dist_,
+                        "x_fake": og["x_fake"]}
         self.launches_per_step = _lib.launch_count() - n0   # our kernels inside one replay
 
     def _step(self):
@@ -91,5 +113,13 @@ class GraphedTrainStep:
         (valid until the next call)."""
         self.x.copy_(x_real, non_blocking=True)
         self.draw()
-        self.graph.replay()
+        if self.segments is None:
+            self.graph.replay()
+        else:
+            g1, g2, g3 = self.segments
+            g1.replay()
+            self.grad_sync.finish(self.d)
+            g2.replay()
+            self.grad_sync.finish(self.g)
+            g3.replay()
         return self.out

@@ -26,19 +26,12 @@ def _set_requires_grad(module, flag: bool) -> None:
         p.requires_grad = flag
 
 
-def train_step(x_real: torch.Tensor, generator, discriminator, generator_optim, discriminator_optim,
-               alpha, *, noise: Optional[torch.Tensor] = None, z_d: Optional[torch.Tensor] = None,
-               z_g: Optional[torch.Tensor] = None, eps: Optional[torch.Tensor] = None,
-               apply: bool = True, grad_sync=None) -> Dict[str, torch.Tensor]:
-    """One D update followed by one G update (train.py:133-190).
-
-    grad_sync: optional ``comm.DataParallel``; ``arm(module)`` is called before ``backward()``
-    and ``finish(module)`` before ``optim.step()`` (the data-parallel gradient all-reduce,
-    reference: hvd.DistributedOptimizer, main.py:153-160)."""
+def d_phase(x_real: torch.Tensor, generator, discriminator, discriminator_optim, alpha, *,
+            noise: Optional[torch.Tensor] = None, z_d: Optional[torch.Tensor] = None,
+            eps: Optional[torch.Tensor] = None, grad_sync=None) -> Dict[str, torch.Tensor]:
+    """train.py:134-159: D forward passes, gradient penalty, d_loss.backward() (no optimiser step)."""
     dev = discriminator.device
     batch = x_real.shape[0]
-
-    # ---- discriminator (train.py:134-161)
     generator.eval()
     discriminator.train()
     _set_requires_grad(generator, False)
@@ -65,40 +58,54 @@ def train_step(x_real: torch.Tensor, generator, discriminator, generator_optim, 
     if grad_sync is not None:
         grad_sync.arm(discriminator)
     d_loss.backward()
-    if grad_sync is not None:
-        grad_sync.finish(discriminator)
-    if apply:
-        discriminator_optim.step()
-    out = {"d_loss": d_loss.detach(), "gp": gp_loss.detach(), "d_real_mean": real_loss.detach()}
-    del z_d, d_fake, gp_loss, real_loss, fake_loss, d_loss
+    return {"d_loss": d_loss.detach(), "gp": gp_loss.detach(), "d_real_mean": real_loss.detach(),
+            "x_real": x_real}
 
-    # ---- generator (train.py:166-185)
+
+def g_phase(batch: int, generator, discriminator, generator_optim, alpha, *,
+            z_g: Optional[torch.Tensor] = None, grad_sync=None) -> Dict[str, torch.Tensor]:
+    """train.py:166-184: G forward, D forward on the fakes, g_loss.backward() (no optimiser step)."""
     generator.train()
     discriminator.eval()
     _set_requires_grad(generator, True)
     _set_requires_grad(discriminator, False)
-
     if z_g is None:
         z_g = torch.randn(batch, generator.latent_dim)
     x_fake = generator(z_g, alpha)[-1]
     d_fake = discriminator(x_fake, alpha)
     g_loss = -wasserstein_loss(d_fake)
-
     generator_optim.zero_grad()
     if grad_sync is not None:
         grad_sync.arm(generator)
     g_loss.backward()
+    _set_requires_grad(generator, True)
+    _set_requires_grad(discriminator, True)
+    return {"g_loss": g_loss.detach(), "d_fake_mean": d_fake.detach().mean(), "x_fake": x_fake.detach()}
+
+
+def train_step(x_real: torch.Tensor, generator, discriminator, generator_optim, discriminator_optim,
+               alpha, *, noise: Optional[torch.Tensor] = None, z_d: Optional[torch.Tensor] = None,
+               z_g: Optional[torch.Tensor] = None, eps: Optional[torch.Tensor] = None,
+               apply: bool = True, grad_sync=None) -> Dict[str, torch.Tensor]:
+    """One D update followed by one G update (train.py:133-190).
+
+    grad_sync: optional ``comm.DataParallel``; ``arm(module)`` is called before ``backward()``
+    and ``finish(module)`` before ``optim.step()`` (the data-parallel gradient all-reduce,
+    reference: hvd.DistributedOptimizer, main.py:153-160)."""
+    out = d_phase(x_real, generator, discriminator, discriminator_optim, alpha, noise=noise, z_d=z_d, eps=eps,
+                  grad_sync=grad_sync)
+    if grad_sync is not None:
+        grad_sync.finish(discriminator)
+    if apply:
+        discriminator_optim.step()
+    g = g_phase(x_real.shape[0], generator, discriminator, generator_optim, alpha, z_g=z_g, grad_sync=grad_sync)
     if grad_sync is not None:
         grad_sync.finish(generator)
     if apply:
         generator_optim.step()
-
-    out["g_loss"] = g_loss.detach()
-    out["distance"] = out["d_real_mean"] - d_fake.detach().mean()
-    out["x_fake"] = x_fake.detach()
-    out["x_real"] = x_real
-    _set_requires_grad(generator, True)
-    _set_requires_grad(discriminator, True)
+    out["g_loss"] = g["g_loss"]
+    out["distance"] = out["d_real_mean"] - g["d_fake_mean"]
+    out["x_fake"] = g["x_fake"]
     return out
 
 

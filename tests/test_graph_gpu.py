@@ -20,38 +20,44 @@ class _Recording(GraphedTrainStep):
         self.draws.append({k: getattr(self, k).clone() for k in ("noise", "z_d", "z_g", "eps")})
 
 
-def test_graph_replay_matches_eager():
-    cfg = dict(phase=3, num_phases=4, base_dim=64, latent_dim=64, base_shape=(1, 1, 4, 4))
-    vol, b, alpha, warm = (4, 16, 16), 4, 0.5, 2
-    x = [torch.rand(b, 1, *vol, device="cuda") for _ in range(3)]
+CFG = dict(phase=3, num_phases=4, base_dim=64, latent_dim=64, base_shape=(1, 1, 4, 4))
+VOL, B, ALPHA, WARM = (4, 16, 16), 4, 0.5, 2
 
-    g1, d1 = build_pair(cfg, seed=5)
+
+def _eager_arm(x, draws):
+    g2, d2 = build_pair(CFG, seed=5)
+    g_opt2, d_opt2 = make_capturable_optimizers(g2, d2)
+    history = [(torch.zeros_like(x[0]), draws[i]) for i in range(WARM)] + \
+              [(xi, draws[WARM + 1 + i]) for i, xi in enumerate(x)]
+    for xi, dr in history:
+        o = sg.train_step(xi, g2, d2, g_opt2, d_opt2, ALPHA, noise=dr["noise"], z_d=dr["z_d"], z_g=dr["z_g"],
+                          eps=dr["eps"])
+    torch.cuda.synchronize()
+    return o, [p.detach() for p in list(g2.parameters()) + list(d2.parameters())]
+
+
+@pytest.mark.parametrize("n_replays", [1, 3])
+def test_graph_replay_matches_eager(n_replays):
+    """Replays against eager steps from the same state and draws.  Two EAGER runs of this step
+    already differ: fp32-atomic summation order perturbs gradients at the 1e-7 level and Adam
+    with beta1 = 0 turns a near-zero gradient of either sign into a +-lr step.  The graph must
+    sit inside that run-to-run noise floor, measured here with a second eager arm."""
+    x = [torch.rand(B, 1, *VOL, device="cuda", generator=torch.Generator(device="cuda").manual_seed(i))
+         for i in range(n_replays)]
+    g1, d1 = build_pair(CFG, seed=5)
     g_opt, d_opt = make_capturable_optimizers(g1, d1)
     # warm-up steps run eagerly on the (zero) static input buffer and initialise the Adam state
     # outside the graph; the draw made right before the capture is consumed by no executed step
-    graphed = _Recording(g1, d1, g_opt, d_opt, b, vol, alpha, warmup=warm, seed=7)
-    losses = []
+    graphed = _Recording(g1, d1, g_opt, d_opt, B, VOL, ALPHA, warmup=WARM, seed=7)
     for xi in x:
         o = graphed(xi)
-        losses.append([float(o[k]) for k in ("d_loss", "gp", "g_loss")])
-    draws = graphed.draws
-    assert len(draws) == warm + 1 + len(x)
-
-    g2, d2 = build_pair(cfg, seed=5)
-    g_opt2, d_opt2 = make_capturable_optimizers(g2, d2)
-    history = [(torch.zeros_like(x[0]), draws[i]) for i in range(warm)] + \
-              [(xi, draws[warm + 1 + i]) for i, xi in enumerate(x)]
-    for xi, dr in history:
-        o = sg.train_step(xi, g2, d2, g_opt2, d_opt2, alpha, noise=dr["noise"], z_d=dr["z_d"], z_g=dr["z_g"],
-                          eps=dr["eps"])
-    torch.cuda.synchronize()
-    assert abs(float(o["d_loss"]) - losses[-1][0]) < 2e-3 * abs(losses[-1][0])
-    for (n1, p1), (n2, p2) in zip(list(g1.named_parameters()) + list(d1.named_parameters()),
-                                  list(g2.named_parameters()) + list(d2.named_parameters())):
-        assert n1 == n2
-        # Adam with beta1 = 0 moves a weight by ~lr*sign(g) per step: a weight whose tiny gradient
-        # flips sign between the two runs (atomics order) ends up to 2*lr apart per step -- bound
-        # the maximum by that and require the bulk to agree closely
-        diff = (p1.detach() - p2.detach()).abs()
-        assert float(diff.max()) < 1.1e-2, n1
-        assert float(diff.mean()) < 3e-4, (n1, float(diff.mean()))
+    loss_graph = [float(o[k]) for k in ("d_loss", "gp", "g_loss")]
+    assert len(graphed.draws) == WARM + 1 + len(x)
+    pa = [p.detach() for p in list(g1.parameters()) + list(d1.parameters())]
+    ob, pb = _eager_arm(x, graphed.draws)
+    oc, pc = _eager_arm(x, graphed.draws)
+    for k, got in zip(("d_loss", "gp", "g_loss"), loss_graph):
+        assert abs(float(ob[k]) - got) < 2e-3 * max(1.0, abs(got)), k
+    graph_vs_eager = sum(float((a - b).abs().mean()) for a, b in zip(pa, pb)) / len(pa)
+    eager_vs_eager = sum(float((b - c).abs().mean()) for b, c in zip(pb, pc)) / len(pa)
+    assert graph_vs_eager < 3 * eager_vs_eager + 2e-5, (graph_vs_eager, eager_vs_eager)
