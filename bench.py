@@ -45,8 +45,8 @@ def parse():
     ap.add_argument("--alpha", type=float, default=0.5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=2)
-    ap.add_argument("--graph", type=int, default=-1, help="1: replay the step as a CUDA graph; 0: eager; "
-                    "-1: graph on one GPU, eager with the overlapped all-reduce on several")
+    ap.add_argument("--graph", type=int, default=1, help="1: replay the step as CUDA graph(s) (on several GPUs: three "
+                    "segments with the NCCL all-reduce between them); 0: eager with the bucketed, overlapped all-reduce")
     return ap.parse_args()
 
 
@@ -174,7 +174,7 @@ def main():
     torch.manual_seed(0)
     g = sg.Generator(cfg["phase"], cfg["num_phases"], cfg["base_dim"], cfg["latent_dim"], C.BASE_SHAPE)
     d = sg.Discriminator(cfg["phase"], cfg["num_phases"], cfg["base_dim"], cfg["latent_dim"], C.BASE_SHAPE)
-    use_graph = args.graph == 1 or (args.graph == -1 and world == 1)
+    use_graph = args.graph == 1
     if use_graph:
         from saragan_b200.graph import GraphedTrainStep, make_capturable_optimizers
         g_opt, d_opt = make_capturable_optimizers(g, d, world_size=world)
@@ -210,12 +210,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # dominant kernel: the conv fprop launch shape with the most FLOPs (D's top block conv2)
+    # kernels reported against the roofline: the top D block's convolutions (the launch shapes with
+    # the largest time shares in profiles/): wgrad of conv2 (k_wgrad_tc is the kernel with the largest
+    # share of the step), fprop of conv2, and conv2's dgrad
     layers = C.conv_layers("d", cfg["phase"], cfg["num_phases"], cfg["base_dim"])
     name, ci, co, v = max(layers, key=lambda l: l[1] * l[2] * int(np.prod(l[3])))
-    probe = kernels.ConvProbe(("fprop", B, ci, co, *v))
     flops_per_launch = 2.0 * B * int(np.prod(v)) * ci * co * 27
-
+    probe_keys = {"wgrad": ("wgrad", B, ci, co, *v), "fprop": ("fprop", B, ci, co, *v), "dgrad": ("fprop", B, co, ci, *v)}
+    probe = kernels.ConvProbe(probe_keys.values())
+    # dram__bytes_read+write per launch from the committed `ncu --set full` capture (profiles/), cfg3 only
+    ncu_traffic = {"wgrad": 409.3e6, "fprop": 351.0e6, "dgrad": None} if (args.config == "cfg3" and B == 4) else {}
     for i in range(args.warmup):
         step(dev_pool[i % n_pool])
     barrier()
@@ -243,7 +247,6 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step = float(ms) / args.steps
     value = world * B / (ms_step * 1e-3)
-    kd = probe.durations_ms()
 
     # end-to-end: pinned host batch -> H2D -> step -> D2H of the three losses, every step
     def e2e_step(i):
@@ -274,7 +277,8 @@ def main():
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": cfg["desc"], "name": args.config, "per_gpu_batch": B, "global_batch": B * world,
                        "alpha": alpha, "parallelism": f"dp{world}",
-                       "launch": "cuda-graph replay of the whole step" if use_graph else "eager",
+                       "launch": ("cuda-graph replay of the whole step" if world == 1 else
+                                  "3 cuda-graph segments + eager NCCL all-reduce") if use_graph else "eager",
                        "l2": "per-step working set (GBs of activations) >> 126 MB L2; 4 rotating input batches",
                        "step_gflop_per_image": step_flops / 1e9,
                        "step_tensor_frac": step_flops * value / world / (pk["bf16"] * 1e12)},
@@ -284,13 +288,21 @@ def main():
             "clocks": clocks.summary(),
             "losses": [float(v) for v in losses],
         }
-        if kd:
-            dur = float(np.mean(kd)) * 1e-3
+        def roof(kind, label):
+            kd_ = probe.durations_ms(probe_keys[kind])
+            if not kd_:
+                return None
+            dur = float(np.mean(kd_)) * 1e-3
             ach = flops_per_launch / dur / 1e12
-            line["roofline"] = {"bound": "tensor", "kernel": f"conv3d fprop {name} {ci}->{co} @{'x'.join(map(str, v))} B={B}",
-                                "achieved": ach, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": ach / pk["bf16"],
-                                "traffic": None, "launches_timed": len(kd), "ms_per_launch": dur * 1e3,
-                                "peak_source": pk["src"]}
+            return {"bound": "tensor", "kernel": label, "achieved": ach, "peak": pk["bf16"], "unit": "TFLOP/s",
+                    "frac": ach / pk["bf16"], "traffic": ncu_traffic.get(kind), "launches_timed": len(kd_),
+                    "ms_per_launch": dur * 1e3, "flop_per_launch": flops_per_launch, "peak_source": pk["src"]}
+        shape = f"{ci}->{co} @{'x'.join(map(str, v))} B={B}"
+        r = roof("wgrad", f"k_wgrad_tc: conv3d wgrad {name} {shape}")
+        if r:
+            line["roofline"] = r
+            line["roofline_more"] = [x for x in (roof("fprop", f"k_conv_tc_res: conv3d fprop {name} {shape}"),
+                                                 roof("dgrad", f"k_conv_tc_res: conv3d dgrad {name} {shape}")) if x]
         if world == 1 and not args.no_cpu_baseline:
             rate, t, threads = cpu_step_rate(cfg, args.cpu_batch, 1, 0, alpha)
             line["cpu_baseline"] = {"value": rate, "unit": "img/s", "cores": threads, "kind": "port",

@@ -22,27 +22,29 @@ conv_probe = None
 
 
 class ConvProbe:
-    """Records CUDA-event pairs around the conv launches whose (kind, N, Cin, Cout, D, H, W)
-    matches `select`; `durations_ms()` after a synchronize."""
+    """Records CUDA-event pairs around the conv launches whose (kind, N, Cin, Cout, D, H, W) is in
+    `select`; `durations_ms(key)` after a synchronize."""
 
     def __init__(self, select):
-        self.select = tuple(select)
-        self.pairs = []
+        self.select = {tuple(k) for k in select}
+        self.pairs = {k: [] for k in self.select}
 
     def start(self, kind, n, cin, cout, d, h, w):
-        if (kind, n, cin, cout, d, h, w) != self.select:
+        key = (kind, n, cin, cout, d, h, w)
+        if key not in self.select:
             return None
         e0 = torch.cuda.Event(enable_timing=True)
         e0.record(torch.cuda.current_stream())
-        return e0
+        return key, e0
 
-    def stop(self, e0):
+    def stop(self, tok):
+        key, e0 = tok
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record(torch.cuda.current_stream())
-        self.pairs.append((e0, e1))
+        self.pairs[key].append((e0, e1))
 
-    def durations_ms(self):
-        return [a.elapsed_time(b) for a, b in self.pairs]
+    def durations_ms(self, key):
+        return [a.elapsed_time(b) for a, b in self.pairs[tuple(key)]]
 
 
 def _vox(t: torch.Tensor) -> int:
