@@ -179,7 +179,8 @@ def main():
         from saragan_b200.graph import GraphedTrainStep, make_capturable_optimizers
         g_opt, d_opt = make_capturable_optimizers(g, d, world_size=world)
     else:
-        g_opt, d_opt = sg.make_optimizers(g, d, world_size=world)
+        from saragan_b200.graph import make_capturable_optimizers
+        g_opt, d_opt = make_capturable_optimizers(g, d, world_size=world)      # fused Adam in eager mode too
     if world > 1:
         dp = comm.FlatAllReduce(g, d) if use_graph else comm.DataParallel(g, d)
     else:

@@ -120,6 +120,20 @@ int sg_linear_fwd(const float* x, const float* w, const float* bias, float* y, i
 int sg_linear_dgrad(const float* g, const float* w, float* gx, int B, int In, int Out, float scale, cudaStream_t stream);
 int sg_linear_wgrad(const float* g, const float* x, float* gw, float* gb, int B, int In, int Out, float scale, cudaStream_t stream);
 
+/* ---- fused multi-tensor Adam (+ optional weight EMA)  (main.py:141-142 torch.optim.Adam(betas=(0,.99));
+ * EMA: SURFGAN_3D/ExtendedEMA.py).  `tensors`: device array of
+ *   struct { float* p; const float* g; float* m; float* v; float* ema; int64_t n; }   (m, ema nullable)
+ * block b updates elements [block_offset[b], +1024) of tensor block_tensor[b]; `step` is a device
+ * counter holding t-1 (graph-capturable); sg_adam_advance increments it. */
+int sg_adam_step(const void* tensors, const int* block_tensor, const int64_t* block_offset, int n_blocks,
+                 const int* step, float lr, float beta1, float beta2, float eps, float ema_beta, cudaStream_t stream);
+int sg_adam_advance(int* step, cudaStream_t stream);
+
+/* ---- input preparation (main.py:85-87 `np.load -> float32 / 1024`, train.py:144 `+ 0.01*randn`):
+ * out = raw_u16 * scale + sigma * noise (noise nullable) */
+int sg_prepare_real(const void* raw_u16, const float* noise, float* out, int64_t n, float scale, float sigma,
+                    cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,7 @@ from .loss import compute_gradient_penalty, wasserstein_loss  # noqa: F401
 from .network import (ChannelNormalization, Discriminator, DiscriminatorBlock,  # noqa: F401
                       EqualizedConv3d, EqualizedLinear, FromRGB, Generator, GeneratorBlock,
                       MinibatchStandardDeviation, ToRGB, num_filters)
+from .optim import FusedAdam  # noqa: F401
 from .train import make_optimizers, train_epoch, train_step  # noqa: F401
 
 __version__ = "0.1.0"

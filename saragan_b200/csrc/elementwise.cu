@@ -699,3 +699,83 @@ extern "C" int sg_linear_wgrad(const float* g, const float* x, float* gw, float*
   k_linear_wgrad<<<sg_grid(total, 256), 256, 0, s>>>(g, x, gw, gb, B, In, Out, scale);
   return sg_check_launch("sg_linear_wgrad");
 }
+
+// ------------------------------------------------------ fused multi-tensor Adam (+ EMA)
+// main.py:141-142 `torch.optim.Adam(params, lr, betas=(0, 0.99))` for every active parameter of a
+// network in ONE launch (memory-bound: 16-20 B/parameter), optionally followed
+// by the generator-weight EMA of the TF path (SURFGAN_3D/ExtendedEMA.py).  Same update as
+// torch.optim.Adam (no amsgrad, no weight decay):
+//   m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g*g;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+// `step` is a device counter (t-1 before the call) so the launch can live in a CUDA graph;
+// sg_adam_advance increments it.
+struct SgAdamTensor {
+  float* p;
+  const float* g;
+  float* m;       // may be null when beta1 == 0
+  float* v;
+  float* ema;     // may be null
+  int64_t n;
+};
+__global__ void k_adam_multi(const SgAdamTensor* __restrict__ tensors, const int* __restrict__ block_tensor,
+                             const int64_t* __restrict__ block_offset, const int* __restrict__ step, float lr,
+                             float beta1, float beta2, float eps, float ema_beta) {
+  const SgAdamTensor t = tensors[block_tensor[blockIdx.x]];
+  const int64_t base = block_offset[blockIdx.x];
+  const float tt = (float)(*step + 1);
+  const float bc1 = beta1 > 0.f ? 1.f - powf(beta1, tt) : 1.f;
+  const float bc2_sqrt = sqrtf(1.f - powf(beta2, tt));
+  const float step_size = lr / bc1;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t i = base + (int64_t)k * blockDim.x + threadIdx.x;
+    if (i >= t.n) break;
+    const float g = t.g[i];
+    float m = g;
+    if (beta1 > 0.f) {
+      m = beta1 * t.m[i] + (1.f - beta1) * g;
+      t.m[i] = m;
+    }
+    const float v = beta2 * t.v[i] + (1.f - beta2) * g * g;
+    t.v[i] = v;
+    const float p = t.p[i] - step_size * m / (sqrtf(v) / bc2_sqrt + eps);
+    t.p[i] = p;
+    if (t.ema) t.ema[i] = ema_beta * t.ema[i] + (1.f - ema_beta) * p;
+  }
+}
+__global__ void k_adam_advance(int* step) { *step += 1; }
+
+extern "C" int sg_adam_step(const void* tensors, const int* block_tensor, const int64_t* block_offset, int n_blocks,
+                            const int* step, float lr, float beta1, float beta2, float eps, float ema_beta,
+                            cudaStream_t s) {
+  if (n_blocks == 0) return 0;
+  k_adam_multi<<<(unsigned)n_blocks, 256, 0, s>>>((const SgAdamTensor*)tensors, block_tensor, block_offset, step, lr,
+                                                  beta1, beta2, eps, ema_beta);
+  return sg_check_launch("sg_adam_step");
+}
+extern "C" int sg_adam_advance(int* step, cudaStream_t s) {
+  k_adam_advance<<<1, 1, 0, s>>>(step);
+  return sg_check_launch("sg_adam_advance");
+}
+
+// --------------------------------------------------------------- input preparation
+// main.py:85-87 loader (`np.load -> float32 -> [None] / 1024`) + train.py:144 instance noise in one
+// pass over the raw uint16 voxels: out = raw * scale + sigma * noise.
+__global__ void k_prepare_real(const uint16_t* __restrict__ raw, const float* __restrict__ noise,
+                               float* __restrict__ out, int64_t n, float scale, float sigma) {
+  for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4; i < n; i += (int64_t)gridDim.x * blockDim.x * 4) {
+    if (i + 3 < n) {
+      const ushort4 r = *reinterpret_cast<const ushort4*>(raw + i);
+      float4 z = noise ? *reinterpret_cast<const float4*>(noise + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(out + i) = make_float4(r.x * scale + sigma * z.x, r.y * scale + sigma * z.y,
+                                                        r.z * scale + sigma * z.z, r.w * scale + sigma * z.w);
+    } else {
+      for (int64_t j = i; j < n; ++j) out[j] = raw[j] * scale + (noise ? sigma * noise[j] : 0.f);
+    }
+  }
+}
+extern "C" int sg_prepare_real(const void* raw_u16, const float* noise, float* out, int64_t n, float scale,
+                               float sigma, cudaStream_t s) {
+  if (n == 0) return 0;
+  k_prepare_real<<<sg_grid((n + 3) / 4, 256), 256, 0, s>>>((const uint16_t*)raw_u16, noise, out, n, scale, sigma);
+  return sg_check_launch("sg_prepare_real");
+}

@@ -23,12 +23,19 @@ import torch
 from .train import d_phase, g_phase, train_step
 
 
-def make_capturable_optimizers(generator, discriminator, lr: float = 1e-3, world_size: int = 1):
-    """main.py:138-145's Adam(lr*sqrt(world), betas=(0, .99)) with device-side step counters
-    (capturable=True) so `optim.step()` can live inside a CUDA graph."""
+def make_capturable_optimizers(generator, discriminator, lr: float = 1e-3, world_size: int = 1,
+                               fused: bool = True, ema_beta: Optional[float] = None):
+    """main.py:138-145's Adam(lr*sqrt(world), betas=(0, .99)) in a form whose `step()` can live inside
+    a CUDA graph: our fused multi-tensor kernel (optim.FusedAdam, device-side step counter; optional
+    generator-weight EMA), or torch's capturable Adam with fused=False."""
     lr = lr * float(world_size) ** 0.5
-    d_optim = torch.optim.Adam(discriminator.parameters(), lr=lr, betas=(0.0, 0.99), capturable=True)
-    g_optim = torch.optim.Adam(generator.parameters(), lr=lr, betas=(0.0, 0.99), capturable=True)
+    if fused:
+        from .optim import FusedAdam
+        d_optim = FusedAdam(discriminator.parameters(), lr=lr, betas=(0.0, 0.99))
+        g_optim = FusedAdam(generator.parameters(), lr=lr, betas=(0.0, 0.99), ema_beta=ema_beta)
+    else:
+        d_optim = torch.optim.Adam(discriminator.parameters(), lr=lr, betas=(0.0, 0.99), capturable=True)
+        g_optim = torch.optim.Adam(generator.parameters(), lr=lr, betas=(0.0, 0.99), capturable=True)
     return g_optim, d_optim
 
 
@@ -71,6 +78,9 @@ class GraphedTrainStep:
                 if hasattr(m, "_packed"):
                     m._packed = type(m._packed)(m.weight)
         self.draw()
+        for opt in (g_optim, d_optim):
+            if hasattr(opt, "reserve_capture_tables"):
+                opt.reserve_capture_tables()
         from . import _lib
         n0 = _lib.launch_count()
         if grad_sync is None:
