@@ -175,3 +175,16 @@ def test_error_reporting():
         K._lib.call("sg_down2", x, x, 1, 1, 1, 1, 3, 2, 2, 1.0)
     with pytest.raises(RuntimeError, match="CUDA tensors"):
         K.lrelu_fwd(torch.zeros(8))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_fused_mask_variants(dtype):
+    """LeakyReLU-backward masks fused into the avg-pool backward and the pixel-norm backward."""
+    xa, xg = act(2, 24, 2, 4, 8, dtype, seed=30)
+    ra, rg = act(2, 24, 4, 8, 16, dtype, seed=31)
+    close(K.up2(xg, 0.125, dtype, rg), E.up2(xa, 0.125, dtype, ra), dtype, "up2 + mask")
+    pa, pg = act(2, 16, 2, 4, 8, dtype, seed=32)
+    ga, gg = act(2, 16, 2, 4, 8, dtype, seed=33)
+    for lrelu_after in (False, True):
+        close(K.pixelnorm_bwd(pg, gg, 16, lrelu_after, True), E.pixelnorm_bwd(pa, ga, 16, lrelu_after, True), dtype,
+              "pixelnorm bwd + input mask")
