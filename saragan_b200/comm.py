@@ -195,9 +195,13 @@ class FlatAllReduce:
         pass
 
     def finish(self, module) -> None:
-        if self.world == 1:
+        self.finish_tensors([p.grad for p in module.parameters() if p.grad is not None])
+
+    def finish_tensors(self, grads) -> None:
+        """Average the given gradient tensors in place (graph.GraphedTrainStep passes the static
+        gradient buffers of its capture, which `p.grad` stops pointing at once an eager step runs)."""
+        if self.world == 1 or not grads:
             return
-        grads = [p.grad for p in module.parameters() if p.grad is not None]
         flat = torch.cat([g.reshape(-1) for g in grads])
         flat.mul_(1.0 / self.world)
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)

@@ -95,10 +95,13 @@ class GraphedTrainStep:
             with torch.cuda.graph(g1):
                 od = d_phase(self.x, self.g, self.d, self.d_optim, self.alpha, noise=self.noise, z_d=self.z_d,
                              eps=self.eps)
+            # the gradient buffers the captured backward writes (p.grad is re-bound by any later eager step)
+            self._d_grads = [p.grad for p in self.d.parameters() if p.grad is not None]
             with torch.cuda.graph(g2, pool=g1.pool()):
                 self.d_optim.step()
                 og = g_phase(self.x.shape[0], self.g, self.d, self.g_optim, self.alpha, z_g=self.z_g)
                 dist_ = od["d_real_mean"] - og["d_fake_mean"]
+            self._g_grads = [p.grad for p in self.g.parameters() if p.grad is not None]
             with torch.cuda.graph(g3, pool=g1.pool()):
                 self.g_optim.step()
             self.segments = (g1, g2, g3)
@@ -128,8 +131,8 @@ class GraphedTrainStep:
         else:
             g1, g2, g3 = self.segments
             g1.replay()
-            self.grad_sync.finish(self.d)
+            self.grad_sync.finish_tensors(self._d_grads)
             g2.replay()
-            self.grad_sync.finish(self.g)
+            self.grad_sync.finish_tensors(self._g_grads)
             g3.replay()
         return self.out

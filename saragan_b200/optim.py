@@ -25,6 +25,7 @@ class FusedAdam(torch.optim.Optimizer):
         self._step_dev: Optional[torch.Tensor] = None
         self._tables: Dict[int, dict] = {}
         self._spare: Dict[int, dict] = {}
+        self._graph_keepalive = []      # pinned tables that captured H2D copies re-read on every replay
 
     def reserve_capture_tables(self) -> None:
         """Call right before capturing ``step()`` in a CUDA graph: inside the capture the gradient
@@ -72,6 +73,7 @@ class FusedAdam(torch.optim.Optimizer):
                 raise RuntimeError("FusedAdam: call reserve_capture_tables() before capturing step() in a CUDA graph")
             host = dict(t=spare["t"][:len(rows)], bt=spare["bt"][:len(block_tensor)], bo=spare["bo"][:len(block_offset)])
             host["t"].copy_(t_rows), host["bt"].copy_(t_bt), host["bo"].copy_(t_bo)
+            self._graph_keepalive.append(spare)   # must outlive the graph even if an eager step rebuilds the table
         else:
             host = dict(t=t_rows.pin_memory(), bt=t_bt.pin_memory(), bo=t_bo.pin_memory())
         tab = dict(key=key, host=host, n_blocks=len(block_tensor),
