@@ -286,6 +286,7 @@ def main():
             "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": B * int(np.prod(vol)) * 4,
                     "d2h_bytes_per_step": 12},
             "gpu_launches": int(launches),
+            "cuda_core_conv_fallbacks_per_step": graphed.cuda_core_conv_fallbacks if use_graph else None,
             "clocks": clocks.summary(),
             "losses": [float(v) for v in losses],
         }

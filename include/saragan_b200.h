@@ -41,6 +41,8 @@ int sg_version(void);
 const char* sg_last_error(void);
 /* number of kernels this library has launched in this process (optionally reset) */
 int64_t sg_launch_count(int reset);
+/* number of bf16 convolutions the tcgen05 planners declined (run by the CUDA-core kernels instead) */
+int64_t sg_cuda_core_fallbacks(int reset);
 
 /* ---- layout conversion at the network boundary (network.py:171,271: input.to(device)) */
 int sg_plain_to_act(const float* plain, void* act, int dtype, int N, int C, int64_t V, cudaStream_t stream);

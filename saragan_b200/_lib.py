@@ -25,6 +25,7 @@ SIGNATURES = {
     "sg_version": [],
     "sg_last_error": [],
     "sg_launch_count": [_c_int],
+    "sg_cuda_core_fallbacks": [_c_int],
     "sg_plain_to_act": [_c_p, _c_p, _c_int, _c_int, _c_int, _c_i64, _c_p],
     "sg_act_to_plain": [_c_p, _c_p, _c_int, _c_int, _c_int, _c_i64, _c_p],
     "sg_packed_weight_elems": [_c_int, _c_int, _c_int],
@@ -57,7 +58,7 @@ SIGNATURES = {
     "sg_prepare_real": [_c_p, _c_p, _c_p, _c_i64, _c_f, _c_f, _c_p],
 }
 _RESTYPES = {"sg_last_error": ctypes.c_char_p, "sg_packed_weight_elems": ctypes.c_int64,
-             "sg_conv3d_workspace_bytes": ctypes.c_int64, "sg_launch_count": ctypes.c_int64,
+             "sg_conv3d_workspace_bytes": ctypes.c_int64, "sg_launch_count": ctypes.c_int64, "sg_cuda_core_fallbacks": ctypes.c_int64,
              "sg_tc_force_streaming": None}
 
 _lib = None

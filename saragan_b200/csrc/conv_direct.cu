@@ -17,6 +17,15 @@ int sg_tc_wgrad(const void* x, const void* gy, float* gw, float* gb, int N, int 
                 cudaStream_t s);
 int64_t sg_tc_workspace_bytes(int kind, int N, int Cin, int Cout, int D, int H, int W);
 
+// bf16 convolutions that the tcgen05 planners declined and the CUDA-core kernels ran instead
+// (bench.py reports the count: a non-zero value on a large layer is a performance bug)
+static unsigned long long g_cuda_core_fallbacks = 0;
+extern "C" int64_t sg_cuda_core_fallbacks(int reset) {
+  unsigned long long v = g_cuda_core_fallbacks;
+  if (reset) g_cuda_core_fallbacks = 0;
+  return (int64_t)v;
+}
+
 // ---------------------------------------------------------------------- weight packing
 // src: fp32 [Cout][Cin][27] (torch (Cout,Cin,3,3,3) contiguous).
 // fwd packing  (transpose_flip = 0): dst[tap][CCin ][CoutP][8]: elem(tap, ci, co) = w[co][ci][tap]
@@ -294,6 +303,7 @@ extern "C" int sg_conv3d_fprop(const void* x, const void* wp, const float* bias,
     int rc = sg_tc_fprop(x, wp, bias, mask_src, y, N, Cin, Cout, D, H, W, scale, lrelu, ws, ws_bytes, s);
     if (rc != 1) return rc;
     SG_REQUIRE(impl != SG_IMPL_TCGEN05, "sg_conv3d_fprop: shape not covered by the tcgen05 kernel");
+    if (impl == SG_IMPL_AUTO) ++g_cuda_core_fallbacks;
   } else {
     SG_REQUIRE(impl != SG_IMPL_TCGEN05, "sg_conv3d_fprop: tcgen05 path needs bf16 activations");
   }
@@ -446,6 +456,7 @@ extern "C" int sg_conv3d_wgrad(const void* x, const void* gy, float* gw, float* 
     int rc = sg_tc_wgrad(x, gy, gw, gb, N, Cin, Cout, D, H, W, scale, ws, ws_bytes, s);
     if (rc != 1) return rc;
     SG_REQUIRE(impl != SG_IMPL_TCGEN05, "sg_conv3d_wgrad: shape not covered by the tcgen05 kernel");
+    if (impl == SG_IMPL_AUTO) ++g_cuda_core_fallbacks;
   } else {
     SG_REQUIRE(impl != SG_IMPL_TCGEN05 || N == 0, "sg_conv3d_wgrad: tcgen05 path needs bf16 activations");
   }

@@ -194,25 +194,26 @@ WgPlan make_wgrad_plan(int N, int Cin, int Cout, int D, int H, int W) {
   if (H % th) return pl;
   p.th = th;
   p.g_chunks = CoutP / 8 < 16 ? CoutP / 8 : 16;
-  // td: as many planes per tile (1, 2, 4) as leave room for two pipeline stages
-  int td = 0;
-  for (int cand = 1; cand <= D && cand <= 4; cand *= 2) {
-    if (D % cand) continue;
-    int gb = cand * th * 8 * 16, xb = cand * (th + 2) * 8 * 16;
-    if (p.g_chunks * gb + 3 * (NT / 8) * xb <= 100 * 1024) td = cand;
+  // td: as many planes per tile (4, 2, 1) as leave room for >= 2 pipeline stages.  The M = 128 operand
+  // reads 16 chunk strides of gy: with fewer real chunks the rest are garbage rows (discarded) read
+  // from the following bytes -- `slack` keeps those reads of the LAST stage inside the allocation.
+  int td = 0, stages = 0;
+  for (int cand = 4; cand >= 1; cand /= 2) {
+    if (cand > D || D % cand) continue;
+    const int gb = cand * th * 8 * 16, xb = cand * (th + 2) * 8 * 16;
+    const int stage = p.g_chunks * gb + 3 * (NT / 8) * xb;
+    const int over = 16 * gb - stage;
+    const int slack = over > 0 ? (over + 255) / 128 * 128 : 128;
+    int st = (200 * 1024 - slack) / stage;
+    if (st > 8) st = 8;
+    if (st >= 2) {
+      td = cand; stages = st;
+      p.g_chunk_bytes = gb; p.x_chunk_bytes = xb; p.stage_bytes = stage; p.slack_bytes = slack;
+      break;
+    }
   }
   if (td == 0) return pl;
   p.td = td;
-  p.g_chunk_bytes = td * th * 8 * 16;
-  p.x_chunk_bytes = td * (th + 2) * 8 * 16;
-  p.stage_bytes = p.g_chunks * p.g_chunk_bytes + 3 * (NT / 8) * p.x_chunk_bytes;
-  // the M = 128 operand reads 16 chunk strides of gy: with fewer real chunks the rest are
-  // garbage rows (discarded) read from the following bytes -- keep them inside the allocation
-  int over = 16 * p.g_chunk_bytes - p.stage_bytes;
-  p.slack_bytes = over > 0 ? (over + 255) / 128 * 128 : 128;
-  int stages = (int)((200 * 1024 - p.slack_bytes) / p.stage_bytes);
-  if (stages > 8) stages = 8;
-  if (stages < 2) return pl;
   size_t total = (size_t)stages * p.stage_bytes;
   p.stages = stages;
   p.N = N; p.D = D; p.H = H; p.W = W;

@@ -83,6 +83,7 @@ class GraphedTrainStep:
                 opt.reserve_capture_tables()
         from . import _lib
         n0 = _lib.launch_count()
+        f0 = int(_lib.load().sg_cuda_core_fallbacks(0))
         if grad_sync is None:
             with torch.cuda.graph(self.graph):
                 self.out = self._step()
@@ -108,6 +109,7 @@ class GraphedTrainStep:
             self.out = {"d_loss": od["d_loss"], "gp": od["gp"], "g_loss": og["g_loss"], "distance": dist_,
                         "x_fake": og["x_fake"]}
         self.launches_per_step = _lib.launch_count() - n0   # our kernels inside one replay
+        self.cuda_core_conv_fallbacks = int(_lib.load().sg_cuda_core_fallbacks(0)) - f0
 
     def _step(self):
         o = train_step(self.x, self.g, self.d, self.g_optim, self.d_optim, self.alpha, noise=self.noise,
