@@ -253,3 +253,36 @@ def linear_wgrad(g: torch.Tensor, x: torch.Tensor, scale: float, want_bias: bool
     gb = torch.empty((fout,), dtype=torch.float32, device=g.device) if want_bias else None
     call("sg_linear_wgrad", g, x, gw, gb, b, fin, fout, float(scale))
     return gw, gb
+
+
+# ------------------------------------------------------------------ minibatch stddev
+def mbstd_fwd(x: torch.Tensor, group: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """x plain fp32 (B,C,D,H,W) -> out (B,C+1,D,H,W) = cat(group-centred x, stat channel), s (M, C*V)."""
+    b, c, d, h, w = x.shape
+    m, v = b // group, d * h * w
+    out = torch.empty((b, c + 1, d, h, w), dtype=torch.float32, device=x.device)
+    s = torch.empty((m, c * v), dtype=torch.float32, device=x.device)
+    t = torch.empty((m,), dtype=torch.float32, device=x.device)
+    call("sg_mbstd_fwd", x, out, s, t, group, m, c, v, 1e-8)
+    return out, s
+
+
+def mbstd_bwd(gout: torch.Tensor, out: torch.Tensor, s: torch.Tensor, group: int
+              ) -> Tuple[torch.Tensor, torch.Tensor]:
+    b, c1, d, h, w = out.shape
+    c, m, v = c1 - 1, b // group, d * h * w
+    gx = torch.empty((b, c, d, h, w), dtype=torch.float32, device=out.device)
+    gt = torch.empty((m,), dtype=torch.float32, device=out.device)
+    call("sg_mbstd_bwd", gout, out, s, gt, gx, group, m, c, v)
+    return gx, gt
+
+
+def mbstd_bwdbwd(u: torch.Tensor, gt: torch.Tensor, out: torch.Tensor, s: torch.Tensor, group: int
+                 ) -> Tuple[torch.Tensor, torch.Tensor]:
+    b, c1, d, h, w = out.shape
+    c, m, v = c1 - 1, b // group, d * h * w
+    d_gout = torch.empty_like(out)
+    d_gt = torch.empty((m,), dtype=torch.float32, device=out.device)
+    d_x = torch.empty((b, c, d, h, w), dtype=torch.float32, device=out.device)
+    call("sg_mbstd_bwdbwd", u, gt, out, s, d_gout, d_gt, d_x, group, m, c, v)
+    return d_gout, d_x

@@ -187,9 +187,10 @@ class FromRGB(nn.Sequential):
 
 
 class MinibatchStandardDeviation(nn.Module):
-    """network.py:113-133 on the plain fp32 (B,C,1,4,4) base-level tensor.  Tiny (B*C*16
-    elements): composed of torch tensor ops so that autograd supplies its exact second
-    derivative for the gradient penalty (the only non-piecewise-linear op of D)."""
+    """network.py:113-133 on the plain fp32 (B,C,D,H,W) base-level tensor: hand-written forward,
+    backward and double-backward kernels (ops.Mbstd).  The group size follows the reference's rule
+    (min(4, B), bumped to the next divisor of B); the returned features are the group-centred ones,
+    as the reference's in-place `y -= mean` produces."""
 
     def __init__(self, group_size=4):
         super().__init__()
@@ -202,13 +203,7 @@ class MinibatchStandardDeviation(nn.Module):
                 if len(input) % i == 0:
                     group_size = i
                     break
-        s = input.shape
-        y = input.reshape(group_size, -1, s[1], s[2], s[3], s[4])
-        yc = y - torch.mean(y, dim=0, keepdim=True)
-        sd = torch.sqrt(torch.mean(yc ** 2, dim=0) + 1e-8)
-        t = torch.mean(sd, dim=[1, 2, 3, 4], keepdim=True)
-        t = t.repeat([group_size, 1, s[2], s[3], s[4]])
-        return torch.cat([yc.reshape(s), t], dim=1)
+        return ops.Mbstd.apply(input.float(), group_size)
 
 
 class Discriminator(nn.Module):

@@ -440,6 +440,45 @@ class LinearWgrad(Function):
         return gg, gx, None
 
 
+# ================================================================== minibatch stddev
+class Mbstd(Function):
+    """MinibatchStandardDeviation (network.py:113-133) on the plain fp32 base-level tensor.  The only
+    non-piecewise-linear op of D: its backward is a Function with its own backward (the second
+    derivative of sqrt(mean xc^2) that the gradient penalty's double backward needs)."""
+
+    @staticmethod
+    def forward(ctx, x, group: int):
+        x = _c(x)
+        out, s = K.mbstd_fwd(x, group)
+        ctx.save_for_backward(x, out, s)
+        ctx.group = group
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, out, s = ctx.saved_tensors
+        return MbstdBwd.apply(_c(gout), x, out.detach(), s, ctx.group), None
+
+
+class MbstdBwd(Function):
+    """gx of Mbstd; `x` is passed only as the handle the second-order gradient flows back to
+    (`out` and `s` are functions of it and enter as constants)."""
+
+    @staticmethod
+    def forward(ctx, gout, x, out, s, group: int):
+        gx, gt = K.mbstd_bwd(gout, out, s, group)
+        ctx.save_for_backward(gt, out, s)
+        ctx.group = group
+        return gx
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, u):
+        gt, out, s = ctx.saved_tensors
+        d_gout, d_x = K.mbstd_bwdbwd(_c(u), gt, out, s, ctx.group)
+        return d_gout, d_x, None, None, None
+
+
 # ==================================================================== gradient penalty
 class RowNorm(Function):
     """norm[n] = ||x[n].flatten()||_2   (loss.py:25-26 `gradients.norm(2, dim=1)`).  The

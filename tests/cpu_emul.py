@@ -182,4 +182,51 @@ def linear_wgrad(g, x, scale, want_bias):
     return (g.t() @ x) * scale, (g.sum(0) if want_bias else None)
 
 
+def _mbstd_ref(x, group):
+    """the reference formula (network.py:118-133), differentiable by torch autograd"""
+    b, c, d, h, w = x.shape
+    y = x.reshape(group, -1, c, d, h, w)
+    yc = y - torch.mean(y, dim=0, keepdim=True)
+    sd = torch.sqrt(torch.mean(yc ** 2, dim=0) + 1e-8)
+    t = torch.mean(sd, dim=[1, 2, 3, 4], keepdim=True).repeat([group, 1, d, h, w])
+    return torch.cat([yc.reshape(b, c, d, h, w), t], dim=1), sd
+
+
+def mbstd_fwd(x, group):
+    out, sd = _mbstd_ref(x, group)
+    return out, sd.reshape(sd.shape[0], -1)
+
+
+def _recover_x(out):
+    # any x with the same group-centred values gives the same derivatives
+    return out[:, :-1].detach().clone()
+
+
+def mbstd_bwd(gout, out, s, group):
+    """independent of the hand-derived kernel formulas: torch autograd through the reference"""
+    x = _recover_x(out).requires_grad_(True)
+    with torch.enable_grad():
+        o, _ = _mbstd_ref(x, group)
+        (gx,) = torch.autograd.grad(o, x, gout)
+    b, c1, d, h, w = out.shape
+    m = b // group
+    gt = gout[:, -1].reshape(group, m, -1).sum(dim=(0, 2))
+    return gx, gt
+
+
+def mbstd_bwdbwd(u, gt, out, s, group):
+    """torch double backward through the reference; gout's stat channel is rebuilt from gt"""
+    b, c1, d, h, w = out.shape
+    m = b // group
+    x = _recover_x(out).requires_grad_(True)
+    gout = torch.zeros_like(out)
+    gout[:, -1] = (gt / (group * d * h * w)).repeat(group).view(b, 1, 1, 1)
+    gout.requires_grad_(True)
+    with torch.enable_grad():
+        o, _ = _mbstd_ref(x, group)
+        (gx,) = torch.autograd.grad(o, x, gout, create_graph=True)
+        d_gout, d_x = torch.autograd.grad(gx, [gout, x], u)
+    return d_gout, d_x
+
+
 ALL = [n for n in dir() if not n.startswith("_") and n not in ("torch", "F", "chunks", "ALL")]

@@ -188,3 +188,25 @@ def test_fused_mask_variants(dtype):
     for lrelu_after in (False, True):
         close(K.pixelnorm_bwd(pg, gg, 16, lrelu_after, True), E.pixelnorm_bwd(pa, ga, 16, lrelu_after, True), dtype,
               "pixelnorm bwd + input mask")
+
+
+@pytest.mark.parametrize("b,group", [(4, 4), (8, 4), (6, 6), (2, 2), (3, 3)])
+def test_mbstd_kernels(b, group):
+    """forward, backward and double backward of minibatch-stddev against torch autograd through the
+    reference formula (tests/cpu_emul.py does not use the hand-derived expressions of the kernels)."""
+    c = 40
+    x = rnd(b, c, 1, 4, 4, seed=40) + 0.3 * rnd(1, c, 1, 4, 4, seed=41)
+    out, s = K.mbstd_fwd(x.cuda(), group)
+    eo, es = E.mbstd_fwd(x, group)
+    close(out, eo, torch.float32, "mbstd fwd")
+    close(s, es, torch.float32, "mbstd s")
+    gout = rnd(b, c + 1, 1, 4, 4, seed=42)
+    gx, gt = K.mbstd_bwd(gout.cuda(), out, s, group)
+    egx, egt = E.mbstd_bwd(gout, eo, es, group)
+    close(gx, egx, torch.float32, "mbstd bwd")
+    close(gt, egt, torch.float32, "mbstd gt")
+    u = rnd(b, c, 1, 4, 4, seed=43)
+    d_gout, d_x = K.mbstd_bwdbwd(u.cuda(), gt, out, s, group)
+    e_gout, e_x = E.mbstd_bwdbwd(u, egt, eo, es, group)
+    assert rel_err(d_gout.cpu(), e_gout) < 1e-4, "mbstd bwdbwd d_gout"
+    assert rel_err(d_x.cpu(), e_x) < 1e-4, "mbstd bwdbwd d_x"
