@@ -209,4 +209,7 @@ def test_mbstd_kernels(b, group):
     d_gout, d_x = K.mbstd_bwdbwd(u.cuda(), gt, out, s, group)
     e_gout, e_x = E.mbstd_bwdbwd(u, egt, eo, es, group)
     assert rel_err(d_gout.cpu(), e_gout) < 1e-4, "mbstd bwdbwd d_gout"
-    assert rel_err(d_x.cpu(), e_x) < 1e-4, "mbstd bwdbwd d_x"
+    # for a group of 2 the stddev is |xc| and its second derivative vanishes: d_x is pure rounding
+    # residue (1e-9), so the error is measured against the scale of the inputs as well
+    scale = float(e_x.norm()) + 1e-3 * float(u.norm()) * float(egt.abs().max())
+    assert float((d_x.cpu() - e_x).norm()) < 1e-4 * scale, "mbstd bwdbwd d_x"
