@@ -14,6 +14,9 @@
 // instead of one of 10), into consecutive chunk slots; one B descriptor then spans
 // 3 x NT/8 slots = the N = 3*NT columns [kw][ci] and one MMA does three taps.  The three kh taps
 // shift the descriptor start by one line; the three kd planes are separate CTAs (blockIdx.y).
+// The BIAS gradient sum_p gy[co,p] rides along for free: two extra chunk slots behind the x copies are
+// filled with ones once per CTA, and the (kd = 1, kh = 1, first ci tile) MMAs run with N = 3*NT + 16, so
+// 16 more accumulator columns hold gy (x) 1 (replaces a separate pass over gy per layer).
 // Each CTA keeps its 3 accumulators [128 x 3*NT] in tensor memory while it streams through its
 // share of the voxel tiles (persistent, multi-stage TMA pipeline), then adds them to gw with
 // fp32 atomics.
@@ -26,6 +29,7 @@ constexpr int kThreadsW = 192;
 
 struct WgParams {
   float* gw;               // [Cout][Cin][27]
+  float* gb;               // nullable [Cout]: bias gradient = sum of gy over batch and voxels
   int N, D, H, W;
   int Cin, Cout, CCin, CCout;
   int td, th;              // tile = td x th x 8 voxels
@@ -59,6 +63,16 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
   const int co_tile = blockIdx.z / p.ci_tiles, ci_tile = blockIdx.z % p.ci_tiles;
   const int x_chunks = NT / 8;
   const int halo_h = p.th + 2;
+  const bool do_bias = p.gb != nullptr && kd == 1 && ci_tile == 0;
+  if (do_bias) {
+    // ones slots (bf16 1.0 = 0x3F80) behind the 3*x_chunks x slots of every stage; the TMA never writes them
+    for (int st = 0; st < p.stages; ++st) {
+      uint32_t* ones = reinterpret_cast<uint32_t*>(smem + (size_t)st * p.stage_bytes + p.g_chunks * p.g_chunk_bytes +
+                                                   3 * x_chunks * p.x_chunk_bytes);
+      for (int i = threadIdx.x; i < 2 * p.x_chunk_bytes / 4; i += blockDim.x) ones[i] = 0x3F803F80u;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&gmap) : "memory");
@@ -114,6 +128,10 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
       // D=f32, A=B=bf16, both MN-major (bits 15,16), N = 3*NT ([kw][ci]), M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)((3 * NT) >> 3) << 17) | ((128u >> 4) << 24);
+      // the kh = 1 MMA of a bias-computing CTA also spans the two ones slots: N = 3*NT + 16
+      const uint32_t idesc_mid = do_bias ? ((1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                            ((uint32_t)((3 * NT + 16) >> 3) << 17) | ((128u >> 4) << 24))
+                                         : idesc;
       // descriptors: bases hoisted, per-MMA cost = one 64-bit add (offsets in 16-byte units = voxels)
       const uint64_t g_desc0 = make_desc(smem_base, 128u, (uint32_t)p.g_chunk_bytes);
       const uint64_t x_desc0 = make_desc(smem_base + p.g_chunks * p.g_chunk_bytes, 128u, (uint32_t)p.x_chunk_bytes);
@@ -130,9 +148,10 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
           uint64_t a_k = g_stage + (uint64_t)(dl * th * 8);
           uint64_t b_k = x_stage + (uint64_t)(dl * halo_h * 8);
           for (int j = 0; j < ksteps_per_plane; ++j) {
-#pragma unroll
-            for (int kh = 0; kh < 3; ++kh)
-              tc_mma(tmem_base + kh * 3 * NT, a_k, b_k + (uint64_t)(kh * 8), idesc, acc, leader);
+            // accumulator columns: kh=0 at 0, kh=1 at 3*NT (3*NT + 16 wide), kh=2 at 6*NT + 16
+            tc_mma(tmem_base, a_k, b_k, idesc, acc, leader);
+            tc_mma(tmem_base + 3 * NT, a_k, b_k + 8, idesc_mid, acc, leader);
+            tc_mma(tmem_base + 6 * NT + 16, a_k, b_k + 16, idesc, acc, leader);
             acc = 1;
             a_k += 16;   // two lines of 8 voxels (gy tile and x copies alike)
             b_k += 16;
@@ -156,7 +175,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
       for (int c0 = 0; c0 < NT; c0 += 16) {
         float v[16];
         __syncwarp();
-        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(t9 * NT + c0), v);
+        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(t9 * NT + (t9 >= 6 ? 16 : 0) + c0), v);
         if (any_tile && co < p.Cout) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -166,6 +185,15 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
         }
       }
     }
+  }
+  if (warp >= 2 && do_bias) {
+    // 16 identical columns gy (x) 1 behind the kh = 1 accumulator: column 0 is the bias gradient
+    const int quad = warp & 3;
+    const int co = co_tile * 128 + quad * 32 + lane;
+    float v[16];
+    __syncwarp();
+    tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(6 * NT), v);
+    if (blockIdx.x < p.n_tiles && co < p.Cout) atomicAdd(p.gb + co, v[0]);
   }
   tc_fence_before();
   __syncthreads();
@@ -201,7 +229,7 @@ WgPlan make_wgrad_plan(int N, int Cin, int Cout, int D, int H, int W) {
   for (int cand = 4; cand >= 1; cand /= 2) {
     if (cand > D || D % cand) continue;
     const int gb = cand * th * 8 * 16, xb = cand * (th + 2) * 8 * 16;
-    const int stage = p.g_chunks * gb + 3 * (NT / 8) * xb;
+    const int stage = p.g_chunks * gb + (3 * (NT / 8) + 2) * xb;   // + two ones slots for the bias gradient
     const int over = 16 * gb - stage;
     const int slack = over > 0 ? (over + 255) / 128 * 128 : 128;
     int st = (200 * 1024 - slack) / stage;
@@ -221,7 +249,7 @@ WgPlan make_wgrad_plan(int N, int Cin, int Cout, int D, int H, int W) {
   p.tiles_w = W / 8; p.tiles_h = H / th; p.tiles_d = D / td;
   p.n_tiles = p.tiles_w * p.tiles_h * p.tiles_d * N;
   p.ci_tiles = CinP / NT;
-  p.tmem_cols = 9 * NT <= 256 ? 256 : 512;
+  p.tmem_cols = 9 * NT + 16 <= 256 ? 256 : 512;
   const int co_tiles = (CoutP + 127) / 128;
   const int groups = 3 * co_tiles * p.ci_tiles;
   int per_group = sg_num_sms() / groups;   // one CTA per SM (smem-limited): never more than one wave
@@ -281,6 +309,7 @@ int sg_tc_wgrad(const void* x, const void* gy, float* gw, float* gb, int N, int 
   if (!pl.ok) return 1;
   WgParams& p = pl.p;
   p.gw = gw;
+  p.gb = gb;
   p.scale = scale;
   CUtensorMap gmap, xmap;
   int rc = encode_act_map(&gmap, gy, N, p.CCout, D, H, W, 8, p.th, p.td);
@@ -288,9 +317,6 @@ int sg_tc_wgrad(const void* x, const void* gy, float* gw, float* gb, int N, int 
   rc = encode_act_map(&xmap, x, N, p.CCin, D, H, W, 8, p.th + 2, p.td);
   if (rc) return rc;
   cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)Cout * Cin * 27, s);
-  if (gb) {
-    rc = sg_pw_wgrad(gy, nullptr, nullptr, gb, SG_DTYPE_BF16, N, Cout, (int64_t)D * H * W, 1.f, s);
-    if (rc) return rc;
-  }
+  if (gb) cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)Cout, s);
   return pl.NT == 32 ? launch_wgrad<32>(pl, gmap, xmap, s) : launch_wgrad<16>(pl, gmap, xmap, s);
 }
