@@ -125,10 +125,11 @@ int sg_linear_wgrad(const float* g, const float* x, float* gw, float* gb, int B,
 /* ---- MinibatchStandardDeviation (network.py:113-133) on the plain fp32 base-level tensor x[B][C][V],
  * B = G*M (n = g*M + m).  fwd: out[B][C+1][V] = cat(x - mean_g x, t[n % M]); s[M][C*V], t[M] are saved.
  * bwd: gx[B][C][V] from gout[B][C+1][V] (also returns gt[M] = summed stat-channel gradient).
- * bwdbwd (for the gradient penalty's double backward): from u = d/d(gx) returns d/d(gout) and d/dx. */
-int sg_mbstd_fwd(const float* x, float* out, float* s, float* t, int G, int M, int C, int V, float eps, cudaStream_t stream);
-int sg_mbstd_bwd(const float* gout, const float* out, const float* s, float* gt, float* gx, int G, int M, int C, int V, cudaStream_t stream);
-int sg_mbstd_bwdbwd(const float* u, const float* gt, const float* out, const float* s, float* d_gout, float* d_gt, float* d_x, int G, int M, int C, int V, cudaStream_t stream);
+ * bwdbwd (for the gradient penalty's double backward): from u = d/d(gx) returns d/d(gout) and d/dx.
+ * S = number of independent minibatches of G*M samples stacked along the batch axis (B = S*G*M). */
+int sg_mbstd_fwd(const float* x, float* out, float* s, float* t, int S, int G, int M, int C, int V, float eps, cudaStream_t stream);
+int sg_mbstd_bwd(const float* gout, const float* out, const float* s, float* gt, float* gx, int S, int G, int M, int C, int V, cudaStream_t stream);
+int sg_mbstd_bwdbwd(const float* u, const float* gt, const float* out, const float* s, float* d_gout, float* d_gt, float* d_x, int S, int G, int M, int C, int V, cudaStream_t stream);
 
 /* ---- fused multi-tensor Adam (+ optional weight EMA)  (main.py:141-142 torch.optim.Adam(betas=(0,.99));
  * EMA: SURFGAN_3D/ExtendedEMA.py).  `tensors`: device array of

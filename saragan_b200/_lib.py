@@ -53,9 +53,9 @@ SIGNATURES = {
     "sg_linear_fwd": [_c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_f, _c_int, _c_p],
     "sg_linear_dgrad": [_c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_f, _c_p],
     "sg_linear_wgrad": [_c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_f, _c_p],
-    "sg_mbstd_fwd": [_c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_int, _c_f, _c_p],
-    "sg_mbstd_bwd": [_c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_int, _c_p],
-    "sg_mbstd_bwdbwd": [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_int, _c_p],
+    "sg_mbstd_fwd": [_c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _c_p],
+    "sg_mbstd_bwd": [_c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_p],
+    "sg_mbstd_bwdbwd": [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_p],
     "sg_adam_step": [_c_p, _c_p, _c_p, _c_int, _c_p, _c_f, _c_f, _c_f, _c_f, _c_f, _c_p],
     "sg_adam_advance": [_c_p, _c_p],
     "sg_prepare_real": [_c_p, _c_p, _c_p, _c_i64, _c_f, _c_f, _c_p],

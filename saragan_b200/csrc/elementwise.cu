@@ -783,7 +783,9 @@ extern "C" int sg_prepare_real(const void* raw_u16, const float* noise, float* o
 // ------------------------------------------------------------- minibatch standard deviation
 // network.py:113-133 on the plain fp32 base-level tensor x[B][C][V] viewed as [G][M][F], B = G*M,
 // F = C*V (n = g*M + m):  xc = x - mean_g x;  s = sqrt(mean_g xc^2 + eps);  t[m] = mean_f s;
-// out[B][C+1][V] = cat(xc, t[n % M] broadcast).  It is the only non-piecewise-linear op of D, so the
+// out[B][C+1][V] = cat(xc, t[n % M] broadcast).  S independent minibatches of G*M samples each may share
+// a launch (sample = sb*G*M + g*M + m; s, t, gt are [S*M]...) so D(real) and D(fake) can run as one
+// batch-2B forward without mixing their statistics.  It is the only non-piecewise-linear op of D, so the
 // gradient penalty needs its SECOND derivative: the backward is its own kernel and has a backward.
 //   bwd   : gx = gxc - mean_g gxc + gt[m] * xc / (F*G*s),   gt[m] = sum of the stat channel's gradient
 //   bwdbwd: given u = d/d(gx):  d/d(gxc) = u - mean_g u;  d/d(gt[m]) = sum_{g,f} u*xc/(F*G*s);
@@ -793,7 +795,8 @@ extern "C" int sg_prepare_real(const void* raw_u16, const float* noise, float* o
 __global__ void k_mbstd_fwd(const float* __restrict__ x, float* __restrict__ out, float* __restrict__ s_out,
                             float* __restrict__ t, int G, int M, int C, int V, float eps) {
   const int F = C * V;
-  const int m = blockIdx.y;
+  const int mm = blockIdx.y;              // (sub-batch, m) pair: independent minibatches share a launch
+  const int sb = mm / M, m = mm % M;
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   float sv = 0.f;
   if (f < F) {
@@ -801,14 +804,14 @@ __global__ void k_mbstd_fwd(const float* __restrict__ x, float* __restrict__ out
     float xv[MB_MAXG], mean = 0.f;
 #pragma unroll
     for (int g = 0; g < MB_MAXG; ++g)
-      if (g < G) { xv[g] = x[((int64_t)(g * M + m) * C + c) * V + v]; mean += xv[g]; }
+      if (g < G) { xv[g] = x[((int64_t)(sb * G * M + g * M + m) * C + c) * V + v]; mean += xv[g]; }
     mean /= (float)G;
     float var = 0.f;
 #pragma unroll
     for (int g = 0; g < MB_MAXG; ++g)
-      if (g < G) { xv[g] -= mean; var += xv[g] * xv[g]; out[((int64_t)(g * M + m) * (C + 1) + c) * V + v] = xv[g]; }
+      if (g < G) { xv[g] -= mean; var += xv[g] * xv[g]; out[((int64_t)(sb * G * M + g * M + m) * (C + 1) + c) * V + v] = xv[g]; }
     sv = sqrtf(var / (float)G + eps);
-    s_out[(int64_t)m * F + f] = sv;
+    s_out[(int64_t)mm * F + f] = sv;
   }
   sv = warp_sum(sv);
   __shared__ float sm[8];
@@ -817,45 +820,49 @@ __global__ void k_mbstd_fwd(const float* __restrict__ x, float* __restrict__ out
   if (threadIdx.x == 0) {
     float tot = 0.f;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += sm[w];
-    atomicAdd(t + m, tot / (float)F);
+    atomicAdd(t + mm, tot / (float)F);
   }
 }
 // writes the stat channel out[n][C][v] = t[n % M]
-__global__ void k_mbstd_stat(float* __restrict__ out, const float* __restrict__ t, int B, int M, int C, int V) {
+__global__ void k_mbstd_stat(float* __restrict__ out, const float* __restrict__ t, int B, int G, int M, int C,
+                             int V) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * V) return;
   const int n = i / V, v = i % V;
-  out[((int64_t)n * (C + 1) + C) * V + v] = t[n % M];
+  const int sb = n / (G * M), m = (n % (G * M)) % M;
+  out[((int64_t)n * (C + 1) + C) * V + v] = t[sb * M + m];
 }
 // gt[m] = sum over g, v of gout[(g*M+m)][C][v]
 __global__ void k_mbstd_gt(const float* __restrict__ gout, float* __restrict__ gt, int G, int M, int C, int V) {
-  const int m = blockIdx.x;
+  const int mm = blockIdx.x;
+  const int sb = mm / M, m = mm % M;
   float acc = 0.f;
   for (int i = threadIdx.x; i < G * V; i += blockDim.x) {
     const int g = i / V, v = i % V;
-    acc += gout[((int64_t)(g * M + m) * (C + 1) + C) * V + v];
+    acc += gout[((int64_t)(sb * G * M + g * M + m) * (C + 1) + C) * V + v];
   }
   acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) atomicAdd(gt + m, acc);
+  if ((threadIdx.x & 31) == 0) atomicAdd(gt + mm, acc);
 }
 __global__ void k_mbstd_bwd(const float* __restrict__ gout, const float* __restrict__ gt, const float* __restrict__ out,
                             const float* __restrict__ s, float* __restrict__ gx, int G, int M, int C, int V) {
   const int F = C * V;
-  const int m = blockIdx.y;
+  const int mm = blockIdx.y;              // (sub-batch, m) pair: independent minibatches share a launch
+  const int sb = mm / M, m = mm % M;
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= F) return;
   const int c = f / V, v = f % V;
   float gv[MB_MAXG], mean = 0.f;
 #pragma unroll
   for (int g = 0; g < MB_MAXG; ++g)
-    if (g < G) { gv[g] = gout[((int64_t)(g * M + m) * (C + 1) + c) * V + v]; mean += gv[g]; }
+    if (g < G) { gv[g] = gout[((int64_t)(sb * G * M + g * M + m) * (C + 1) + c) * V + v]; mean += gv[g]; }
   mean /= (float)G;
-  const float k = gt[m] / ((float)F * (float)G * s[(int64_t)m * F + f]);
+  const float k = gt[mm] / ((float)F * (float)G * s[(int64_t)mm * F + f]);
 #pragma unroll
   for (int g = 0; g < MB_MAXG; ++g)
     if (g < G) {
-      const float xc = out[((int64_t)(g * M + m) * (C + 1) + c) * V + v];
-      gx[((int64_t)(g * M + m) * C + c) * V + v] = gv[g] - mean + k * xc;
+      const float xc = out[((int64_t)(sb * G * M + g * M + m) * (C + 1) + c) * V + v];
+      gx[((int64_t)(sb * G * M + g * M + m) * C + c) * V + v] = gv[g] - mean + k * xc;
     }
 }
 // u = d/d(gx) [B][C][V];  outputs: d_gout [B][C+1][V] (feature part here, stat part by k_mbstd_stat
@@ -864,25 +871,26 @@ __global__ void k_mbstd_bwdbwd(const float* __restrict__ u, const float* __restr
                                const float* __restrict__ s, float* __restrict__ d_gout, float* __restrict__ d_gt,
                                float* __restrict__ d_x, int G, int M, int C, int V) {
   const int F = C * V;
-  const int m = blockIdx.y;
+  const int mm = blockIdx.y;              // (sub-batch, m) pair: independent minibatches share a launch
+  const int sb = mm / M, m = mm % M;
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   float part = 0.f;
   if (f < F) {
     const int c = f / V, v = f % V;
-    const float sv = s[(int64_t)m * F + f];
+    const float sv = s[(int64_t)mm * F + f];
     float uv[MB_MAXG], xc[MB_MAXG], umean = 0.f, uxc = 0.f;
 #pragma unroll
     for (int g = 0; g < MB_MAXG; ++g)
       if (g < G) {
-        uv[g] = u[((int64_t)(g * M + m) * C + c) * V + v];
-        xc[g] = out[((int64_t)(g * M + m) * (C + 1) + c) * V + v];
+        uv[g] = u[((int64_t)(sb * G * M + g * M + m) * C + c) * V + v];
+        xc[g] = out[((int64_t)(sb * G * M + g * M + m) * (C + 1) + c) * V + v];
         umean += uv[g];
         uxc += uv[g] * xc[g];
       }
     umean /= (float)G;
     const float fg = (float)F * (float)G;
     part = uxc / (fg * sv);                         // contribution to d_gt[m]
-    const float a = gt[m] / fg;
+    const float a = gt[mm] / fg;
     float dxc[MB_MAXG], dmean = 0.f;
 #pragma unroll
     for (int g = 0; g < MB_MAXG; ++g)
@@ -894,44 +902,44 @@ __global__ void k_mbstd_bwdbwd(const float* __restrict__ u, const float* __restr
 #pragma unroll
     for (int g = 0; g < MB_MAXG; ++g)
       if (g < G) {
-        d_gout[((int64_t)(g * M + m) * (C + 1) + c) * V + v] = uv[g] - umean;
-        d_x[((int64_t)(g * M + m) * C + c) * V + v] = dxc[g] - dmean;
+        d_gout[((int64_t)(sb * G * M + g * M + m) * (C + 1) + c) * V + v] = uv[g] - umean;
+        d_x[((int64_t)(sb * G * M + g * M + m) * C + c) * V + v] = dxc[g] - dmean;
       }
   }
   part = warp_sum(part);
-  if ((threadIdx.x & 31) == 0 && part != 0.f) atomicAdd(d_gt + m, part);
+  if ((threadIdx.x & 31) == 0 && part != 0.f) atomicAdd(d_gt + mm, part);
 }
 
-extern "C" int sg_mbstd_fwd(const float* x, float* out, float* s, float* t, int G, int M, int C, int V, float eps,
-                            cudaStream_t st) {
+extern "C" int sg_mbstd_fwd(const float* x, float* out, float* s, float* t, int S, int G, int M, int C, int V,
+                            float eps, cudaStream_t st) {
   SG_REQUIRE(G >= 1 && G <= MB_MAXG, "sg_mbstd_fwd: group size %d not in [1, %d]", G, MB_MAXG);
   const int F = C * V;
-  cudaMemsetAsync(t, 0, sizeof(float) * M, st);
-  k_mbstd_fwd<<<dim3((F + 255) / 256, M), 256, 0, st>>>(x, out, s, t, G, M, C, V, eps);
+  cudaMemsetAsync(t, 0, sizeof(float) * S * M, st);
+  k_mbstd_fwd<<<dim3((F + 255) / 256, S * M), 256, 0, st>>>(x, out, s, t, G, M, C, V, eps);
   int rc = sg_check_launch("sg_mbstd_fwd");
   if (rc) return rc;
-  k_mbstd_stat<<<(G * M * V + 255) / 256, 256, 0, st>>>(out, t, G * M, M, C, V);
+  k_mbstd_stat<<<(S * G * M * V + 255) / 256, 256, 0, st>>>(out, t, S * G * M, G, M, C, V);
   return sg_check_launch("sg_mbstd_fwd(stat)");
 }
-extern "C" int sg_mbstd_bwd(const float* gout, const float* out, const float* s, float* gt, float* gx, int G, int M,
-                            int C, int V, cudaStream_t st) {
+extern "C" int sg_mbstd_bwd(const float* gout, const float* out, const float* s, float* gt, float* gx, int S, int G,
+                            int M, int C, int V, cudaStream_t st) {
   SG_REQUIRE(G >= 1 && G <= MB_MAXG, "sg_mbstd_bwd: group size %d not in [1, %d]", G, MB_MAXG);
   const int F = C * V;
-  cudaMemsetAsync(gt, 0, sizeof(float) * M, st);
-  k_mbstd_gt<<<M, 128, 0, st>>>(gout, gt, G, M, C, V);
+  cudaMemsetAsync(gt, 0, sizeof(float) * S * M, st);
+  k_mbstd_gt<<<S * M, 128, 0, st>>>(gout, gt, G, M, C, V);
   int rc = sg_check_launch("sg_mbstd_bwd(gt)");
   if (rc) return rc;
-  k_mbstd_bwd<<<dim3((F + 255) / 256, M), 256, 0, st>>>(gout, gt, out, s, gx, G, M, C, V);
+  k_mbstd_bwd<<<dim3((F + 255) / 256, S * M), 256, 0, st>>>(gout, gt, out, s, gx, G, M, C, V);
   return sg_check_launch("sg_mbstd_bwd");
 }
 extern "C" int sg_mbstd_bwdbwd(const float* u, const float* gt, const float* out, const float* s, float* d_gout,
-                               float* d_gt, float* d_x, int G, int M, int C, int V, cudaStream_t st) {
+                               float* d_gt, float* d_x, int S, int G, int M, int C, int V, cudaStream_t st) {
   SG_REQUIRE(G >= 1 && G <= MB_MAXG, "sg_mbstd_bwdbwd: group size %d not in [1, %d]", G, MB_MAXG);
   const int F = C * V;
-  cudaMemsetAsync(d_gt, 0, sizeof(float) * M, st);
-  k_mbstd_bwdbwd<<<dim3((F + 255) / 256, M), 256, 0, st>>>(u, gt, out, s, d_gout, d_gt, d_x, G, M, C, V);
+  cudaMemsetAsync(d_gt, 0, sizeof(float) * S * M, st);
+  k_mbstd_bwdbwd<<<dim3((F + 255) / 256, S * M), 256, 0, st>>>(u, gt, out, s, d_gout, d_gt, d_x, G, M, C, V);
   int rc = sg_check_launch("sg_mbstd_bwdbwd");
   if (rc) return rc;
-  k_mbstd_stat<<<(G * M * V + 255) / 256, 256, 0, st>>>(d_gout, d_gt, G * M, M, C, V);
+  k_mbstd_stat<<<(S * G * M * V + 255) / 256, 256, 0, st>>>(d_gout, d_gt, S * G * M, G, M, C, V);
   return sg_check_launch("sg_mbstd_bwdbwd(stat)");
 }

@@ -256,33 +256,34 @@ def linear_wgrad(g: torch.Tensor, x: torch.Tensor, scale: float, want_bias: bool
 
 
 # ------------------------------------------------------------------ minibatch stddev
-def mbstd_fwd(x: torch.Tensor, group: int) -> Tuple[torch.Tensor, torch.Tensor]:
-    """x plain fp32 (B,C,D,H,W) -> out (B,C+1,D,H,W) = cat(group-centred x, stat channel), s (M, C*V)."""
+def mbstd_fwd(x: torch.Tensor, group: int, sub_batches: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
+    """x plain fp32 (B,C,D,H,W) -> out (B,C+1,D,H,W) = cat(group-centred x, stat channel), s (S*M, C*V).
+    B = sub_batches * group * M: `sub_batches` independent minibatches stacked along the batch axis."""
     b, c, d, h, w = x.shape
-    m, v = b // group, d * h * w
+    m, v = b // (group * sub_batches), d * h * w
     out = torch.empty((b, c + 1, d, h, w), dtype=torch.float32, device=x.device)
-    s = torch.empty((m, c * v), dtype=torch.float32, device=x.device)
-    t = torch.empty((m,), dtype=torch.float32, device=x.device)
-    call("sg_mbstd_fwd", x, out, s, t, group, m, c, v, 1e-8)
+    s = torch.empty((sub_batches * m, c * v), dtype=torch.float32, device=x.device)
+    t = torch.empty((sub_batches * m,), dtype=torch.float32, device=x.device)
+    call("sg_mbstd_fwd", x, out, s, t, sub_batches, group, m, c, v, 1e-8)
     return out, s
 
 
-def mbstd_bwd(gout: torch.Tensor, out: torch.Tensor, s: torch.Tensor, group: int
+def mbstd_bwd(gout: torch.Tensor, out: torch.Tensor, s: torch.Tensor, group: int, sub_batches: int = 1
               ) -> Tuple[torch.Tensor, torch.Tensor]:
     b, c1, d, h, w = out.shape
-    c, m, v = c1 - 1, b // group, d * h * w
+    c, m, v = c1 - 1, b // (group * sub_batches), d * h * w
     gx = torch.empty((b, c, d, h, w), dtype=torch.float32, device=out.device)
-    gt = torch.empty((m,), dtype=torch.float32, device=out.device)
-    call("sg_mbstd_bwd", gout, out, s, gt, gx, group, m, c, v)
+    gt = torch.empty((sub_batches * m,), dtype=torch.float32, device=out.device)
+    call("sg_mbstd_bwd", gout, out, s, gt, gx, sub_batches, group, m, c, v)
     return gx, gt
 
 
-def mbstd_bwdbwd(u: torch.Tensor, gt: torch.Tensor, out: torch.Tensor, s: torch.Tensor, group: int
-                 ) -> Tuple[torch.Tensor, torch.Tensor]:
+def mbstd_bwdbwd(u: torch.Tensor, gt: torch.Tensor, out: torch.Tensor, s: torch.Tensor, group: int,
+                 sub_batches: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
     b, c1, d, h, w = out.shape
-    c, m, v = c1 - 1, b // group, d * h * w
+    c, m, v = c1 - 1, b // (group * sub_batches), d * h * w
     d_gout = torch.empty_like(out)
-    d_gt = torch.empty((m,), dtype=torch.float32, device=out.device)
+    d_gt = torch.empty((sub_batches * m,), dtype=torch.float32, device=out.device)
     d_x = torch.empty((b, c, d, h, w), dtype=torch.float32, device=out.device)
-    call("sg_mbstd_bwdbwd", u, gt, out, s, d_gout, d_gt, d_x, group, m, c, v)
+    call("sg_mbstd_bwdbwd", u, gt, out, s, d_gout, d_gt, d_x, sub_batches, group, m, c, v)
     return d_gout, d_x

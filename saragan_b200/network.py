@@ -196,14 +196,17 @@ class MinibatchStandardDeviation(nn.Module):
         super().__init__()
         self.group_size = group_size
 
-    def forward(self, input):
-        group_size = min(self.group_size, input.shape[0])
-        if group_size < len(input):
-            for i in range(group_size, len(input) + 1):
-                if len(input) % i == 0:
+    def forward(self, input, sub_batches: int = 1):
+        """sub_batches > 1: `input` stacks that many independent minibatches along the batch axis
+        (each gets the statistics it would get alone)."""
+        n = input.shape[0] // sub_batches
+        group_size = min(self.group_size, n)
+        if group_size < n:
+            for i in range(group_size, n + 1):
+                if n % i == 0:
                     group_size = i
                     break
-        return ops.Mbstd.apply(input.float(), group_size)
+        return ops.Mbstd.apply(input.float(), group_size, sub_batches)
 
 
 class Discriminator(nn.Module):
@@ -240,7 +243,10 @@ class Discriminator(nn.Module):
         self.device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
         self.to(self.device)
 
-    def forward(self, input, alpha):
+    def forward(self, input, alpha, sub_batches: int = 1):
+        """sub_batches (extension): `input` stacks that many independent minibatches along the batch
+        axis -- e.g. D(cat(real, fake)) in one pass; minibatch-stddev treats them separately, so the
+        result equals the concatenation of the separate calls."""
         alpha = _as_float(alpha)
         img = input.to(self.device).float().contiguous()
         # at phase > 1 the top FromRGB feeds only the first block's conv1, whose dgrad epilogue
@@ -253,7 +259,7 @@ class Discriminator(nn.Module):
             x = ops.Lincomb.apply(prev, x, alpha, 1.0 - alpha)
         out = self.discriminator_out
         c = out[1].in_channels - 1
-        x = out[0](ops.ToPlain.apply(x, c))
+        x = out[0](ops.ToPlain.apply(x, c), sub_batches)
         x = out[1](ops.ToAct.apply(x, config.act_dtype(_voxels(x))), lrelu=True)
         x = torch.flatten(ops.ToPlain.apply(x, out[1].out_channels), 1)
         x = out[4](x, lrelu=True)

@@ -447,17 +447,17 @@ class Mbstd(Function):
     derivative of sqrt(mean xc^2) that the gradient penalty's double backward needs)."""
 
     @staticmethod
-    def forward(ctx, x, group: int):
+    def forward(ctx, x, group: int, sub_batches: int = 1):
         x = _c(x)
-        out, s = K.mbstd_fwd(x, group)
+        out, s = K.mbstd_fwd(x, group, sub_batches)
         ctx.save_for_backward(x, out, s)
-        ctx.group = group
+        ctx.group, ctx.sub = group, sub_batches
         return out
 
     @staticmethod
     def backward(ctx, gout):
         x, out, s = ctx.saved_tensors
-        return MbstdBwd.apply(_c(gout), x, out.detach(), s, ctx.group), None
+        return MbstdBwd.apply(_c(gout), x, out.detach(), s, ctx.group, ctx.sub), None, None
 
 
 class MbstdBwd(Function):
@@ -465,18 +465,18 @@ class MbstdBwd(Function):
     (`out` and `s` are functions of it and enter as constants)."""
 
     @staticmethod
-    def forward(ctx, gout, x, out, s, group: int):
-        gx, gt = K.mbstd_bwd(gout, out, s, group)
+    def forward(ctx, gout, x, out, s, group: int, sub_batches: int = 1):
+        gx, gt = K.mbstd_bwd(gout, out, s, group, sub_batches)
         ctx.save_for_backward(gt, out, s)
-        ctx.group = group
+        ctx.group, ctx.sub = group, sub_batches
         return gx
 
     @staticmethod
     @once_differentiable
     def backward(ctx, u):
         gt, out, s = ctx.saved_tensors
-        d_gout, d_x = K.mbstd_bwdbwd(_c(u), gt, out, s, ctx.group)
-        return d_gout, d_x, None, None, None
+        d_gout, d_x = K.mbstd_bwdbwd(_c(u), gt, out, s, ctx.group, ctx.sub)
+        return d_gout, d_x, None, None, None, None
 
 
 # ==================================================================== gradient penalty

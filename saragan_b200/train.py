@@ -46,8 +46,11 @@ def d_phase(x_real: torch.Tensor, generator, discriminator, discriminator_optim,
     with torch.no_grad():
         x_fake = generator(z_d, alpha)[-1].detach()
 
-    d_real = discriminator(x_real, alpha)
-    d_fake = discriminator(x_fake, alpha)
+    # D(real) and D(fake) as ONE batch-2B pass (minibatch-stddev keeps the two minibatches apart, so
+    # the values equal the reference's two calls, train.py:148-149): half the launches and twice the
+    # tiles per launch at the low-resolution levels
+    d_both = discriminator(torch.cat([x_real, x_fake]), alpha, sub_batches=2)
+    d_real, d_fake = d_both[:batch], d_both[batch:]
     gp_loss = compute_gradient_penalty(discriminator, x_real, x_fake, alpha, random_uniform=eps)
     real_loss = wasserstein_loss(d_real)
     fake_loss = wasserstein_loss(d_fake)

@@ -182,19 +182,23 @@ def linear_wgrad(g, x, scale, want_bias):
     return (g.t() @ x) * scale, (g.sum(0) if want_bias else None)
 
 
-def _mbstd_ref(x, group):
-    """the reference formula (network.py:118-133), differentiable by torch autograd"""
-    b, c, d, h, w = x.shape
-    y = x.reshape(group, -1, c, d, h, w)
-    yc = y - torch.mean(y, dim=0, keepdim=True)
-    sd = torch.sqrt(torch.mean(yc ** 2, dim=0) + 1e-8)
-    t = torch.mean(sd, dim=[1, 2, 3, 4], keepdim=True).repeat([group, 1, d, h, w])
-    return torch.cat([yc.reshape(b, c, d, h, w), t], dim=1), sd
+def _mbstd_ref(x, group, sub=1):
+    """the reference formula (network.py:118-133) applied to each of `sub` stacked minibatches,
+    differentiable by torch autograd"""
+    outs, sds = [], []
+    for xs in x.chunk(sub, dim=0):
+        b, c, d, h, w = xs.shape
+        y = xs.reshape(group, -1, c, d, h, w)
+        yc = y - torch.mean(y, dim=0, keepdim=True)
+        sd = torch.sqrt(torch.mean(yc ** 2, dim=0) + 1e-8)
+        t = torch.mean(sd, dim=[1, 2, 3, 4], keepdim=True).repeat([group, 1, d, h, w])
+        outs.append(torch.cat([yc.reshape(b, c, d, h, w), t], dim=1))
+        sds.append(sd.reshape(sd.shape[0], -1))
+    return torch.cat(outs), torch.cat(sds)
 
 
-def mbstd_fwd(x, group):
-    out, sd = _mbstd_ref(x, group)
-    return out, sd.reshape(sd.shape[0], -1)
+def mbstd_fwd(x, group, sub_batches=1):
+    return _mbstd_ref(x, group, sub_batches)
 
 
 def _recover_x(out):
@@ -202,28 +206,32 @@ def _recover_x(out):
     return out[:, :-1].detach().clone()
 
 
-def mbstd_bwd(gout, out, s, group):
+def _stat_grad(gout, group, sub):
+    b = gout.shape[0]
+    m = b // (group * sub)
+    return gout[:, -1].reshape(sub, group, m, -1).sum(dim=(1, 3)).reshape(-1)
+
+
+def mbstd_bwd(gout, out, s, group, sub_batches=1):
     """independent of the hand-derived kernel formulas: torch autograd through the reference"""
     x = _recover_x(out).requires_grad_(True)
     with torch.enable_grad():
-        o, _ = _mbstd_ref(x, group)
+        o, _ = _mbstd_ref(x, group, sub_batches)
         (gx,) = torch.autograd.grad(o, x, gout)
-    b, c1, d, h, w = out.shape
-    m = b // group
-    gt = gout[:, -1].reshape(group, m, -1).sum(dim=(0, 2))
-    return gx, gt
+    return gx, _stat_grad(gout, group, sub_batches)
 
 
-def mbstd_bwdbwd(u, gt, out, s, group):
+def mbstd_bwdbwd(u, gt, out, s, group, sub_batches=1):
     """torch double backward through the reference; gout's stat channel is rebuilt from gt"""
     b, c1, d, h, w = out.shape
-    m = b // group
+    m = b // (group * sub_batches)
     x = _recover_x(out).requires_grad_(True)
     gout = torch.zeros_like(out)
-    gout[:, -1] = (gt / (group * d * h * w)).repeat(group).view(b, 1, 1, 1)
+    per_pos = (gt / (group * d * h * w)).reshape(sub_batches, 1, m).expand(sub_batches, group, m).reshape(b)
+    gout[:, -1] = per_pos.view(b, 1, 1, 1)
     gout.requires_grad_(True)
     with torch.enable_grad():
-        o, _ = _mbstd_ref(x, group)
+        o, _ = _mbstd_ref(x, group, sub_batches)
         (gx,) = torch.autograd.grad(o, x, gout, create_graph=True)
         d_gout, d_x = torch.autograd.grad(gx, [gout, x], u)
     return d_gout, d_x

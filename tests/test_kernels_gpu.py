@@ -190,29 +190,29 @@ def test_fused_mask_variants(dtype):
               "pixelnorm bwd + input mask")
 
 
-@pytest.mark.parametrize("b,group", [(4, 4), (8, 4), (6, 6), (2, 2), (3, 3)])
-def test_mbstd_kernels(b, group):
+@pytest.mark.parametrize("b,group,sub", [(4, 4, 1), (8, 4, 1), (6, 6, 1), (2, 2, 1), (3, 3, 1), (8, 4, 2), (24, 4, 3)])
+def test_mbstd_kernels(b, group, sub):
     """forward, backward and double backward of minibatch-stddev against torch autograd through the
     reference formula (tests/cpu_emul.py does not use the hand-derived expressions of the kernels)."""
     c = 40
     x = rnd(b, c, 1, 4, 4, seed=40) + 0.3 * rnd(1, c, 1, 4, 4, seed=41)
-    out, s = K.mbstd_fwd(x.cuda(), group)
-    eo, es = E.mbstd_fwd(x, group)
+    out, s = K.mbstd_fwd(x.cuda(), group, sub)
+    eo, es = E.mbstd_fwd(x, group, sub)
     close(out, eo, torch.float32, "mbstd fwd")
     close(s, es, torch.float32, "mbstd s")
     gout = rnd(b, c + 1, 1, 4, 4, seed=42)
-    gx, gt = K.mbstd_bwd(gout.cuda(), out, s, group)
-    egx, egt = E.mbstd_bwd(gout, eo, es, group)
+    gx, gt = K.mbstd_bwd(gout.cuda(), out, s, group, sub)
+    egx, egt = E.mbstd_bwd(gout, eo, es, group, sub)
     close(gx, egx, torch.float32, "mbstd bwd")
     close(gt, egt, torch.float32, "mbstd gt")
     u = rnd(b, c, 1, 4, 4, seed=43)
-    d_gout, d_x = K.mbstd_bwdbwd(u.cuda(), gt, out, s, group)
-    e_gout, e_x = E.mbstd_bwdbwd(u, egt, eo, es, group)
+    d_gout, d_x = K.mbstd_bwdbwd(u.cuda(), gt, out, s, group, sub)
+    e_gout, e_x = E.mbstd_bwdbwd(u, egt, eo, es, group, sub)
     assert rel_err(d_gout.cpu(), e_gout) < 1e-4, "mbstd bwdbwd d_gout"
     # the second derivative of sqrt(mean xc^2 + 1e-8) blows up where a feature's group spread is ~0
     # (ill-conditioned in any arithmetic): compare where the stddev is not tiny, and measure the
     # error against the scale of the inputs too (for a group of 2 the exact result is ~0)
-    m = b // group
-    ok = (es.reshape(1, m, c, 1, 4, 4) > 3e-2).expand(group, m, c, 1, 4, 4).reshape(b, c, 1, 4, 4)
+    m = b // (group * sub)
+    ok = (es.reshape(sub, 1, m, c, 1, 4, 4) > 3e-2).expand(sub, group, m, c, 1, 4, 4).reshape(b, c, 1, 4, 4)
     scale = float((e_x * ok).norm()) + 1e-3 * float(u.norm()) * float(egt.abs().max())
     assert float(((d_x.cpu() - e_x) * ok).norm()) < 2e-4 * scale, "mbstd bwdbwd d_x"

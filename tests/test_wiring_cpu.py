@@ -36,7 +36,10 @@ def test_step_matches_reference_fp32(name, cpu_kernels):
         got = {k: p.grad for k, p in mod.named_parameters()}
         assert {k for k, v in got.items() if v is not None} == set(want), kind
         for k, v in want.items():
-            assert rel_err(got[k], v) < 1e-4, (kind, k, rel_err(got[k], v))
+            # the 1-element bias gradient of the last linear is (-1 ... +1 ...)/B + drift: a cancelling
+            # sum whose fp32 rounding depends on the summation order (D(real), D(fake) are one batch here)
+            tol = 1e-4 if v.numel() > 1 else 1e-4 + 2e-6 / max(float(v.abs().max()), 1e-12)
+            assert rel_err(got[k], v) < tol, (kind, k, rel_err(got[k], v))
 
 
 def test_generator_returns_list_and_blocks_accept_plain(cpu_kernels):
