@@ -138,17 +138,42 @@ k_conv_direct(const T* __restrict__ x, const T* __restrict__ wp, const float* __
 // ------------------------------------------------- small-volume fp32 fprop (base level)
 // The 1x4x4 base level of both networks runs in fp32 (config.py): tiny M = N*V (64 rows at
 // B=4) against K = 27*Cin up to 13851 and Cout = 512 -- a skinny GEMM bound by streaming the
-// 28 MB of fp32 weights.  Implicit-im2col SGEMM: block = 64 rows x 64 output channels x one
-// tap (split-K over the 27 taps -> 8 x 27 blocks for Cout = 512), 4x4 register tile per
-// thread, fp32 atomics into a zeroed [M][CoutP] workspace, then a finishing kernel applies
-// scale / bias / LeakyReLU / mask and writes the blocked layout.
+// fp32 weights.  Implicit-im2col SGEMM: block = 64 rows x 64 output channels x one LIVE tap x one
+// slice of the input-channel chunks (taps that only ever see padding -- kd != 1 when D == 1 -- are
+// skipped; split-K over taps and chunk slices gives ~600 blocks so the weight stream has enough loads
+// in flight), next k-tile prefetched into registers during the FMAs, 4x4 register tile per thread,
+// fp32 atomics into a zeroed [M][CoutP] workspace, then a finishing kernel applies scale / bias /
+// LeakyReLU / mask and writes the blocked layout.
+struct SmallTaps {
+  int kd_lo, nkd, kh_lo, nkh, kw_lo, nkw;   // live tap ranges
+  int ksplit, cc_per;                       // chunk slices per tap, chunks per slice (even)
+};
+static SmallTaps small_taps(int CCin, int D, int H, int W, int64_t blocks_per_tap_slice) {
+  SmallTaps t;
+  t.kd_lo = D == 1 ? 1 : 0; t.nkd = D == 1 ? 1 : 3;
+  t.kh_lo = H == 1 ? 1 : 0; t.nkh = H == 1 ? 1 : 3;
+  t.kw_lo = W == 1 ? 1 : 0; t.nkw = W == 1 ? 1 : 3;
+  int64_t blocks = blocks_per_tap_slice * t.nkd * t.nkh * t.nkw;
+  int ks = (int)((4 * (int64_t)sg_num_sms() + blocks - 1) / blocks);
+  int max_ks = CCin / 8 > 1 ? CCin / 8 : 1;      // at least four k-tiles (of two chunks) per block
+  if (ks > max_ks) ks = max_ks;
+  if (ks < 1) ks = 1;
+  t.cc_per = 2 * ((CCin / 2 + ks - 1) / ks);
+  t.ksplit = (CCin + t.cc_per - 1) / t.cc_per;
+  return t;
+}
+
 __global__ void __launch_bounds__(256)
 k_conv_small_f32(const float* __restrict__ x, const float* __restrict__ wp, float* __restrict__ acc,
-                 int N, int CCin, int CoutP, int D, int H, int W) {
+                 int N, int CCin, int CoutP, int D, int H, int W, SmallTaps st) {
   __shared__ float As[16][64 + 4];
   __shared__ float Bs[16][64 + 4];
-  int tap = blockIdx.z;
-  int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+  int z = blockIdx.z;
+  const int ks = z % st.ksplit; z /= st.ksplit;
+  const int kw = st.kw_lo + z % st.nkw; z /= st.nkw;
+  const int kh = st.kh_lo + z % st.nkh; z /= st.nkh;
+  const int kd = st.kd_lo + z;
+  const int tap = (kd * 3 + kh) * 3 + kw;
   int V = D * H * W;
   int M = N * V;
   int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
@@ -171,17 +196,27 @@ k_conv_small_f32(const float* __restrict__ x, const float* __restrict__ wp, floa
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
-  for (int cc0 = 0; cc0 < CCin; cc0 += 2) {
-    int chunk = cc0 + (lq >> 1), sub = (lq & 1) * 4;
-    float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (a_off >= 0) av = *reinterpret_cast<const float4*>(x + a_off + (int64_t)chunk * V * 8 + sub);
-    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (co < CoutP)
-      bv = *reinterpret_cast<const float4*>(wp + (((int64_t)tap * CCin + chunk) * CoutP + co) * 8 + sub);
+  const int cc_begin = ks * st.cc_per;
+  const int cc_end = cc_begin + st.cc_per < CCin ? cc_begin + st.cc_per : CCin;
+  const int sub = (lq & 1) * 4;
+  auto load = [&](int cc0, float4& av, float4& bv) {
+    const int chunk = cc0 + (lq >> 1);
+    av = make_float4(0.f, 0.f, 0.f, 0.f);
+    bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (chunk < cc_end) {
+      if (a_off >= 0) av = *reinterpret_cast<const float4*>(x + a_off + (int64_t)chunk * V * 8 + sub);
+      if (co < CoutP)
+        bv = __ldcs(reinterpret_cast<const float4*>(wp + (((int64_t)tap * CCin + chunk) * CoutP + co) * 8 + sub));
+    }
+  };
+  float4 av, bv;
+  load(cc_begin, av, bv);
+  for (int cc0 = cc_begin; cc0 < cc_end; cc0 += 2) {
     int k0 = lq * 4;
     As[k0 + 0][lrow] = av.x; As[k0 + 1][lrow] = av.y; As[k0 + 2][lrow] = av.z; As[k0 + 3][lrow] = av.w;
     Bs[k0 + 0][lrow] = bv.x; Bs[k0 + 1][lrow] = bv.y; Bs[k0 + 2][lrow] = bv.z; Bs[k0 + 3][lrow] = bv.w;
     __syncthreads();
+    if (cc0 + 2 < cc_end) load(cc0 + 2, av, bv);   // in flight during the FMAs below
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       float a[4], b[4];
@@ -257,8 +292,10 @@ static int launch_small_f32(const void* x, const void* wp, const float* bias, co
   SG_REQUIRE(ws != nullptr && ws_bytes >= need, "sg_conv3d_fprop: workspace too small (%lld < %lld)",
              (long long)ws_bytes, (long long)need);
   cudaMemsetAsync(ws, 0, (size_t)need, s);
-  dim3 grid((unsigned)((M + 63) / 64), (unsigned)((CoutP + 63) / 64), 27);
-  k_conv_small_f32<<<grid, 256, 0, s>>>((const float*)x, (const float*)wp, (float*)ws, N, CCin, CoutP, D, H, W);
+  const int64_t mt = (M + 63) / 64, nt = (CoutP + 63) / 64;
+  const SmallTaps st = small_taps(CCin, D, H, W, mt * nt);
+  dim3 grid((unsigned)mt, (unsigned)nt, (unsigned)(st.nkd * st.nkh * st.nkw * st.ksplit));
+  k_conv_small_f32<<<grid, 256, 0, s>>>((const float*)x, (const float*)wp, (float*)ws, N, CCin, CoutP, D, H, W, st);
   int rc = sg_check_launch("sg_conv3d_fprop(small f32)");
   if (rc) return rc;
   int64_t total = (int64_t)N * CCout * V;
@@ -384,7 +421,9 @@ k_wgrad_small_f32(const float* __restrict__ x, const float* __restrict__ gy, flo
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
-  for (int m0 = 0; m0 < M; m0 += 16) {
+  // a tap that only ever sees padding (kd != 1 when D == 1, ...) has a zero gradient: skip the loop
+  const bool dead = (D == 1 && kd != 1) || (H == 1 && kh != 1) || (W == 1 && kw != 1);
+  for (int m0 = 0; m0 < (dead ? 0 : M); m0 += 16) {
     const int m = m0 + lm;
     float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (m < M) {

@@ -181,6 +181,12 @@ __device__ __forceinline__ void issue_tap(uint32_t tmem_acc, uint64_t a_desc, ui
   }
 }
 
+// fp32 vector reduction into global memory (sm_90+): one 16-byte L2 transaction for four adds
+__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
+  asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
 // Same as epilogue16 with the two mask vectors already in registers (prefetched while the MMAs of
 // the tile were still running, so their global-load latency is off the epilogue's critical path).
 __device__ __forceinline__ void epilogue16_regmask(const float (&v)[16], const float* sb, float scale, int lrelu,

@@ -46,6 +46,10 @@ def test_golden_step_fp32(name):
             # bias gradients are signed sums over every voxel of a level (|sum| << sum of |terms|):
             # fp32 summation order alone moves them by a few 1e-3; weights are held to 1e-3
             tol = 5e-3 if k.endswith(".bias") else 1e-3
+            if v.numel() == 1:
+                # the last linear's bias gradient is sum(-1/B ... +1/B ...) + drift ~ 1e-5: a cancelling sum of
+                # O(1) terms, so fp32 summation order moves it by ~1e-7 absolute (D(real), D(fake) are one batch)
+                tol += 1e-6 / max(float(v.abs().max()), 1e-12)
             assert rel_err(got[k], v) < tol, (kind, k, rel_err(got[k], v))
 
 

@@ -20,7 +20,8 @@ vol = C.volume(cfg["phase"])
 torch.manual_seed(0)
 g = sg.Generator(cfg["phase"], cfg["num_phases"], cfg["base_dim"], cfg["latent_dim"], C.BASE_SHAPE)
 d = sg.Discriminator(cfg["phase"], cfg["num_phases"], cfg["base_dim"], cfg["latent_dim"], C.BASE_SHAPE)
-g_opt, d_opt = sg.make_optimizers(g, d)
+from saragan_b200 import graph as G  # noqa: E402
+g_opt, d_opt = G.make_capturable_optimizers(g, d)[:2]
 x = torch.rand(cfg["batch"], 1, *vol, device="cuda") * 2
 sg.train_step(x, g, d, g_opt, d_opt, 0.5)      # warm-up (lazy init, kernel attributes)
 torch.cuda.synchronize()

@@ -58,6 +58,17 @@ def main():
     print("\n-- by (entry point, integer args)")
     for (name, key), (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:args.top]:
         print(f"{ms:9.3f} ms {100 * ms / total:5.1f} %  n/step={n / args.steps:5.1f}  {ms / n * args.steps * 1e3:9.1f} us/call  {name} {key}")
+    print("\n-- conv calls by shape: TFLOP/s and time above a 1100 TFLOP/s kernel")
+    rows = []
+    for (name, key), (n, ms) in agg.items():
+        if name not in ("sg_conv3d_fprop", "sg_conv3d_wgrad"):
+            continue
+        _, nb, ci, co, d, h, w = key[:7]
+        fl = 2.0 * nb * ci * co * 27 * d * h * w * n / args.steps
+        rows.append((ms - fl / 1100e9, ms, fl, n / args.steps, name, key[:7]))
+    for ex, ms, fl, n, name, key in sorted(rows, reverse=True):
+        print(f"excess {ex:7.3f} ms  total {ms:7.3f} ms  n={n:4.1f}  {fl / ms / 1e9:7.1f} TF/s  {name[10:]} {key}")
+    print(f"sum excess {sum(r[0] for r in rows):.3f} ms of {sum(r[1] for r in rows):.3f} ms conv time")
 
 
 if __name__ == "__main__":
