@@ -365,7 +365,10 @@ int encode_halo_map(CUtensorMap* map, const void* x, int N, int CC, int D, int H
 
 extern "C" void sg_tc_force_streaming(int on) { g_force_streaming = on; }
 
+int64_t sg_tc_wgrad_workspace_bytes(int N, int Cin, int Cout, int D, int H, int W);
+
 int64_t sg_tc_workspace_bytes(int kind, int N, int Cin, int Cout, int D, int H, int W) {
+  if (kind == 1) return sg_tc_wgrad_workspace_bytes(N, Cin, Cout, D, H, W);
   if (kind != 0) return 0;
   if (g_force_streaming != 1 && make_res_plan(N, Cin, Cout, D, H, W, g_force_streaming == 2).ok) return 0;
   Plan pl = make_plan(N, Cin, Cout, D, H, W);

@@ -5,21 +5,29 @@
 // over the voxels of a tile.  In the channel-blocked layout a voxel is a 16-byte vector of 8
 // channels, i.e. both operands are "MN-major" UMMA operands straight out of the TMA tiles:
 //   element (channel c, voxel k) at (c/8)*SBO + (k/8)*LBO + (k%8)*16 + (c%8)*2
-// with SBO = the 8-channel chunk stride and LBO = the line pitch (one K=16 MMA step = two
-// consecutive lines x 8 voxels).
+// with LBO = the line pitch (one K=16 MMA step = two consecutive lines x 8 voxels) and SBO = the
+// stride between 8-channel chunks.
 //
 // A tap's output is only [Cout x NT] -- far too small for the tensor core, whose M=128 MMA costs
-// ~45 cycles whatever N <= 64 is (tools/mma_bench.cu).  So the three kw taps are STACKED ALONG N:
-// the x tile is loaded three times, shifted by one voxel in w each (3 TMA boxes of 8 w-voxels
-// instead of one of 10), into consecutive chunk slots; one B descriptor then spans
-// 3 x NT/8 slots = the N = 3*NT columns [kw][ci] and one MMA does three taps.  The three kh taps
-// shift the descriptor start by one line; the three kd planes are separate CTAs (blockIdx.y).
+// ~45 cycles whatever N <= 64 is (tools/mma_bench.cu).  So taps are STACKED along both MMA axes:
+//  * N: the three kw taps.  The x tile is loaded three times, shifted by one voxel in w each (3 TMA
+//    boxes of 8 w-voxels instead of one of 10), into consecutive chunk slots; one B descriptor then
+//    spans 3 x NT/8 slots = the N = 3*NT columns [kw][ci] and one MMA does three taps.
+//  * M: the kd taps, when Cout < 128 leaves M = 128 rows to spare.  The gy tile sits in shared memory
+//    as [plane][chunk][line] (one TMA box per plane), so with SBO = one plane of one chunk the 16 chunk
+//    strides of the A operand walk through chunk 0..g-1 of plane d, then chunk 0..g-1 of plane d+1, ...:
+//    row block s of the accumulator pairs x plane d with gy plane d + s + first_shift, i.e. it IS the tap
+//    kd = 1 - (s + first_shift).  Cout <= 32: all three kd in one MMA (gy tile with a +-1 plane halo);
+//    Cout <= 64: two (kd = 1, 0), a second CTA group does kd = 2; Cout > 64: one kd per CTA group.
+//  * the three kh taps shift the B descriptor start by one line (3 MMAs per K step).
 // The BIAS gradient sum_p gy[co,p] rides along for free: two extra chunk slots behind the x copies are
-// filled with ones once per CTA, and the (kd = 1, kh = 1, first ci tile) MMAs run with N = 3*NT + 16, so
-// 16 more accumulator columns hold gy (x) 1 (replaces a separate pass over gy per layer).
+// filled with ones once per CTA, and the kh = 1 MMAs of one CTA group run with N = 3*NT + 16, so 16 more
+// accumulator columns hold gy (x) 1 (the rows of the unshifted block are the bias gradient).
 // Each CTA keeps its 3 accumulators [128 x 3*NT] in tensor memory while it streams through its
-// share of the voxel tiles (persistent, multi-stage TMA pipeline), then adds them to gw with
-// fp32 atomics.
+// share of the voxel tiles (persistent, multi-stage TMA pipeline), then adds them -- 16-byte vector
+// reductions, or plain stores when it is the only CTA of its group -- into a tap-major fp32 workspace
+// [27][Cout][CinP]; k_wgrad_finish transposes that into the parameter layout [Cout][Cin][27] (scattered
+// 4-byte atomics straight into that layout cost more than the MMAs at the low-resolution levels).
 #include "../../include/saragan_b200.h"
 #include "tc_common.cuh"
 
@@ -28,22 +36,24 @@ namespace {
 constexpr int kThreadsW = 192;
 
 struct WgParams {
-  float* gw;               // [Cout][Cin][27]
+  float* ws;               // [27][Cout][CinP] tap-major sums
   float* gb;               // nullable [Cout]: bias gradient = sum of gy over batch and voxels
   int N, D, H, W;
-  int Cin, Cout, CCin, CCout;
+  int Cin, Cout, CCin, CCout, CinP;
   int td, th;              // tile = td x th x 8 voxels
   int tiles_w, tiles_h, tiles_d;
   int n_tiles;             // tiles_w * tiles_h * tiles_d * N
-  int g_chunk_bytes;       // td*th*8*16
+  int g_chunks;            // 8-channel chunks of gy per plane box (<= 16)
+  int shifts;              // kd taps stacked along M: 3, 2 or 1
+  int g_planes;            // gy planes loaded per tile: td + shifts - 1
+  int g_plane_bytes;       // g_chunks * th * 8 * 16
   int x_chunk_bytes;       // td*(th+2)*8*16: one (kw copy, 8-channel chunk) slot of the x tile
-  int g_chunks;            // 8-channel chunks of gy loaded per tile (<= 16)
   int stage_bytes;
   int stages;
   int slack_bytes;         // room after the last stage for the garbage-row reads of the M = 128 operand
   int ci_tiles;            // CinP / NT
   int tmem_cols;
-  float scale;
+  int direct;              // one CTA per group: plain stores, no zero-fill of ws needed
 };
 
 template <int NT>
@@ -51,7 +61,7 @@ __global__ void __launch_bounds__(kThreadsW)
 k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUtensorMap xmap,
            const __grid_constant__ WgParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  // carve-up: stages x [gy tile (g_chunks chunks) | x halo tile (NT/8 chunks)], then barriers
+  // carve-up: stages x [gy planes | 3 kw copies of the x halo tile | ones], then barriers
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes + p.slack_bytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * 8 + 1);
   const uint32_t bar0 = smem_u32(bars);
@@ -59,15 +69,27 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
   const int FULL = 0, EMPTY = p.stages, ACC_FULL = 2 * p.stages;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kd = blockIdx.y;
+  const int grp = blockIdx.y;
   const int co_tile = blockIdx.z / p.ci_tiles, ci_tile = blockIdx.z % p.ci_tiles;
   const int x_chunks = NT / 8;
   const int halo_h = p.th + 2;
-  const bool do_bias = p.gb != nullptr && kd == 1 && ci_tile == 0;
+  // CTA group -> which planes it pairs.  Row block s of the accumulator holds the tap kd_hi - s.
+  //   shifts 3: gy planes from d0 - 1, x plane d0      -> kd = 2, 1, 0
+  //   shifts 2: group 0: gy from d0, x plane d0        -> kd = 1, 0;  group 1: x plane d0 + 1 -> kd = 2 (s = 0 only)
+  //   shifts 1: group g: gy from d0, x plane d0 + g - 1 -> kd = g
+  const int g_plane0 = p.shifts == 3 ? -1 : 0;
+  const int x_plane0 = p.shifts == 3 ? 0 : p.shifts == 2 ? grp : grp - 1;
+  const int kd_hi = p.shifts == 3 ? 2 : p.shifts == 2 ? 1 + grp : grp;
+  const int live_shifts = (p.shifts == 2 && grp == 1) ? 1 : p.shifts;
+  const int rows_per_shift = 8 * p.g_chunks;
+  // the row block whose gy plane is unshifted against its own voxels (kd = 1) carries the bias gradient
+  const int bias_row0 = (kd_hi - 1) * rows_per_shift;
+  const bool do_bias = p.gb != nullptr && ci_tile == 0 && kd_hi >= 1 && kd_hi - 1 < live_shifts;
+  const int g_bytes = p.g_planes * p.g_plane_bytes;
   if (do_bias) {
     // ones slots (bf16 1.0 = 0x3F80) behind the 3*x_chunks x slots of every stage; the TMA never writes them
     for (int st = 0; st < p.stages; ++st) {
-      uint32_t* ones = reinterpret_cast<uint32_t*>(smem + (size_t)st * p.stage_bytes + p.g_chunks * p.g_chunk_bytes +
+      uint32_t* ones = reinterpret_cast<uint32_t*>(smem + (size_t)st * p.stage_bytes + g_bytes +
                                                    3 * x_chunks * p.x_chunk_bytes);
       for (int i = threadIdx.x; i < 2 * p.x_chunk_bytes / 4; i += blockDim.x) ones[i] = 0x3F803F80u;
     }
@@ -99,7 +121,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
   if (warp == 0) {
     // ================================ producer ================================
     if (lane == 0) {
-      const uint32_t tx = (uint32_t)(p.g_chunks * p.g_chunk_bytes + 3 * x_chunks * p.x_chunk_bytes);
+      const uint32_t tx = (uint32_t)(g_bytes + 3 * x_chunks * p.x_chunk_bytes);
       int it = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
         int t = tile;
@@ -112,13 +134,13 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
         mbar_wait(BAR(EMPTY + s), ((it / p.stages) & 1) ^ 1);
         mbar_expect_tx(BAR(FULL + s), tx);
         const uint32_t g_dst = smem_base + s * p.stage_bytes;
-        const uint32_t x_dst = g_dst + p.g_chunks * p.g_chunk_bytes;
-        for (int c = 0; c < p.g_chunks; ++c)
-          tma_load_5d(g_dst + c * p.g_chunk_bytes, &gmap, BAR(FULL + s), w0 * 8, h0, d0, co_tile * 16 + c, n);
+        const uint32_t x_dst = g_dst + g_bytes;
+        for (int pl = 0; pl < p.g_planes; ++pl)   // one box = all chunks of one plane (planes outside D: zeros)
+          tma_load_5d(g_dst + pl * p.g_plane_bytes, &gmap, BAR(FULL + s), w0 * 8, h0, d0 + g_plane0 + pl, co_tile * 16, n);
         for (int k = 0; k < 3; ++k)        // kw copy k = the tile shifted by k - 1 voxels in w
           for (int c = 0; c < x_chunks; ++c)
             tma_load_5d(x_dst + (k * x_chunks + c) * p.x_chunk_bytes, &xmap, BAR(FULL + s), (w0 - 1 + k) * 8, h0 - 1,
-                        d0 + kd - 1, ci_tile * x_chunks + c, n);
+                        d0 + x_plane0, ci_tile * x_chunks + c, n);
       }
     }
   } else if (warp == 1) {
@@ -133,10 +155,10 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
                                             ((uint32_t)((3 * NT + 16) >> 3) << 17) | ((128u >> 4) << 24))
                                          : idesc;
       // descriptors: bases hoisted, per-MMA cost = one 64-bit add (offsets in 16-byte units = voxels)
-      const uint64_t g_desc0 = make_desc(smem_base, 128u, (uint32_t)p.g_chunk_bytes);
-      const uint64_t x_desc0 = make_desc(smem_base + p.g_chunks * p.g_chunk_bytes, 128u, (uint32_t)p.x_chunk_bytes);
-      const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4;
-      const int ksteps_per_plane = p.th / 2, td = p.td, th = p.th, stages = p.stages;
+      const uint64_t g_desc0 = make_desc(smem_base, 128u, (uint32_t)(p.th * 128));
+      const uint64_t x_desc0 = make_desc(smem_base + g_bytes, 128u, (uint32_t)p.x_chunk_bytes);
+      const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4, plane16 = (uint32_t)p.g_plane_bytes >> 4;
+      const int ksteps_per_plane = p.th / 2, td = p.td, stages = p.stages;
       int s = 0, ph = 0;
       uint32_t acc = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -145,7 +167,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
         const uint64_t g_stage = g_desc0 + (uint64_t)(s * stage16);
         const uint64_t x_stage = x_desc0 + (uint64_t)(s * stage16);
         for (int dl = 0; dl < td; ++dl) {
-          uint64_t a_k = g_stage + (uint64_t)(dl * th * 8);
+          uint64_t a_k = g_stage + (uint64_t)(dl * plane16);
           uint64_t b_k = x_stage + (uint64_t)(dl * halo_h * 8);
           for (int j = 0; j < ksteps_per_plane; ++j) {
             // accumulator columns: kh=0 at 0, kh=1 at 3*NT (3*NT + 16 wide), kh=2 at 6*NT + 16
@@ -153,7 +175,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
             tc_mma(tmem_base + 3 * NT, a_k, b_k + 8, idesc_mid, acc, leader);
             tc_mma(tmem_base + 6 * NT + 16, a_k, b_k + 16, idesc, acc, leader);
             acc = 1;
-            a_k += 16;   // two lines of 8 voxels (gy tile and x copies alike)
+            a_k += 16;   // two lines of 8 voxels (gy plane and x copies alike)
             b_k += 16;
           }
         }
@@ -166,34 +188,40 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
     // ================================ epilogue ================================
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
-    const int co = co_tile * 128 + row;
+    const int shift = row / rows_per_shift;
+    const int co = co_tile * 128 + row - shift * rows_per_shift;
+    const int kd = kd_hi - shift;
     mbar_wait(BAR(ACC_FULL), 0);
     tc_fence_after();
-    const bool any_tile = blockIdx.x < p.n_tiles;
+    const bool mine = blockIdx.x < p.n_tiles && shift < live_shifts && co < p.Cout;
+    float* dst_row = p.ws + ((int64_t)(kd * 9) * p.Cout + co) * p.CinP + ci_tile * NT;
     for (int t9 = 0; t9 < 9; ++t9) {
-      const int tap = kd * 9 + t9;
       for (int c0 = 0; c0 < NT; c0 += 16) {
         float v[16];
         __syncwarp();
         tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(t9 * NT + (t9 >= 6 ? 16 : 0) + c0), v);
-        if (any_tile && co < p.Cout) {
+        if (mine) {
+          float* dst = dst_row + (int64_t)t9 * p.Cout * p.CinP + c0;
+          if (p.direct) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int ci = ci_tile * NT + c0 + j;
-            if (ci < p.Cin && v[j] != 0.f) atomicAdd(p.gw + ((int64_t)co * p.Cin + ci) * 27 + tap, v[j] * p.scale);
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) red_add_v4(dst + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           }
         }
       }
     }
-  }
-  if (warp >= 2 && do_bias) {
-    // 16 identical columns gy (x) 1 behind the kh = 1 accumulator: column 0 is the bias gradient
-    const int quad = warp & 3;
-    const int co = co_tile * 128 + quad * 32 + lane;
-    float v[16];
-    __syncwarp();
-    tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(6 * NT), v);
-    if (blockIdx.x < p.n_tiles && co < p.Cout) atomicAdd(p.gb + co, v[0]);
+    if (do_bias) {
+      // 16 identical columns gy (x) 1 behind the kh = 1 accumulator: column 0 is the bias gradient
+      float v[16];
+      __syncwarp();
+      tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(6 * NT), v);
+      const int cb = co_tile * 128 + row - bias_row0;
+      if (blockIdx.x < p.n_tiles && row >= bias_row0 && row < bias_row0 + rows_per_shift && cb < p.Cout)
+        atomicAdd(p.gb + cb, v[0]);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -204,12 +232,30 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
   }
 }
 
+// ws [27][Cout][CinP] -> gw [Cout][Cin][27] * scale.  block = (64 input channels, one output channel)
+__global__ void __launch_bounds__(256)
+k_wgrad_finish(const float* __restrict__ ws, float* __restrict__ gw, int Cout, int Cin, int CinP, float scale) {
+  __shared__ float s[64 * 27];
+  const int co = blockIdx.y, ci0 = blockIdx.x * 64;
+  for (int idx = threadIdx.x; idx < 27 * 64; idx += 256) {
+    const int tap = idx >> 6, cl = idx & 63;
+    float v = 0.f;
+    if (ci0 + cl < Cin) v = ws[((int64_t)tap * Cout + co) * CinP + ci0 + cl] * scale;
+    s[cl * 27 + tap] = v;
+  }
+  __syncthreads();
+  const int n = (Cin - ci0 < 64 ? Cin - ci0 : 64) * 27;
+  float* dst = gw + ((int64_t)co * Cin + ci0) * 27;
+  for (int idx = threadIdx.x; idx < n; idx += 256) dst[idx] = s[idx];
+}
+
 struct WgPlan {
   bool ok = false;
   int NT = 0;
   WgParams p{};
   size_t smem = 0;
   dim3 grid;
+  int64_t ws_bytes = 0;
 };
 
 WgPlan make_wgrad_plan(int N, int Cin, int Cout, int D, int H, int W) {
@@ -222,21 +268,25 @@ WgPlan make_wgrad_plan(int N, int Cin, int Cout, int D, int H, int W) {
   if (H % th) return pl;
   p.th = th;
   p.g_chunks = CoutP / 8 < 16 ? CoutP / 8 : 16;
+  const int fit = 16 / p.g_chunks;            // row blocks of 8*g_chunks rows in M = 128
+  p.shifts = fit >= 3 ? 3 : fit;
   // td: as many planes per tile (4, 2, 1) as leave room for >= 2 pipeline stages.  The M = 128 operand
-  // reads 16 chunk strides of gy: with fewer real chunks the rest are garbage rows (discarded) read
+  // reads 16 chunk strides from its plane on: past the gy planes these are garbage rows (discarded) read
   // from the following bytes -- `slack` keeps those reads of the LAST stage inside the allocation.
   int td = 0, stages = 0;
   for (int cand = 4; cand >= 1; cand /= 2) {
     if (cand > D || D % cand) continue;
-    const int gb = cand * th * 8 * 16, xb = cand * (th + 2) * 8 * 16;
-    const int stage = p.g_chunks * gb + (3 * (NT / 8) + 2) * xb;   // + two ones slots for the bias gradient
-    const int over = 16 * gb - stage;
+    const int plane = p.g_chunks * th * 128, xb = cand * (th + 2) * 128;
+    const int g_planes = cand + p.shifts - 1;
+    const int stage = g_planes * plane + (3 * (NT / 8) + 2) * xb;   // + two ones slots for the bias gradient
+    const int over = (cand - 1) * plane + 16 * th * 128 - stage;
     const int slack = over > 0 ? (over + 255) / 128 * 128 : 128;
     int st = (200 * 1024 - slack) / stage;
     if (st > 8) st = 8;
     if (st >= 2) {
       td = cand; stages = st;
-      p.g_chunk_bytes = gb; p.x_chunk_bytes = xb; p.stage_bytes = stage; p.slack_bytes = slack;
+      p.g_planes = g_planes; p.g_plane_bytes = plane; p.x_chunk_bytes = xb; p.stage_bytes = stage;
+      p.slack_bytes = slack;
       break;
     }
   }
@@ -245,18 +295,21 @@ WgPlan make_wgrad_plan(int N, int Cin, int Cout, int D, int H, int W) {
   size_t total = (size_t)stages * p.stage_bytes;
   p.stages = stages;
   p.N = N; p.D = D; p.H = H; p.W = W;
-  p.Cin = Cin; p.Cout = Cout; p.CCin = sg_chunks(Cin); p.CCout = sg_chunks(Cout);
+  p.Cin = Cin; p.Cout = Cout; p.CCin = sg_chunks(Cin); p.CCout = sg_chunks(Cout); p.CinP = CinP;
   p.tiles_w = W / 8; p.tiles_h = H / th; p.tiles_d = D / td;
   p.n_tiles = p.tiles_w * p.tiles_h * p.tiles_d * N;
   p.ci_tiles = CinP / NT;
   p.tmem_cols = 9 * NT + 16 <= 256 ? 256 : 512;
   const int co_tiles = (CoutP + 127) / 128;
-  const int groups = 3 * co_tiles * p.ci_tiles;
+  const int kd_groups = p.shifts == 3 ? 1 : p.shifts == 2 ? 2 : 3;
+  const int groups = kd_groups * co_tiles * p.ci_tiles;
   int per_group = sg_num_sms() / groups;   // one CTA per SM (smem-limited): never more than one wave
   if (per_group > p.n_tiles) per_group = p.n_tiles;
   if (per_group < 1) per_group = 1;
-  pl.grid = dim3((unsigned)per_group, 3, (unsigned)(co_tiles * p.ci_tiles));
+  p.direct = per_group == 1;
+  pl.grid = dim3((unsigned)per_group, (unsigned)kd_groups, (unsigned)(co_tiles * p.ci_tiles));
   pl.smem = total + p.slack_bytes + 8 * (2 * 8 + 1) + 16;
+  pl.ws_bytes = (int64_t)27 * Cout * CinP * (int64_t)sizeof(float);
   pl.NT = NT;
   pl.ok = true;
   return pl;
@@ -278,7 +331,7 @@ int launch_wgrad(const WgPlan& pl, const CUtensorMap& gmap, const CUtensorMap& x
 }
 
 int encode_act_map(CUtensorMap* map, const void* base, int N, int CC, int D, int H, int W, int box_w_vox, int box_h,
-                   int box_d) {
+                   int box_d, int box_c) {
   EncodeTiledFn encode = get_encode();
   if (!encode) {
     sg_set_error("conv_tc: cuTensorMapEncodeTiled not available");
@@ -287,7 +340,7 @@ int encode_act_map(CUtensorMap* map, const void* base, int N, int CC, int D, int
   cuuint64_t dims[5] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)CC, (cuuint64_t)N};
   cuuint64_t strides[4] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16,
                            (cuuint64_t)CC * D * H * W * 16};
-  cuuint32_t box[5] = {(cuuint32_t)box_w_vox * 8, (cuuint32_t)box_h, (cuuint32_t)box_d, 1, 1};
+  cuuint32_t box[5] = {(cuuint32_t)box_w_vox * 8, (cuuint32_t)box_h, (cuuint32_t)box_d, (cuuint32_t)box_c, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -301,22 +354,31 @@ int encode_act_map(CUtensorMap* map, const void* base, int N, int CC, int D, int
 
 }  // namespace
 
+int64_t sg_tc_wgrad_workspace_bytes(int N, int Cin, int Cout, int D, int H, int W) {
+  WgPlan pl = make_wgrad_plan(N, Cin, Cout, D, H, W);
+  return pl.ok ? pl.ws_bytes : 0;
+}
+
 // returns 1 if the shape is not covered (caller falls through to the direct kernel)
 int sg_tc_wgrad(const void* x, const void* gy, float* gw, float* gb, int N, int Cin, int Cout, int D, int H, int W,
                 float scale, void* ws, int64_t ws_bytes, cudaStream_t s) {
-  (void)ws; (void)ws_bytes;
   WgPlan pl = make_wgrad_plan(N, Cin, Cout, D, H, W);
   if (!pl.ok) return 1;
   WgParams& p = pl.p;
-  p.gw = gw;
+  SG_REQUIRE(ws != nullptr && ws_bytes >= pl.ws_bytes, "sg_conv3d_wgrad(tcgen05): workspace too small (%lld < %lld)",
+             (long long)ws_bytes, (long long)pl.ws_bytes);
+  p.ws = (float*)ws;
   p.gb = gb;
-  p.scale = scale;
   CUtensorMap gmap, xmap;
-  int rc = encode_act_map(&gmap, gy, N, p.CCout, D, H, W, 8, p.th, p.td);
+  int rc = encode_act_map(&gmap, gy, N, p.CCout, D, H, W, 8, p.th, 1, p.g_chunks);
   if (rc) return rc;
-  rc = encode_act_map(&xmap, x, N, p.CCin, D, H, W, 8, p.th + 2, p.td);
+  rc = encode_act_map(&xmap, x, N, p.CCin, D, H, W, 8, p.th + 2, p.td, 1);
   if (rc) return rc;
-  cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)Cout * Cin * 27, s);
+  if (!p.direct) cudaMemsetAsync(ws, 0, (size_t)pl.ws_bytes, s);
   if (gb) cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)Cout, s);
-  return pl.NT == 32 ? launch_wgrad<32>(pl, gmap, xmap, s) : launch_wgrad<16>(pl, gmap, xmap, s);
+  rc = pl.NT == 32 ? launch_wgrad<32>(pl, gmap, xmap, s) : launch_wgrad<16>(pl, gmap, xmap, s);
+  if (rc) return rc;
+  k_wgrad_finish<<<dim3((unsigned)((Cin + 63) / 64), (unsigned)Cout), 256, 0, s>>>((const float*)ws, gw, Cout, Cin,
+                                                                                p.CinP, scale);
+  return sg_check_launch("sg_conv3d_wgrad(tcgen05 finish)");
 }

@@ -98,7 +98,10 @@ WGRAD_SHAPES = [
     (3, 256, 128, 2, 8, 8),    # ragged batch, many channel tiles
     (2, 16, 8, 4, 16, 16),     # Cout=8 padded
     (1, 24, 48, 2, 16, 8),     # padded Cin/Cout
-    (2, 32, 32, 8, 32, 32),    # persistent CTAs loop over many tiles
+    (2, 32, 32, 8, 32, 32),    # persistent CTAs loop over many tiles; all three kd stacked along M
+    (2, 32, 32, 1, 16, 16),    # D=1: the kd = 0, 2 row blocks only ever see out-of-volume gy planes
+    (1, 48, 80, 2, 16, 16),    # 10 gy chunks: no room for a second kd block
+    (8, 32, 16, 4, 32, 32),    # Cout=16: eight row blocks fit, three are live
 ]
 
 
