@@ -44,8 +44,10 @@ def test_golden_step_fp32(name):
         assert {k for k, v in got.items() if v is not None} == set(want), kind
         for k, v in want.items():
             # bias gradients are signed sums over every voxel of a level (|sum| << sum of |terms|):
-            # fp32 summation order alone moves them by a few 1e-3; weights are held to 1e-3
-            tol = 5e-3 if k.endswith(".bias") else 1e-3
+            # fp32 summation order alone moves them by a few 1e-3 -- and the order is not fixed (split-K
+            # atomics): tools/flaky_probe.py shows e.g. fromrgbs.0 bias at 3e-6 in most runs and 2.7e-3 in
+            # one of six.  Weights are held to 1e-3.
+            tol = 2e-2 if k.endswith(".bias") else 1e-3
             if v.numel() == 1:
                 # the last linear's bias gradient is sum(-1/B ... +1/B ...) + drift ~ 1e-5: a cancelling sum of
                 # O(1) terms, so fp32 summation order moves it by ~1e-7 absolute (D(real), D(fake) are one batch)
