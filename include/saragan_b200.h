@@ -66,10 +66,14 @@ int sg_conv3d_fprop(const void* x, const void* wp, const float* bias, const void
  * sums); kind 0 = fprop/dgrad, 1 = wgrad.  The library never allocates. */
 int64_t sg_conv3d_workspace_bytes(int kind, int dtype, int N, int Cin, int Cout, int D, int H, int W);
 /* introspection: tiling of the tcgen05 path for a shape; out[16] = ok, NT, tn, td, th, n_sub,
- * kb_chunks, w_stages, splits, kblocks_per_split, grid.x, grid.y, grid.z, smem bytes, tmem cols, a_bytes */
+ * kb_chunks + 100 * taps_per_stage, w_stages, splits, kblocks_per_split, grid.x, grid.y, grid.z, smem bytes, tmem cols, a_bytes */
 /* test hook: 0 = auto; 1 = always the streaming tcgen05 kernel; 2 = the weight-resident kernel
  * whenever its geometry constraints hold (ignoring the tile-count heuristic) */
 void sg_tc_force_streaming(int mode);
+/* test / tuning hook for the streaming kernel: force the tiling (output channels per CTA nt in
+ * {128,64,32,16}; big = tiles for one CTA per SM; td_max = planes per tile cap; splits = split-K
+ * factor) instead of choosing by estimated cost; nt = 0 restores the automatic choice */
+void sg_tc_force_plan(int nt, int big, int td_max, int splits);
 int sg_tc_plan_debug(int N, int Cin, int Cout, int D, int H, int W, int* out);
 /* wgrad (autograd of network.py:55): gw[Cout][Cin][27] = scale * sum gy (x) x,  gb[Cout] = sum gy
  * (gb nullable).  Outputs are fp32 and overwritten. */

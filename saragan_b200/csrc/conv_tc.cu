@@ -13,11 +13,18 @@
 //    27 im2col loads (L2->SMEM traffic /9);
 //  * an MMA covers 16 consecutive lines x 8 voxels = 128 rows (M=128) and N = NT output
 //    channels; rows that fall on halo lines/columns are computed and discarded;
-//  * weights [tap][C/8][CoutP][8] stream through a ring of bulk-copy stages;
+//  * weights [tap][C/8][CoutP][8] stream through a ring of TMA stages of `tps` taps each: ONE tiled load
+//    (box = [tps taps][K-block chunks][NT channels]) per stage -- issuing a copy costs the producer thread
+//    ~90 cycles plus ~360 for the barrier bookkeeping (tools/bulk_bench.cu), so per-tap stages of four
+//    2 KB bulk copies (the first version) capped the whole kernel at ~1300 cycles per tap;
 //  * warp roles: warp 0 = TMA/bulk producer, warp 1 = TMEM allocator + single-thread MMA
 //    issuer, warps 2-5 = epilogue (tcgen05.ld -> scale, bias, LeakyReLU, mask -> 16-byte stores,
 //    or fp32 atomics into the split-K workspace).
 #include <cuda.h>
+
+#include <array>
+#include <map>
+#include <mutex>
 
 #include "../../include/saragan_b200.h"
 #include "common.cuh"
@@ -51,25 +58,56 @@ struct TcParams {
   int splits;
   int sw;                    // weight ring stages
   int a_bytes, w_stage_bytes;
+  int tps;                   // taps per weight stage (9, 3 or 1)
+  int w_tap_bytes;           // kb_chunks * NT * 16
+  int a_stages;              // 1 or 2 halo-block buffers
   int tmem_cols;
   float scale;
   int lrelu;
 };
 
+// greedy cover of a tile's valid output lines with 16-line MMA tiles (same rule as cover_lines on the host),
+// evaluated at compile time for the specialised kernels
+struct CoverCE {
+  int n;
+  int line[kMaxSub + 1];
+};
+constexpr CoverCE cover_ce(int tn, int td, int th) {
+  CoverCE c{};
+  const int halo_d = td + 2, halo_h = th + 2;
+  int covered_to = -1;
+  for (int nl = 0; nl < tn; ++nl)
+    for (int dl = 0; dl < td; ++dl)
+      for (int hl = 0; hl < th; ++hl) {
+        const int line = (nl * halo_d + dl + 1) * halo_h + hl + 1;
+        if (line <= covered_to) continue;
+        if (c.n < kMaxSub) c.line[c.n] = line;
+        ++c.n;
+        covered_to = line + 15;
+      }
+  return c;
+}
+
 // --------------------------------------------------------------------------------- kernel
-template <int NT>
+// TD = 0: generic geometry (tile extents, K block, taps per stage from TcParams at run time).
+// TD > 0: geometry fixed at compile time -- tile TN x TD x TH x 8 voxels, K block of 2 chunks, 9 taps per
+// weight stage -- so that every descriptor offset of the 27 x n_sub MMAs of a K block is a constant and
+// the fully unrolled issue loop costs one uniform add per MMA (the generic loop costs the single issuing
+// warp ~200 cycles per tap plus ~100 per MMA: more than the MMAs themselves).
+template <int NT, int TD, int TH, int TN>
 __global__ void __launch_bounds__(kThreads)
-k_conv_tc(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ TcParams p) {
+k_conv_tc(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap,
+          const __grid_constant__ TcParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   // carve-up: [A halo block][weight ring][barriers][tmem base]
   uint8_t* a_smem = smem;
-  uint8_t* w_smem = smem + p.a_bytes;
+  uint8_t* w_smem = smem + p.a_stages * p.a_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + p.sw * p.w_stage_bytes);
-  // bars: [0] full_a, [1] empty_a, [2] acc_full, [3 .. 3+sw) full_w, [3+sw .. 3+2sw) empty_w
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 + 2 * kMaxSub + 2);
+  // bars: [0,1] full_a, [2,3] empty_a, [4] acc_full, [5 .. 5+sw) full_w, [5+sw .. 5+2sw) empty_w   (sw <= 8)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-  const int FULL_A = 0, EMPTY_A = 1, ACC_FULL = 2, FULL_W = 3, EMPTY_W = 3 + p.sw;
+  const int FULL_A = 0, EMPTY_A = 2, ACC_FULL = 4, FULL_W = 5, EMPTY_W = 5 + p.sw;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -85,8 +123,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ TcPa
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
-    mbar_init(BAR(FULL_A), 1);
-    mbar_init(BAR(EMPTY_A), 1);
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(BAR(FULL_A + i), 1);
+      mbar_init(BAR(EMPTY_A + i), 1);
+    }
     mbar_init(BAR(ACC_FULL), 1);
     for (int i = 0; i < p.sw; ++i) {
       mbar_init(BAR(FULL_W + i), 1);
@@ -111,22 +152,24 @@ k_conv_tc(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ TcPa
       const uint32_t a_addr = smem_u32(a_smem);
       const uint32_t w_addr = smem_u32(w_smem);
       const uint32_t a_tx = (uint32_t)p.kb_chunks * (uint32_t)p.chunk_tx_bytes;
-      const uint32_t w_tx = (uint32_t)p.kb_chunks * NT * 16u;
+      const uint32_t w_tx = (uint32_t)p.w_stage_bytes;
+      const int groups = 27 / p.tps;
       int it = 0;
       for (int kb = 0; kb < p.kblocks_per_split; ++kb) {
-        mbar_wait(BAR(EMPTY_A), (kb & 1) ^ 1);
-        mbar_expect_tx(BAR(FULL_A), a_tx);
+        // the halo block of K block kb + 1 is loaded (second A stage) while the MMAs of kb still run
+        const int sa = kb % p.a_stages;
+        mbar_wait(BAR(EMPTY_A + sa), ((kb / p.a_stages) & 1) ^ 1);
         const int chunk0 = (kb0 + kb) * p.kb_chunks;
+        mbar_expect_tx(BAR(FULL_A + sa), a_tx);
         for (int c = 0; c < p.kb_chunks; ++c)
-          tma_load_5d(a_addr + c * p.chunk_bytes, &xmap, BAR(FULL_A), (w0 - 1) * 8, h0 - 1, d0 - 1, chunk0 + c, n0);
-        for (int tap = 0; tap < 27; ++tap, ++it) {
+          tma_load_5d(a_addr + sa * p.a_bytes + c * p.chunk_bytes, &xmap, BAR(FULL_A + sa), (w0 - 1) * 8, h0 - 1, d0 - 1,
+                      chunk0 + c, n0);
+        for (int g = 0; g < groups; ++g, ++it) {
           const int s = it % p.sw;
           mbar_wait(BAR(EMPTY_W + s), ((it / p.sw) & 1) ^ 1);
           mbar_expect_tx(BAR(FULL_W + s), w_tx);
-          for (int c = 0; c < p.kb_chunks; ++c) {
-            const __nv_bfloat16* src = p.wp + (((int64_t)tap * p.CCin + chunk0 + c) * p.CoutP + co0) * 8;
-            bulk_load(w_addr + s * p.w_stage_bytes + c * NT * 16, src, NT * 16u, BAR(FULL_W + s));
-          }
+          // weights as [64 = 8 co x 8 ci | CoutP/8 | CCin | 27]: box [tps][kb_chunks][NT/8][64] lands as [tap][chunk][co][8]
+          tma_load_4d(w_addr + s * p.w_stage_bytes, &wmap, BAR(FULL_W + s), 0, co0 / 8, chunk0, g * p.tps);
         }
       }
     }
@@ -146,25 +189,70 @@ k_conv_tc(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ TcPa
       const uint64_t a_desc0 = make_desc(smem_u32(a_smem), (uint32_t)p.chunk_bytes, line_pitch);
       const uint64_t w_desc0 = make_desc(smem_u32(w_smem), NT * 16u, 128u);
       const uint32_t kk_a = (uint32_t)(2 * p.chunk_bytes) >> 4;
-      const uint32_t w_stage16 = (uint32_t)p.w_stage_bytes >> 4;
+      const uint32_t w_stage16 = (uint32_t)p.w_stage_bytes >> 4, w_tap16 = (uint32_t)p.w_tap_bytes >> 4;
+      const int tps = p.tps;
+      int tl = 0;   // tap within the current weight stage
       const int kpairs = p.kb_chunks / 2, n_sub = p.n_sub, halo_w = p.halo_w, halo_h = p.halo_h, sw = p.sw;
       int s = 0, ph = 0;
+      if constexpr (TD > 0) {
+        constexpr CoverCE cov = cover_ce(TN, TD, TH);
+        constexpr int HALO_H = TH + 2, HALO_W = 10;
+        constexpr int BIAS_VOX = (HALO_H + 1) * HALO_W;
+        constexpr uint32_t W_TAP16 = 2u * NT;   // one tap of a stage: 2 chunks x NT rows x 16 B
+        for (int kb = 0; kb < p.kblocks_per_split; ++kb) {
+          const int sa = kb % p.a_stages;
+          mbar_wait(BAR(FULL_A + sa), (kb / p.a_stages) & 1);
+          const uint64_t a_kb = a_desc0 + (uint64_t)((uint32_t)(sa * p.a_bytes) >> 4);
+          const uint32_t acc0 = kb != 0;
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            mbar_wait(BAR(FULL_W + s), ph);
+            tc_fence_after();
+            const uint64_t b_stage = w_desc0 + (uint64_t)(s * w_stage16);
+#pragma unroll
+            for (int t9 = 0; t9 < 9; ++t9) {
+              constexpr int dummy = 0;
+              (void)dummy;
+              const int tap = g * 9 + t9;
+              // tap (kd,kh,kw) reads halo voxel (line + (kd-1)*HALO_H + (kh-1), w + kw): all offsets >= 0 after
+              // folding the first valid line's position (BIAS_VOX) into the sub-tile offsets
+              const uint32_t tap_off = (uint32_t)((((tap / 9) - 1) * HALO_H + ((tap / 3) % 3 - 1)) * HALO_W + BIAS_VOX + tap % 3);
+#pragma unroll
+              for (int sub = 0; sub < cov.n; ++sub)
+                tc_mma(tmem_base + sub * NT, a_kb + (uint64_t)(tap_off + (uint32_t)(cov.line[sub] * HALO_W - BIAS_VOX)),
+                       b_stage + (uint64_t)(t9 * W_TAP16), idesc, tap ? 1u : acc0, leader);
+            }
+            tc_commit(BAR(EMPTY_W + s), leader);
+            if (++s == sw) { s = 0; ph ^= 1; }
+          }
+          tc_commit(BAR(EMPTY_A + sa), leader);
+        }
+      } else {
       for (int kb = 0; kb < p.kblocks_per_split; ++kb) {
-        mbar_wait(BAR(FULL_A), kb & 1);
+        const int sa = kb % p.a_stages;
+        mbar_wait(BAR(FULL_A + sa), (kb / p.a_stages) & 1);
+        const uint64_t a_desc_kb = a_desc0 + (uint64_t)((uint32_t)(sa * p.a_bytes) >> 4);
         int tap = 0;
         for (int kd = 0; kd < 3; ++kd)
           for (int kh = 0; kh < 3; ++kh) {
             const int row_off = ((kd - 1) * halo_h + (kh - 1)) * halo_w + bias_vox;
             for (int kw = 0; kw < 3; ++kw, ++tap) {
-              mbar_wait(BAR(FULL_W + s), ph);
-              tc_fence_after();
-              issue_tap<NT>(tmem_base, a_desc0 + (uint64_t)(uint32_t)(row_off + kw), w_desc0 + (uint64_t)(s * w_stage16),
-                            sub_off, n_sub, kpairs, kk_a, idesc, (kb | tap) != 0, leader);
-              tc_commit(BAR(EMPTY_W + s), leader);
-              if (++s == sw) { s = 0; ph ^= 1; }
+              if (tl == 0) {
+                mbar_wait(BAR(FULL_W + s), ph);
+                tc_fence_after();
+              }
+              issue_tap<NT>(tmem_base, a_desc_kb + (uint64_t)(uint32_t)(row_off + kw),
+                            w_desc0 + (uint64_t)(s * w_stage16 + tl * w_tap16), sub_off, n_sub, kpairs, kk_a, idesc,
+                            (kb | tap) != 0, leader);
+              if (++tl == tps) {
+                tl = 0;
+                tc_commit(BAR(EMPTY_W + s), leader);
+                if (++s == sw) { s = 0; ph ^= 1; }
+              }
             }
           }
-        tc_commit(BAR(EMPTY_A), leader);
+        tc_commit(BAR(EMPTY_A + sa), leader);
+      }
       }
       tc_commit(BAR(ACC_FULL), leader);
     }
@@ -227,7 +315,17 @@ struct Plan {
   TcParams p{};
   size_t smem = 0;
   dim3 grid;
+  double cost = 0;   // estimated cycles (make_plan_cfg)
+  bool big = false;
+  bool spec = false; // compile-time-geometry kernel (k_conv_tc<NT, TD, TH, TN>)
 };
+
+// cost-model constants (cycles at ~1.9 GHz)
+constexpr double kL2BytesPerCycle = 4500.0;   // sustained L2 -> SM bytes per cycle, whole chip
+constexpr double kCtaFixedCycles = 6000.0;    // launch, tensor-map fetch, first loads, epilogue
+constexpr double kSplitFixedCycles = 12000.0; // zero-fill + finishing kernel of a split-K launch
+constexpr double kLoadLatencyCycles = 4000.0; // TMA round trip seen by a stage whose data is not in L2 yet
+constexpr double kStageIssueCycles = 500.0;   // floor per weight stage: TMA issue + barrier round (tools/bulk_bench.cu)
 
 int round_pow2_cols(int c) {
   int r = 32;
@@ -250,24 +348,31 @@ int cover_lines(int tn, int td, int th, int halo_d, int halo_h, int* out) {
   return n_sub;
 }
 
-Plan make_plan(int N, int Cin, int Cout, int D, int H, int W) {
+// One candidate tiling of the streaming kernel.  `big` = sized for ONE CTA per SM (<= 512 TMEM columns,
+// ~200 KB of shared memory) instead of two (<= 256 columns, ~110 KB each); NT = output channels per CTA;
+// td_max caps the planes per tile; splits = split-K factor (must divide the K-block count).
+Plan make_plan_cfg(int N, int Cin, int Cout, int D, int H, int W, int NT, bool big, int td_max, int splits) {
   Plan pl;
   TcParams& p = pl.p;
   if (W % 8 != 0 || H < 8) return pl;
   const int CCin = sg_chunks(Cin), CoutP = 16 * ((Cout + 15) / 16);
-  int NT = CoutP % 128 == 0 ? 128 : CoutP % 64 == 0 ? 64 : CoutP % 32 == 0 ? 32 : 16;
-  const int max_sub = 256 / NT < kMaxSub ? 256 / NT : kMaxSub;
+  if (CoutP % NT != 0) return pl;
+  const int tmem_budget = big ? 512 : 256;
+  const int max_sub = tmem_budget / NT < kMaxSub ? tmem_budget / NT : kMaxSub;
   int th = H < 16 ? H : 16;
   if (H % th != 0) return pl;
-  // largest (tn, td) whose MMA tiles fit the TMEM budget of two co-resident CTAs
+  const int a_cap = (big ? 96 : 72) * 1024;
+  // largest (tn, td) whose MMA tiles fit the TMEM budget
   int best_tn = 0, best_td = 0, best_sub = 0, best_lines[kMaxSub];
-  for (int td = 1; td <= D && td <= 8; ++td) {
+  for (int td = 1; td <= D && td <= 8 && td <= td_max; ++td) {
     if (D % td) continue;
     for (int tn = 1; tn <= N && tn <= 8; ++tn) {
       if (td < D && tn > 1) continue;   // span samples only when a tile already holds a whole volume
+      if (tn > 1 && tn * td > td_max) continue;
       int lines[kMaxSub];
       int ns = cover_lines(tn, td, th, td + 2, th + 2, lines);
       if (ns > max_sub) continue;
+      if (tn * (td + 2) * (th + 2) * 10 * 16 * 2 > a_cap) continue;   // >= 2 chunks per K block must fit
       if (tn * td > best_tn * best_td) {
         best_tn = tn; best_td = td; best_sub = ns;
         for (int i = 0; i < ns; ++i) best_lines[i] = lines[i];
@@ -281,53 +386,152 @@ Plan make_plan(int N, int Cin, int Cout, int D, int H, int W) {
   p.halo_w = 10; p.halo_h = th + 2; p.halo_d = p.td + 2;
   p.chunk_tx_bytes = p.tn * p.halo_d * p.halo_h * p.halo_w * 16;
   p.chunk_bytes = (p.chunk_tx_bytes + 127) / 128 * 128;
-  p.kb_chunks = (CCin % 4 == 0 && 4 * p.chunk_bytes <= 72 * 1024) ? 4 : 2;
-  p.a_bytes = p.kb_chunks * p.chunk_bytes;
+  // K block (4 or 2 chunks), taps per weight stage (9, 3, 1) and ring depth: the largest stage that still
+  // leaves a ring of >= 3 (else >= 2) stages; two halo buffers when more than one K block follows
+  const int total_budget = (big ? 200 : 110) * 1024 - 256;
+  static const int cand[6][2] = {{4, 9}, {2, 9}, {4, 3}, {2, 3}, {4, 1}, {2, 1}};
+  // geometries with a specialised (fully unrolled) kernel: those always use K blocks of 2 chunks, 9 taps per stage
+  const bool spec_geom = (NT == 128 || NT == 64) &&
+                         ((th == 16 && p.tn == 1 && (p.td == 1 || p.td == 2 || p.td == 4)) ||
+                          (th == 8 && p.td == 2 && (p.tn == 1 || p.tn == 2)));
+  int pick = -1, pick_sw = 0, pick_as = 1;
+  for (int want_sw = 3; want_sw >= 2 && pick < 0; --want_sw)
+    for (int i = 0; i < 6 && pick < 0; ++i) {
+      const int kb = cand[i][0], tps = cand[i][1];
+      if (spec_geom && i != 1) continue;
+      if (CCin % kb || kb * p.chunk_bytes > a_cap) continue;
+      const int n_kb = CCin / kb;
+      if (splits < 1 || n_kb % splits) continue;
+      const int a_b = (kb * p.chunk_bytes + 127) / 128 * 128, stage = tps * kb * NT * 16;
+      int as = n_kb / splits > 1 ? 2 : 1;
+      int sw = (total_budget - as * a_b) / stage;
+      if (sw < want_sw && as == 2) { as = 1; sw = (total_budget - a_b) / stage; }
+      if (sw < want_sw) continue;
+      pick = i; pick_sw = sw > 8 ? 8 : sw; pick_as = as;
+    }
+  pl.spec = spec_geom && pick == 1;
+  if (pick < 0) return pl;
+  p.kb_chunks = cand[pick][0];
+  p.tps = cand[pick][1];
+  p.a_bytes = (p.kb_chunks * p.chunk_bytes + 127) / 128 * 128;
+  p.w_tap_bytes = p.kb_chunks * NT * 16;
+  p.w_stage_bytes = p.tps * p.w_tap_bytes;
+  p.a_stages = pick_as;
+  const int n_kblocks = CCin / p.kb_chunks;
+  p.splits = splits;
+  p.kblocks_per_split = n_kblocks / splits;
+  const int sw = pick_sw;
   // garbage rows of the last MMA tile may read past the block: keep those reads inside the allocation
   int last_line = p.sub_line[p.n_sub - 1] + 15 + p.halo_h + 1;
   int over = (last_line + 1) * p.halo_w * 16 + 8 * 16 + (p.kb_chunks - 1) * p.chunk_bytes - p.a_bytes;
-  p.w_stage_bytes = p.kb_chunks * NT * 16;
-  p.a_bytes = (p.a_bytes + 127) / 128 * 128;
-  int budget = 110 * 1024 - p.a_bytes - 256;
-  int sw = budget / p.w_stage_bytes;
-  if (sw > 8) sw = 8;
-  if (sw < 2) return pl;
   if (over > sw * p.w_stage_bytes) return pl;
   p.sw = sw;
   p.tiles_w = W / 8; p.tiles_h = H / th; p.tiles_d = D / p.td; p.tiles_n = (N + p.tn - 1) / p.tn;
   p.N = N; p.D = D; p.H = H; p.W = W;
   p.CCin = CCin; p.Cout = Cout; p.CoutP = CoutP; p.CCout = sg_chunks(Cout);
   p.tmem_cols = round_pow2_cols(p.n_sub * NT);
-  const int n_kblocks = CCin / p.kb_chunks;
   const int64_t ctas = (int64_t)p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n * (CoutP / NT);
-  int splits = 1;
-  if (ctas < sg_num_sms()) {
-    int want = (int)((2 * sg_num_sms() + ctas - 1) / ctas);
-    for (int s = 1; s <= n_kblocks; ++s)
-      if (n_kblocks % s == 0 && s <= want) splits = s;
-  }
-  p.splits = splits;
-  p.kblocks_per_split = n_kblocks / splits;
   pl.NT = NT;
-  pl.smem = (size_t)p.a_bytes + (size_t)p.sw * p.w_stage_bytes + 8 * 24 + 4 * 128 + 16;
+  pl.big = big;
+  pl.smem = (size_t)p.a_stages * p.a_bytes + (size_t)p.sw * p.w_stage_bytes + 8 * 24 + 4 * 128 + 16;
   pl.grid = dim3((unsigned)(p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n), (unsigned)(CoutP / NT), (unsigned)splits);
   pl.ok = true;
+  // ---- estimated cycles (constants fitted to tools/plan_sweep.py measurements)
+  const double mma_cyc = NT == 128 ? 64.0 : NT == 64 ? 48.0 : 45.5;
+  const int co_res = (big || pl.smem > 112 * 1024 || p.tmem_cols > 256) ? 1 : 2;
+  const double n_cta = (double)ctas * splits;
+  const double slots = (double)sg_num_sms() * co_res;
+  const double waves = (double)(int64_t)((n_cta + slots - 1) / slots);
+  const double sharing = n_cta > sg_num_sms() ? co_res : 1.0;   // co-resident CTAs share one tensor pipe
+  // the generic kernel's issuing warp spends ~200 cycles per tap and ~100 per MMA; the specialised one keeps up
+  const double mmas_per_tap = (double)p.n_sub * (p.kb_chunks / 2);
+  double tap_cyc = mmas_per_tap * mma_cyc;
+  if (!pl.spec) {
+    const double issue = 200.0 + 100.0 * mmas_per_tap;
+    if (issue > tap_cyc) tap_cyc = issue;
+  }
+  // a weight stage: its MMAs (shared with the co-resident CTA), >= ~500 cycles of issue + barrier round
+  // (tools/bulk_bench.cu), and the load latency a shallow ring exposes (hidden in part by a co-resident CTA)
+  double stage = (double)p.tps * tap_cyc * sharing;
+  if (stage < kStageIssueCycles) stage = kStageIssueCycles;
+  const double exposed = kLoadLatencyCycles / ((p.sw - 1) * sharing);
+  if (stage < exposed) stage = exposed;
+  double body = (double)p.kblocks_per_split * (27 / p.tps) * stage;
+  if (p.a_stages == 1) body += (double)p.kblocks_per_split * kLoadLatencyCycles / sharing;   // single halo buffer
+  const double per_cta_bytes = (double)p.kblocks_per_split * (27.0 * p.w_tap_bytes + (double)p.kb_chunks * p.chunk_tx_bytes);
+  const double active = n_cta < slots ? n_cta : slots;
+  const double stream = active * per_cta_bytes / kL2BytesPerCycle;
+  if (stream > body) body = stream;
+  // epilogue: ~330 cycles per 16 accumulator columns per MMA tile; overlapped by the co-resident CTA's MMAs
+  const double epi = (double)p.n_sub * (NT / 16) * 330.0 * (sharing > 1.0 ? 0.5 : 1.0);
+  const double ws_bytes = (double)N * D * H * W * CoutP * 4.0;
+  pl.cost = waves * (body + kCtaFixedCycles + epi) +
+            (splits > 1 ? kSplitFixedCycles + ws_bytes * (2.5 + splits) / kL2BytesPerCycle : 0.0);
   return pl;
 }
 
-template <int NT>
-int launch(const Plan& pl, const CUtensorMap& map, cudaStream_t s) {
+// test / tuning hook: NT, big, td_max, splits (0 = choose by estimated cost)
+int g_force_plan[4] = {0, 0, 0, 0};
+
+Plan make_plan(int N, int Cin, int Cout, int D, int H, int W) {
+  if (g_force_plan[0] > 0)
+    return make_plan_cfg(N, Cin, Cout, D, H, W, g_force_plan[0], g_force_plan[1] != 0, g_force_plan[2] > 0 ? g_force_plan[2] : 8,
+                         g_force_plan[3] > 0 ? g_force_plan[3] : 1);
+  // the search walks ~1000 candidates: remember the winner per shape (launch-time cost matters in eager mode)
+  static std::mutex mu;
+  static std::map<std::array<int, 6>, Plan> cache;
+  const std::array<int, 6> key = {N, Cin, Cout, D, H, W};
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+  }
+  Plan best;
+  const int CCin = sg_chunks(Cin);
+  static const int nts[4] = {128, 64, 32, 16};
+  for (int ni = 0; ni < 4; ++ni)
+    for (int big = 0; big < 2; ++big)
+      for (int td_max = 8; td_max >= 1; td_max /= 2)
+        for (int splits = 1; splits <= CCin / 2; ++splits) {
+          if ((CCin / 2) % splits && (CCin / 4 == 0 || (CCin / 4) % splits)) continue;
+          Plan c = make_plan_cfg(N, Cin, Cout, D, H, W, nts[ni], big != 0, td_max, splits);
+          if (c.ok && (!best.ok || c.cost < best.cost)) best = c;
+        }
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    cache[key] = best;
+  }
+  return best;
+}
+
+template <int NT, int TD, int TH, int TN>
+int launch(const Plan& pl, const CUtensorMap& map, const CUtensorMap& wmap, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_tc<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_conv_tc<NT, TD, TH, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
     if (e != cudaSuccess) {
       sg_set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return (int)e;
     }
     attr_set = true;
   }
-  k_conv_tc<NT><<<pl.grid, kThreads, pl.smem, s>>>(map, pl.p);
+  k_conv_tc<NT, TD, TH, TN><<<pl.grid, kThreads, pl.smem, s>>>(map, wmap, pl.p);
   return sg_check_launch("sg_conv3d_fprop(tcgen05)");
+}
+
+template <int NT>
+int launch_spec(const Plan& pl, const CUtensorMap& map, const CUtensorMap& wmap, cudaStream_t s) {
+  const TcParams& p = pl.p;
+  if (p.th == 16 && p.tn == 1) {
+    if (p.td == 1) return launch<NT, 1, 16, 1>(pl, map, wmap, s);
+    if (p.td == 2) return launch<NT, 2, 16, 1>(pl, map, wmap, s);
+    if (p.td == 4) return launch<NT, 4, 16, 1>(pl, map, wmap, s);
+  } else if (p.th == 8 && p.td == 2) {
+    if (p.tn == 1) return launch<NT, 2, 8, 1>(pl, map, wmap, s);
+    if (p.tn == 2) return launch<NT, 2, 8, 2>(pl, map, wmap, s);
+  }
+  sg_set_error("conv_tc: no specialised kernel for tile %dx%dx%d", p.tn, p.td, p.th);
+  return -4;
 }
 
 }  // namespace
@@ -364,6 +568,9 @@ int encode_halo_map(CUtensorMap* map, const void* x, int N, int CC, int D, int H
 }  // namespace
 
 extern "C" void sg_tc_force_streaming(int on) { g_force_streaming = on; }
+extern "C" void sg_tc_force_plan(int nt, int big, int td_max, int splits) {
+  g_force_plan[0] = nt; g_force_plan[1] = big; g_force_plan[2] = td_max; g_force_plan[3] = splits;
+}
 
 int64_t sg_tc_wgrad_workspace_bytes(int N, int Cin, int Cout, int D, int H, int W);
 
@@ -433,12 +640,31 @@ int sg_tc_fprop(const void* x, const void* wp, const float* bias, const void* ma
     sg_set_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
     return -3;
   }
+  // packed weights [27][CCin][CoutP][8] as a 4-D tensor [64 = 8 co x 8 ci | CoutP/8 | CCin | 27]; box = one stage
+  CUtensorMap wmap;
+  {
+    cuuint64_t wd[4] = {64, (cuuint64_t)p.CoutP / 8, (cuuint64_t)p.CCin, 27};
+    cuuint64_t wst[3] = {128, (cuuint64_t)p.CoutP * 16, (cuuint64_t)p.CCin * p.CoutP * 16};
+    cuuint32_t wbox[4] = {64, (cuuint32_t)pl.NT / 8, (cuuint32_t)p.kb_chunks, (cuuint32_t)p.tps};
+    cuuint32_t we[4] = {1, 1, 1, 1};
+    r = encode(&wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(wp), wd, wst, wbox, we,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      sg_set_error("conv_tc: cuTensorMapEncodeTiled (weights) failed (%d)", (int)r);
+      return -3;
+    }
+  }
   int rc;
-  switch (pl.NT) {
-    case 16: rc = launch<16>(pl, map, s); break;
-    case 32: rc = launch<32>(pl, map, s); break;
-    case 64: rc = launch<64>(pl, map, s); break;
-    default: rc = launch<128>(pl, map, s); break;
+  if (pl.spec) {
+    rc = pl.NT == 128 ? launch_spec<128>(pl, map, wmap, s) : launch_spec<64>(pl, map, wmap, s);
+  } else {
+    switch (pl.NT) {
+      case 16: rc = launch<16, 0, 0, 0>(pl, map, wmap, s); break;
+      case 32: rc = launch<32, 0, 0, 0>(pl, map, wmap, s); break;
+      case 64: rc = launch<64, 0, 0, 0>(pl, map, wmap, s); break;
+      default: rc = launch<128, 0, 0, 0>(pl, map, wmap, s); break;
+    }
   }
   if (rc) return rc;
   if (p.splits > 1)
@@ -452,7 +678,7 @@ int sg_tc_fprop(const void* x, const void* wp, const float* bias, const void* ma
 extern "C" int sg_tc_plan_debug(int N, int Cin, int Cout, int D, int H, int W, int* out) {
   Plan pl = make_plan(N, Cin, Cout, D, H, W);
   const TcParams& p = pl.p;
-  int v[16] = {pl.ok, pl.NT, p.tn, p.td, p.th, p.n_sub, p.kb_chunks, p.sw, p.splits, p.kblocks_per_split,
+  int v[16] = {pl.ok, pl.NT, p.tn, p.td, p.th, p.n_sub, p.kb_chunks + 100 * p.tps + (pl.spec ? 10000 : 0), p.sw, p.splits, p.kblocks_per_split,
                (int)pl.grid.x, (int)pl.grid.y, (int)pl.grid.z, (int)pl.smem, p.tmem_cols, p.a_bytes};
   for (int i = 0; i < 16; ++i) out[i] = v[i];
   return 0;
