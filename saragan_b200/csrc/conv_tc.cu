@@ -281,20 +281,32 @@ k_conv_tc(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUte
       const bool valid = nl < p.tn && dh >= 1 && dh <= p.td && hh >= 1 && hh <= p.th && n < p.N && d < p.D &&
                          h < p.H && w < p.W;
       const int64_t vox = ((int64_t)d * p.H + h) * p.W + w;
-      for (int c0 = 0; c0 < NT; c0 += 16) {
-        float v[16];
+      constexpr int CB = NT < 64 ? NT : 64;   // accumulator columns per TMEM round trip
+      const bool direct = valid && p.splits == 1;
+#pragma unroll 1
+      for (int c0 = 0; c0 < NT; c0 += CB) {
+        const int64_t o = (((int64_t)n * p.CCout + (co0 + c0) / 8) * V + vox) * 8;
+        // the LeakyReLU-mask vectors of these columns are fetched before the accumulator round trip
+        uint4 mk[CB / 8];
+        if (direct && mask) {
+#pragma unroll
+          for (int q = 0; q < CB / 8; ++q) mk[q] = __ldg(reinterpret_cast<const uint4*>(mask + o + (int64_t)q * V * 8));
+        }
+        float v[CB];
         __syncwarp();   // tcgen05.ld is .sync.aligned: the warp must be converged here
-        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(sub * NT + c0), v);
+        tmem_ld_block<CB>(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(sub * NT + c0), v);
         if (!valid) {
           // row lies on a halo line / column or outside the volume: computed, discarded
         } else if (p.splits > 1) {
           float* dst = p.ws + ((int64_t)n * V + vox) * p.CoutP + co0 + c0;
-          // 16 consecutive fp32 of one workspace row: four 16-byte vector reductions instead of 16 scalar ones
+          // consecutive fp32 of one workspace row: 16-byte vector reductions instead of scalar ones
 #pragma unroll
-          for (int q = 0; q < 4; ++q) red_add_v4(dst + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          for (int q = 0; q < CB / 4; ++q) red_add_v4(dst + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         } else {
-          const int64_t o = (((int64_t)n * p.CCout + (co0 + c0) / 8) * V + vox) * 8;
-          epilogue16(v, s_bias + c0, scale, lrelu, mask ? mask + o : nullptr, yout + o, V * 8);
+#pragma unroll
+          for (int j = 0; j < CB / 16; ++j)
+            epilogue16_regmask(v + 16 * j, s_bias + c0 + 16 * j, scale, lrelu, mask != nullptr, mk[2 * j], mk[2 * j + 1],
+                               yout + o + (int64_t)(2 * j) * V * 8, V * 8);
         }
       }
     }

@@ -597,19 +597,34 @@ extern "C" int sg_interp(const float* real, const float* fake, const float* eps,
 // EqualizedLinear (network.py:59-77) with batch <= a few dozen rows: weight-bandwidth bound.
 // y[b][o] = act(scale * sum_i x[b][i]*w[o][i] + bias[o]);  one warp per output feature.
 #define LIN_BT 8
-// one 128-thread block per output feature: 512-8192 blocks keep every SM streaming weight rows
-__global__ void __launch_bounds__(128)
+// one 256-thread block per output feature streams that feature's weight row with 16-byte loads, four in
+// flight per thread (the first version's scalar loads left the 16.8 MB of D's 8192 -> 512 linear at
+// 0.36 TB/s); scalar tail / fallback when In is not a multiple of 4
+__global__ void __launch_bounds__(256)
 k_linear_fwd(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
              float* __restrict__ y, int B, int In, int Out, float scale, int lrelu) {
   const int o = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* wr = w + (int64_t)o * In;
-  __shared__ float red[4][LIN_BT];
+  const bool vec = (In & 3) == 0;
+  const int In4 = vec ? In >> 2 : 0;
+  __shared__ float red[8][LIN_BT];
   for (int b0 = 0; b0 < B; b0 += LIN_BT) {
     float acc[LIN_BT];
 #pragma unroll
     for (int k = 0; k < LIN_BT; ++k) acc[k] = 0.f;
-    for (int i = threadIdx.x; i < In; i += 128) {
+    const float4* wr4 = reinterpret_cast<const float4*>(wr);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < In4; i += 256) {
+      const float4 wv = __ldcs(wr4 + i);
+#pragma unroll
+      for (int k = 0; k < LIN_BT; ++k)
+        if (b0 + k < B) {
+          const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (int64_t)(b0 + k) * In) + i);
+          acc[k] = fmaf(wv.x, xv.x, fmaf(wv.y, xv.y, fmaf(wv.z, xv.z, fmaf(wv.w, xv.w, acc[k]))));
+        }
+    }
+    for (int i = 4 * In4 + threadIdx.x; i < In; i += 256) {
       const float wv = wr[i];
 #pragma unroll
       for (int k = 0; k < LIN_BT; ++k)
@@ -623,35 +638,55 @@ k_linear_fwd(const float* __restrict__ x, const float* __restrict__ w, const flo
     __syncthreads();
     if (threadIdx.x < LIN_BT && b0 + threadIdx.x < B) {
       const int k = threadIdx.x;
-      const float t = red[0][k] + red[1][k] + red[2][k] + red[3][k];
+      float t = 0.f;
+#pragma unroll
+      for (int wq = 0; wq < 8; ++wq) t += red[wq][k];
       const float r = scale * t + (bias ? bias[o] : 0.f);
       y[(int64_t)(b0 + k) * Out + o] = lrelu ? lrelu02(r) : r;
     }
     __syncthreads();
   }
 }
-// gx[b][i] = scale * sum_o g[b][o]*w[o][i];  thread per input feature, outputs split over
-// gridDim.y slices with atomics (gx zeroed by the entry point).
+// gx[b][i] = scale * sum_o g[b][o]*w[o][i];  a thread owns four consecutive input features (16-byte weight
+// loads, coalesced across the warp), the outputs are split over gridDim.y slices with atomics (gx zeroed by
+// the entry point).  V = 4 needs In % 4 == 0; V = 1 is the general form.
+template <int V>
 __global__ void k_linear_dgrad(const float* __restrict__ g, const float* __restrict__ w,
                                float* __restrict__ gx, int B, int In, int Out, float scale,
                                int o_per) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) * V;
   if (i >= In) return;
-  int o_lo = blockIdx.y * o_per;
-  int o_hi = o_lo + o_per < Out ? o_lo + o_per : Out;
+  const int o_lo = blockIdx.y * o_per;
+  const int o_hi = o_lo + o_per < Out ? o_lo + o_per : Out;
   for (int b0 = 0; b0 < B; b0 += LIN_BT) {
-    float acc[LIN_BT];
+    float acc[LIN_BT][V];
 #pragma unroll
-    for (int k = 0; k < LIN_BT; ++k) acc[k] = 0.f;
+    for (int k = 0; k < LIN_BT; ++k)
+#pragma unroll
+      for (int q = 0; q < V; ++q) acc[k][q] = 0.f;
+#pragma unroll 4
     for (int o = o_lo; o < o_hi; ++o) {
-      float wv = w[(int64_t)o * In + i];
+      float wv[V];
+      if (V == 4) {
+        const float4 t = __ldcs(reinterpret_cast<const float4*>(w + (int64_t)o * In + i));
+        wv[0] = t.x; wv[1 % V] = t.y; wv[2 % V] = t.z; wv[3 % V] = t.w;
+      } else {
+        wv[0] = w[(int64_t)o * In + i];
+      }
 #pragma unroll
       for (int k = 0; k < LIN_BT; ++k)
-        if (b0 + k < B) acc[k] += wv * __ldg(g + (int64_t)(b0 + k) * Out + o);
+        if (b0 + k < B) {
+          const float gv = __ldg(g + (int64_t)(b0 + k) * Out + o);
+#pragma unroll
+          for (int q = 0; q < V; ++q) acc[k][q] = fmaf(wv[q], gv, acc[k][q]);
+        }
     }
 #pragma unroll
     for (int k = 0; k < LIN_BT; ++k)
-      if (b0 + k < B) atomicAdd(gx + (int64_t)(b0 + k) * In + i, scale * acc[k]);
+      if (b0 + k < B) {
+#pragma unroll
+        for (int q = 0; q < V; ++q) atomicAdd(gx + (int64_t)(b0 + k) * In + i + q, scale * acc[k][q]);
+      }
   }
 }
 // gw[o][i] = scale * sum_b g[b][o]*x[b][i];  gb[o] = sum_b g[b][o]
@@ -676,20 +711,24 @@ __global__ void k_linear_wgrad(const float* __restrict__ g, const float* __restr
 extern "C" int sg_linear_fwd(const float* x, const float* w, const float* bias, float* y, int B,
                              int In, int Out, float scale, int lrelu, cudaStream_t s) {
   if (B == 0 || Out == 0) return 0;
-  k_linear_fwd<<<(unsigned)Out, 128, 0, s>>>(x, w, bias, y, B, In, Out, scale, lrelu);
+  k_linear_fwd<<<(unsigned)Out, 256, 0, s>>>(x, w, bias, y, B, In, Out, scale, lrelu);
   return sg_check_launch("sg_linear_fwd");
 }
 extern "C" int sg_linear_dgrad(const float* g, const float* w, float* gx, int B, int In, int Out,
                                float scale, cudaStream_t s) {
   if (B == 0 || In == 0) return 0;
   cudaMemsetAsync(gx, 0, sizeof(float) * (size_t)B * In, s);
-  int bx = (In + 127) / 128;
-  int splits = (sg_num_sms() * 2 + bx - 1) / bx;
+  const int V = (In & 3) == 0 ? 4 : 1;
+  int bx = (In / V + 127) / 128;
+  int splits = (sg_num_sms() * 4 + bx - 1) / bx;
   if (splits > Out) splits = Out;
   if (splits < 1) splits = 1;
   int o_per = (Out + splits - 1) / splits;
   splits = (Out + o_per - 1) / o_per;
-  k_linear_dgrad<<<dim3(bx, splits), 128, 0, s>>>(g, w, gx, B, In, Out, scale, o_per);
+  if (V == 4)
+    k_linear_dgrad<4><<<dim3(bx, splits), 128, 0, s>>>(g, w, gx, B, In, Out, scale, o_per);
+  else
+    k_linear_dgrad<1><<<dim3(bx, splits), 128, 0, s>>>(g, w, gx, B, In, Out, scale, o_per);
   return sg_check_launch("sg_linear_dgrad");
 }
 extern "C" int sg_linear_wgrad(const float* g, const float* x, float* gw, float* gb, int B, int In,

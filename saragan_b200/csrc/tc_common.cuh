@@ -119,6 +119,30 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// CB (16, 32 or 64) consecutive accumulator columns of this thread's row: all loads issued back to back, ONE
+// wait (a wait per 16 columns cost the epilogue ~300 cycles per block).  The empty asm statements after the
+// wait pin every consumer of the registers behind it (volatile asms keep their order).
+template <int CB>
+__device__ __forceinline__ void tmem_ld_block(uint32_t taddr, float (&v)[CB]) {
+  uint32_t r[CB];
+#pragma unroll
+  for (int j = 0; j < CB / 16; ++j) {
+    uint32_t* q = r + 16 * j;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+        "%15}, [%16];"
+        : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+          "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
+        : "r"(taddr + 16u * j));
+  }
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < CB; ++i) {
+    asm volatile("" : "+r"(r[i]));
+    v[i] = __uint_as_float(r[i]);
+  }
+}
+
 constexpr int kMaxSub = 8;   // MMA tiles (128 rows each) per CTA tile
 
 __device__ __forceinline__ F8 unpack8(const uint4& u) {
@@ -197,7 +221,7 @@ __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c
 
 // Same as epilogue16 with the two mask vectors already in registers (prefetched while the MMAs of
 // the tile were still running, so their global-load latency is off the epilogue's critical path).
-__device__ __forceinline__ void epilogue16_regmask(const float (&v)[16], const float* sb, float scale, int lrelu,
+__device__ __forceinline__ void epilogue16_regmask(const float* v, const float* sb, float scale, int lrelu,
                                                    bool has_mask, const uint4& m0, const uint4& m1, __nv_bfloat16* y,
                                                    int64_t chunk_stride) {
   float r[16];
