@@ -70,6 +70,9 @@ int64_t sg_conv3d_workspace_bytes(int kind, int dtype, int N, int Cin, int Cout,
 /* test hook: 0 = auto; 1 = always the streaming tcgen05 kernel; 2 = the weight-resident kernel
  * whenever its geometry constraints hold (ignoring the tile-count heuristic) */
 void sg_tc_force_streaming(int mode);
+/* test hook for the weight-resident kernel: 0 = z-stacked form (kd taps stacked along the MMA N dimension)
+ * whenever NT <= 32 allows it; 1 = never */
+void sg_tc_res_zs_mode(int mode);
 /* test / tuning hook for the streaming kernel: force the tiling (output channels per CTA nt in
  * {128,64,32,16}; big = tiles for one CTA per SM; td_max = planes per tile cap; splits = split-K
  * factor) instead of choosing by estimated cost; nt = 0 restores the automatic choice */

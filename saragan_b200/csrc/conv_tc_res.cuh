@@ -8,6 +8,16 @@
 //     tile boundaries through a ring of halo stages;
 //   * two TMEM accumulator sets: the epilogue of tile i overlaps the MMAs of tile i+1.
 // Geometry, operand descriptors and epilogue are those of k_conv_tc.
+//
+// ZS ("z-stacked") variant for NT <= 32.  An M = 128 MMA costs ~45 cycles for any N <= 32 (the A operand read
+// bounds it, tools/mma_bench.cu), so a 32-channel layer reaches half the tensor rate of a 64-channel one.
+// Instead of accumulating y[p] += x[p + kd - 1] * W[kd] (three MMAs with three different A operands per
+// output plane), the ZS kernel computes Z[q][kd] = x[q] * W[kd] for every INPUT plane q of the halo tile with
+// the kd taps stacked along N (one MMA, A = plane q, N up to 3*NT: 56 cycles for N = 96), and the epilogue
+// forms y[p] = Z[p-1][0] + Z[p][1] + Z[p+1][2] -- the three terms sit in the SAME accumulator row (TMEM lane)
+// of three different column blocks, so the sum costs the epilogue thread two adds per value.  Per (kh, kw,
+// K step) that is TD + 2 MMAs instead of 3 * TD, each at least as wide: 1.46x fewer tensor cycles at
+// NT = 32, TD = 2 and 2x at NT = 16, TD = 4.  Input plane q only needs the kd with 0 <= q - kd + 1 < TD.
 #pragma once
 
 namespace {
@@ -43,10 +53,28 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // KBC = 8-channel chunks per K block.  With th = 16 and tw = 8 fixed, every descriptor offset of
 // the 27 x KBC/2 x TD MMAs of a K block is a compile-time constant: the fully unrolled issue
 // loop costs one uniform-datapath add per MMA.
-template <int NT, int TD, int KBC>
+// columns of one ZS accumulator set: input plane j - 1 (j = 0 .. TD+1) holds the kd range [kd0(j), kd1(j)]
+struct ZsMap {
+  int col[8], kd0[8], cnt[8], total;
+};
+constexpr ZsMap zs_map(int td, int nt) {
+  ZsMap m{};
+  int c = 0;
+  for (int j = 0; j < td + 2; ++j) {
+    const int q = j - 1;
+    const int lo = q + 2 - td > 0 ? q + 2 - td : 0, hi = q + 1 < 2 ? q + 1 : 2;
+    m.col[j] = c; m.kd0[j] = lo; m.cnt[j] = hi - lo + 1;
+    c += (hi - lo + 1) * nt;
+  }
+  m.total = c;
+  return m;
+}
+
+template <int NT, int TD, int KBC, bool ZS>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ ResParams p) {
   constexpr int HALO_H = 18, HALO_W = 10;
+  constexpr ZsMap ZM = zs_map(TD, NT);
   constexpr int CHUNK_BYTES = ((TD + 2) * HALO_H * HALO_W * 16 + 127) / 128 * 128;
   constexpr uint32_t KK_A = (2u * CHUNK_BYTES) >> 4;
   constexpr uint32_t PLANE = HALO_H * HALO_W;   // voxels (16-byte units) per halo plane
@@ -87,7 +115,7 @@ k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int acc_cols = p.n_sub * NT;      // columns of one accumulator set
+  const int acc_cols = ZS ? ZM.total : p.n_sub * NT;      // columns of one accumulator set
   float* s_bias = reinterpret_cast<float*>(bars + 16);   // NT floats, 16-byte aligned, after the barriers
 
   if (warp == 0) {
@@ -96,8 +124,14 @@ k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
       // resident weights: 27*CCin pieces of NT rows x 16 B, contiguous in the packed tensor
       const uint32_t w_addr = smem_u32(w_smem);
       mbar_expect_tx(BAR(W_FULL), (uint32_t)p.w_bytes);
-      for (int i = 0; i < 27 * p.CCin; ++i)
-        bulk_load(w_addr + i * NT * 16, p.wp + ((int64_t)i * p.CoutP + co0) * 8, NT * 16u, BAR(W_FULL));
+      for (int i = 0; i < 27 * p.CCin; ++i) {
+        uint32_t dst = w_addr + i * NT * 16;
+        if (ZS) {   // [kh][kw][chunk][kd][co][8]: the three kd taps of a (kh, kw, chunk) are consecutive N rows
+          const int tap = i / p.CCin, chunk = i - tap * p.CCin;
+          dst = w_addr + ((((tap % 9) * p.CCin + chunk) * 3 + tap / 9) * NT) * 16;
+        }
+        bulk_load(dst, p.wp + ((int64_t)i * p.CoutP + co0) * 8, NT * 16u, BAR(W_FULL));
+      }
       const uint32_t a_addr = smem_u32(a_smem);
       const uint32_t a_tx = (uint32_t)p.kb_chunks * (uint32_t)p.chunk_tx_bytes;
       int it = 0;
@@ -128,6 +162,8 @@ k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
       const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4;
       const int stages = p.stages, n_kblocks = p.n_kblocks;
       const uint32_t w_tap16 = (uint32_t)(p.CCin * NT);
+      const uint64_t wz_desc0 = make_desc(smem_u32(w_smem), 3 * NT * 16u, 128u);
+      const uint32_t wz_khw16 = (uint32_t)(p.CCin * 3 * NT);
       mbar_wait(BAR(W_FULL), 0);
       int s = 0, ph = 0, ti = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
@@ -139,8 +175,26 @@ k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
           mbar_wait(BAR(A_FULL + s), ph);
           tc_fence_after();
           const uint64_t a_stage = a_desc0 + (uint64_t)(s * stage16);
-          uint64_t b_tap = w_desc0 + (uint64_t)(kb * (KBC * NT));
           const uint32_t acc0 = kb != 0;
+          if constexpr (ZS) {
+            // B rows [kd][co] of a (kh, kw, chunk): chunk stride (LBO) = 3*NT rows
+            uint64_t b_khw = wz_desc0 + (uint64_t)(kb * (KBC * 3 * NT));
+#pragma unroll
+            for (int khw = 0; khw < 9; ++khw) {
+              const uint32_t a_off = (uint32_t)((khw / 3) * HALO_W + khw % 3);
+#pragma unroll
+              for (int kk = 0; kk < KBC / 2; ++kk)
+#pragma unroll
+                for (int j = 0; j < TD + 2; ++j) {
+                  const uint32_t idz = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((ZM.cnt[j] * NT) >> 3) << 17) |
+                                       ((128u >> 4) << 24);
+                  tc_mma(d_tmem + ZM.col[j], a_stage + (uint64_t)(a_off + j * PLANE + kk * KK_A),
+                         b_khw + (uint64_t)(kk * 2 * 3 * NT + ZM.kd0[j] * NT), idz, (khw | kk) ? 1u : acc0, leader);
+                }
+              b_khw += wz_khw16;
+            }
+          } else {
+          uint64_t b_tap = w_desc0 + (uint64_t)(kb * (KBC * NT));
 #pragma unroll
           for (int tap = 0; tap < 27; ++tap) {
             // output voxel (d,h,w) of MMA tile `sub` reads halo voxel (sub+kd, h+kh, w+kw)
@@ -152,6 +206,7 @@ k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
                 tc_mma(d_tmem + sub * NT, a_stage + (uint64_t)(a_off + sub * PLANE + kk * KK_A),
                        b_tap + (uint64_t)(kk * 2 * NT), idesc, (tap | kk) ? 1u : acc0, leader);
             b_tap += w_tap16;
+          }
           }
           tc_commit(BAR(A_EMPTY + s), leader);
           if (++s == stages) { s = 0; ph ^= 1; }
@@ -200,7 +255,18 @@ k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
         for (int c0 = 0; c0 < NT; c0 += 16) {
           float v[16];
           __syncwarp();
-          tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * acc_cols + sub * NT + c0), v);
+          const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * acc_cols);
+          if constexpr (ZS) {
+            // y[plane sub] = Z[sub-1][kd 0] + Z[sub][kd 1] + Z[sub+1][kd 2]: same lane, three column blocks
+            float z[48];
+            tmem_ld3x16(trow + (uint32_t)(ZM.col[sub] + (0 - ZM.kd0[sub]) * NT + c0),
+                        trow + (uint32_t)(ZM.col[sub + 1] + (1 - ZM.kd0[sub + 1]) * NT + c0),
+                        trow + (uint32_t)(ZM.col[sub + 2] + (2 - ZM.kd0[sub + 2]) * NT + c0), z);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = z[i] + z[16 + i] + z[32 + i];
+          } else {
+            tmem_ld16(trow + (uint32_t)(sub * NT + c0), v);
+          }
           epilogue16_regmask(v, s_bias + c0, scale, lrelu, mask != nullptr, mk[sub][c0 / 8], mk[sub][c0 / 8 + 1],
                              yout + obase0 + sub * plane8 + (int64_t)(c0 / 8) * V * 8, V * 8);
         }
@@ -223,10 +289,13 @@ k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
 struct ResPlan {
   bool ok = false;
   int NT = 0;
+  bool zs = false;   // kd taps stacked along N (NT <= 32)
   ResParams p{};
   size_t smem = 0;
   dim3 grid;
 };
+
+int g_res_zs_mode = 0;   // test hook: 0 = auto, 1 = never z-stack, 2 = z-stack whenever possible
 
 // Applies when H >= 16, W % 8 == 0 and the weight slice of one N tile fits next to >= 2 halo stages.
 ResPlan make_res_plan(int N, int Cin, int Cout, int D, int H, int W, bool for_test = false) {
@@ -248,9 +317,22 @@ ResPlan make_res_plan(int N, int Cin, int Cout, int D, int H, int W, bool for_te
   p.halo_w = 10; p.halo_h = 18;
   p.kb_chunks = CCin % 4 == 0 ? 4 : 2;
   p.n_kblocks = CCin / p.kb_chunks;
-  // td: two accumulator sets of td MMA tiles must fit TMEM; >= 2 stages must fit shared memory
+  // td: two accumulator sets of td MMA tiles must fit TMEM; >= 2 stages must fit shared memory.  NT <= 32
+  // prefers the z-stacked form, whose accumulator set is 3*td*NT columns wide (td = 2 at NT = 32, 4 at 16).
   int best_td = 0;
-  for (int td = 1; td <= D && td <= 4; td *= 2) {
+  bool zs = false;
+  if (NT <= 32 && g_res_zs_mode != 1) {
+    for (int td = 1; td <= D && td <= 4; td *= 2) {
+      if (D % td || td == 1) continue;
+      if (2 * 3 * td * NT > 512) continue;
+      int chunk = ((td + 2) * 18 * 10 * 16 + 127) / 128 * 128;
+      int stage = p.kb_chunks * chunk;
+      if (p.w_bytes + 2 * stage + 4096 + 512 > budget) continue;
+      best_td = td;
+      zs = true;
+    }
+  }
+  for (int td = 1; td <= D && td <= 4 && !zs; td *= 2) {
     if (D % td) continue;
     if (2 * td * NT > 512) continue;
     int chunk = ((td + 2) * 18 * 10 * 16 + 127) / 128 * 128;
@@ -273,7 +355,8 @@ ResPlan make_res_plan(int N, int Cin, int Cout, int D, int H, int W, bool for_te
   p.n_tiles = p.tiles_w * p.tiles_h * p.tiles_d * N;
   p.N = N; p.D = D; p.H = H; p.W = W;
   p.CCin = CCin; p.Cout = Cout; p.CoutP = CoutP; p.CCout = sg_chunks(Cout);
-  p.tmem_cols = round_pow2_cols(2 * p.n_sub * NT);
+  p.tmem_cols = round_pow2_cols(2 * (zs ? 3 : 1) * p.n_sub * NT);
+  pl.zs = zs;
   const int n_ntiles = CoutP / NT;
   int ctas = sg_num_sms() / n_ntiles;
   if (ctas > p.n_tiles) ctas = p.n_tiles;
@@ -291,33 +374,46 @@ ResPlan make_res_plan(int N, int Cin, int Cout, int D, int H, int W, bool for_te
   return pl;
 }
 
-template <int NT, int TD, int KBC>
+template <int NT, int TD, int KBC, bool ZS>
 int launch_res_inst(const ResPlan& pl, const CUtensorMap& map, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e =
-        cudaFuncSetAttribute(k_conv_tc_res<NT, TD, KBC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_conv_tc_res<NT, TD, KBC, ZS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       sg_set_error("conv_tc_res: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return (int)e;
     }
     attr_set = true;
   }
-  k_conv_tc_res<NT, TD, KBC><<<pl.grid, kThreads, pl.smem, s>>>(map, pl.p);
+  k_conv_tc_res<NT, TD, KBC, ZS><<<pl.grid, kThreads, pl.smem, s>>>(map, pl.p);
   return sg_check_launch("sg_conv3d_fprop(tcgen05 resident)");
 }
 
 template <int NT>
 int launch_res(const ResPlan& pl, const CUtensorMap& map, cudaStream_t s) {
   const int td = pl.p.td, kbc = pl.p.kb_chunks;
+  if constexpr (NT <= 32) {
+    if (pl.zs) {
+      if (kbc == 4) {
+        if (td == 2) return launch_res_inst<NT, 2, 4, true>(pl, map, s);
+        if (td == 4 && NT == 16) return launch_res_inst<NT == 16 ? 16 : 32, NT == 16 ? 4 : 2, 4, true>(pl, map, s);
+      } else {
+        if (td == 2) return launch_res_inst<NT, 2, 2, true>(pl, map, s);
+        if (td == 4 && NT == 16) return launch_res_inst<NT == 16 ? 16 : 32, NT == 16 ? 4 : 2, 2, true>(pl, map, s);
+      }
+      sg_set_error("conv_tc_res: no z-stacked instantiation for td=%d kb_chunks=%d", td, kbc);
+      return -4;
+    }
+  }
   if (kbc == 4) {
-    if (td == 1) return launch_res_inst<NT, 1, 4>(pl, map, s);
-    if (td == 2) return launch_res_inst<NT, 2, 4>(pl, map, s);
-    if (td == 4) return launch_res_inst<NT, 4, 4>(pl, map, s);
+    if (td == 1) return launch_res_inst<NT, 1, 4, false>(pl, map, s);
+    if (td == 2) return launch_res_inst<NT, 2, 4, false>(pl, map, s);
+    if (td == 4) return launch_res_inst<NT, 4, 4, false>(pl, map, s);
   } else {
-    if (td == 1) return launch_res_inst<NT, 1, 2>(pl, map, s);
-    if (td == 2) return launch_res_inst<NT, 2, 2>(pl, map, s);
-    if (td == 4) return launch_res_inst<NT, 4, 2>(pl, map, s);
+    if (td == 1) return launch_res_inst<NT, 1, 2, false>(pl, map, s);
+    if (td == 2) return launch_res_inst<NT, 2, 2, false>(pl, map, s);
+    if (td == 4) return launch_res_inst<NT, 4, 2, false>(pl, map, s);
   }
   sg_set_error("conv_tc_res: no instantiation for td=%d kb_chunks=%d", td, kbc);
   return -4;

@@ -143,6 +143,28 @@ __device__ __forceinline__ void tmem_ld_block(uint32_t taddr, float (&v)[CB]) {
   }
 }
 
+// three 16-column blocks of this thread's row (three accumulators of the z-stacked kernel), one wait
+__device__ __forceinline__ void tmem_ld3x16(uint32_t t0, uint32_t t1, uint32_t t2, float (&v)[48]) {
+  uint32_t r[48];
+  const uint32_t ta[3] = {t0, t1, t2};
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    uint32_t* q = r + 16 * j;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+        "%15}, [%16];"
+        : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+          "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
+        : "r"(ta[j]));
+  }
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 48; ++i) {
+    asm volatile("" : "+r"(r[i]));
+    v[i] = __uint_as_float(r[i]);
+  }
+}
+
 constexpr int kMaxSub = 8;   // MMA tiles (128 rows each) per CTA tile
 
 __device__ __forceinline__ F8 unpack8(const uint4& u) {

@@ -62,7 +62,8 @@ RES_SHAPES = [
 
 @pytest.mark.parametrize("shape", RES_SHAPES)
 @pytest.mark.parametrize("flip", [False, True])
-def test_tcgen05_resident_kernel_matches_direct(shape, flip):
+@pytest.mark.parametrize("zs", [0, 1])
+def test_tcgen05_resident_kernel_matches_direct(shape, flip, zs):
     """The persistent weight-resident kernel (forced via the test hook so that small shapes take it
     and every CTA walks several tiles) against the direct kernel and the streaming tcgen05 kernel."""
     n, cin, cout, d, h, w = shape
@@ -74,6 +75,7 @@ def test_tcgen05_resident_kernel_matches_direct(shape, flip):
     bias = torch.randn(kout, generator=g).cuda()
     wp = K.pack_conv_weight(wt.cuda(), BF, flip)
     lib = _lib.load()
+    lib.sg_tc_res_zs_mode(zs)   # 0: z-stacked accumulators where NT <= 32 allows; 1: one accumulator per output plane
     try:
         for (b, lrelu, mask) in [(None, False, False), (bias, True, True)]:
             args = (xg, wp, b, mg if mask else None, kin, kout, 0.05, lrelu)
@@ -87,6 +89,7 @@ def test_tcgen05_resident_kernel_matches_direct(shape, flip):
             assert rel_err(res.float(), stream.float()) < 3e-3, (shape, flip, "resident vs streaming")
     finally:
         lib.sg_tc_force_streaming(0)
+        lib.sg_tc_res_zs_mode(0)
 
 
 WGRAD_SHAPES = [
