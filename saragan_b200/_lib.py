@@ -32,6 +32,7 @@ SIGNATURES = {
     "sg_pack_conv_weight": [_c_p, _c_p, _c_int, _c_int, _c_int, _c_int, _c_p],
     "sg_conv3d_fprop": [_c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                         _c_int, _c_f, _c_int, _c_int, _c_p, _c_i64, _c_p],
+    "sg_set_pdl": [_c_int],
     "sg_tc_force_streaming": [_c_int],
     "sg_tc_res_zs_mode": [_c_int],
     "sg_tc_force_plan": [_c_int, _c_int, _c_int, _c_int],
@@ -64,7 +65,7 @@ SIGNATURES = {
 }
 _RESTYPES = {"sg_last_error": ctypes.c_char_p, "sg_packed_weight_elems": ctypes.c_int64,
              "sg_conv3d_workspace_bytes": ctypes.c_int64, "sg_launch_count": ctypes.c_int64, "sg_cuda_core_fallbacks": ctypes.c_int64,
-             "sg_tc_force_streaming": None, "sg_tc_res_zs_mode": None, "sg_tc_force_plan": None}
+             "sg_set_pdl": None, "sg_tc_force_streaming": None, "sg_tc_res_zs_mode": None, "sg_tc_force_plan": None}
 
 _lib = None
 
@@ -83,6 +84,8 @@ def load() -> ctypes.CDLL:
             fn = getattr(lib, name)
             fn.argtypes = argtypes
             fn.restype = _RESTYPES.get(name, ctypes.c_int)
+        if os.environ.get("SARAGAN_PDL", "0") == "1":   # A/B switch for programmatic dependent launch
+            lib.sg_set_pdl(1)
         _lib = lib
     return _lib
 

@@ -114,3 +114,34 @@ __device__ __forceinline__ float warp_sum(float v) {
       return -1;                                                          \
     }                                                                     \
   } while (0)
+
+// ------------------------------------------------------------------- programmatic dependent launch
+// OPTIONAL (sg_set_pdl(1), off by default).  Every kernel of the library goes through sg_launch and starts with
+// sg_pdl_enter(): with the programmatic-stream-serialization attribute set, `launch_dependents` lets the
+// NEXT kernel of the stream be scheduled as soon as all CTAs of this one have started, `wait` blocks until
+// the PREVIOUS kernel has completed and flushed -- so no kernel touches global memory before its producer is
+// done, and completion stays transitive along the stream.  (The tcgen05 kernels run barrier init, TMEM
+// allocation and tensor-map prefetch before the wait.)  Without the attribute both instructions are no-ops.
+// Measured on the cfg3 step (CUDA-graph replay, ~800 kernels): 17.57 ms with the attribute against 17.22 ms
+// without -- early-resident dependents cost more than the launch gaps they hide -- hence off by default.
+__device__ __forceinline__ void sg_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void sg_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void sg_pdl_enter() {
+  sg_pdl_trigger();
+  sg_pdl_wait();
+}
+extern int g_sg_pdl;   // 1 = launch with the attribute, 0 (default) = plain stream order (sg_set_pdl)
+template <typename... KArgs, typename... Args>
+inline void sg_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_sg_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface in sg_check_launch
+}

@@ -35,6 +35,7 @@ extern "C" int64_t sg_cuda_core_fallbacks(int reset) {
 template <typename T>
 __global__ void k_pack_conv_weight(const float* __restrict__ w, T* __restrict__ dst, int Cout,
                                    int Cin, int transpose_flip) {
+  sg_pdl_enter();
   int K = transpose_flip ? Cout : Cin;     // contraction channels
   int R = transpose_flip ? Cin : Cout;     // output rows
   int KC = 2 * ((K + 15) / 16);
@@ -67,7 +68,7 @@ extern "C" int64_t sg_packed_weight_elems(int Cout, int Cin, int transpose_flip)
 extern "C" int sg_pack_conv_weight(const float* w, void* dst, int dtype, int Cout, int Cin,
                                    int transpose_flip, cudaStream_t s) {
   int64_t total = sg_packed_weight_elems(Cout, Cin, transpose_flip);
-  SG_DISPATCH(dtype, k_pack_conv_weight<T><<<sg_grid(total, 256), 256, 0, s>>>(w, (T*)dst, Cout, Cin, transpose_flip););
+  SG_DISPATCH(dtype, sg_launch((k_pack_conv_weight<T>), sg_grid(total, 256), 256, 0, s, w, (T*)dst, Cout, Cin, transpose_flip););
   return sg_check_launch("sg_pack_conv_weight");
 }
 
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(128)
 k_conv_direct(const T* __restrict__ x, const T* __restrict__ wp, const float* __restrict__ bias,
               const T* __restrict__ mask_src, T* __restrict__ y, int Cout, int CCin, int CCout,
               int CoutP, int D, int H, int W, float scale, int lrelu) {
+  sg_pdl_enter();
   int64_t V = (int64_t)D * H * W;
   int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int cco = blockIdx.y;
@@ -166,6 +168,7 @@ static SmallTaps small_taps(int CCin, int D, int H, int W, int64_t blocks_per_ta
 __global__ void __launch_bounds__(256)
 k_conv_small_f32(const float* __restrict__ x, const float* __restrict__ wp, float* __restrict__ acc,
                  int N, int CCin, int CoutP, int D, int H, int W, SmallTaps st) {
+  sg_pdl_enter();
   __shared__ float As[16][64 + 4];
   __shared__ float Bs[16][64 + 4];
   int z = blockIdx.z;
@@ -247,6 +250,7 @@ template <typename T>
 __global__ void k_conv_finish(const float* __restrict__ acc, const float* __restrict__ bias,
                               const T* __restrict__ mask_src, T* __restrict__ y, int N, int Cout,
                               int CCout, int CoutP, int64_t V, float scale, int lrelu) {
+  sg_pdl_enter();
   int64_t total = (int64_t)N * CCout * V;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -275,7 +279,7 @@ int sg_conv_finish_bf16(const float* acc, const float* bias, const void* mask_sr
                         int Cout, int64_t V, float scale, int lrelu, cudaStream_t s) {
   int CCout = sg_chunks(Cout), CoutP = 16 * ((Cout + 15) / 16);
   int64_t total = (int64_t)N * CCout * V;
-  k_conv_finish<__nv_bfloat16><<<sg_grid(total, 256), 256, 0, s>>>(
+  sg_launch((k_conv_finish<__nv_bfloat16>), sg_grid(total, 256), 256, 0, s, 
       acc, bias, (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)y, N, Cout, CCout, CoutP, V, scale, lrelu);
   return sg_check_launch("sg_conv_finish");
 }
@@ -295,11 +299,11 @@ static int launch_small_f32(const void* x, const void* wp, const float* bias, co
   const int64_t mt = (M + 63) / 64, nt = (CoutP + 63) / 64;
   const SmallTaps st = small_taps(CCin, D, H, W, mt * nt);
   dim3 grid((unsigned)mt, (unsigned)nt, (unsigned)(st.nkd * st.nkh * st.nkw * st.ksplit));
-  k_conv_small_f32<<<grid, 256, 0, s>>>((const float*)x, (const float*)wp, (float*)ws, N, CCin, CoutP, D, H, W, st);
+  sg_launch((k_conv_small_f32), grid, 256, 0, s, (const float*)x, (const float*)wp, (float*)ws, N, CCin, CoutP, D, H, W, st);
   int rc = sg_check_launch("sg_conv3d_fprop(small f32)");
   if (rc) return rc;
   int64_t total = (int64_t)N * CCout * V;
-  k_conv_finish<float><<<sg_grid(total, 256), 256, 0, s>>>((const float*)ws, bias, (const float*)mask_src,
+  sg_launch((k_conv_finish<float>), sg_grid(total, 256), 256, 0, s, (const float*)ws, bias, (const float*)mask_src,
                                                           (float*)y, N, Cout, CCout, CoutP, V, scale, lrelu);
   return sg_check_launch("sg_conv3d_fprop(small f32 finish)");
 }
@@ -324,7 +328,7 @@ static int launch_direct_fprop(const void* x, const void* wp, const float* bias,
   int CoutP = 16 * ((Cout + 15) / 16);
   int64_t V = (int64_t)D * H * W;
   dim3 grid((unsigned)((V + 127) / 128), (unsigned)CCout, (unsigned)N);
-  k_conv_direct<T><<<grid, 128, 0, s>>>((const T*)x, (const T*)wp, bias, (const T*)mask_src, (T*)y,
+  sg_launch((k_conv_direct<T>), grid, 128, 0, s, (const T*)x, (const T*)wp, bias, (const T*)mask_src, (T*)y,
                                         Cout, CCin, CCout, CoutP, D, H, W, scale, lrelu);
   return sg_check_launch("sg_conv3d_fprop(direct)");
 }
@@ -358,6 +362,7 @@ __global__ void __launch_bounds__(128)
 k_wgrad_direct(const T* __restrict__ x, const T* __restrict__ gy, float* __restrict__ gw, int N,
                int Cin, int Cout, int CCin, int CCout, int D, int H, int W, float scale,
                int64_t per_slab) {
+  sg_pdl_enter();
   int tap = blockIdx.z;
   int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
   int cco = blockIdx.y / CCin;
@@ -408,6 +413,7 @@ k_wgrad_direct(const T* __restrict__ x, const T* __restrict__ gy, float* __restr
 __global__ void __launch_bounds__(256)
 k_wgrad_small_f32(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gw,
                   int N, int Cin, int Cout, int CCin, int CCout, int D, int H, int W, float scale) {
+  sg_pdl_enter();
   __shared__ float As[16][64 + 4];   // [m][co]
   __shared__ float Bs[16][64 + 4];   // [m][ci]
   const int tap = blockIdx.z;
@@ -480,7 +486,7 @@ static int launch_direct_wgrad(const void* x, const void* gy, float* gw, int N, 
   slabs = (total + per - 1) / per;
   SG_REQUIRE((int64_t)CCin * CCout <= 65535, "sg_conv3d_wgrad(direct): too many channel chunks");
   dim3 grid((unsigned)slabs, (unsigned)(CCin * CCout), 27);
-  k_wgrad_direct<T><<<grid, 128, 0, s>>>((const T*)x, (const T*)gy, gw, N, Cin, Cout, CCin, CCout,
+  sg_launch((k_wgrad_direct<T>), grid, 128, 0, s, (const T*)x, (const T*)gy, gw, N, Cin, Cout, CCin, CCout,
                                          D, H, W, scale, per);
   return sg_check_launch("sg_conv3d_wgrad(direct)");
 }
@@ -506,7 +512,7 @@ extern "C" int sg_conv3d_wgrad(const void* x, const void* gy, float* gw, float* 
   if (impl == SG_IMPL_AUTO && N > 0 && small_f32_applies(dtype, N, D, H, W)) {
     int CCin = sg_chunks(Cin), CCout = sg_chunks(Cout);
     dim3 grid((unsigned)((Cout + 63) / 64), (unsigned)((Cin + 63) / 64), 27);
-    k_wgrad_small_f32<<<grid, 256, 0, s>>>((const float*)x, (const float*)gy, gw, N, Cin, Cout, CCin, CCout, D, H,
+    sg_launch((k_wgrad_small_f32), grid, 256, 0, s, (const float*)x, (const float*)gy, gw, N, Cin, Cout, CCin, CCout, D, H,
                                            W, scale);
     return sg_check_launch("sg_conv3d_wgrad(small f32)");
   }

@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(kThreads)
 k_conv_tc(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap,
           const __grid_constant__ TcParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
+  sg_pdl_trigger();
   // carve-up: [A halo block][weight ring][barriers][tmem base]
   uint8_t* a_smem = smem;
   uint8_t* w_smem = smem + p.a_stages * p.a_bytes;
@@ -145,6 +146,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUte
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  sg_pdl_wait();   // everything above touched only shared / tensor memory and kernel parameters
 
   if (warp == 0) {
     // ================================ producer ================================
@@ -527,7 +529,7 @@ int launch(const Plan& pl, const CUtensorMap& map, const CUtensorMap& wmap, cuda
     }
     attr_set = true;
   }
-  k_conv_tc<NT, TD, TH, TN><<<pl.grid, kThreads, pl.smem, s>>>(map, wmap, pl.p);
+  sg_launch((k_conv_tc<NT, TD, TH, TN>), pl.grid, kThreads, pl.smem, s, map, wmap, pl.p);
   return sg_check_launch("sg_conv3d_fprop(tcgen05)");
 }
 

@@ -79,6 +79,7 @@ k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
   constexpr uint32_t KK_A = (2u * CHUNK_BYTES) >> 4;
   constexpr uint32_t PLANE = HALO_H * HALO_W;   // voxels (16-byte units) per halo plane
   extern __shared__ __align__(128) uint8_t smem[];
+  sg_pdl_trigger();
   // carve-up: [weights][halo stages][slack for garbage-row reads][barriers][tmem slot]
   uint8_t* w_smem = smem;
   uint8_t* a_smem = smem + p.w_bytes;
@@ -115,6 +116,7 @@ k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  sg_pdl_wait();   // everything above touched only shared / tensor memory and kernel parameters
   const int acc_cols = ZS ? ZM.total : p.n_sub * NT;      // columns of one accumulator set
   float* s_bias = reinterpret_cast<float*>(bars + 16);   // NT floats, 16-byte aligned, after the barriers
 
@@ -386,7 +388,7 @@ int launch_res_inst(const ResPlan& pl, const CUtensorMap& map, cudaStream_t s) {
     }
     attr_set = true;
   }
-  k_conv_tc_res<NT, TD, KBC, ZS><<<pl.grid, kThreads, pl.smem, s>>>(map, pl.p);
+  sg_launch((k_conv_tc_res<NT, TD, KBC, ZS>), pl.grid, kThreads, pl.smem, s, map, pl.p);
   return sg_check_launch("sg_conv3d_fprop(tcgen05 resident)");
 }
 

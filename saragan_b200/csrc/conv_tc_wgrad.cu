@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(kThreadsW)
 k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUtensorMap xmap,
            const __grid_constant__ WgParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
+  sg_pdl_trigger();
   // carve-up: stages x [gy planes | 3 kw copies of the x halo tile | ones], then barriers
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes + p.slack_bytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * 8 + 1);
@@ -116,6 +117,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  sg_pdl_wait();   // everything above touched only shared / tensor memory and kernel parameters
   const uint32_t smem_base = smem_u32(smem);
 
   if (warp == 0) {
@@ -235,6 +237,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
 // ws [27][Cout][CinP] -> gw [Cout][Cin][27] * scale.  block = (64 input channels, one output channel)
 __global__ void __launch_bounds__(256)
 k_wgrad_finish(const float* __restrict__ ws, float* __restrict__ gw, int Cout, int Cin, int CinP, float scale) {
+  sg_pdl_enter();
   __shared__ float s[64 * 27];
   const int co = blockIdx.y, ci0 = blockIdx.x * 64;
   for (int idx = threadIdx.x; idx < 27 * 64; idx += 256) {
@@ -326,7 +329,7 @@ int launch_wgrad(const WgPlan& pl, const CUtensorMap& gmap, const CUtensorMap& x
     }
     attr_set = true;
   }
-  k_wgrad_tc<NT><<<pl.grid, kThreadsW, pl.smem, s>>>(gmap, xmap, pl.p);
+  sg_launch((k_wgrad_tc<NT>), pl.grid, kThreadsW, pl.smem, s, gmap, xmap, pl.p);
   return sg_check_launch("sg_conv3d_wgrad(tcgen05)");
 }
 
@@ -378,7 +381,7 @@ int sg_tc_wgrad(const void* x, const void* gy, float* gw, float* gb, int N, int 
   if (gb) cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)Cout, s);
   rc = pl.NT == 32 ? launch_wgrad<32>(pl, gmap, xmap, s) : launch_wgrad<16>(pl, gmap, xmap, s);
   if (rc) return rc;
-  k_wgrad_finish<<<dim3((unsigned)((Cin + 63) / 64), (unsigned)Cout), 256, 0, s>>>((const float*)ws, gw, Cout, Cin,
+  sg_launch((k_wgrad_finish), dim3((unsigned)((Cin + 63) / 64), (unsigned)Cout), 256, 0, s, (const float*)ws, gw, Cout, Cin,
                                                                                 p.CinP, scale);
   return sg_check_launch("sg_conv3d_wgrad(tcgen05 finish)");
 }
