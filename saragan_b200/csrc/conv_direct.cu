@@ -16,6 +16,7 @@ int sg_tc_wgrad(const void* x, const void* gy, float* gw, float* gb, int N, int 
                 int D, int H, int W, float scale, void* workspace, int64_t workspace_bytes,
                 cudaStream_t s);
 int64_t sg_tc_workspace_bytes(int kind, int N, int Cin, int Cout, int D, int H, int W);
+int sg_wgrad_finish(const float* ws, float* gw, int Cout, int Cin, int CinP, float scale, cudaStream_t s);
 
 // bf16 convolutions that the tcgen05 planners declined and the CUDA-core kernels ran instead
 // (bench.py reports the count: a non-zero value on a large layer is a performance bug)
@@ -313,6 +314,8 @@ extern "C" int64_t sg_conv3d_workspace_bytes(int kind, int dtype, int N, int Cin
   int64_t need = 0;
   if (kind == 0 && small_f32_applies(dtype, N, D, H, W))
     need = (int64_t)N * D * H * W * (16 * ((Cout + 15) / 16)) * (int64_t)sizeof(float);
+  if (kind == 1 && small_f32_applies(dtype, N, D, H, W))
+    need = (int64_t)27 * Cout * (16 * ((Cin + 15) / 16)) * (int64_t)sizeof(float);
   if (dtype == SG_DTYPE_BF16) {
     int64_t t = sg_tc_workspace_bytes(kind, N, Cin, Cout, D, H, W);
     if (t > need) need = t;
@@ -409,10 +412,10 @@ k_wgrad_direct(const T* __restrict__ x, const T* __restrict__ gy, float* __restr
 // gw[co][ci][tap] = scale * sum_m gy[m][co] * x[m + tap][ci] with only M = N*V rows (64 at B=4)
 // but Cout*Cin*27 = 7 M outputs: an SGEMM with a tiny K.  block = 64 co x 64 ci x one tap,
 // 4x4 register tile per thread, K = M streamed through shared memory in steps of 16; every
-// output is owned by exactly one thread (no atomics, deterministic).
+// output is owned by exactly one thread (no atomics, deterministic).  Output: tap-major workspace.
 __global__ void __launch_bounds__(256)
-k_wgrad_small_f32(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gw,
-                  int N, int Cin, int Cout, int CCin, int CCout, int D, int H, int W, float scale) {
+k_wgrad_small_f32(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ ws,
+                  int N, int Cin, int Cout, int CCin, int CCout, int D, int H, int W) {
   sg_pdl_enter();
   __shared__ float As[16][64 + 4];   // [m][co]
   __shared__ float Bs[16][64 + 4];   // [m][ci]
@@ -460,15 +463,15 @@ k_wgrad_small_f32(const float* __restrict__ x, const float* __restrict__ gy, flo
     }
     __syncthreads();
   }
+  // tap-major workspace [27][Cout][CinP] (16-byte coalesced stores); k_wgrad_finish transposes it into the
+  // parameter layout [Cout][Cin][27] -- 4-byte stores 108 bytes apart straight into that layout cost 3x more
+  const int CinP = CCin * 8;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int co = co0 + ty * 4 + i;
-    if (co >= Cout) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int ci = ci0 + tx * 4 + j;
-      if (ci < Cin) gw[((int64_t)co * Cin + ci) * 27 + tap] = c[i][j] * scale;
-    }
+    const int ci = ci0 + tx * 4;
+    if (co < Cout && ci < CinP)
+      *reinterpret_cast<float4*>(ws + ((int64_t)tap * Cout + co) * CinP + ci) = make_float4(c[i][0], c[i][1], c[i][2], c[i][3]);
   }
 }
 
@@ -511,10 +514,15 @@ extern "C" int sg_conv3d_wgrad(const void* x, const void* gy, float* gw, float* 
   }
   if (impl == SG_IMPL_AUTO && N > 0 && small_f32_applies(dtype, N, D, H, W)) {
     int CCin = sg_chunks(Cin), CCout = sg_chunks(Cout);
-    dim3 grid((unsigned)((Cout + 63) / 64), (unsigned)((Cin + 63) / 64), 27);
-    sg_launch((k_wgrad_small_f32), grid, 256, 0, s, (const float*)x, (const float*)gy, gw, N, Cin, Cout, CCin, CCout, D, H,
-                                           W, scale);
-    return sg_check_launch("sg_conv3d_wgrad(small f32)");
+    const int64_t need = (int64_t)27 * Cout * CCin * 8 * (int64_t)sizeof(float);
+    SG_REQUIRE(ws != nullptr && ws_bytes >= need, "sg_conv3d_wgrad(small f32): workspace too small (%lld < %lld)",
+               (long long)ws_bytes, (long long)need);
+    dim3 grid((unsigned)((Cout + 63) / 64), (unsigned)((CCin * 8 + 63) / 64), 27);
+    sg_launch((k_wgrad_small_f32), grid, 256, 0, s, (const float*)x, (const float*)gy, (float*)ws, N, Cin, Cout, CCin, CCout,
+              D, H, W);
+    int rc = sg_check_launch("sg_conv3d_wgrad(small f32)");
+    if (rc) return rc;
+    return sg_wgrad_finish((const float*)ws, gw, Cout, Cin, CCin * 8, scale, s);
   }
   cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)Cout * Cin * 27, s);
   if (N == 0) return 0;

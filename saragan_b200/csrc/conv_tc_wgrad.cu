@@ -357,6 +357,12 @@ int encode_act_map(CUtensorMap* map, const void* base, int N, int CC, int D, int
 
 }  // namespace
 
+// ws [27][Cout][CinP] -> gw [Cout][Cin][27] * scale (shared with the small-volume fp32 wgrad of conv_direct.cu)
+int sg_wgrad_finish(const float* ws, float* gw, int Cout, int Cin, int CinP, float scale, cudaStream_t s) {
+  sg_launch((k_wgrad_finish), dim3((unsigned)((Cin + 63) / 64), (unsigned)Cout), 256, 0, s, ws, gw, Cout, Cin, CinP, scale);
+  return sg_check_launch("sg_conv3d_wgrad(finish)");
+}
+
 int64_t sg_tc_wgrad_workspace_bytes(int N, int Cin, int Cout, int D, int H, int W) {
   WgPlan pl = make_wgrad_plan(N, Cin, Cout, D, H, W);
   return pl.ok ? pl.ws_bytes : 0;
@@ -381,7 +387,5 @@ int sg_tc_wgrad(const void* x, const void* gy, float* gw, float* gb, int N, int 
   if (gb) cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)Cout, s);
   rc = pl.NT == 32 ? launch_wgrad<32>(pl, gmap, xmap, s) : launch_wgrad<16>(pl, gmap, xmap, s);
   if (rc) return rc;
-  sg_launch((k_wgrad_finish), dim3((unsigned)((Cin + 63) / 64), (unsigned)Cout), 256, 0, s, (const float*)ws, gw, Cout, Cin,
-                                                                                p.CinP, scale);
-  return sg_check_launch("sg_conv3d_wgrad(tcgen05 finish)");
+  return sg_wgrad_finish((const float*)ws, gw, Cout, Cin, p.CinP, scale, s);
 }

@@ -328,13 +328,15 @@ __global__ void k_pixelnorm_fwd(const T* __restrict__ x, T* __restrict__ y, int 
     const T* px = x + (n * CC * V + v) * 8;
     T* py = y + (n * CC * V + v) * 8;
     float ss = 0.f;
-    for (int cc = 0; cc < CC; ++cc) {
+#pragma unroll 8
+    for (int cc = 0; cc < CC; ++cc) {   // 8 loads in flight: at the base level CC = 64 and only N*V = 64 threads run
       F8 r = ld8(px + (int64_t)cc * V * 8);
 #pragma unroll
       for (int j = 0; j < 8; ++j) ss += r.v[j] * r.v[j];
     }
     float r_ = rsqrtf(ss * invC + eps);
-    for (int cc = 0; cc < CC; ++cc) {
+#pragma unroll 8
+    for (int cc = 0; cc < CC; ++cc) {   // 8 loads in flight: at the base level CC = 64 and only N*V = 64 threads run
       F8 r = ld8(px + (int64_t)cc * V * 8);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -359,7 +361,8 @@ __global__ void k_pixelnorm_bwd(const T* __restrict__ x, const T* __restrict__ g
     int64_t n = i / V;
     int64_t off = (n * CC * V + v) * 8;
     float ss = 0.f, xg = 0.f;
-    for (int cc = 0; cc < CC; ++cc) {
+#pragma unroll 8
+    for (int cc = 0; cc < CC; ++cc) {   // 8 loads in flight: at the base level CC = 64 and only N*V = 64 threads run
       F8 a = ld8(x + off + (int64_t)cc * V * 8);
       F8 g = ld8(gy + off + (int64_t)cc * V * 8);
 #pragma unroll
@@ -371,7 +374,8 @@ __global__ void k_pixelnorm_bwd(const T* __restrict__ x, const T* __restrict__ g
     }
     float r_ = rsqrtf(ss * invC + eps);
     float k = r_ * r_ * r_ * xg * invC;
-    for (int cc = 0; cc < CC; ++cc) {
+#pragma unroll 8
+    for (int cc = 0; cc < CC; ++cc) {   // 8 loads in flight: at the base level CC = 64 and only N*V = 64 threads run
       F8 a = ld8(x + off + (int64_t)cc * V * 8);
       F8 g = ld8(gy + off + (int64_t)cc * V * 8);
 #pragma unroll
@@ -444,7 +448,8 @@ __global__ void k_pw_reduce(const T* __restrict__ x, const float* __restrict__ w
     int64_t n = i / V;
     const T* px = x + (n * CC * V + v) * 8;
     float acc = 0.f;
-    for (int cc = 0; cc < CC; ++cc) {
+#pragma unroll 8
+    for (int cc = 0; cc < CC; ++cc) {   // 8 loads in flight: at the base level CC = 64 and only N*V = 64 threads run
       F8 r = ld8(px + (int64_t)cc * V * 8);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
