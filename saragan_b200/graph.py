@@ -76,7 +76,7 @@ class GraphedTrainStep:
         for net in (generator, discriminator):
             for m in net.modules():
                 if hasattr(m, "_packed"):
-                    m._packed = type(m._packed)(m.weight)
+                    m._packed = type(m._packed)(m.weight, known=m._packed.known)
         self.draw()
         for opt in (g_optim, d_optim):
             if hasattr(opt, "reserve_capture_tables"):

@@ -47,11 +47,12 @@ class PackedWeight:
     """Per-parameter cache of the two bf16/fp32 packings of a (Cout,Cin,3,3,3) weight; refreshed
     when the optimiser bumps the parameter's version counter."""
 
-    def __init__(self, weight: torch.Tensor, cache: bool = True):
+    def __init__(self, weight: torch.Tensor, cache: bool = True, known=None):
         self.weight = weight
         self.cache = cache
         self._key = None
         self._packs = {}
+        self.known = set() if known is None else known   # every (dtype, flip) ever asked for
 
     def get(self, dtype: torch.dtype, flip: bool) -> torch.Tensor:
         w = self.weight
@@ -59,9 +60,24 @@ class PackedWeight:
         if key != self._key:
             self._key, self._packs = key, {}
         k = (dtype, flip)
+        self.known.add(k)
         if k not in self._packs:
             self._packs[k] = K.pack_conv_weight(w.detach().contiguous(), dtype, flip)
         return self._packs[k]
+
+    def prepack(self) -> None:
+        """Refresh every packing used so far on the CURRENT stream (before work forks onto a second stream,
+        where a lazy first use would race with the other stream's)."""
+        for k in tuple(self.known):
+            self.get(*k)
+
+
+def prepack(net) -> None:
+    """`PackedWeight.prepack` for every conv layer of a network."""
+    for m in net.modules():
+        pw = getattr(m, "_packed", None)
+        if pw is not None:
+            pw.prepack()
 
 
 # ================================================================================ conv

@@ -18,7 +18,17 @@ import numpy as np
 import torch
 
 from . import kernels as K
+from . import ops
 from .loss import compute_gradient_penalty, wasserstein_loss
+
+_side_streams: Dict[torch.device, "torch.cuda.Stream"] = {}
+
+
+def _side_stream(dev) -> "torch.cuda.Stream":
+    dev = torch.device(dev)
+    if dev not in _side_streams:
+        _side_streams[dev] = torch.cuda.Stream(device=dev)
+    return _side_streams[dev]
 
 
 def _set_requires_grad(module, flag: bool) -> None:
@@ -28,7 +38,7 @@ def _set_requires_grad(module, flag: bool) -> None:
 
 def d_phase(x_real: torch.Tensor, generator, discriminator, discriminator_optim, alpha, *,
             noise: Optional[torch.Tensor] = None, z_d: Optional[torch.Tensor] = None,
-            eps: Optional[torch.Tensor] = None, grad_sync=None) -> Dict[str, torch.Tensor]:
+            eps: Optional[torch.Tensor] = None, grad_sync=None, overlap_gp: bool = True) -> Dict[str, torch.Tensor]:
     """train.py:134-159: D forward passes, gradient penalty, d_loss.backward() (no optimiser step)."""
     dev = discriminator.device
     batch = x_real.shape[0]
@@ -46,21 +56,45 @@ def d_phase(x_real: torch.Tensor, generator, discriminator, discriminator_optim,
     with torch.no_grad():
         x_fake = generator(z_d, alpha)[-1].detach()
 
+    # The gradient-penalty chain (D(interpolates), its input gradient and the double backward) shares
+    # nothing with the D(real)/D(fake) chain but the weights: on a GPU the two run on two streams and meet at
+    # the gradient sum.  The low-resolution levels of either chain occupy a fraction of the SMs, which the
+    # other chain's kernels fill.  (Hook-based gradient sync fires per accumulated gradient, so it keeps
+    # the single-stream order.)
+    two_streams = overlap_gp and x_real.is_cuda and grad_sync is None
+    if two_streams:
+        d_params = [p for p in discriminator.parameters() if p.requires_grad]
+        ops.prepack(discriminator)            # a lazy first packing on one stream would race with the other
+        main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            gp_loss = compute_gradient_penalty(discriminator, x_real, x_fake, alpha, random_uniform=eps)
+            gp_grads = torch.autograd.grad(gp_loss, d_params, allow_unused=True)
     # D(real) and D(fake) as ONE batch-2B pass (minibatch-stddev keeps the two minibatches apart, so
     # the values equal the reference's two calls, train.py:148-149): half the launches and twice the
     # tiles per launch at the low-resolution levels
     d_both = discriminator(torch.cat([x_real, x_fake]), alpha, sub_batches=2)
     d_real, d_fake = d_both[:batch], d_both[batch:]
-    gp_loss = compute_gradient_penalty(discriminator, x_real, x_fake, alpha, random_uniform=eps)
     real_loss = wasserstein_loss(d_real)
     fake_loss = wasserstein_loss(d_fake)
     drift_loss = 1e-3 * (d_real ** 2).mean()
-    d_loss = -real_loss + fake_loss + gp_loss + drift_loss
-
     discriminator_optim.zero_grad()
-    if grad_sync is not None:
-        grad_sync.arm(discriminator)
-    d_loss.backward()
+    if two_streams:
+        d_loss = -real_loss + fake_loss + drift_loss
+        d_loss.backward()
+        main.wait_stream(side)
+        pairs = [(p.grad, g) for p, g in zip(d_params, gp_grads) if g is not None and p.grad is not None]
+        torch._foreach_add_([a for a, _ in pairs], [b for _, b in pairs])
+        for p, g in zip(d_params, gp_grads):
+            if g is not None and p.grad is None:
+                p.grad = g
+        d_loss = d_loss.detach() + gp_loss.detach()
+    else:
+        gp_loss = compute_gradient_penalty(discriminator, x_real, x_fake, alpha, random_uniform=eps)
+        d_loss = -real_loss + fake_loss + gp_loss + drift_loss
+        if grad_sync is not None:
+            grad_sync.arm(discriminator)
+        d_loss.backward()
     return {"d_loss": d_loss.detach(), "gp": gp_loss.detach(), "d_real_mean": real_loss.detach(),
             "x_real": x_real}
 
