@@ -66,8 +66,9 @@ int sg_pack_conv_weight(const float* w, void* dst, int dtype, int Cout, int Cin,
 int sg_conv3d_fprop(const void* x, const void* wp, const float* bias, const void* mask_src, void* y,
                     int dtype, int N, int Cin, int Cout, int D, int H, int W, float scale, int lrelu,
                     int impl, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
-/* bytes of caller-provided scratch the conv entry points need for this shape (split-K partial
- * sums); kind 0 = fprop/dgrad, 1 = wgrad.  The library never allocates. */
+/* bytes of caller-provided scratch the conv entry points need for this shape; kind 0 = fprop/dgrad
+ * (split-K partial sums [N*V][CoutP] fp32), 1 = wgrad (tap-major sums [27][Cout][CinP] fp32 that the
+ * finishing kernel transposes into gw).  The library never allocates. */
 int64_t sg_conv3d_workspace_bytes(int kind, int dtype, int N, int Cin, int Cout, int D, int H, int W);
 /* introspection: tiling of the tcgen05 path for a shape; out[16] = ok, NT, tn, td, th, n_sub,
  * kb_chunks + 100 * taps_per_stage, w_stages, splits, kblocks_per_split, grid.x, grid.y, grid.z, smem bytes, tmem cols, a_bytes */
