@@ -50,6 +50,53 @@ def test_tcgen05_fprop_matches_direct(shape, flip):
     assert rel_err(got.float().cpu(), want.float()) < 3e-3
 
 
+# (shape, forced tiling nt/big/td_max/splits): every specialised (compile-time-geometry) streaming kernel, a
+# generic one, split-K with vector reductions, tiles spanning two samples
+FORCED = [
+    ((2, 64, 128, 4, 16, 16), (128, 0, 1, 1)),    # k_conv_tc<128,1,16,1>
+    ((2, 64, 128, 4, 16, 16), (128, 0, 2, 2)),    # <128,2,16,1>, split-K 2
+    ((1, 64, 128, 8, 16, 16), (128, 1, 4, 1)),    # <128,4,16,1>: 512 TMEM columns
+    ((2, 128, 64, 4, 16, 16), (64, 0, 1, 4)),     # <64,1,16,1>, split-K 4
+    ((2, 128, 64, 4, 32, 16), (64, 0, 2, 1)),     # <64,2,16,1>
+    ((1, 64, 64, 8, 16, 16), (64, 0, 4, 1)),      # <64,4,16,1>
+    ((4, 64, 128, 2, 8, 8), (128, 0, 2, 2)),      # <128,2,8,1>: th = 8, MMA tiles straddle halo lines
+    ((4, 64, 128, 2, 8, 8), (128, 1, 4, 1)),      # <128,2,8,2>: a tile spans two samples
+    ((3, 64, 64, 2, 8, 8), (64, 0, 4, 2)),        # <64,2,8,2>, ragged batch
+    ((2, 32, 32, 4, 16, 16), (32, 0, 2, 1)),      # generic kernel (NT = 32)
+    ((1, 64, 64, 8, 16, 16), (64, 1, 8, 1)),      # generic kernel: td = 8, 8 MMA tiles per CTA
+]
+
+
+@pytest.mark.parametrize("shape,plan", FORCED)
+def test_tcgen05_streaming_forced_tilings(shape, plan):
+    """The cost model may pick any of these tilings: each one is forced through the tuning hook and held to the
+    CUDA-core kernel (also checks that the tiling the test names is the one that ran)."""
+    import ctypes
+    n, cin, cout, d, h, w = shape
+    g = torch.Generator().manual_seed(sum(shape) + 11)
+    wt = torch.randn(cout, cin, 3, 3, 3, generator=g).cuda()
+    xg = E.plain_to_act(torch.randn(n, cin, d, h, w, generator=g), BF).cuda()
+    mg = E.plain_to_act(torch.randn(n, cout, d, h, w, generator=g), BF).cuda()
+    bias = torch.randn(cout, generator=g).cuda()
+    wp = K.pack_conv_weight(wt, BF, False)
+    lib = _lib.load()
+    try:
+        lib.sg_tc_force_streaming(1)
+        lib.sg_tc_force_plan(*plan)
+        out = (ctypes.c_int * 16)()
+        lib.sg_tc_plan_debug(n, cin, cout, d, h, w, out)
+        assert out[0] == 1 and out[1] == plan[0] and out[8] == plan[3], list(out)
+        for (b, lrelu, mask) in [(None, False, False), (bias, True, True)]:
+            args = (xg, wp, b, mg if mask else None, cin, cout, 0.05, lrelu)
+            got = K.conv3d_fprop(*args, _lib.IMPL_TCGEN05)
+            ref = K.conv3d_fprop(*args, _lib.IMPL_DIRECT)
+            torch.cuda.synchronize()
+            assert rel_err(got.float(), ref.float()) < 3e-3, (shape, plan, lrelu)
+    finally:
+        lib.sg_tc_force_plan(0, 0, 0, 0)
+        lib.sg_tc_force_streaming(0)
+
+
 RES_SHAPES = [
     (1, 32, 64, 8, 32, 16),    # D.b6.conv2 class: NT=64, td=2, one K block, 16 tiles
     (2, 64, 32, 4, 16, 32),    # its dgrad class: two K blocks per tile through the halo ring

@@ -236,6 +236,49 @@ def test_step_bf16_matches_bf16_emulation(monkeypatch):
     assert float(np.median(list(errs.values()))) < 1e-2
 
 
+def test_stacked_minibatches_equal_separate_calls():
+    """Discriminator.forward(cat(a, b), sub_batches=2) == cat(D(a), D(b)): what lets the step evaluate
+    D(real) and D(fake) as one pass (train.py:148-149 are two calls)."""
+    z, cfg = load_golden("tiny_p3")
+    for prec, tol in (("fp32", 1e-5), ("bf16", 2e-2)):
+        with sg.use_precision(prec):
+            _, d = build_pair(cfg)
+            inp = _golden_inputs(z)
+            a, b = inp["x_real"].cuda(), (inp["x_real"] + 0.3 * inp["noise"]).cuda()
+            with torch.no_grad():
+                both = d(torch.cat([a, b]), cfg["alpha"], sub_batches=2)
+                sep = torch.cat([d(a, cfg["alpha"]), d(b, cfg["alpha"])])
+        assert rel_err(both, sep) < tol, (prec, rel_err(both, sep))
+        with sg.use_precision(prec), torch.no_grad():
+            mixed = d(torch.cat([a, b]), cfg["alpha"])          # ONE minibatch of 2B: different statistics
+        assert rel_err(mixed, sep) > 10 * tol or prec == "bf16"
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 3e-2)])
+def test_two_stream_d_phase_matches_single_stream(precision, tol):
+    """d_phase(overlap_gp=True) (gradient-penalty chain on a second stream, gradients summed afterwards)
+    against the single-stream order of the reference: same loss, same gradients up to summation order."""
+    from saragan_b200.train import d_phase
+    z, cfg = load_golden("tiny_p3")
+    inp = _golden_inputs(z)
+    res = {}
+    for overlap in (False, True):
+        with sg.use_precision(precision):
+            g, d = build_pair(cfg)
+            _, d_opt = sg.make_optimizers(g, d)
+            out = d_phase(inp["x_real"], g, d, d_opt, cfg["alpha"], noise=inp["noise"], z_d=inp["z_d"],
+                          eps=inp["eps"], overlap_gp=overlap)
+            torch.cuda.synchronize()
+            res[overlap] = (float(out["d_loss"]), float(out["gp"]), {k: p.grad.clone() for k, p in d.named_parameters()
+                                                                     if p.grad is not None})
+    assert abs(res[True][0] - res[False][0]) < tol * max(1.0, abs(res[False][0]))
+    assert abs(res[True][1] - res[False][1]) < tol * max(1.0, abs(res[False][1]))
+    assert set(res[True][2]) == set(res[False][2])
+    for k, v in res[False][2].items():
+        if v.numel() > 1:
+            assert rel_err(res[True][2][k], v) < 50 * tol, (k, rel_err(res[True][2][k], v))
+
+
 def test_drop_in_api_surface():
     """Constructor signature, attributes, state_dict keys and return types of network.py."""
     g, d = build_pair(dict(phase=2, num_phases=3, base_dim=32, latent_dim=32, base_shape=(1, 1, 4, 4)))
