@@ -56,3 +56,20 @@ def test_generator_returns_list_and_blocks_accept_plain(cpu_kernels):
         assert y.shape == (2, blk.conv1.out_channels, 4, 16, 16)
         y2 = d.blocks[-1](torch.randn(2, d.blocks[-1].filters_in, 2, 8, 8))
         assert y2.shape == (2, d.blocks[-1].filters_out, 1, 4, 4)
+
+
+def test_stacked_minibatches_equal_separate_calls(cpu_kernels):
+    """Discriminator.forward(cat(a, b), sub_batches=2) == cat(D(a), D(b)) on the emulated kernels (the step
+    evaluates D(real) and D(fake) as one pass; the reference makes two calls, train.py:148-149)."""
+    z, cfg = load_golden("tiny_p2_b8")
+    with sg.use_precision("fp32"):
+        _, d = build_pair(cfg)
+        a = torch.from_numpy(z["in.x_real"])
+        b = a + 0.3 * torch.from_numpy(z["in.noise"])
+        with torch.no_grad():
+            both = d(torch.cat([a, b]), cfg["alpha"], sub_batches=2)
+            sep = torch.cat([d(a, cfg["alpha"]), d(b, cfg["alpha"])])
+            mixed = d(torch.cat([a, b]), cfg["alpha"])
+    assert rel_err(both, sep) < 1e-6
+    assert rel_err(mixed, sep) > 1e-4      # one minibatch of 2B has different group statistics
+
