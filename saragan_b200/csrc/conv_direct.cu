@@ -145,8 +145,9 @@ k_conv_direct(const T* __restrict__ x, const T* __restrict__ wp, const float* __
 // slice of the input-channel chunks (taps that only ever see padding -- kd != 1 when D == 1 -- are
 // skipped; split-K over taps and chunk slices gives ~600 blocks so the weight stream has enough loads
 // in flight), next k-tile prefetched into registers during the FMAs, 4x4 register tile per thread,
-// fp32 atomics into a zeroed [M][CoutP] workspace, then a finishing kernel applies scale / bias /
-// LeakyReLU / mask and writes the blocked layout.
+// partial sums into a [slices][M][CoutP] workspace, then a finishing kernel adds the slices, applies scale / bias /
+// LeakyReLU / mask and writes the blocked layout.  (Partial sums per (tap, slice) in a workspace, added in a
+// fixed order by the finishing kernel: deterministic.)
 struct SmallTaps {
   int kd_lo, nkd, kh_lo, nkh, kw_lo, nkw;   // live tap ranges
   int ksplit, cc_per;                       // chunk slices per tap, chunks per slice (even)
@@ -235,22 +236,23 @@ k_conv_small_f32(const float* __restrict__ x, const float* __restrict__ wp, floa
     }
     __syncthreads();
   }
+  // this block's partial sums go to its own slice [blockIdx.z][M][CoutP] (plain 16-byte stores): the finishing
+  // kernel adds the slices in a fixed order, so the forward value -- and with it every LeakyReLU mask
+  // downstream -- does not depend on the order atomics would have landed in
+  float* slice = acc + (int64_t)blockIdx.z * M * CoutP;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     int mm = m0 + ty * 4 + i;
-    if (mm >= M) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int nn = n0 + tx * 4 + j;
-      if (nn < CoutP && c[i][j] != 0.f) atomicAdd(acc + (int64_t)mm * CoutP + nn, c[i][j]);
-    }
+    int nn = n0 + tx * 4;
+    if (mm < M && nn < CoutP)
+      *reinterpret_cast<float4*>(slice + (int64_t)mm * CoutP + nn) = make_float4(c[i][0], c[i][1], c[i][2], c[i][3]);
   }
 }
 // acc [M][CoutP] fp32 -> y blocked (T), y = [mask][lrelu](scale*acc + bias)
 template <typename T>
 __global__ void k_conv_finish(const float* __restrict__ acc, const float* __restrict__ bias,
                               const T* __restrict__ mask_src, T* __restrict__ y, int N, int Cout,
-                              int CCout, int CoutP, int64_t V, float scale, int lrelu) {
+                              int CCout, int CoutP, int64_t V, float scale, int lrelu, int slices) {
   sg_pdl_enter();
   int64_t total = (int64_t)N * CCout * V;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
@@ -260,6 +262,16 @@ __global__ void k_conv_finish(const float* __restrict__ acc, const float* __rest
     int cc = (int)(t % CCout);
     int64_t n = t / CCout;
     const float* a = acc + (n * V + v) * CoutP + cc * 8;
+    const int64_t slice_stride = (int64_t)N * V * CoutP;
+    float sum[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum[j] = a[j];
+    for (int z = 1; z < slices; ++z) {   // fixed order: deterministic
+      const float4 p0 = *reinterpret_cast<const float4*>(a + z * slice_stride);
+      const float4 p1 = *reinterpret_cast<const float4*>(a + z * slice_stride + 4);
+      sum[0] += p0.x; sum[1] += p0.y; sum[2] += p0.z; sum[3] += p0.w;
+      sum[4] += p1.x; sum[5] += p1.y; sum[6] += p1.z; sum[7] += p1.w;
+    }
     F8 o, m;
     if (mask_src) m = ld8(mask_src + i * 8);
 #pragma unroll
@@ -267,7 +279,7 @@ __global__ void k_conv_finish(const float* __restrict__ acc, const float* __rest
       int co = cc * 8 + j;
       float r = 0.f;
       if (co < Cout) {
-        r = a[j] * scale + (bias ? __ldg(bias + co) : 0.f);
+        r = sum[j] * scale + (bias ? __ldg(bias + co) : 0.f);
         if (lrelu) r = lrelu02(r);
         if (mask_src) r *= lmask02(m.v[j]);
       }
@@ -281,7 +293,7 @@ int sg_conv_finish_bf16(const float* acc, const float* bias, const void* mask_sr
   int CCout = sg_chunks(Cout), CoutP = 16 * ((Cout + 15) / 16);
   int64_t total = (int64_t)N * CCout * V;
   sg_launch((k_conv_finish<__nv_bfloat16>), sg_grid(total, 256), 256, 0, s, 
-      acc, bias, (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)y, N, Cout, CCout, CoutP, V, scale, lrelu);
+      acc, bias, (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)y, N, Cout, CCout, CoutP, V, scale, lrelu, 1);
   return sg_check_launch("sg_conv_finish");
 }
 
@@ -293,27 +305,30 @@ static int launch_small_f32(const void* x, const void* wp, const float* bias, co
                             int lrelu, void* ws, int64_t ws_bytes, cudaStream_t s) {
   int CCin = sg_chunks(Cin), CCout = sg_chunks(Cout), CoutP = 16 * ((Cout + 15) / 16);
   int64_t V = (int64_t)D * H * W, M = (int64_t)N * V;
-  int64_t need = M * CoutP * (int64_t)sizeof(float);
-  SG_REQUIRE(ws != nullptr && ws_bytes >= need, "sg_conv3d_fprop: workspace too small (%lld < %lld)",
-             (long long)ws_bytes, (long long)need);
-  cudaMemsetAsync(ws, 0, (size_t)need, s);
   const int64_t mt = (M + 63) / 64, nt = (CoutP + 63) / 64;
   const SmallTaps st = small_taps(CCin, D, H, W, mt * nt);
-  dim3 grid((unsigned)mt, (unsigned)nt, (unsigned)(st.nkd * st.nkh * st.nkw * st.ksplit));
+  const int slices = st.nkd * st.nkh * st.nkw * st.ksplit;
+  int64_t need = (int64_t)slices * M * CoutP * (int64_t)sizeof(float);
+  SG_REQUIRE(ws != nullptr && ws_bytes >= need, "sg_conv3d_fprop: workspace too small (%lld < %lld)",
+             (long long)ws_bytes, (long long)need);
+  dim3 grid((unsigned)mt, (unsigned)nt, (unsigned)slices);
   sg_launch((k_conv_small_f32), grid, 256, 0, s, (const float*)x, (const float*)wp, (float*)ws, N, CCin, CoutP, D, H, W, st);
   int rc = sg_check_launch("sg_conv3d_fprop(small f32)");
   if (rc) return rc;
   int64_t total = (int64_t)N * CCout * V;
   sg_launch((k_conv_finish<float>), sg_grid(total, 256), 256, 0, s, (const float*)ws, bias, (const float*)mask_src,
-                                                          (float*)y, N, Cout, CCout, CoutP, V, scale, lrelu);
+                                                          (float*)y, N, Cout, CCout, CoutP, V, scale, lrelu, slices);
   return sg_check_launch("sg_conv3d_fprop(small f32 finish)");
 }
 
 extern "C" int64_t sg_conv3d_workspace_bytes(int kind, int dtype, int N, int Cin, int Cout, int D,
                                              int H, int W) {
   int64_t need = 0;
-  if (kind == 0 && small_f32_applies(dtype, N, D, H, W))
-    need = (int64_t)N * D * H * W * (16 * ((Cout + 15) / 16)) * (int64_t)sizeof(float);
+  if (kind == 0 && small_f32_applies(dtype, N, D, H, W)) {
+    const int64_t M = (int64_t)N * D * H * W, CoutP = 16 * ((Cout + 15) / 16);
+    const SmallTaps st = small_taps(sg_chunks(Cin), D, H, W, ((M + 63) / 64) * ((CoutP + 63) / 64));
+    need = (int64_t)(st.nkd * st.nkh * st.nkw * st.ksplit) * M * CoutP * (int64_t)sizeof(float);
+  }
   if (kind == 1 && small_f32_applies(dtype, N, D, H, W))
     need = (int64_t)27 * Cout * (16 * ((Cin + 15) / 16)) * (int64_t)sizeof(float);
   if (dtype == SG_DTYPE_BF16) {

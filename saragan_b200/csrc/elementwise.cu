@@ -315,28 +315,31 @@ extern "C" int sg_up2(const void* x, void* y, const void* mask_ref, int dtype_in
 // ------------------------------------------------------------------------ pixel-norm
 // y = x * rsqrt(mean_c(x^2) + eps)   (network.py:196-197), optionally followed by LeakyReLU
 // (GeneratorBlock's second conv: conv -> pixel-norm -> lrelu, network.py:214-216).
-template <typename T>
+// LPV = lanes per voxel: 1 (a thread walks all channel chunks of its voxel) at the high-resolution levels;
+// 32 (a warp shares the chunks, shuffle reduction) at the low-resolution levels, where N*V is a few hundred
+// and C = 512 -- a thread per voxel would leave 64 dependent 16-byte loads on one thread of one block.
+template <typename T, int LPV>
 __global__ void k_pixelnorm_fwd(const T* __restrict__ x, T* __restrict__ y, int N, int C, int CC,
                                 int64_t V, float eps, int lrelu_after) {
   sg_pdl_enter();
   int64_t total = (int64_t)N * V;
   float invC = 1.f / (float)C;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  const int lane = LPV == 1 ? 0 : (int)(threadIdx.x & (LPV - 1));
+  for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPV; i < total;
+       i += (int64_t)gridDim.x * blockDim.x / LPV) {
     int64_t v = i % V;
     int64_t n = i / V;
     const T* px = x + (n * CC * V + v) * 8;
     T* py = y + (n * CC * V + v) * 8;
     float ss = 0.f;
-#pragma unroll 8
-    for (int cc = 0; cc < CC; ++cc) {   // 8 loads in flight: at the base level CC = 64 and only N*V = 64 threads run
+    for (int cc = lane; cc < CC; cc += LPV) {
       F8 r = ld8(px + (int64_t)cc * V * 8);
 #pragma unroll
       for (int j = 0; j < 8; ++j) ss += r.v[j] * r.v[j];
     }
+    if (LPV > 1) ss = warp_sum(ss);
     float r_ = rsqrtf(ss * invC + eps);
-#pragma unroll 8
-    for (int cc = 0; cc < CC; ++cc) {   // 8 loads in flight: at the base level CC = 64 and only N*V = 64 threads run
+    for (int cc = lane; cc < CC; cc += LPV) {
       F8 r = ld8(px + (int64_t)cc * V * 8);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -348,21 +351,21 @@ __global__ void k_pixelnorm_fwd(const T* __restrict__ x, T* __restrict__ y, int 
   }
 }
 // g' = gy * m(x) if lrelu_after;  gx = r*g' - x * r^3 * mean_c(x*g')   
-template <typename T>
+template <typename T, int LPV>
 __global__ void k_pixelnorm_bwd(const T* __restrict__ x, const T* __restrict__ gy,
                                 T* __restrict__ gx, int N, int C, int CC, int64_t V, float eps,
                                 int lrelu_after, int mask_input) {
   sg_pdl_enter();
   int64_t total = (int64_t)N * V;
   float invC = 1.f / (float)C;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  const int lane = LPV == 1 ? 0 : (int)(threadIdx.x & (LPV - 1));
+  for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPV; i < total;
+       i += (int64_t)gridDim.x * blockDim.x / LPV) {
     int64_t v = i % V;
     int64_t n = i / V;
     int64_t off = (n * CC * V + v) * 8;
     float ss = 0.f, xg = 0.f;
-#pragma unroll 8
-    for (int cc = 0; cc < CC; ++cc) {   // 8 loads in flight: at the base level CC = 64 and only N*V = 64 threads run
+    for (int cc = lane; cc < CC; cc += LPV) {
       F8 a = ld8(x + off + (int64_t)cc * V * 8);
       F8 g = ld8(gy + off + (int64_t)cc * V * 8);
 #pragma unroll
@@ -372,10 +375,13 @@ __global__ void k_pixelnorm_bwd(const T* __restrict__ x, const T* __restrict__ g
         xg += a.v[j] * gj;
       }
     }
+    if (LPV > 1) {
+      ss = warp_sum(ss);
+      xg = warp_sum(xg);
+    }
     float r_ = rsqrtf(ss * invC + eps);
     float k = r_ * r_ * r_ * xg * invC;
-#pragma unroll 8
-    for (int cc = 0; cc < CC; ++cc) {   // 8 loads in flight: at the base level CC = 64 and only N*V = 64 threads run
+    for (int cc = lane; cc < CC; cc += LPV) {
       F8 a = ld8(x + off + (int64_t)cc * V * 8);
       F8 g = ld8(gy + off + (int64_t)cc * V * 8);
 #pragma unroll
@@ -389,12 +395,18 @@ __global__ void k_pixelnorm_bwd(const T* __restrict__ x, const T* __restrict__ g
     }
   }
 }
+// a warp per voxel pays off when the voxels alone cannot fill the GPU and there are chunks to share
+static bool sg_warp_per_voxel(int64_t total, int CC) { return total <= 16384 && CC >= 8; }
 extern "C" int sg_pixelnorm_fwd(const void* x, void* y, int dtype, int N, int C, int64_t V,
                                 float eps, int lrelu_after, cudaStream_t s) {
   int64_t total = (int64_t)N * V;
   if (total == 0) return 0;
   int CC = sg_chunks(C);
-  SG_DISPATCH(dtype, sg_launch((k_pixelnorm_fwd<T>), sg_grid(total, 256), 256, 0, s, (const T*)x, (T*)y, N, C, CC, V, eps, lrelu_after););
+  if (sg_warp_per_voxel(total, CC)) {
+    SG_DISPATCH(dtype, sg_launch((k_pixelnorm_fwd<T, 32>), sg_grid(total * 32, 256), 256, 0, s, (const T*)x, (T*)y, N, C, CC, V, eps, lrelu_after););
+  } else {
+    SG_DISPATCH(dtype, sg_launch((k_pixelnorm_fwd<T, 1>), sg_grid(total, 256), 256, 0, s, (const T*)x, (T*)y, N, C, CC, V, eps, lrelu_after););
+  }
   return sg_check_launch("sg_pixelnorm_fwd");
 }
 extern "C" int sg_pixelnorm_bwd(const void* x, const void* gy, void* gx, int dtype, int N, int C,
@@ -402,7 +414,11 @@ extern "C" int sg_pixelnorm_bwd(const void* x, const void* gy, void* gx, int dty
   int64_t total = (int64_t)N * V;
   if (total == 0) return 0;
   int CC = sg_chunks(C);
-  SG_DISPATCH(dtype, sg_launch((k_pixelnorm_bwd<T>), sg_grid(total, 256), 256, 0, s, (const T*)x, (const T*)gy, (T*)gx, N, C, CC, V, eps, lrelu_after, mask_input););
+  if (sg_warp_per_voxel(total, CC)) {
+    SG_DISPATCH(dtype, sg_launch((k_pixelnorm_bwd<T, 32>), sg_grid(total * 32, 256), 256, 0, s, (const T*)x, (const T*)gy, (T*)gx, N, C, CC, V, eps, lrelu_after, mask_input););
+  } else {
+    SG_DISPATCH(dtype, sg_launch((k_pixelnorm_bwd<T, 1>), sg_grid(total, 256), 256, 0, s, (const T*)x, (const T*)gy, (T*)gx, N, C, CC, V, eps, lrelu_after, mask_input););
+  }
   return sg_check_launch("sg_pixelnorm_bwd");
 }
 
@@ -436,20 +452,20 @@ __global__ void k_pw_expand(const float* __restrict__ img, const float* __restri
   }
 }
 // ToRGB (network.py:219-225): img[n][v] = scale*sum_c w[c]*x[n][c][v] + bias[0]
-template <typename T>
+template <typename T, int LPV>
 __global__ void k_pw_reduce(const T* __restrict__ x, const float* __restrict__ w,
                             const float* __restrict__ bias, float* __restrict__ img, int N, int C,
                             int CC, int64_t V, float scale) {
   sg_pdl_enter();
   int64_t total = (int64_t)N * V;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  const int lane = LPV == 1 ? 0 : (int)(threadIdx.x & (LPV - 1));
+  for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPV; i < total;
+       i += (int64_t)gridDim.x * blockDim.x / LPV) {
     int64_t v = i % V;
     int64_t n = i / V;
     const T* px = x + (n * CC * V + v) * 8;
     float acc = 0.f;
-#pragma unroll 8
-    for (int cc = 0; cc < CC; ++cc) {   // 8 loads in flight: at the base level CC = 64 and only N*V = 64 threads run
+    for (int cc = lane; cc < CC; cc += LPV) {
       F8 r = ld8(px + (int64_t)cc * V * 8);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -457,7 +473,8 @@ __global__ void k_pw_reduce(const T* __restrict__ x, const float* __restrict__ w
         if (c < C) acc += __ldg(w + c) * r.v[j];
       }
     }
-    img[i] = scale * acc + (bias ? __ldg(bias) : 0.f);
+    if (LPV > 1) acc = warp_sum(acc);
+    if (lane == 0) img[i] = scale * acc + (bias ? __ldg(bias) : 0.f);
   }
 }
 // gw[c] = scale * sum_{n,v} g[n][c][v]*img[n][v]  (img == null: plain channel sum),
@@ -522,7 +539,11 @@ extern "C" int sg_pw_reduce(const void* x, const float* w, const float* bias, fl
   int CC = sg_chunks(C);
   int64_t total = (int64_t)N * V;
   if (total == 0) return 0;
-  SG_DISPATCH(dtype, sg_launch((k_pw_reduce<T>), sg_grid(total, 256), 256, 0, s, (const T*)x, w, bias, img, N, C, CC, V, scale););
+  if (sg_warp_per_voxel(total, CC)) {
+    SG_DISPATCH(dtype, sg_launch((k_pw_reduce<T, 32>), sg_grid(total * 32, 256), 256, 0, s, (const T*)x, w, bias, img, N, C, CC, V, scale););
+  } else {
+    SG_DISPATCH(dtype, sg_launch((k_pw_reduce<T, 1>), sg_grid(total, 256), 256, 0, s, (const T*)x, w, bias, img, N, C, CC, V, scale););
+  }
   return sg_check_launch("sg_pw_reduce");
 }
 extern "C" int sg_pw_wgrad(const void* g, const float* img, float* gw, float* gb, int dtype, int N,
@@ -865,7 +886,6 @@ __global__ void k_mbstd_fwd(const float* __restrict__ x, float* __restrict__ out
   const int mm = blockIdx.y;              // (sub-batch, m) pair: independent minibatches share a launch
   const int sb = mm / M, m = mm % M;
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  float sv = 0.f;
   if (f < F) {
     const int c = f / V, v = f % V;
     float xv[MB_MAXG], mean = 0.f;
@@ -877,17 +897,25 @@ __global__ void k_mbstd_fwd(const float* __restrict__ x, float* __restrict__ out
 #pragma unroll
     for (int g = 0; g < MB_MAXG; ++g)
       if (g < G) { xv[g] -= mean; var += xv[g] * xv[g]; out[((int64_t)(sb * G * M + g * M + m) * (C + 1) + c) * V + v] = xv[g]; }
-    sv = sqrtf(var / (float)G + eps);
-    s_out[(int64_t)mm * F + f] = sv;
+    s_out[(int64_t)mm * F + f] = sqrtf(var / (float)G + eps);
   }
-  sv = warp_sum(sv);
+}
+// t[mm] = mean_f s[mm][f]: one block per (sub-batch, m), fixed summation order (the stat channel feeds the
+// last conv of D: with atomics its last bits -- and now and then a LeakyReLU mask behind it -- changed from
+// run to run)
+__global__ void __launch_bounds__(256) k_mbstd_tmean(const float* __restrict__ s, float* __restrict__ t, int F) {
+  sg_pdl_enter();
+  const int mm = blockIdx.x;
+  float acc = 0.f;
+  for (int f = threadIdx.x; f < F; f += 256) acc += s[(int64_t)mm * F + f];
+  acc = warp_sum(acc);
   __shared__ float sm[8];
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = sv;
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
     float tot = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += sm[w];
-    atomicAdd(t + mm, tot / (float)F);
+    for (int w = 0; w < 8; ++w) tot += sm[w];
+    t[mm] = tot / (float)F;
   }
 }
 // writes the stat channel out[n][C][v] = t[n % M]
@@ -985,9 +1013,11 @@ extern "C" int sg_mbstd_fwd(const float* x, float* out, float* s, float* t, int 
                             float eps, cudaStream_t st) {
   SG_REQUIRE(G >= 1 && G <= MB_MAXG, "sg_mbstd_fwd: group size %d not in [1, %d]", G, MB_MAXG);
   const int F = C * V;
-  cudaMemsetAsync(t, 0, sizeof(float) * S * M, st);
   sg_launch((k_mbstd_fwd), dim3((F + 255) / 256, S * M), 256, 0, st, x, out, s, t, G, M, C, V, eps);
   int rc = sg_check_launch("sg_mbstd_fwd");
+  if (rc) return rc;
+  sg_launch((k_mbstd_tmean), S * M, 256, 0, st, (const float*)s, t, F);
+  rc = sg_check_launch("sg_mbstd_fwd(mean)");
   if (rc) return rc;
   sg_launch((k_mbstd_stat), (S * G * M * V + 255) / 256, 256, 0, st, out, t, S * G * M, G, M, C, V);
   return sg_check_launch("sg_mbstd_fwd(stat)");

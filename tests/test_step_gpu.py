@@ -43,11 +43,12 @@ def test_golden_step_fp32(name):
         got = {k: p.grad for k, p in mod.named_parameters()}
         assert {k for k, v in got.items() if v is not None} == set(want), kind
         for k, v in want.items():
-            # bias gradients are signed sums over every voxel of a level (|sum| << sum of |terms|):
-            # fp32 summation order alone moves them by a few 1e-3 -- and the order is not fixed (split-K
-            # atomics): tools/flaky_probe.py shows e.g. fromrgbs.0 bias at 3e-6 in most runs and 2.7e-3 in
-            # one of six.  Weights are held to 1e-3.
-            tol = 2e-2 if k.endswith(".bias") else 1e-3
+            # The fp32 forward is deterministic (base-level conv partial sums and the minibatch-stddev mean are
+            # added in a fixed order), so no LeakyReLU mask depends on the run; tools/flaky_probe.py: worst
+            # gradient error 3.6e-6 over 120 runs.  (With atomics in those two kernels one mask flipped in ~10 %
+            # of the runs and moved fromrgbs.0's bias gradient by 2.7e-3.)  Bias gradients are signed sums over
+            # every voxel of a level (|sum| << sum of |terms|), hence the looser bound.
+            tol = 5e-3 if k.endswith(".bias") else 1e-3
             if v.numel() == 1:
                 # the last linear's bias gradient is sum(-1/B ... +1/B ...) + drift ~ 1e-5: a cancelling sum of
                 # O(1) terms, so fp32 summation order moves it by ~1e-7 absolute (D(real), D(fake) are one batch)
