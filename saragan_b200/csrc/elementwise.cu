@@ -227,12 +227,14 @@ __global__ void k_up2(const T* __restrict__ x, TO* __restrict__ y, const TO* __r
   int H2 = 2 * H, W2 = 2 * W;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
-    int w = (int)(i % W);
-    int64_t t = i / W;
-    int h = (int)(t % H);
-    t /= H;
-    int d = (int)(t % D);
-    int64_t p = t / D;
+    // 32-bit index arithmetic (the entry point checks total < 2^31): 64-bit div/mod cost more than the stores
+    const unsigned ii = (unsigned)i;
+    const unsigned w = ii % (unsigned)W;
+    unsigned t = ii / (unsigned)W;
+    const unsigned h = t % (unsigned)H;
+    t /= (unsigned)H;
+    const unsigned d = t % (unsigned)D;
+    const int64_t p = t / (unsigned)D;
     TO* base = y + ((((p * 2 * D + 2 * d) * H2 + 2 * h) * (int64_t)W2) + 2 * w) * VEC;
     if (VEC == 8) {
       F8 r = ld8(x + i * 8);
@@ -303,6 +305,7 @@ extern "C" int sg_up2(const void* x, void* y, const void* mask_ref, int dtype_in
   SG_REQUIRE(mask_ref == nullptr || vec == 8, "sg_up2: mask_ref needs an activation tensor (vec 8)");
   int64_t total = P * D * H * W;
   if (total == 0) return 0;
+  SG_REQUIRE(total < (1ll << 31), "sg_up2: %lld input vectors exceed the 32-bit index range", (long long)total);
   unsigned g = sg_grid(total, 256);
   if (vec == 8) {
     SG_DISPATCH2(dtype_in, dtype_out, sg_launch((k_up2<T, TO, 8>), g, 256, 0, s, (const T*)x, (TO*)y, (const TO*)mask_ref, P, D, H, W, scale););
@@ -424,31 +427,46 @@ extern "C" int sg_pixelnorm_bwd(const void* x, const void* gy, void* gx, int dty
 
 // ------------------------------------------------------------------ 1x1x1 to/from RGB
 // FromRGB (network.py:101-110): y[n][c][v] = act(scale*w[c]*img[n][v] + bias[c])
+// grid.y = (n, chunk): the 8 weights / biases of the chunk live in registers, a thread turns 4 consecutive
+// voxels (one 16-byte image load) into four 16-byte stores -- no index division, no per-element weight loads
+// (the first version spent 16 __ldg and two 64-bit divisions per 16 bytes written: 1.4 TB/s)
 template <typename T>
 __global__ void k_pw_expand(const float* __restrict__ img, const float* __restrict__ w,
                             const float* __restrict__ bias, T* __restrict__ y, int N, int C, int CC,
                             int64_t V, float scale, int lrelu) {
   sg_pdl_enter();
-  int64_t total = (int64_t)N * CC * V;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t v = i % V;
-    int64_t t = i / V;
-    int cc = (int)(t % CC);
-    int64_t n = t / CC;
-    float p = img[n * V + v];
-    F8 r;
+  const int row = blockIdx.y, cc = row % CC, n = row / CC;
+  float ws[8], bs[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int c = cc * 8 + j;
-      float o = 0.f;
-      if (c < C) {
-        o = scale * __ldg(w + c) * p + (bias ? __ldg(bias + c) : 0.f);
-        if (lrelu) o = lrelu02(o);
-      }
-      r.v[j] = o;
+  for (int j = 0; j < 8; ++j) {
+    const int c = cc * 8 + j;
+    ws[j] = c < C ? scale * __ldg(w + c) : 0.f;
+    bs[j] = (c < C && bias) ? __ldg(bias + c) : 0.f;
+  }
+  const float* pi = img + (int64_t)n * V;
+  T* py = y + (int64_t)row * V * 8;
+  const bool vec = (V & 3) == 0;
+  for (int64_t v = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4; v < V; v += (int64_t)gridDim.x * blockDim.x * 4) {
+    float p[4] = {0.f, 0.f, 0.f, 0.f};
+    const int cnt = V - v < 4 ? (int)(V - v) : 4;
+    if (vec) {
+      const float4 t = *reinterpret_cast<const float4*>(pi + v);
+      p[0] = t.x; p[1] = t.y; p[2] = t.z; p[3] = t.w;
+    } else {
+      for (int q = 0; q < cnt; ++q) p[q] = pi[v + q];
     }
-    st8(y + i * 8, r);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (q < cnt) {
+        F8 r;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float o = fmaf(ws[j], p[q], bs[j]);
+          r.v[j] = lrelu ? lrelu02(o) : o;
+        }
+        st8(py + (v + q) * 8, r);
+      }
+    }
   }
 }
 // ToRGB (network.py:219-225): img[n][v] = scale*sum_c w[c]*x[n][c][v] + bias[0]
@@ -459,6 +477,11 @@ __global__ void k_pw_reduce(const T* __restrict__ x, const float* __restrict__ w
   sg_pdl_enter();
   int64_t total = (int64_t)N * V;
   const int lane = LPV == 1 ? 0 : (int)(threadIdx.x & (LPV - 1));
+  // the C weights once per block in shared memory (zero for pad channels): broadcast reads instead of 8 global
+  // loads per 16 bytes of activations
+  extern __shared__ float w_s[];
+  for (int c = threadIdx.x; c < CC * 8; c += blockDim.x) w_s[c] = c < C ? w[c] : 0.f;
+  __syncthreads();
   for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPV; i < total;
        i += (int64_t)gridDim.x * blockDim.x / LPV) {
     int64_t v = i % V;
@@ -467,11 +490,9 @@ __global__ void k_pw_reduce(const T* __restrict__ x, const float* __restrict__ w
     float acc = 0.f;
     for (int cc = lane; cc < CC; cc += LPV) {
       F8 r = ld8(px + (int64_t)cc * V * 8);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        int c = cc * 8 + j;
-        if (c < C) acc += __ldg(w + c) * r.v[j];
-      }
+      const float4 w0 = *reinterpret_cast<const float4*>(w_s + cc * 8), w1 = *reinterpret_cast<const float4*>(w_s + cc * 8 + 4);
+      acc += w0.x * r.v[0] + w0.y * r.v[1] + w0.z * r.v[2] + w0.w * r.v[3] + w1.x * r.v[4] + w1.y * r.v[5] +
+             w1.z * r.v[6] + w1.w * r.v[7];
     }
     if (LPV > 1) acc = warp_sum(acc);
     if (lane == 0) img[i] = scale * acc + (bias ? __ldg(bias) : 0.f);
@@ -492,11 +513,14 @@ __global__ void k_pw_wgrad(const T* __restrict__ g, const float* __restrict__ im
   float aw[8], ab[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) aw[j] = ab[j] = 0.f;
-  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    int64_t v = i % V;
-    int64_t n = i / V;
+  // (n, v) advance with the loop: one division per thread instead of two per element
+  int64_t i0 = lo + threadIdx.x;
+  int64_t n = i0 / V, v = i0 - n * V;
+  for (int64_t i = i0; i < hi; i += blockDim.x) {
     F8 r = ld8(g + ((n * CC + cc) * V + v) * 8);
     float p = img ? img[i] : 0.f;
+    v += blockDim.x;
+    while (v >= V) { v -= V; ++n; }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       aw[j] += r.v[j] * p;
@@ -531,7 +555,13 @@ extern "C" int sg_pw_expand(const float* img, const float* w, const float* bias,
   int CC = sg_chunks(C);
   int64_t total = (int64_t)N * CC * V;
   if (total == 0) return 0;
-  SG_DISPATCH(dtype, sg_launch((k_pw_expand<T>), sg_grid(total, 256), 256, 0, s, img, w, bias, (T*)y, N, C, CC, V, scale, lrelu););
+  SG_REQUIRE((int64_t)N * CC <= 65535, "sg_pw_expand: N * channel chunks = %lld exceeds the grid", (long long)N * CC);
+  const int64_t per_row = (V + 3) / 4;
+  int64_t gx = (per_row + 255) / 256;
+  const int64_t cap = ((int64_t)sg_num_sms() * 8 + (int64_t)N * CC - 1) / ((int64_t)N * CC);   // ~8 blocks per SM in total
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  SG_DISPATCH(dtype, sg_launch((k_pw_expand<T>), dim3((unsigned)gx, (unsigned)(N * CC)), 256, 0, s, img, w, bias, (T*)y, N, C, CC, V, scale, lrelu););
   return sg_check_launch("sg_pw_expand");
 }
 extern "C" int sg_pw_reduce(const void* x, const float* w, const float* bias, float* img, int dtype,
@@ -540,9 +570,9 @@ extern "C" int sg_pw_reduce(const void* x, const float* w, const float* bias, fl
   int64_t total = (int64_t)N * V;
   if (total == 0) return 0;
   if (sg_warp_per_voxel(total, CC)) {
-    SG_DISPATCH(dtype, sg_launch((k_pw_reduce<T, 32>), sg_grid(total * 32, 256), 256, 0, s, (const T*)x, w, bias, img, N, C, CC, V, scale););
+    SG_DISPATCH(dtype, sg_launch((k_pw_reduce<T, 32>), sg_grid(total * 32, 256), 256, CC * 8 * sizeof(float), s, (const T*)x, w, bias, img, N, C, CC, V, scale););
   } else {
-    SG_DISPATCH(dtype, sg_launch((k_pw_reduce<T, 1>), sg_grid(total, 256), 256, 0, s, (const T*)x, w, bias, img, N, C, CC, V, scale););
+    SG_DISPATCH(dtype, sg_launch((k_pw_reduce<T, 1>), sg_grid(total, 256), 256, CC * 8 * sizeof(float), s, (const T*)x, w, bias, img, N, C, CC, V, scale););
   }
   return sg_check_launch("sg_pw_reduce");
 }

@@ -69,6 +69,46 @@ def main():
     for ex, ms, fl, n, name, key in sorted(rows, reverse=True):
         print(f"excess {ex:7.3f} ms  total {ms:7.3f} ms  n={n:4.1f}  {fl / ms / 1e9:7.1f} TF/s  {name[10:]} {key}")
     print(f"sum excess {sum(r[0] for r in rows):.3f} ms of {sum(r[1] for r in rows):.3f} ms conv time")
+    print("\n-- memory-bound entry points: algorithmic bytes / event time (eager; small calls are launch-latency bound), "
+          "peak = 6555.8 GB/s measured copy bandwidth")
+
+    def pad(c):
+        return 16 * ((c + 15) // 16)
+
+    def esz(code):
+        return 2 if code == 0 else 4
+
+    def nbytes(name, k):
+        if name == "sg_up2":          # dtype_in, dtype_out, N, C, D, H, W of the INPUT (mask_ref read not counted)
+            v = k[2] * pad(k[3]) * k[4] * k[5] * k[6]
+            return v * esz(k[0]) + 8 * v * esz(k[1])
+        if name == "sg_down2":
+            v = k[2] * pad(k[3]) * k[4] * k[5] * k[6]
+            return v * esz(k[0]) + v // 8 * esz(k[1])
+        if name == "sg_mask_mul":
+            return 3 * k[1] * esz(k[0])
+        if name == "sg_lincomb":      # b may be null: lower bound
+            return 2 * k[1] * esz(k[0])
+        if name == "sg_pw_expand":
+            return k[1] * k[3] * 4 + k[1] * pad(k[2]) * k[3] * esz(k[0])
+        if name in ("sg_pw_reduce", "sg_pw_wgrad"):
+            return k[1] * k[3] * 4 + k[1] * pad(k[2]) * k[3] * esz(k[0])
+        if name == "sg_pixelnorm_fwd":
+            return 3 * k[1] * pad(k[2]) * k[3] * esz(k[0])
+        if name == "sg_pixelnorm_bwd":
+            return 5 * k[1] * pad(k[2]) * k[3] * esz(k[0])
+        return None
+
+    mem = []
+    for (name, key), (n, ms) in agg.items():
+        b = nbytes(name, key)
+        if b is not None:
+            mem.append((ms, n / args.steps, b, name, key))
+    tot_ms = sum(m[0] for m in mem)
+    tot_b = sum(m[2] * m[1] for m in mem)
+    print(f"all of them: {tot_ms:.3f} ms/step for {tot_b / 1e9:.2f} GB/step = {tot_b / tot_ms / 1e6:.0f} GB/s average")
+    for ms, n, b, name, key in sorted(mem, reverse=True)[:24]:
+        print(f"{ms:8.3f} ms  n={n:4.1f}  {b / 1e6:8.1f} MB/call  {b * n / ms / 1e6:7.0f} GB/s  {name} {key}")
 
 
 if __name__ == "__main__":
