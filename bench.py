@@ -233,15 +233,19 @@ def main():
             out = step(dev_pool[i % n_pool])
         e1.record()
         barrier()
+    if os.environ.get("SARAGAN_BENCH_DEBUG") and rank == 0:
+        print("debug: losses after the timed region", [float(out[k]) for k in ("d_loss", "g_loss", "gp")], file=sys.stderr)
     kernels.conv_probe = None
     if use_graph:
         # a graph replay cannot carry per-kernel events: time the dominant kernel in two eager
         # passes of the same step (same shapes, same in-step cache state) right after the timed region
         kernels.conv_probe = probe
-        for i in range(2):
+        for i in range(0 if os.environ.get("SARAGAN_BENCH_SKIP_PROBE") else 2):
             sg.train_step(dev_pool[i % n_pool], g, d, g_opt, d_opt, alpha, grad_sync=dp, **draws())
         barrier()
         kernels.conv_probe = None
+        if os.environ.get("SARAGAN_BENCH_DEBUG") and rank == 0:
+            print("debug: eager probe steps done", file=sys.stderr)
     launches = graphed.launches_per_step * args.steps if use_graph else _lib.launch_count() - launches0
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:

@@ -89,23 +89,32 @@ class GraphedTrainStep:
                 self.out = self._step()
             self.segments = None
         else:
-            # several GPUs: the gradient all-reduce runs EAGERLY between three graph segments
-            # (D forward/backward | D update + G forward/backward | G update) that share one memory
-            # pool, so NCCL never has to be captured; the gradients are static buffers of the pool
-            g1, g2, g3 = self.graph, torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            # several GPUs: the gradient all-reduce runs EAGERLY between graph segments
+            #   g1: D forward/backward | g2a: the G update's generator forward | g2b: D update + D(fakes) +
+            #   backward | g3: G update
+            # that share one memory pool, so NCCL never has to be captured; the gradients are static buffers of
+            # the pool.  g2a needs nothing the D update changes, so it replays WHILE the D gradients are being
+            # averaged on a side stream; only the G gradients' all-reduce is exposed.
+            g1, g2a, g2b, g3 = self.graph, torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(g1):
                 od = d_phase(self.x, self.g, self.d, self.d_optim, self.alpha, noise=self.noise, z_d=self.z_d,
                              eps=self.eps)
             # the gradient buffers the captured backward writes (p.grad is re-bound by any later eager step)
             self._d_grads = [p.grad for p in self.d.parameters() if p.grad is not None]
-            with torch.cuda.graph(g2, pool=g1.pool()):
+            with torch.cuda.graph(g2a, pool=g1.pool()):
+                self.g.train()
+                for p in self.g.parameters():
+                    p.requires_grad = True
+                x_fake_g = self.g(self.z_g, self.alpha)[-1]
+            with torch.cuda.graph(g2b, pool=g1.pool()):
                 self.d_optim.step()
-                og = g_phase(self.x.shape[0], self.g, self.d, self.g_optim, self.alpha, z_g=self.z_g)
+                og = g_phase(self.x.shape[0], self.g, self.d, self.g_optim, self.alpha, z_g=self.z_g, x_fake=x_fake_g)
                 dist_ = od["d_real_mean"] - og["d_fake_mean"]
             self._g_grads = [p.grad for p in self.g.parameters() if p.grad is not None]
             with torch.cuda.graph(g3, pool=g1.pool()):
                 self.g_optim.step()
-            self.segments = (g1, g2, g3)
+            self.segments = (g1, g2a, g2b, g3)
+            self._comm_stream = torch.cuda.Stream(device=dev)
             self.out = {"d_loss": od["d_loss"], "gp": od["gp"], "g_loss": og["g_loss"], "distance": dist_,
                         "x_fake": og["x_fake"]}
         self.launches_per_step = _lib.launch_count() - n0   # our kernels inside one replay
@@ -131,10 +140,15 @@ class GraphedTrainStep:
         if self.segments is None:
             self.graph.replay()
         else:
-            g1, g2, g3 = self.segments
+            g1, g2a, g2b, g3 = self.segments
+            main, comm = torch.cuda.current_stream(self.dev), self._comm_stream
             g1.replay()
-            self.grad_sync.finish_tensors(self._d_grads)
-            g2.replay()
+            comm.wait_stream(main)
+            with torch.cuda.stream(comm):
+                self.grad_sync.finish_tensors(self._d_grads)     # overlaps the generator forward below
+            g2a.replay()
+            main.wait_stream(comm)
+            g2b.replay()
             self.grad_sync.finish_tensors(self._g_grads)
             g3.replay()
         return self.out

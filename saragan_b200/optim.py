@@ -97,6 +97,9 @@ class FusedAdam(torch.optim.Optimizer):
             tab = self._table(gi, params, beta1)
             call("sg_adam_step", tab["t"], tab["bt"], tab["bo"], tab["n_blocks"], self._step_dev, float(group["lr"]),
                  float(beta1), float(beta2), float(group["eps"]), float(self.ema_beta or 0.0))
+            # the kernel wrote the parameters through raw pointers: tell torch (the packed-weight caches of the conv
+            # layers key on the version counter -- without this they kept serving the weights of the first step)
+            torch.autograd.graph.increment_version(params)
         if first is not None:
             call("sg_adam_advance", self._step_dev)
 

@@ -100,15 +100,19 @@ def d_phase(x_real: torch.Tensor, generator, discriminator, discriminator_optim,
 
 
 def g_phase(batch: int, generator, discriminator, generator_optim, alpha, *,
-            z_g: Optional[torch.Tensor] = None, grad_sync=None) -> Dict[str, torch.Tensor]:
-    """train.py:166-184: G forward, D forward on the fakes, g_loss.backward() (no optimiser step)."""
+            z_g: Optional[torch.Tensor] = None, grad_sync=None, x_fake: Optional[torch.Tensor] = None
+            ) -> Dict[str, torch.Tensor]:
+    """train.py:166-184: G forward, D forward on the fakes, g_loss.backward() (no optimiser step).
+    x_fake: G(z_g, alpha)[-1] with its autograd graph, when the caller ran the generator forward ahead of
+    time (graph.GraphedTrainStep overlaps it with the D gradients' all-reduce)."""
     generator.train()
     discriminator.eval()
     _set_requires_grad(generator, True)
     _set_requires_grad(discriminator, False)
-    if z_g is None:
-        z_g = torch.randn(batch, generator.latent_dim)
-    x_fake = generator(z_g, alpha)[-1]
+    if x_fake is None:
+        if z_g is None:
+            z_g = torch.randn(batch, generator.latent_dim)
+        x_fake = generator(z_g, alpha)[-1]
     d_fake = discriminator(x_fake, alpha)
     g_loss = -wasserstein_loss(d_fake)
     generator_optim.zero_grad()

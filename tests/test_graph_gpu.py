@@ -36,8 +36,23 @@ def _eager_arm(x, draws):
     return o, [p.detach() for p in list(g2.parameters()) + list(d2.parameters())]
 
 
-@pytest.mark.parametrize("n_replays", [1, 3])
-def test_graph_replay_matches_eager(n_replays):
+class _NoSync:
+    """stands in for comm.FlatAllReduce on one GPU: selects the segmented capture (what several GPUs run)"""
+    world = 1
+
+    def arm(self, module):
+        pass
+
+    def finish(self, module):
+        pass
+
+    def finish_tensors(self, grads):
+        for g in grads:          # touch the buffers on the comm stream like an all-reduce would
+            g.mul_(1.0)
+
+
+@pytest.mark.parametrize("n_replays,segmented", [(1, False), (3, False), (3, True)])
+def test_graph_replay_matches_eager(n_replays, segmented):
     """Replays against eager steps from the same state and draws.  Two EAGER runs of this step
     already differ: fp32-atomic summation order perturbs gradients at the 1e-7 level and Adam
     with beta1 = 0 turns a near-zero gradient of either sign into a +-lr step.  The graph must
@@ -48,7 +63,9 @@ def test_graph_replay_matches_eager(n_replays):
     g_opt, d_opt = make_capturable_optimizers(g1, d1)
     # warm-up steps run eagerly on the (zero) static input buffer and initialise the Adam state
     # outside the graph; the draw made right before the capture is consumed by no executed step
-    graphed = _Recording(g1, d1, g_opt, d_opt, B, VOL, ALPHA, warmup=WARM, seed=7)
+    graphed = _Recording(g1, d1, g_opt, d_opt, B, VOL, ALPHA, warmup=WARM, seed=7,
+                         grad_sync=_NoSync() if segmented else None)
+    assert (graphed.segments is not None) == segmented
     for xi in x:
         o = graphed(xi)
     loss_graph = [float(o[k]) for k in ("d_loss", "gp", "g_loss")]

@@ -59,3 +59,24 @@ def test_prepare_real_and_loader(tmp_path):
     assert torch.allclose(x0, want - 1e-2 * noise, rtol=1e-6, atol=1e-6)
     ragged = torch.arange(7, dtype=torch.int32).to(torch.uint16).cuda().reshape(1, 1, 1, 7)   # scalar tail path
     assert torch.allclose(data.prepare_real(ragged).flatten(), torch.arange(7, device="cuda") / 1024)
+
+
+def test_fused_adam_step_invalidates_packed_weight_caches():
+    """FusedAdam writes the parameters through raw pointers; the conv layers cache packed copies of their weights
+    keyed on the version counter.  After a step the next forward must see the NEW weights."""
+    import saragan_b200 as sg
+    from saragan_b200.optim import FusedAdam
+    conv = sg.EqualizedConv3d(16, 16, 3, padding=1).cuda()
+    opt = FusedAdam(conv.parameters(), lr=0.5, betas=(0.0, 0.99))
+    x = torch.randn(2, 16, 2, 8, 8, device="cuda")
+    y0 = conv(x)
+    y0.sum().backward()
+    v0 = conv.weight._version
+    opt.step()
+    assert conv.weight._version > v0
+    with torch.no_grad():
+        y1 = conv(x)
+        ref = torch.nn.functional.conv3d(x, conv.weight * conv.std, conv.bias, 1, 1)
+    assert float((y1 - y0.detach()).abs().max()) > 1e-2          # lr 0.5: the output must move
+    assert float((y1.float() - ref).abs().max()) < 5e-2 * float(ref.abs().max())
+
