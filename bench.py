@@ -240,8 +240,10 @@ def main():
         # a graph replay cannot carry per-kernel events: time the dominant kernel in two eager
         # passes of the same step (same shapes, same in-step cache state) right after the timed region
         kernels.conv_probe = probe
-        for i in range(0 if os.environ.get("SARAGAN_BENCH_SKIP_PROBE") else 2):
-            sg.train_step(dev_pool[i % n_pool], g, d, g_opt, d_opt, alpha, grad_sync=dp, **draws())
+        for i in range(2):
+            # single-stream order: with the gradient-penalty chain on its second stream the events around a launch
+            # would also time whatever the other stream runs meanwhile
+            sg.train_step(dev_pool[i % n_pool], g, d, g_opt, d_opt, alpha, grad_sync=dp, overlap_gp=False, **draws())
         barrier()
         kernels.conv_probe = None
         if os.environ.get("SARAGAN_BENCH_DEBUG") and rank == 0:
@@ -283,7 +285,7 @@ def main():
             "config": {"workload": cfg["desc"], "name": args.config, "per_gpu_batch": B, "global_batch": B * world,
                        "alpha": alpha, "parallelism": f"dp{world}",
                        "launch": ("cuda-graph replay of the whole step" if world == 1 else
-                                  "3 cuda-graph segments + eager NCCL all-reduce") if use_graph else "eager",
+                                  "4 cuda-graph segments + eager NCCL all-reduce (D-gradient all-reduce overlapped with the generator forward)") if use_graph else "eager",
                        "l2": "per-step working set (GBs of activations) >> 126 MB L2; 4 rotating input batches",
                        "step_gflop_per_image": step_flops / 1e9,
                        "step_tensor_frac": step_flops * value / world / (pk["bf16"] * 1e12)},

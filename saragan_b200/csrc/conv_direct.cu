@@ -266,7 +266,8 @@ __global__ void k_conv_finish(const float* __restrict__ acc, const float* __rest
     float sum[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) sum[j] = a[j];
-    for (int z = 1; z < slices; ++z) {   // fixed order: deterministic
+#pragma unroll 8
+    for (int z = 1; z < slices; ++z) {   // fixed order: deterministic (unrolled: 8 slices' loads in flight)
       const float4 p0 = *reinterpret_cast<const float4*>(a + z * slice_stride);
       const float4 p1 = *reinterpret_cast<const float4*>(a + z * slice_stride + 4);
       sum[0] += p0.x; sum[1] += p0.y; sum[2] += p0.z; sum[3] += p0.w;

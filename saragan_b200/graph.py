@@ -6,7 +6,7 @@ minibatch-stddev, Adam); issued one by one from Python they cost more host time 
 needs to execute them once the convolutions run on tcgen05.  Capturing the step removes the
 host from the loop (the north-star's "CUDA streams and graphs instead of a tracing compiler").
 
-On several GPUs the step is captured as three segments with the (eager) NCCL gradient all-reduce
+On several GPUs the step is captured as four segments with the (eager) NCCL gradient all-reduce
 between them -- see __init__.
 
 Inputs live in static buffers: the real batch, the instance-noise draw, the two latent draws and

@@ -127,14 +127,14 @@ def g_phase(batch: int, generator, discriminator, generator_optim, alpha, *,
 def train_step(x_real: torch.Tensor, generator, discriminator, generator_optim, discriminator_optim,
                alpha, *, noise: Optional[torch.Tensor] = None, z_d: Optional[torch.Tensor] = None,
                z_g: Optional[torch.Tensor] = None, eps: Optional[torch.Tensor] = None,
-               apply: bool = True, grad_sync=None) -> Dict[str, torch.Tensor]:
+               apply: bool = True, grad_sync=None, overlap_gp: bool = True) -> Dict[str, torch.Tensor]:
     """One D update followed by one G update (train.py:133-190).
 
     grad_sync: optional ``comm.DataParallel``; ``arm(module)`` is called before ``backward()``
     and ``finish(module)`` before ``optim.step()`` (the data-parallel gradient all-reduce,
     reference: hvd.DistributedOptimizer, main.py:153-160)."""
     out = d_phase(x_real, generator, discriminator, discriminator_optim, alpha, noise=noise, z_d=z_d, eps=eps,
-                  grad_sync=grad_sync)
+                  grad_sync=grad_sync, overlap_gp=overlap_gp)
     if grad_sync is not None:
         grad_sync.finish(discriminator)
     if apply:
