@@ -43,6 +43,13 @@ int sg_version(void);
  * 0 (default): plain stream order.  Results are identical; on the cfg3 step PDL measured 2 % slower. */
 void sg_set_pdl(int on);
 const char* sg_last_error(void);
+/* negative slope of every fused LeakyReLU (forward flag `lrelu`) and of every LeakyReLU-backward mask
+ * (`mask_src`, `mask_ref`, `mask_input`, sg_mask_mul) below.  Default 0.2 = nn.LeakyReLU(0.2) of network.py;
+ * network_dict.py's NONLINEARITY_DICT (network_dict.py:18-23) uses 0.3 ('leaky_relu') or 0 ('relu').
+ * Process-wide like the reference's module constant; synchronises the device, so call it when a model is
+ * built, not per step.  0 <= slope <= 1. */
+int sg_set_leaky_slope(float slope);
+float sg_get_leaky_slope(void);
 /* number of kernels this library has launched in this process (optionally reset) */
 int64_t sg_launch_count(int reset);
 /* number of bf16 convolutions the tcgen05 planners declined (run by the CUDA-core kernels instead) */

@@ -33,6 +33,8 @@ SIGNATURES = {
     "sg_conv3d_fprop": [_c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                         _c_int, _c_f, _c_int, _c_int, _c_p, _c_i64, _c_p],
     "sg_set_pdl": [_c_int],
+    "sg_set_leaky_slope": [_c_f],
+    "sg_get_leaky_slope": [],
     "sg_tc_force_streaming": [_c_int],
     "sg_tc_res_zs_mode": [_c_int],
     "sg_tc_force_plan": [_c_int, _c_int, _c_int, _c_int],
@@ -65,7 +67,7 @@ SIGNATURES = {
 }
 _RESTYPES = {"sg_last_error": ctypes.c_char_p, "sg_packed_weight_elems": ctypes.c_int64,
              "sg_conv3d_workspace_bytes": ctypes.c_int64, "sg_launch_count": ctypes.c_int64, "sg_cuda_core_fallbacks": ctypes.c_int64,
-             "sg_set_pdl": None, "sg_tc_force_streaming": None, "sg_tc_res_zs_mode": None, "sg_tc_force_plan": None}
+             "sg_set_pdl": None, "sg_get_leaky_slope": ctypes.c_float, "sg_tc_force_streaming": None, "sg_tc_res_zs_mode": None, "sg_tc_force_plan": None}
 
 _lib = None
 

@@ -91,8 +91,18 @@ __device__ __forceinline__ float ld1(const float* p) { return *p; }
 __device__ __forceinline__ void st1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 __device__ __forceinline__ void st1(float* p, float v) { *p = v; }
 
-__device__ __forceinline__ float lrelu02(float x) { return x > 0.f ? x : 0.2f * x; }
-__device__ __forceinline__ float lmask02(float ref) { return ref > 0.f ? 1.f : 0.2f; }
+// Negative slope of the fused LeakyReLU and of its backward masks.  One copy of the constant per translation
+// unit (the library is built without relocatable device code); sg_set_leaky_slope() writes all of them.
+// Default 0.2 = pgan_pytorch/network.py; network_dict.py uses LEAKINESS = 0.3 (network_dict.py:18) or ReLU (0).
+static __constant__ float c_sg_leak = 0.2f;
+#define SG_DEFINE_LEAK_SETTER(name) \
+  int name(float slope) { return (int)cudaMemcpyToSymbol(c_sg_leak, &slope, sizeof(float)); }
+int sg_set_leak_elementwise(float slope);
+int sg_set_leak_conv_direct(float slope);
+int sg_set_leak_conv_tc(float slope);
+int sg_set_leak_conv_tc_wgrad(float slope);
+__device__ __forceinline__ float lrelu02(float x) { return x > 0.f ? x : c_sg_leak * x; }
+__device__ __forceinline__ float lmask02(float ref) { return ref > 0.f ? 1.f : c_sg_leak; }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

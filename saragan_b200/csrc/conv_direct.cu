@@ -6,6 +6,7 @@
 // dgrad is fprop with the flipped/transposed packing: no third kernel.
 #include "../../include/saragan_b200.h"
 #include "common.cuh"
+SG_DEFINE_LEAK_SETTER(sg_set_leak_conv_direct)
 
 // tcgen05 paths (conv_tc.cu); return 1 when the shape is not covered so the caller can
 // fall through to the direct kernel, 0 on success, <0 / cudaError on failure.

@@ -33,6 +33,7 @@ int sg_conv_finish_bf16(const float* acc, const float* bias, const void* mask_sr
                         int Cout, int64_t V, float scale, int lrelu, cudaStream_t s);
 
 #include "tc_common.cuh"
+SG_DEFINE_LEAK_SETTER(sg_set_leak_conv_tc)
 
 namespace {
 

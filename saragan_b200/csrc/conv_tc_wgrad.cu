@@ -30,6 +30,7 @@
 // 4-byte atomics straight into that layout cost more than the MMAs at the low-resolution levels).
 #include "../../include/saragan_b200.h"
 #include "tc_common.cuh"
+SG_DEFINE_LEAK_SETTER(sg_set_leak_conv_tc_wgrad)
 
 namespace {
 

@@ -35,6 +35,28 @@ int sg_check_launch(const char* what) {
 int g_sg_pdl = 0;   // measured on cfg3 (graph replay): 17.57 ms/step with the attribute, 17.22 ms without
 extern "C" void sg_set_pdl(int on) { g_sg_pdl = on; }
 extern "C" const char* sg_last_error(void) { return g_err; }
+SG_DEFINE_LEAK_SETTER(sg_set_leak_elementwise)
+static float g_sg_leak = 0.2f;
+extern "C" float sg_get_leaky_slope(void) { return g_sg_leak; }
+extern "C" int sg_set_leaky_slope(float slope) {
+  SG_REQUIRE(slope >= 0.f && slope <= 1.f, "leaky slope %g outside [0, 1]", (double)slope);
+  if (slope == g_sg_leak) return 0;
+  // configuration call, not on the hot path: everything already enqueued keeps the old slope, everything
+  // enqueued afterwards (including replays of captured graphs) sees the new one
+  cudaError_t e = cudaDeviceSynchronize();
+  int rc = (int)e;
+  if (!rc) rc = sg_set_leak_elementwise(slope);
+  if (!rc) rc = sg_set_leak_conv_direct(slope);
+  if (!rc) rc = sg_set_leak_conv_tc(slope);
+  if (!rc) rc = sg_set_leak_conv_tc_wgrad(slope);
+  if (!rc) rc = (int)cudaDeviceSynchronize();
+  if (rc) {
+    sg_set_error("sg_set_leaky_slope: %s", cudaGetErrorString((cudaError_t)rc));
+    return rc;
+  }
+  g_sg_leak = slope;
+  return 0;
+}
 extern "C" int sg_version(void) { return 100; }
 
 // -------------------------------------------------------------------- layout conversion

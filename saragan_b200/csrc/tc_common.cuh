@@ -197,7 +197,7 @@ __device__ __forceinline__ void epilogue16(const float (&v)[16], const float* sb
   }
   if (lrelu) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) r[j] = fmaxf(r[j], 0.2f * r[j]);
+    for (int j = 0; j < 16; ++j) r[j] = lrelu02(r[j]);
   }
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
@@ -257,7 +257,7 @@ __device__ __forceinline__ void epilogue16_regmask(const float* v, const float* 
   }
   if (lrelu) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) r[j] = fmaxf(r[j], 0.2f * r[j]);
+    for (int j = 0; j < 16; ++j) r[j] = lrelu02(r[j]);
   }
   if (has_mask) {
     const F8 a = unpack8(m0), b = unpack8(m1);

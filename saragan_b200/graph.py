@@ -20,7 +20,7 @@ from typing import Dict, Optional
 
 import torch
 
-from .train import d_phase, g_phase, train_step
+from .train import d_phase, g_phase, top_image, train_step
 
 
 def make_capturable_optimizers(generator, discriminator, lr: float = 1e-3, world_size: int = 1,
@@ -105,7 +105,7 @@ class GraphedTrainStep:
                 self.g.train()
                 for p in self.g.parameters():
                     p.requires_grad = True
-                x_fake_g = self.g(self.z_g, self.alpha)[-1]
+                x_fake_g = top_image(self.g(self.z_g, self.alpha))
             with torch.cuda.graph(g2b, pool=g1.pool()):
                 self.d_optim.step()
                 og = g_phase(self.x.shape[0], self.g, self.d, self.g_optim, self.alpha, z_g=self.z_g, x_fake=x_fake_g)

@@ -47,6 +47,26 @@ class ConvProbe:
         return [a.elapsed_time(b) for a, b in self.pairs[tuple(key)]]
 
 
+def set_leaky_slope(slope: float) -> None:
+    """Negative slope of every fused LeakyReLU and LeakyReLU-backward mask (process-wide; 0.2 = network.py,
+    0.3 / 0.0 = network_dict.py's 'leaky_relu' / 'relu').  Synchronises the device when the value changes."""
+    lib = _lib.load()
+    rc = lib.sg_set_leaky_slope(float(slope))
+    if rc != 0:
+        msg = lib.sg_last_error()
+        raise RuntimeError(f"sg_set_leaky_slope failed (status {rc}): {msg.decode() if msg else ''}")
+
+
+def get_leaky_slope() -> float:
+    return float(_lib.load().sg_get_leaky_slope())
+
+
+def ensure_leaky_slope(want: float) -> None:
+    """Set the library's slope if it differs (a float compare on the host when it does not)."""
+    if abs(get_leaky_slope() - want) > 1e-7:
+        set_leaky_slope(want)
+
+
 def _vox(t: torch.Tensor) -> int:
     return t.shape[2] * t.shape[3] * t.shape[4]
 

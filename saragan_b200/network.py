@@ -21,7 +21,9 @@ import torch
 from torch import nn
 from torch.nn.modules.utils import _triple
 
-from . import config, ops
+from . import config, kernels, ops
+
+LEAKINESS = 0.2     # nn.LeakyReLU(negative_slope=0.2) everywhere in network.py
 
 
 def num_filters(phase, num_phases, base_dim):
@@ -77,9 +79,13 @@ class EqualizedConv3d(nn.Module, _Blocked):
         self.reset_parameters()
         self._packed = ops.PackedWeight(self.weight)
 
+    def _gain(self):
+        """torch's calculate_gain('conv3d') == 1 (network.py:16-23); network_dict.py's layers override."""
+        return 1.0
+
     def reset_parameters(self):
         fan_in = _fan_in(self.weight)
-        self.std = 1.0 / np.sqrt(fan_in)
+        self.std = self._gain() / np.sqrt(fan_in)
         with torch.no_grad():
             self.weight.normal_(0, 1)
             bound = 1 / np.sqrt(fan_in)
@@ -132,9 +138,12 @@ class EqualizedLinear(nn.Module):
         self.std = None
         self.reset_parameters()
 
+    def _gain(self):
+        return 1.0
+
     def reset_parameters(self):
         fan_in = self.weight.shape[1]
-        self.std = 1.0 / np.sqrt(fan_in)
+        self.std = self._gain() / np.sqrt(fan_in)
         with torch.no_grad():
             self.weight.normal_(0, 1)
             bound = 1 / np.sqrt(fan_in)
@@ -247,6 +256,7 @@ class Discriminator(nn.Module):
         """sub_batches (extension): `input` stacks that many independent minibatches along the batch
         axis -- e.g. D(cat(real, fake)) in one pass; minibatch-stddev treats them separately, so the
         result equals the concatenation of the separate calls."""
+        kernels.ensure_leaky_slope(LEAKINESS)
         alpha = _as_float(alpha)
         img = input.to(self.device).float().contiguous()
         # at phase > 1 the top FromRGB feeds only the first block's conv1, whose dgrad epilogue
@@ -357,6 +367,7 @@ class Generator(nn.Module):
         self.to(self.device)
 
     def forward(self, input, alpha):
+        kernels.ensure_leaky_slope(LEAKINESS)
         alpha = _as_float(alpha)
         gin = self.generator_in
         x = gin[0](input.to(self.device), lrelu=True)

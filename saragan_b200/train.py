@@ -31,6 +31,12 @@ def _side_stream(dev) -> "torch.cuda.Stream":
     return _side_streams[dev]
 
 
+def top_image(images) -> torch.Tensor:
+    """network.py's generator returns the list of images at every resolution (network.py:274-284), network_dict.py's
+    the image at the current one (network_dict.py:385-390): the step trains on the latter either way."""
+    return images[-1] if isinstance(images, (list, tuple)) else images
+
+
 def _set_requires_grad(module, flag: bool) -> None:
     for p in module.parameters():
         p.requires_grad = flag
@@ -54,7 +60,7 @@ def d_phase(x_real: torch.Tensor, generator, discriminator, discriminator_optim,
     if z_d is None:
         z_d = torch.randn(batch, generator.latent_dim)
     with torch.no_grad():
-        x_fake = generator(z_d, alpha)[-1].detach()
+        x_fake = top_image(generator(z_d, alpha)).detach()
 
     # The gradient-penalty chain (D(interpolates), its input gradient and the double backward) shares
     # nothing with the D(real)/D(fake) chain but the weights: on a GPU the two run on two streams and meet at
@@ -112,7 +118,7 @@ def g_phase(batch: int, generator, discriminator, generator_optim, alpha, *,
     if x_fake is None:
         if z_g is None:
             z_g = torch.randn(batch, generator.latent_dim)
-        x_fake = generator(z_g, alpha)[-1]
+        x_fake = top_image(generator(z_g, alpha))
     d_fake = discriminator(x_fake, alpha)
     g_loss = -wasserstein_loss(d_fake)
     generator_optim.zero_grad()

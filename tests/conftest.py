@@ -23,3 +23,16 @@ def cpu_kernels(monkeypatch):
         monkeypatch.setattr(kernels, name, getattr(cpu_emul, name))
     torch.manual_seed(0)
     return cpu_emul
+
+
+@pytest.fixture(autouse=True)
+def _default_leaky_slope():
+    """The LeakyReLU slope is a process-wide constant of the kernel library (and of its emulation): tests that
+    build network_dict.py models change it, every test starts and ends at network.py's 0.2."""
+    yield
+    import torch
+    from tests import cpu_emul
+    cpu_emul.set_leaky_slope(0.2)
+    if torch.cuda.is_available():
+        from saragan_b200 import kernels
+        kernels.ensure_leaky_slope(0.2)

@@ -10,6 +10,19 @@ import torch
 import torch.nn.functional as F
 
 
+LEAK = 0.2   # sg_set_leaky_slope / sg_get_leaky_slope (process-wide, like the library's)
+
+
+def set_leaky_slope(slope):
+    global LEAK
+    assert 0.0 <= slope <= 1.0
+    LEAK = float(slope)
+
+
+def get_leaky_slope():
+    return LEAK
+
+
 def chunks(c):
     return 2 * ((c + 15) // 16)
 
@@ -40,7 +53,7 @@ def pack_conv_weight(w, dtype, flip):
 
 
 def _mask(ref):
-    return torch.where(ref.float() > 0, 1.0, 0.2)
+    return torch.where(ref.float() > 0, 1.0, LEAK)
 
 
 def conv3d_fprop(x, wp, bias, mask_src, cin, cout, scale, lrelu, impl=0):
@@ -53,7 +66,7 @@ def conv3d_fprop(x, wp, bias, mask_src, cin, cout, scale, lrelu, impl=0):
     if bias is not None:
         y = y + bias.view(1, -1, 1, 1, 1)
     if lrelu:
-        y = F.leaky_relu(y, 0.2)
+        y = F.leaky_relu(y, LEAK)
     out = plain_to_act(y, x.dtype)
     if mask_src is not None:
         out = (out.float() * _mask(mask_src)).to(x.dtype)
@@ -73,7 +86,7 @@ def pw_expand(img, w, bias, dtype, c, scale, lrelu):
     if bias is not None:
         y = y + bias.view(1, -1, 1, 1, 1)
     if lrelu:
-        y = F.leaky_relu(y, 0.2)
+        y = F.leaky_relu(y, LEAK)
     return plain_to_act(y, dtype)
 
 
@@ -127,7 +140,7 @@ def lincomb(a, b, alpha, beta):
 
 
 def lrelu_fwd(x):
-    return F.leaky_relu(x.float(), 0.2).to(x.dtype)
+    return F.leaky_relu(x.float(), LEAK).to(x.dtype)
 
 
 def mask_mul(g, ref):
@@ -138,7 +151,7 @@ def pixelnorm_fwd(x, c, lrelu_after):
     xp = act_to_plain(x, c)
     y = xp * torch.rsqrt(torch.mean(xp ** 2, dim=1, keepdim=True) + 1e-8)
     if lrelu_after:
-        y = F.leaky_relu(y, 0.2)
+        y = F.leaky_relu(y, LEAK)
     return plain_to_act(y, x.dtype)
 
 
@@ -147,7 +160,7 @@ def pixelnorm_bwd(x, gy, c, lrelu_after, mask_input=False):
     with torch.enable_grad():
         y = xp * torch.rsqrt(torch.mean(xp ** 2, dim=1, keepdim=True) + 1e-8)
         if lrelu_after:
-            y = F.leaky_relu(y, 0.2)
+            y = F.leaky_relu(y, LEAK)
         (gx,) = torch.autograd.grad(y, xp, act_to_plain(gy, c))
     if mask_input:
         gx = gx * _mask(xp.detach())
@@ -171,7 +184,7 @@ def linear_fwd(x, w, bias, scale, lrelu):
     y = F.linear(x, w) * scale
     if bias is not None:
         y = y + bias
-    return F.leaky_relu(y, 0.2) if lrelu else y
+    return F.leaky_relu(y, LEAK) if lrelu else y
 
 
 def linear_dgrad(g, w, scale):
@@ -237,4 +250,4 @@ def mbstd_bwdbwd(u, gt, out, s, group, sub_batches=1):
     return d_gout, d_x
 
 
-ALL = [n for n in dir() if not n.startswith("_") and n not in ("torch", "F", "chunks", "ALL")]
+ALL = [n for n in dir() if not n.startswith("_") and n not in ("torch", "F", "chunks", "ALL", "LEAK")]
