@@ -164,6 +164,30 @@ int sg_adam_advance(int* step, cudaStream_t stream);
 int sg_prepare_real(const void* raw_u16, const float* noise, float* out, int64_t n, float scale, float sigma,
                     cudaStream_t stream);
 
+/* ---- evaluation metrics of the training loop (train.py:12-27 get_metrics; pgan_pytorch/metrics/swd.py, kms.py)
+ * Volumes are fp32 x[P][D][H][W] (P = batch * channels planes).
+ * pyr_down (swd.py:61-63): y = convolve(x, G5x5x5, mode='mirror')[::2, ::2, ::2], y is [P][(D+1)/2][(H+1)/2][(W+1)/2].
+ * pyr_up_sub (swd.py:65-78): lap = fine - convolve(zero_insert_x2(coarse), 4*G, mode='mirror'); coarse is
+ *   [P][cD][cH][cW], fine and lap [P][2cD][2cH][2cW] (lap may alias fine).  Stencil sums in fp64 like scipy. */
+int sg_pyr_down(const float* x, float* y, int64_t P, int D, int H, int W, cudaStream_t stream);
+int sg_pyr_up_sub(const float* fine, const float* coarse, float* lap, int64_t P, int cD, int cH, int cW, cudaStream_t stream);
+/* descriptors (swd.py:8-32) of one pyramid level level[B][D][H][W] (one channel): for each of the N positions
+ * (pos_z[j], pos_y[j], pos_x[j]) -- pos_x indexes the LAST axis -- the 3x9x9 neighbourhoods of all B images,
+ * standardised per position over (images, neighbourhood); a[b][j*243 + (dz*9 + dx)*9 + dy], rows row_stride apart.
+ * This is the reference's (N, N, 3, 9, 9) array without its 128 duplicate rows per image. */
+int sg_swd_descriptors(const float* level, const int* pos_z, const int* pos_y, const int* pos_x, float* a, int B,
+                       int D, int H, int W, int N, int64_t row_stride, cudaStream_t stream);
+/* projection (swd.py:43-44): p[r][c] = sum_k a[r][k] * dirs[k][c], dirs is [K][128]; colsq (nullable) receives
+ * sum_k dirs[k][c]^2 for directions that were not normalised beforehand (swd.py:42).  p, colsq are overwritten. */
+int sg_swd_project(const float* a, const float* dirs, float* p, float* colsq, int R, int64_t K, int64_t row_stride,
+                   cudaStream_t stream);
+/* one repeat of swd.py:44-47: p is [2B][128] (B real rows, then B fake rows); per direction both arms are sorted and
+ * out[0] = mean |real - fake| (p scaled by rsqrt(colsq) first when colsq is given).  B <= 64. */
+int sg_swd_finish(const float* p, const float* colsq, float* out, int B, cudaStream_t stream);
+/* kms.py:6-10: hist[n][q - lo] = #{ v : clip((long)((x[n][v] * intercept) + intercept), lo, hi) == q }, fp32
+ * arithmetic rounded after the multiply and after the add like numpy.  hist is overwritten. */
+int sg_value_hist(const float* x, int* hist, int N, int64_t V, float intercept, int lo, int hi, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,6 +64,12 @@ SIGNATURES = {
     "sg_adam_step": [_c_p, _c_p, _c_p, _c_int, _c_p, _c_f, _c_f, _c_f, _c_f, _c_f, _c_p],
     "sg_adam_advance": [_c_p, _c_p],
     "sg_prepare_real": [_c_p, _c_p, _c_p, _c_i64, _c_f, _c_f, _c_p],
+    "sg_pyr_down": [_c_p, _c_p, _c_i64, _c_int, _c_int, _c_int, _c_p],
+    "sg_pyr_up_sub": [_c_p, _c_p, _c_p, _c_i64, _c_int, _c_int, _c_int, _c_p],
+    "sg_swd_descriptors": [_c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_i64, _c_p],
+    "sg_swd_project": [_c_p, _c_p, _c_p, _c_p, _c_int, _c_i64, _c_i64, _c_p],
+    "sg_swd_finish": [_c_p, _c_p, _c_p, _c_int, _c_p],
+    "sg_value_hist": [_c_p, _c_p, _c_int, _c_i64, _c_f, _c_int, _c_int, _c_p],
 }
 _RESTYPES = {"sg_last_error": ctypes.c_char_p, "sg_packed_weight_elems": ctypes.c_int64,
              "sg_conv3d_workspace_bytes": ctypes.c_int64, "sg_launch_count": ctypes.c_int64, "sg_cuda_core_fallbacks": ctypes.c_int64,

@@ -307,3 +307,57 @@ def mbstd_bwdbwd(u: torch.Tensor, gt: torch.Tensor, out: torch.Tensor, s: torch.
     d_x = torch.empty((b, c, d, h, w), dtype=torch.float32, device=out.device)
     call("sg_mbstd_bwdbwd", u, gt, out, s, d_gout, d_gt, d_x, sub_batches, group, m, c, v)
     return d_gout, d_x
+
+
+# ------------------------------------------------------------------ evaluation metrics
+def pyr_down(x: torch.Tensor) -> torch.Tensor:
+    """swd.py:61-63 on a (N, C, D, H, W) fp32 volume."""
+    n, c, d, h, w = x.shape
+    y = torch.empty((n, c, (d + 1) // 2, (h + 1) // 2, (w + 1) // 2), dtype=torch.float32, device=x.device)
+    call("sg_pyr_down", x, y, n * c, d, h, w)
+    return y
+
+
+def pyr_up_sub(fine: torch.Tensor, coarse: torch.Tensor) -> torch.Tensor:
+    """fine - pyr_up(coarse)  (swd.py:65-78)."""
+    n, c, cd, ch, cw = coarse.shape
+    if tuple(fine.shape) != (n, c, 2 * cd, 2 * ch, 2 * cw):
+        raise ValueError(f"pyr_up_sub: {tuple(fine.shape)} is not twice {tuple(coarse.shape)} (odd extents have no "
+                         "Laplacian level in the reference either: its subtraction cannot broadcast)")
+    lap = torch.empty_like(fine)
+    call("sg_pyr_up_sub", fine, coarse, lap, n * c, cd, ch, cw)
+    return lap
+
+
+def swd_descriptors(level: torch.Tensor, pos_z: torch.Tensor, pos_y: torch.Tensor, pos_x: torch.Tensor,
+                    out: torch.Tensor) -> None:
+    """Standardised 3x9x9 descriptors of `level` (B, 1, D, H, W) at the N positions into out[b, j*243 + e]
+    (out: a (B, N*243) row-major view, e.g. one arm's rows of the stacked real/fake matrix)."""
+    b, c, d, h, w = level.shape
+    assert c == 1 and out.shape[0] == b and out.stride(1) == 1
+    n = pos_z.numel()
+    call("sg_swd_descriptors", level, pos_z, pos_y, pos_x, out, b, d, h, w, n, out.stride(0))
+
+
+def swd_project(a: torch.Tensor, dirs: torch.Tensor, want_colsq: bool) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """p = a @ dirs (a: (R, K), dirs: (K, 128)); colsq = squared column norms of dirs when asked for."""
+    r, k = a.shape
+    assert dirs.shape == (k, 128)
+    p = torch.empty((r, 128), dtype=torch.float32, device=a.device)
+    colsq = torch.empty(128, dtype=torch.float32, device=a.device) if want_colsq else None
+    call("sg_swd_project", a, dirs, p, colsq, r, k, a.stride(0))
+    return p, colsq
+
+
+def swd_finish(p: torch.Tensor, colsq: Optional[torch.Tensor], out: torch.Tensor) -> None:
+    """out[0] = mean over directions and sorted ranks of |real - fake| for one repeat (p: (2B, 128))."""
+    call("sg_swd_finish", p, colsq, out, p.shape[0] // 2)
+
+
+def value_hist(x: torch.Tensor, intercept: float, lo: int, hi: int) -> torch.Tensor:
+    """Per-image counts of clip(int(x*intercept + intercept), lo, hi): (N, hi-lo+1) int32 (kms.py:6-10)."""
+    n = x.shape[0]
+    v = x[0].numel() if n else 0
+    hist = torch.empty((n, hi - lo + 1), dtype=torch.int32, device=x.device)
+    call("sg_value_hist", x, hist, n, v, float(intercept), lo, hi)
+    return hist

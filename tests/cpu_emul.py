@@ -251,3 +251,58 @@ def mbstd_bwdbwd(u, gt, out, s, group, sub_batches=1):
 
 
 ALL = [n for n in dir() if not n.startswith("_") and n not in ("torch", "F", "chunks", "ALL", "LEAK")]
+
+
+# ------------------------------------------------------------------ evaluation metrics (csrc/metrics.cu)
+# restated with numpy / scipy directly from the kernels' contracts in include/saragan_b200.h
+def _binom3():
+    import numpy as np
+    f = np.array([1, 4, 6, 4, 1], dtype=np.float64) / 16
+    return f[:, None, None] * f[None, :, None] * f[None, None, :]
+
+
+def pyr_down(x):
+    import scipy.ndimage
+    y = scipy.ndimage.convolve(x.numpy().astype("float64"), _binom3()[None, None], mode="mirror")
+    return torch.from_numpy(y[:, :, ::2, ::2, ::2].astype("float32"))
+
+
+def pyr_up_sub(fine, coarse):
+    import numpy as np
+    import scipy.ndimage
+    n, c, cd, ch, cw = coarse.shape
+    assert tuple(fine.shape) == (n, c, 2 * cd, 2 * ch, 2 * cw)
+    z = np.zeros(tuple(fine.shape), dtype=np.float64)
+    z[:, :, ::2, ::2, ::2] = coarse.numpy()
+    up = scipy.ndimage.convolve(z, 4.0 * _binom3()[None, None], mode="mirror").astype("float32")
+    return fine - torch.from_numpy(up)
+
+
+def swd_descriptors(level, pos_z, pos_y, pos_x, out):
+    b = level.shape[0]
+    dz, dx, dy = torch.meshgrid(torch.arange(-1, 2), torch.arange(-4, 5), torch.arange(-4, 5), indexing="ij")
+    for j in range(pos_z.numel()):
+        patch = level[:, 0, (int(pos_z[j]) + dz), (int(pos_y[j]) + dy), (int(pos_x[j]) + dx)].reshape(b, -1).double()
+        patch = (patch - patch.mean()).float().double()
+        patch = (patch / patch.std(unbiased=False).float().double()).float()
+        out[:, j * 243:(j + 1) * 243] = patch
+
+
+def swd_project(a, dirs, want_colsq):
+    return a @ dirs, ((dirs * dirs).sum(0) if want_colsq else None)
+
+
+def swd_finish(p, colsq, out):
+    b = p.shape[0] // 2
+    if colsq is not None:
+        p = p * torch.rsqrt(colsq)
+    out[0] = (p[:b].sort(0).values - p[b:].sort(0).values).abs().mean()
+
+
+def value_hist(x, intercept, lo, hi):
+    import numpy as np
+    v = ((x.numpy() * np.float32(intercept)) + np.float32(intercept)).astype(np.int64).clip(lo, hi)
+    return torch.from_numpy(np.stack([np.bincount(r - lo, minlength=hi - lo + 1) for r in v]).astype(np.int32))
+
+
+ALL = [n for n in dir() if not n.startswith("_") and n not in ("torch", "F", "chunks", "ALL", "LEAK")]
