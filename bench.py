@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--alpha", type=float, default=0.5)
+    ap.add_argument("--network", default="network", choices=["network", "network_dict"],
+                    help="network: the pgan_pytorch/network.py API (BASELINE north star); network_dict: the network_dict.py "
+                         "variant main.py imports (LeakyReLU 0.3, He gain, no minibatch-stddev, top-level fade-in; SURVEY 8f row 3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=2)
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as CUDA graph(s) (on several GPUs: three "
@@ -108,16 +111,51 @@ class ClockSampler:
                     reasons=reasons, samples=len(sm))
 
 
-def cpu_step_rate(cfg, batch, steps, warmup, alpha, threads=None):
+def dict_oracle_state(cfg):
+    """network_dict.py parameters (reference names and distributions: weight ~ N(0,1), bias ~ U(+-1/sqrt(fan_in)))
+    for oracle/pgan_dict_oracle.py, laid out like the reference's state_dict at cfg's phase."""
+    from saragan_b200 import costmodel as C
+    from saragan_b200.network import num_filters
+    f = lambda i: int(num_filters(i, cfg["num_phases"], cfg["base_dim"]))     # noqa: E731
+    ph, bd, ld, vol0 = cfg["phase"], cfg["base_dim"], cfg["latent_dim"], int(np.prod(C.BASE_SHAPE[1:]))
+    g = {"generator_in.0": (vol0 * bd, ld), "generator_in.3": (bd, bd, 3, 3, 3), "torgb_current.conv": (1, f(ph), 1, 1, 1)}
+    d = {"fromrgb_current.fromrgb.0": (f(ph), 1, 1, 1, 1), "discriminator_out.0": (bd, bd, 3, 3, 3),
+         "discriminator_out.3": (ld, vol0 * bd), "discriminator_out.5": (1, ld)}
+    if ph > 1:
+        g["torgb_prev.conv"] = (1, f(ph - 1), 1, 1, 1)
+        d["fromrgb_prev.fromrgb.0"] = (f(ph - 1), 1, 1, 1, 1)
+    for i in range(2, ph + 1):
+        g[f"blocks.block_phase_{i}.conv1"] = (f(i), f(i - 1), 3, 3, 3)
+        g[f"blocks.block_phase_{i}.conv2"] = (f(i), f(i), 3, 3, 3)
+        d[f"blocks.block_phase_{i}.conv1"] = (f(i), f(i), 3, 3, 3)
+        d[f"blocks.block_phase_{i}.conv2"] = (f(i - 1), f(i), 3, 3, 3)
+    gen = torch.Generator().manual_seed(0)
+    out = []
+    for shapes in (g, d):
+        p = {}
+        for name, shp in shapes.items():
+            w = torch.empty(shp).normal_(0, 1, generator=gen)
+            bound = 1.0 / float(np.sqrt(w[0].numel()))
+            p[name + ".weight"], p[name + ".bias"] = w, torch.empty(shp[0]).uniform_(-bound, bound, generator=gen)
+        out.append(p)
+    return out
+
+
+def cpu_step_rate(cfg, batch, steps, warmup, alpha, threads=None, network="network"):
     """images/s of the oracle (CPU restatement of the reference step) on the host cores."""
     from oracle import pgan_oracle as O
     from saragan_b200 import costmodel as C
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
-    gen = torch.Generator().manual_seed(0)
-    pg = O.init_params("g", cfg["num_phases"], cfg["base_dim"], cfg["latent_dim"], C.BASE_SHAPE, gen)
-    pd = O.init_params("d", cfg["num_phases"], cfg["base_dim"], cfg["latent_dim"], C.BASE_SHAPE, gen)
-    st = O.TrainState(pg, pd, cfg["phase"], cfg["num_phases"])
+    if network == "network_dict":
+        from oracle import pgan_dict_oracle as OD
+        pg, pd = dict_oracle_state(cfg)
+        st = OD.DictTrainState(pg, pd, cfg["phase"], "leaky_relu", 0.3)
+    else:
+        gen = torch.Generator().manual_seed(0)
+        pg = O.init_params("g", cfg["num_phases"], cfg["base_dim"], cfg["latent_dim"], C.BASE_SHAPE, gen)
+        pd = O.init_params("d", cfg["num_phases"], cfg["base_dim"], cfg["latent_dim"], C.BASE_SHAPE, gen)
+        st = O.TrainState(pg, pd, cfg["phase"], cfg["num_phases"])
     vol = C.volume(cfg["phase"])
     x = smooth_volumes(batch, vol, seed=1)
     times = []
@@ -135,12 +173,13 @@ def run_reference(args, cfg, rank):
     if rank != 0:
         return
     b = args.cpu_batch
-    rate, t, threads = cpu_step_rate(cfg, b, args.steps, args.warmup, args.alpha)
-    sample = f"{args.steps} full train steps (after {args.warmup} warm-up) at batch {b} of {args.config}, fp32, torch CPU"
+    rate, t, threads = cpu_step_rate(cfg, b, args.steps, args.warmup, args.alpha, network=args.network)
+    sample = (f"{args.steps} full train steps (after {args.warmup} warm-up) at batch {b} of {args.config} "
+              f"({args.network}.py), fp32, torch CPU")
     line = {"impl": "reference", "metric": "G+D train images/s", "value": rate, "unit": "img/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["desc"], "per_gpu_batch": b, "name": args.config},
+            "config": {"workload": cfg["desc"], "per_gpu_batch": b, "name": args.config, "network": args.network + ".py"},
             "cpu_baseline": {"value": rate, "unit": "img/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -172,8 +211,13 @@ def main():
     vol = C.volume(cfg["phase"])
 
     torch.manual_seed(0)
-    g = sg.Generator(cfg["phase"], cfg["num_phases"], cfg["base_dim"], cfg["latent_dim"], C.BASE_SHAPE)
-    d = sg.Discriminator(cfg["phase"], cfg["num_phases"], cfg["base_dim"], cfg["latent_dim"], C.BASE_SHAPE)
+    if args.network == "network_dict":
+        from saragan_b200 import network_dict as nd
+        margs = (cfg["phase"], cfg["num_phases"], cfg["base_dim"], cfg["latent_dim"], C.BASE_SHAPE, "leaky_relu")
+        g, d = nd.Generator(*margs, param=0.3), nd.Discriminator(*margs, param=0.3)     # main.py:203-204 defaults
+    else:
+        g = sg.Generator(cfg["phase"], cfg["num_phases"], cfg["base_dim"], cfg["latent_dim"], C.BASE_SHAPE)
+        d = sg.Discriminator(cfg["phase"], cfg["num_phases"], cfg["base_dim"], cfg["latent_dim"], C.BASE_SHAPE)
     use_graph = args.graph == 1
     if use_graph:
         from saragan_b200.graph import GraphedTrainStep, make_capturable_optimizers
@@ -277,12 +321,13 @@ def main():
 
     if rank == 0:
         pk = peaks()
-        step_flops = C.step_flops_per_image(**cfg)
+        step_flops = (C.step_flops_per_image_dict if args.network == "network_dict" else C.step_flops_per_image)(**cfg)
         line = {
             "metric": "G+D train images/s", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": cfg["desc"], "name": args.config, "per_gpu_batch": B, "global_batch": B * world,
+            "config": {"workload": cfg["desc"], "name": args.config, "network": args.network + ".py",
+                       "per_gpu_batch": B, "global_batch": B * world,
                        "alpha": alpha, "parallelism": f"dp{world}",
                        "launch": ("cuda-graph replay of the whole step" if world == 1 else
                                   "4 cuda-graph segments + eager NCCL all-reduce (D-gradient all-reduce overlapped with the generator forward)") if use_graph else "eager",
@@ -312,7 +357,7 @@ def main():
             line["roofline_more"] = [x for x in (roof("fprop", f"k_conv_tc_res: conv3d fprop {name} {shape}"),
                                                  roof("dgrad", f"k_conv_tc_res: conv3d dgrad {name} {shape}")) if x]
         if world == 1 and not args.no_cpu_baseline:
-            rate, t, threads = cpu_step_rate(cfg, args.cpu_batch, 1, 0, alpha)
+            rate, t, threads = cpu_step_rate(cfg, args.cpu_batch, 1, 0, alpha, network=args.network)
             line["cpu_baseline"] = {"value": rate, "unit": "img/s", "cores": threads, "kind": "port",
                                     "sample": f"1 full train step at batch {args.cpu_batch} of {args.config} "
                                               f"({t:.1f} s), fp32 torch CPU oracle"}

@@ -59,3 +59,19 @@ def step_flops_per_image(phase, num_phases, base_dim, latent_dim, **_):
     gf = forward_flops_per_image("g", phase, num_phases, base_dim, latent_dim)
     df = forward_flops_per_image("d", phase, num_phases, base_dim, latent_dim)
     return 4 * gf + 14 * df
+
+
+def step_flops_per_image_dict(phase, num_phases, base_dim, latent_dim, **_):
+    """4*Gf + 14*Df for the network_dict.py variant: generator block i is f(i-1) -> f(i) -> f(i)
+    (network_dict.py:352-356; network.py's is f(i) -> f(i+1)), no minibatch-stddev channel, To/FromRGB at the
+    two top levels only."""
+    f = lambda i: num_filters(i, num_phases, base_dim)    # noqa: E731
+    vol0 = int(np.prod(BASE_SHAPE[1:]))
+    vox = lambda i: int(np.prod(volume(i)))               # noqa: E731
+    gf = 2.0 * latent_dim * vol0 * base_dim + 2.0 * base_dim * base_dim * 27 * vol0
+    gf += sum(2.0 * 27 * (f(i - 1) * f(i) + f(i) * f(i)) * vox(i) for i in range(2, phase + 1))
+    gf += 2.0 * f(phase) * vox(phase) + (2.0 * f(phase - 1) * vox(phase - 1) if phase > 1 else 0.0)
+    df = sum(2.0 * 27 * (f(i) * f(i) + f(i) * f(i - 1)) * vox(i) for i in range(2, phase + 1))
+    df += 2.0 * base_dim * base_dim * 27 * vol0 + 2.0 * vol0 * base_dim * latent_dim + 2.0 * latent_dim
+    df += 2.0 * f(phase) * vox(phase) + (2.0 * f(phase - 1) * vox(phase - 1) if phase > 1 else 0.0)
+    return 4 * gf + 14 * df

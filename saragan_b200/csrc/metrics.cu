@@ -26,6 +26,7 @@ constexpr int kPatch = 3 * 9 * 9;   // swd.py:99 nhood_size (1, 2, 8, 8) -> (2*1
 
 // scipy.ndimage mode='mirror': reflect about the centre of the edge sample (d c b | a b c d | c b a)
 __device__ __forceinline__ int mirror(int i, int n) {
+  if ((unsigned)i < (unsigned)n) return i;       // interior taps: no integer division
   if (n == 1) return 0;
   const int p = 2 * (n - 1);
   i %= p;
@@ -74,20 +75,26 @@ __global__ void k_pyr_up_sub(const float* __restrict__ fine, const float* __rest
     const int w = (int)(i % W), h = (int)((i / W) % H), d = (int)((i / ((int64_t)W * H)) % D);
     const int64_t p = i / ((int64_t)W * H * D);
     const float* cp = coarse + p * (int64_t)cD * cH * cW;
-    double acc = 0.0;
-    for (int a = 0; a < 5; ++a) {
-      const int zd = mirror(d + a - 2, D);
-      if (zd & 1) continue;                      // zero-inserted sample
-      for (int b = 0; b < 5; ++b) {
-        const int zh = mirror(h + b - 2, H);
-        if (zh & 1) continue;
-        const float wab = c_binom[a] * c_binom[b];
+    int zd[5], zh[5], zw[5];                       // -1: the tap falls on a zero-inserted sample
 #pragma unroll
-        for (int c = 0; c < 5; ++c) {
-          const int zw = mirror(w + c - 2, W);
-          if (zw & 1) continue;
-          acc += (double)(wab * c_binom[c] * 4.0f) * (double)cp[((int64_t)(zd >> 1) * cH + (zh >> 1)) * cW + (zw >> 1)];
-        }
+    for (int t = 0; t < 5; ++t) {
+      const int md = mirror(d + t - 2, D), mh = mirror(h + t - 2, H), mw = mirror(w + t - 2, W);
+      zd[t] = (md & 1) ? -1 : md >> 1;
+      zh[t] = (mh & 1) ? -1 : mh >> 1;
+      zw[t] = (mw & 1) ? -1 : mw >> 1;
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+      if (zd[a] < 0) continue;
+#pragma unroll
+      for (int b = 0; b < 5; ++b) {
+        if (zh[b] < 0) continue;
+        const float wab = c_binom[a] * c_binom[b] * 4.0f;
+        const float* row = cp + ((int64_t)zd[a] * cH + zh[b]) * cW;
+#pragma unroll
+        for (int c = 0; c < 5; ++c)
+          if (zw[c] >= 0) acc += (double)(wab * c_binom[c]) * (double)row[zw[c]];
       }
     }
     lap[i] = fine[i] - (float)acc;
@@ -152,52 +159,90 @@ __global__ void k_swd_descriptors(const float* __restrict__ level, const int* __
 // Block = 128 columns x KY k-lanes over one slice of K.  dirs dominates the traffic (K x 512 bytes against R x K x 4)
 // and is read straight from global memory, each element once, 512 contiguous bytes per row; the A tile [R][KT] goes
 // through shared memory and is broadcast to the 128 columns.
-constexpr int kProjRows = 16, kProjKY = 4, kProjKT = 64;
+constexpr int kProjKY = 4, kProjKT = 64;
+template <int ROWS>      // ROWS in {4, 8, 16}: rows of A per pass, a multiple of 4 (float4 shared-memory reads)
 __global__ void __launch_bounds__(kDirs* kProjKY)
     k_swd_project(const float* __restrict__ a, const float* __restrict__ dirs, float* __restrict__ p,
-                  float* __restrict__ colsq, int R, int64_t K, int64_t row_stride, int64_t k_per_block) {
+                  float* __restrict__ colsq, int R, int64_t K, int64_t row_stride) {
   sg_pdl_enter();
-  __shared__ float as[kProjRows][kProjKT];
-  __shared__ float part[kProjKY][kProjRows + 1][kDirs];
+  // A tile transposed to [k][row]: a thread reads the ROWS values of one k as ROWS/4 broadcast float4 loads (the
+  // first version read them as 16 scalar loads per k and was bound by shared-memory wavefronts: ncu 8.3 M per
+  // launch, l1tex 77 % busy at 19 % of the HBM peak).  The grid is ONE wave of resident blocks striding over the
+  // 64-row tiles of dirs (v2 launched 1.09 waves), and a thread has 8 independent loads of dirs in flight.
+  __shared__ __align__(16) float as[kProjKT][ROWS];
+  __shared__ float part[kProjKY][ROWS + 1][kDirs];
   const int c = threadIdx.x, ky = threadIdx.y;
   const int tid = ky * kDirs + c;
-  const int64_t k0 = blockIdx.x * k_per_block;
-  const int64_t k1 = min(K, k0 + k_per_block);
-  float acc[kProjRows];
+  const int64_t n_tiles = (K + kProjKT - 1) / kProjKT;
+  float acc[ROWS];
 #pragma unroll
-  for (int r = 0; r < kProjRows; ++r) acc[r] = 0.f;
+  for (int r = 0; r < ROWS; ++r) acc[r] = 0.f;
   float sq = 0.f;
-  for (int64_t kt = k0; kt < k1; kt += kProjKT) {
-    const int len = (int)min((int64_t)kProjKT, k1 - kt);
-    __syncthreads();
-    for (int i = tid; i < kProjRows * kProjKT; i += kDirs * kProjKY) {
-      const int r = i / kProjKT, k = i % kProjKT;
-      as[r][k] = (r < R && k < len) ? a[(int64_t)r * row_stride + kt + k] : 0.f;
+  auto accumulate = [&](int k, float d) {
+    sq = fmaf(d, d, sq);
+#pragma unroll
+    for (int q = 0; q < ROWS / 4; ++q) {
+      const float4 v = *reinterpret_cast<const float4*>(&as[k][4 * q]);
+      acc[4 * q + 0] = fmaf(v.x, d, acc[4 * q + 0]);
+      acc[4 * q + 1] = fmaf(v.y, d, acc[4 * q + 1]);
+      acc[4 * q + 2] = fmaf(v.z, d, acc[4 * q + 2]);
+      acc[4 * q + 3] = fmaf(v.w, d, acc[4 * q + 3]);
+    }
+  };
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int64_t kt = t * kProjKT;
+    const int len = (int)min((int64_t)kProjKT, K - kt);
+    const float* dp = dirs + kt * kDirs + c;
+    float d0[8];
+    if (len == kProjKT) {                      // issue the first batch of loads before waiting on the A tile
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d0[j] = dp[(int64_t)(ky + kProjKY * j) * kDirs];
     }
     __syncthreads();
-#pragma unroll 4
-    for (int k = ky; k < len; k += kProjKY) {
-      const float d = dirs[(kt + k) * kDirs + c];
-      sq = fmaf(d, d, sq);
+    for (int i = tid; i < ROWS * kProjKT; i += kDirs * kProjKY) {
+      const int r = i / kProjKT, k = i % kProjKT;          // consecutive threads read consecutive k of one row
+      as[k][r] = (r < R && k < len) ? a[(int64_t)r * row_stride + kt + k] : 0.f;
+    }
+    __syncthreads();
+    if (len == kProjKT) {
+      float d1[8];
 #pragma unroll
-      for (int r = 0; r < kProjRows; ++r) acc[r] = fmaf(as[r][k], d, acc[r]);
+      for (int j = 0; j < 8; ++j) d1[j] = dp[(int64_t)(ky + kProjKY * (8 + j)) * kDirs];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) accumulate(ky + kProjKY * j, d0[j]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) accumulate(ky + kProjKY * (8 + j), d1[j]);
+    } else {
+      for (int k = ky; k < len; k += kProjKY) accumulate(k, dp[(int64_t)k * kDirs]);
     }
   }
 #pragma unroll
-  for (int r = 0; r < kProjRows; ++r) part[ky][r][c] = acc[r];
-  part[ky][kProjRows][c] = sq;
+  for (int r = 0; r < ROWS; ++r) part[ky][r][c] = acc[r];
+  part[ky][ROWS][c] = sq;
   __syncthreads();
   if (ky == 0) {
-    for (int r = 0; r <= kProjRows; ++r) {
-      if (r < R || r == kProjRows) {
+    for (int r = 0; r <= ROWS; ++r) {
+      if (r < R || r == ROWS) {
         float v = 0.f;
 #pragma unroll
         for (int y = 0; y < kProjKY; ++y) v += part[y][r][c];
-        if (r < kProjRows) atomicAdd(p + (int64_t)r * kDirs + c, v);
+        if (r < ROWS) atomicAdd(p + (int64_t)r * kDirs + c, v);
         else if (colsq) atomicAdd(colsq + c, v);
       }
     }
   }
+}
+
+template <int ROWS>
+static unsigned project_grid(int64_t K) {
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_swd_project<ROWS>, kDirs * kProjKY, 0);
+    if (per_sm < 1) per_sm = 1;
+  }
+  const int64_t tiles = (K + kProjKT - 1) / kProjKT;
+  const int64_t wave = (int64_t)sg_num_sms() * per_sm;
+  return (unsigned)(tiles < wave ? tiles : wave);
 }
 
 // swd.py:44-47 for one repeat: per direction sort the B projections of each arm, sum |real - fake|;
@@ -300,16 +345,19 @@ extern "C" int sg_swd_project(const float* a, const float* dirs, float* p, float
     sg_set_error("sg_swd_project: %s", cudaGetErrorString(e));
     return (int)e;
   }
-  // ~4 blocks per SM; slices are whole tiles
-  int64_t per = (K + (int64_t)sg_num_sms() * 4 - 1) / ((int64_t)sg_num_sms() * 4);
-  per = (per + kProjKT - 1) / kProjKT * kProjKT;
-  const unsigned blocks = (unsigned)((K + per - 1) / per);
-  for (int r0 = 0; r0 < R; r0 += kProjRows) {     // 16 rows per pass; only the first pass accumulates the norms
-    const int rows = R - r0 < kProjRows ? R - r0 : kProjRows;
-    sg_launch((k_swd_project), blocks, dim3(kDirs, kProjKY), 0, s, a + (int64_t)r0 * row_stride, dirs,
-              p + (int64_t)r0 * kDirs, r0 == 0 ? colsq : (float*)nullptr, rows, K, row_stride, per);
+  for (int r0 = 0; r0 < R;) {     // up to 16 rows per pass; only the first pass accumulates the column norms
+    const int left = R - r0;
+    const int rows = left > 8 ? (left < 16 ? left : 16) : left;
+    const float* ap = a + (int64_t)r0 * row_stride;
+    float* pp = p + (int64_t)r0 * kDirs;
+    float* cs = r0 == 0 ? colsq : (float*)nullptr;
+    const dim3 block(kDirs, kProjKY);
+    if (rows > 8) sg_launch((k_swd_project<16>), project_grid<16>(K), block, 0, s, ap, dirs, pp, cs, rows, K, row_stride);
+    else if (rows > 4) sg_launch((k_swd_project<8>), project_grid<8>(K), block, 0, s, ap, dirs, pp, cs, rows, K, row_stride);
+    else sg_launch((k_swd_project<4>), project_grid<4>(K), block, 0, s, ap, dirs, pp, cs, rows, K, row_stride);
     int rc = sg_check_launch("sg_swd_project");
     if (rc) return rc;
+    r0 += rows;
   }
   return 0;
 }

@@ -22,7 +22,7 @@ for r in csv.DictReader(lines):
         name += " grid=" + r.get("Grid Size", "")
     rows.append((name, v))
 tot = sum(v for _, v in rows)
-ours = sum(v for n, v in rows if "k_" in n.split("<")[0])
+ours = sum(v for n, v in rows if re.search(r"\bk_[a-z]", n))
 print(f"{len(rows)} kernel launches, sum {tot:.2f} ms; libsaragan_b200 kernels (k_*): {ours:.2f} ms = {100 * ours / tot:.1f} %")
 agg = collections.defaultdict(lambda: [0.0, 0])
 for n, v in rows:
