@@ -293,3 +293,40 @@ def test_drop_in_api_surface():
     assert tuple(out.shape) == (4, 1) and out.dtype == torch.float32
     g.phase = 3                                            # phase is a mutable attribute
     assert len(g(torch.randn(4, 32), 1.0)) == 3
+
+
+_PROGRESSION_ORACLE = {}
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 2e-2)])
+def test_cfg2_progression_every_phase(precision, tol):
+    """BASELINE cfg2: the 'xs' networks (base_dim 256, 6 levels built up front, network.py:146-152,258-263) stepped
+    through the growth phases 1..5 (1x4x4 ... 16x64x64) by assigning `.phase` on the SAME module instances, with the
+    fade-in active (alpha 0.5) and the per-phase batch max(2, 128 // resolution) (main.py:99 floored at 2): losses of
+    one train step per phase against the fp32 CPU oracle on the same weights and draws, and exactly the parameters of
+    the active levels receive gradients."""
+    cfg = dict(phase=5, num_phases=6, base_dim=256, latent_dim=256, base_shape=(1, 1, 4, 4), batch=2)
+    with sg.use_precision(precision):
+        g, d = build_pair(cfg, seed=1)
+        pg = {k: v.detach().cpu() for k, v in g.state_dict().items()}
+        pd = {k: v.detach().cpu() for k, v in d.state_dict().items()}
+        for phase in range(1, 6):
+            c = dict(cfg, phase=phase, batch=max(2, 128 // (4 * 2 ** (phase - 1))))
+            g.phase = d.phase = phase
+            inp = draw_inputs(c, seed=40 + phase)
+            inp["x_real"] = _smooth_volume(c["batch"], inp["x_real"].shape[2:], seed=50 + phase)
+            if phase not in _PROGRESSION_ORACLE:      # same weights and draws for both precisions: one oracle pass
+                _PROGRESSION_ORACLE[phase] = O.TrainState(pg, pd, phase, cfg["num_phases"]).step(
+                    inp["x_real"], inp["noise"], inp["z_d"], inp["eps"], inp["z_g"], 0.5, apply=False)
+            want = _PROGRESSION_ORACLE[phase]
+            for p in list(g.parameters()) + list(d.parameters()):
+                p.grad = None
+            got = run_step(g, d, inp, 0.5)
+            assert got["x_fake"].shape == inp["x_real"].shape
+            for k in ("d_loss", "gp"):
+                assert abs(float(got[k]) - want[k]) < tol * abs(want[k]), (phase, k, float(got[k]), want[k])
+            assert abs(float(got["g_loss"]) - want["g_loss"]) < tol * max(1.0, abs(want["g_loss"])), (phase, float(got["g_loss"]), want["g_loss"])
+            for kind, mod, key in (("d", d, "d_grads"), ("g", g, "g_grads")):
+                active = {k for k, p in mod.named_parameters() if p.grad is not None}
+                assert active == set(O.active_names(kind, phase, cfg["num_phases"])) == \
+                    {k for k, v in want[key].items() if v is not None}, (phase, kind)
