@@ -75,7 +75,7 @@ def smooth_volumes(n, vol, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -85,7 +85,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -95,20 +95,27 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([c.strip() for c in line.split(",")] + [time.perf_counter()])
 
     def __exit__(self, *a):
         if self.proc is not None:
             self.proc.terminate()
             self.t.join(timeout=2)
 
-    def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+    def summary(self, t0=None, t1=None):
+        """Samples that arrived inside the timed region [t0, t1]; a region shorter than nvidia-smi's sampling
+        period may hold none, then the samples of the warm-up steps right before it (same load) are used."""
+        rows = [r for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        inside = [r for r in rows if t0 is not None and t0 <= r[-1] <= t1]
+        window = "timed region"
+        if not inside:
+            inside, window = [r for r in rows if t1 is None or r[-1] <= t1][-5:], "warm-up + timed region (timed region shorter than the sampling period)"
+        sm = [float(r[0]) for r in inside]
+        mx = [float(r[1]) for r in inside if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        reasons = sorted({names[i] for r in inside for i in range(4) if r[2 + i] == "Active"})
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=reasons, samples=len(sm))
+                    reasons=reasons, samples=len(sm), window=window)
 
 
 def dict_oracle_state(cfg):
@@ -265,18 +272,20 @@ def main():
     probe = kernels.ConvProbe(probe_keys.values())
     # dram__bytes_read+write per launch from the committed `ncu --set full` capture (profiles/), cfg3 only
     ncu_traffic = {"wgrad": 407.1e6, "fprop": 349.9e6, "dgrad": 381.5e6} if (args.config == "cfg3" and B == 4) else {}
-    for i in range(args.warmup):
-        step(dev_pool[i % n_pool])
-    barrier()
-    kernels.conv_probe = probe
-    launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local) as clocks:          # started before the warm-up: nvidia-smi needs ~100 ms to deliver
+        for i in range(args.warmup):
+            step(dev_pool[i % n_pool])
+        barrier()
+        kernels.conv_probe = probe
+        launches0 = _lib.launch_count()
+        t_region0 = time.perf_counter()
         e0.record()
         for i in range(args.steps):
             out = step(dev_pool[i % n_pool])
         e1.record()
         barrier()
+        t_region1 = time.perf_counter()
     if os.environ.get("SARAGAN_BENCH_DEBUG") and rank == 0:
         print("debug: losses after the timed region", [float(out[k]) for k in ("d_loss", "g_loss", "gp")], file=sys.stderr)
     kernels.conv_probe = None
@@ -338,7 +347,7 @@ def main():
                     "d2h_bytes_per_step": 12},
             "gpu_launches": int(launches),
             "cuda_core_conv_fallbacks_per_step": graphed.cuda_core_conv_fallbacks if use_graph else None,
-            "clocks": clocks.summary(),
+            "clocks": clocks.summary(t_region0, t_region1),
             "losses": [float(v) for v in losses],
         }
         def roof(kind, label):
