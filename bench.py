@@ -248,6 +248,9 @@ def main():
                     z_g=torch.randn((B, cfg["latent_dim"]), device=dev, generator=rng),
                     eps=torch.rand((B, 1, 1, 1, 1), device=dev, generator=rng))
 
+    # nvidia-smi needs a few hundred ms before its first sample: start it before the capture's own warm-up steps
+    clocks = ClockSampler(local)
+    clocks.__enter__()
     if use_graph:
         graphed = GraphedTrainStep(g, d, g_opt, d_opt, B, vol, alpha, warmup=2, seed=1000 + rank, grad_sync=dp)
 
@@ -273,7 +276,7 @@ def main():
     # dram__bytes_read+write per launch from the committed `ncu --set full` capture (profiles/), cfg3 only
     ncu_traffic = {"wgrad": 407.1e6, "fprop": 349.9e6, "dgrad": 381.5e6} if (args.config == "cfg3" and B == 4) else {}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:          # started before the warm-up: nvidia-smi needs ~100 ms to deliver
+    try:
         for i in range(args.warmup):
             step(dev_pool[i % n_pool])
         barrier()
@@ -286,6 +289,8 @@ def main():
         e1.record()
         barrier()
         t_region1 = time.perf_counter()
+    finally:
+        clocks.__exit__(None, None, None)
     if os.environ.get("SARAGAN_BENCH_DEBUG") and rank == 0:
         print("debug: losses after the timed region", [float(out[k]) for k in ("d_loss", "g_loss", "gp")], file=sys.stderr)
     kernels.conv_probe = None
