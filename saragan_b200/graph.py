@@ -20,6 +20,7 @@ from typing import Dict, Optional
 
 import torch
 
+from . import kernels
 from .train import d_phase, g_phase, top_image, train_step
 
 
@@ -117,6 +118,9 @@ class GraphedTrainStep:
             self._comm_stream = torch.cuda.Stream(device=dev)
             self.out = {"d_loss": od["d_loss"], "gp": od["gp"], "g_loss": og["g_loss"], "distance": dist_,
                         "x_fake": og["x_fake"]}
+        # the LeakyReLU slope is a constant of the kernel library read at run time: a replay must see the value the
+        # capture's forward passes set (another model variant may have changed it in between)
+        self._leaky_slope = kernels.get_leaky_slope()
         self.launches_per_step = _lib.launch_count() - n0   # our kernels inside one replay
         self.cuda_core_conv_fallbacks = int(_lib.load().sg_cuda_core_fallbacks(0)) - f0
 
@@ -135,6 +139,7 @@ class GraphedTrainStep:
     def __call__(self, x_real: torch.Tensor) -> Dict[str, torch.Tensor]:
         """x_real: host (pinned) or device batch.  Returns the step's scalars as device tensors
         (valid until the next call)."""
+        kernels.ensure_leaky_slope(self._leaky_slope)
         self.x.copy_(x_real, non_blocking=True)
         self.draw()
         if self.segments is None:
