@@ -117,6 +117,12 @@ CONFIGS = {
                        batch=8, alpha=0.25, full=True),
     "tiny_p1": dict(phase=1, num_phases=3, base_dim=32, latent_dim=32, base_shape=(1, 1, 4, 4),
                     batch=4, alpha=0.0, full=True),
+    # edge cases of the fade-in and of the minibatch-stddev group rule (network.py:119-124): alpha at both ends of
+    # its schedule (train.py:33,82), batch 6 -> one group of 6, batch 3 -> one group of 3
+    "tiny_p3_b6_a1": dict(phase=3, num_phases=3, base_dim=32, latent_dim=32, base_shape=(1, 1, 4, 4),
+                          batch=6, alpha=1.0, full=True),
+    "tiny_p2_b3_a0": dict(phase=2, num_phases=3, base_dim=32, latent_dim=32, base_shape=(1, 1, 4, 4),
+                          batch=3, alpha=0.0, full=True),
     # BASELINE cfg1 (xs, 4x16x16, B=4): weights regenerated from the seed by the oracle's own
     # modules is not bit-identical to the reference's stream, so only scalars + grad norms of
     # the reference run are stored together with the reference's initial state digest.

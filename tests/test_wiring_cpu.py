@@ -9,7 +9,7 @@ import saragan_b200 as sg
 from tests.util import build_pair, golden_tensors, load_golden, rel_err, run_step
 
 
-@pytest.mark.parametrize("name", ["tiny_p3", "tiny_p2_b8", "tiny_p1"])
+@pytest.mark.parametrize("name", ["tiny_p3", "tiny_p2_b8", "tiny_p1", "tiny_p3_b6_a1", "tiny_p2_b3_a0"])
 def test_init_matches_reference_rng_stream(name):
     """torch.manual_seed(0); Generator(...); Discriminator(...) draws the reference's weights."""
     z, cfg = load_golden(name)
@@ -22,7 +22,7 @@ def test_init_matches_reference_rng_stream(name):
             assert torch.equal(want[k], got[k].cpu()), k
 
 
-@pytest.mark.parametrize("name", ["tiny_p3", "tiny_p2_b8", "tiny_p1"])
+@pytest.mark.parametrize("name", ["tiny_p3", "tiny_p2_b8", "tiny_p1", "tiny_p3_b6_a1", "tiny_p2_b3_a0"])
 def test_step_matches_reference_fp32(name, cpu_kernels):
     z, cfg = load_golden(name)
     with sg.use_precision("fp32"):
