@@ -29,7 +29,7 @@ def _golden_inputs(z):
     return {k: torch.from_numpy(z["in." + k]) for k in ("x_real", "noise", "z_d", "z_g", "eps")}
 
 
-@pytest.mark.parametrize("name", ["tiny_p3", "tiny_p2_b8", "tiny_p1"])
+@pytest.mark.parametrize("name", ["tiny_p3", "tiny_p2_b8", "tiny_p1", "tiny_p3_b6_a1", "tiny_p2_b3_a0"])
 def test_golden_step_fp32(name):
     z, cfg = load_golden(name)
     with sg.use_precision("fp32"):
