@@ -56,6 +56,10 @@ class VolumeLoader:
         self.batch_size, self.device, self.shuffle, self.drop_last = batch_size, torch.device(device), shuffle, drop_last
         self.rng = np.random.default_rng(seed + rank)
         self.stream = torch.cuda.Stream(device=self.device)
+        # per staging slot: `_free` is set by the consumer once the copy out of the slot has been ENQUEUED, `_copied`
+        # is the CUDA event recorded right behind that copy; the producer re-fills a slot only after both
+        self._free = [threading.Event(), threading.Event()]
+        self._copied = [None, None]
 
     def __len__(self):
         n = len(self.files) // self.batch_size
@@ -71,20 +75,32 @@ class VolumeLoader:
             slot = bi & 1
             if pinned[slot] is None or pinned[slot].shape != arr.shape:
                 pinned[slot] = torch.empty(arr.shape, dtype=torch.uint16).pin_memory()
+            self._free[slot].wait()
+            self._free[slot].clear()
+            if self._copied[slot] is not None:
+                self._copied[slot].synchronize()     # the asynchronous copy out of this slot has finished
             pinned[slot].numpy()[...] = arr
-            q.put(pinned[slot])
+            q.put((slot, pinned[slot]))
         q.put(None)
 
     def __iter__(self) -> Iterator[torch.Tensor]:
         q: Queue = Queue(maxsize=1)      # one batch being filled while one is in flight
+        for f in self._free:
+            f.set()
+        self._copied = [None, None]
         t = threading.Thread(target=self._host_batches, args=(q,), daemon=True)
         t.start()
         while True:
-            host = q.get()
-            if host is None:
+            item = q.get()
+            if item is None:
                 break
+            slot, host = item
             with torch.cuda.stream(self.stream):
                 dev = host.to(self.device, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(self.stream)
+            self._copied[slot] = done
+            self._free[slot].set()
             torch.cuda.current_stream(self.device).wait_stream(self.stream)
             dev.record_stream(torch.cuda.current_stream(self.device))
             yield dev

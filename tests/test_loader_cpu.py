@@ -1,0 +1,101 @@
+"""Host logic of the input pipeline (saragan_b200/data.py) without a GPU: file order like the
+reference's make_dataset (data.py:16-31), rank sharding like DistributedSampler without shuffling, batching,
+drop_last, deterministic shuffling, and the hand-over of the double-buffered staging slots.  CUDA streams, events
+and pinned memory are replaced by inert stand-ins; the copies and the kernel are covered by the GPU tests."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from saragan_b200 import data
+
+
+class _Stream:
+    def __init__(self, device=None):
+        pass
+
+    def wait_stream(self, other):
+        pass
+
+
+class _Event:
+    log = []
+
+    def record(self, stream=None):
+        _Event.log.append("record")
+
+    def synchronize(self):
+        _Event.log.append("sync")
+
+
+class _Ctx:
+    def __init__(self, stream):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+@pytest.fixture
+def no_gpu(monkeypatch):
+    monkeypatch.setattr(torch.cuda, "Stream", _Stream)
+    monkeypatch.setattr(torch.cuda, "Event", _Event)
+    monkeypatch.setattr(torch.cuda, "stream", _Ctx)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: _Stream())
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    orig_to = torch.Tensor.to
+    # host -> "device" must be a COPY like the real H2D transfer (Tensor.to on a CPU tensor returns the tensor itself,
+    # which would alias the staging slot the producer thread re-fills)
+    monkeypatch.setattr(torch.Tensor, "to", lambda self, *a, **k: orig_to(self, *a, **k).clone())
+    monkeypatch.setattr(torch.Tensor, "record_stream", lambda self, s: None)
+    _Event.log = []
+
+
+def _dataset(tmp_path, n):
+    d = tmp_path / "16x16"
+    os.makedirs(d)
+    vols = []
+    for i in range(n):
+        v = np.full((2, 4, 4), i, dtype=np.uint16)
+        np.save(d / f"{i:04d}.npy", v)
+        vols.append(v)
+    (d / "notes.txt").write_text("ignored")
+    return vols
+
+
+def test_loader_order_sharding_and_slots(tmp_path, no_gpu):
+    _dataset(tmp_path, 11)
+    assert [os.path.basename(f) for f in data.list_volumes(str(tmp_path))] == [f"{i:04d}.npy" for i in range(11)]
+    seen = []
+    for rank in range(2):
+        loader = data.VolumeLoader(str(tmp_path), batch_size=2, device="cpu", rank=rank, world=2, shuffle=False)
+        assert len(loader) == (3 if rank == 0 else 2)            # 6 and 5 files, drop_last
+        batches = [b.clone() for b in loader]
+        assert all(b.dtype == torch.uint16 and tuple(b.shape) == (2, 2, 4, 4) for b in batches)
+        seen.append([int(b[i, 0, 0, 0]) for b in batches for i in range(2)])
+    assert seen == [[0, 2, 4, 6, 8, 10], [1, 3, 5, 7]]            # rank r takes files r, r + world, ...
+    # a staging slot is re-filled only after the copy out of it was waited for: every refill of a used slot syncs
+    assert _Event.log.count("record") == 5 and _Event.log.count("sync") >= 1
+
+
+def test_loader_keeps_the_last_partial_batch_on_request(tmp_path, no_gpu):
+    _dataset(tmp_path, 5)
+    loader = data.VolumeLoader(str(tmp_path), batch_size=2, device="cpu", shuffle=False, drop_last=False)
+    shapes = [tuple(b.shape) for b in loader]
+    assert len(loader) == 3 and shapes == [(2, 2, 4, 4), (2, 2, 4, 4), (1, 2, 4, 4)]
+
+
+def test_loader_shuffle_is_deterministic_per_seed_and_rank(tmp_path, no_gpu):
+    _dataset(tmp_path, 8)
+    order = lambda seed: [int(b[i, 0, 0, 0]) for b in data.VolumeLoader(str(tmp_path), 2, "cpu", seed=seed) for i in range(2)]   # noqa: E731
+    a, b, c = order(3), order(3), order(4)
+    assert a == b and sorted(a) == list(range(8)) and a != c
+
+
+def test_empty_directory_raises(tmp_path, no_gpu):
+    with pytest.raises(FileNotFoundError):
+        data.VolumeLoader(str(tmp_path), 2, "cpu")
