@@ -54,6 +54,7 @@ class GradBucketer:
         self._armed = False
         self._hooks = []
         self._comm_stream = None
+        self._phase = getattr(module, "phase", None)     # the active parameter set follows `module.phase`
         if self.world > 1:
             for i, p in enumerate(self.params):
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(i)))
@@ -78,6 +79,17 @@ class GradBucketer:
         """Call right before ``loss.backward()`` of the step whose gradients are to be reduced."""
         if self.world == 1:
             return
+        phase = getattr(self.module, "phase", None)
+        if phase != self._phase:
+            # network.py / network_dict.py select the active levels by `.phase` (grow() adds modules): the bucket plan
+            # of the previous phase would skip the newly active parameters.  Record the ready order again on this pass
+            # (its gradients are reduced in finish(), un-overlapped for this one step).
+            self._phase, self._plan, self._where, self._order = phase, None, {}, []
+            known = {id(p) for p in self.params}
+            for p in self.module.parameters():           # parameters created by grow()
+                if id(p) not in known:
+                    self.params.append(p)
+                    self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(len(self.params) - 1)))
         self._armed = True
         self._inflight = []
         if self._plan is not None:

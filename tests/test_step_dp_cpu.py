@@ -29,7 +29,7 @@ def _grads(g, d):
     return [None if p.grad is None else p.grad.clone() for p in list(g.parameters()) + list(d.parameters())]
 
 
-def _worker(rank, world, port, variant, sync, q):
+def _worker(rank, world, port, variant, sync, grow, q):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -48,6 +48,22 @@ def _worker(rank, world, port, variant, sync, q):
     mine = inputs[rank]
     kw = lambda i: dict(noise=i["noise"], z_d=i["z_d"], z_g=i["z_g"], eps=i["eps"], apply=False)     # noqa: E731
     sg.train_step(mine["x_real"], g, d, *opts, 0.5, grad_sync=dp, **kw(mine))
+    if grow:
+        # the next growth phase on the same replicas: more parameters become active (network.py) / are created
+        # (network_dict.py grow()); the exchange must follow
+        if variant == "network_dict":
+            torch.manual_seed(7)                          # same new weights on both ranks, as main.py's deepcopy + grow
+            g.grow()
+            d.grow()
+            opts = sg.make_optimizers(g, d)
+        else:
+            g.phase = d.phase = CFG["phase"] + 1
+        cfg3 = dict(CFG, phase=CFG["phase"] + 1)
+        inputs = [draw_inputs(cfg3, seed=600 + r) for r in range(world)]
+        mine = inputs[rank]
+        for p in list(g.parameters()) + list(d.parameters()):
+            p.grad = None
+        sg.train_step(mine["x_real"], g, d, *opts, 0.5, grad_sync=dp, **kw(mine))
     got = _grads(g, d)
     if rank == 0:
         truth = None
@@ -68,12 +84,14 @@ def _worker(rank, world, port, variant, sync, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("variant,sync", [("network", "buckets"), ("network", "flat"), ("network_dict", "buckets")])
-def test_train_step_two_ranks_gloo(variant, sync):
+@pytest.mark.parametrize("variant,sync,grow", [("network", "buckets", False), ("network", "flat", False),
+                                               ("network_dict", "buckets", False), ("network", "buckets", True),
+                                               ("network_dict", "buckets", True)])
+def test_train_step_two_ranks_gloo(variant, sync, grow):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 31500 + (os.getpid() + hash((variant, sync))) % 2000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, variant, sync, q)) for r in range(2)]
+    port = 31500 + (os.getpid() + hash((variant, sync, grow))) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, variant, sync, grow, q)) for r in range(2)]
     for p in procs:
         p.start()
     ok, n_active, n_total = q.get(timeout=240)
@@ -81,4 +99,5 @@ def test_train_step_two_ranks_gloo(variant, sync):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert ok
-    assert 0 < n_active and (n_active < n_total if variant == "network" else n_active == n_total)
+    all_active = variant == "network_dict" or grow        # phase 3 of 3: every level of network.py is active
+    assert 0 < n_active and (n_active == n_total if all_active else n_active < n_total)
