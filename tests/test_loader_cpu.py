@@ -99,3 +99,21 @@ def test_loader_shuffle_is_deterministic_per_seed_and_rank(tmp_path, no_gpu):
 def test_empty_directory_raises(tmp_path, no_gpu):
     with pytest.raises(FileNotFoundError):
         data.VolumeLoader(str(tmp_path), 2, "cpu")
+
+
+def test_synthetic_pyramid_has_the_reference_layout(tmp_path, no_gpu):
+    """tools/make_synthetic_volumes.py writes what main.py:69-91 expects: {res}x{res}/NNNN.npy, (res/4, res, res)
+    uint16 in [0, 3072]; the loader reads it back in file order."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mk", os.path.join(os.path.dirname(os.path.dirname(__file__)),
+                                                                    "tools", "make_synthetic_volumes.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    d = mk.write_phase(str(tmp_path), 3, 6)
+    assert os.path.basename(d) == "16x16" and sorted(os.listdir(d)) == [f"{i:04d}.npy" for i in range(6)]
+    v = np.load(os.path.join(d, "0003.npy"))
+    assert v.shape == (4, 16, 16) and v.dtype == np.uint16 and v.max() <= 3072 and 600 < v.mean() < 1400
+    again = mk.synthetic_volume(np.random.default_rng(1234 + 3), 16)
+    assert np.array_equal(again, np.load(os.path.join(d, "0000.npy")))             # deterministic per phase
+    batches = list(data.VolumeLoader(d, batch_size=3, device="cpu", shuffle=False))
+    assert len(batches) == 2 and np.array_equal(batches[1][0].numpy(), v)
