@@ -3,7 +3,6 @@ gradients must equal the single-process gradient of the concatenated (mean) loss
 import os
 import sys
 
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp

@@ -1,7 +1,6 @@
 """Host logic above the C ABI (autograd wiring incl. the GP double backward, module plumbing)
 checked on CPU against the golden fixtures minted from the reference, with the kernels
 emulated by tests/cpu_emul.py in fp32."""
-import numpy as np
 import pytest
 import torch
 

@@ -2,7 +2,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import saragan_b200 as sg
-from saragan_b200.graph import GraphedTrainStep, make_capturable_optimizers
+from saragan_b200.graph import make_capturable_optimizers
 from tests.util import build_pair
 from tests.test_graph_gpu import _Recording
 
