@@ -72,3 +72,21 @@ def test_stacked_minibatches_equal_separate_calls(cpu_kernels):
     assert rel_err(both, sep) < 1e-6
     assert rel_err(mixed, sep) > 1e-4      # one minibatch of 2B has different group statistics
 
+
+
+def test_reference_checkpoint_loads_and_refreshes_packed_weights(cpu_kernels):
+    """reference checkpoints load with load_state_dict.  A model built from another seed and already
+    used once (so its packed-weight caches are warm) must, after load_state_dict, compute with the loaded weights."""
+    z, cfg = load_golden("tiny_p3")
+    with sg.use_precision("fp32"):
+        g, d = build_pair(cfg, seed=99)
+        inp = {k: torch.from_numpy(z["in." + k]) for k in ("x_real", "noise", "z_d", "z_g", "eps")}
+        stale = run_step(g, d, inp, cfg["alpha"])
+        assert abs(float(stale["d_loss"]) - float(z["ref.d_loss"])) > 1e-3          # other weights, other loss
+        g.load_state_dict(golden_tensors(z, "g."))
+        d.load_state_dict(golden_tensors(z, "d."))
+        for p in list(g.parameters()) + list(d.parameters()):
+            p.grad = None
+        out = run_step(g, d, inp, cfg["alpha"])
+    for k in ("d_loss", "gp", "g_loss"):
+        assert abs(float(out[k]) - float(z["ref." + k])) < 2e-5 * max(1.0, abs(float(z["ref." + k]))), k
