@@ -41,3 +41,30 @@ def test_step_flop_model_matches_survey():
     """4*Gf + 14*Df per image = 2507 GFLOP at cfg3, 55.9 at cfg1"""
     assert abs(O.step_flops_per_image(6, 7, 512, 512) / 1e9 - 2507) < 1
     assert abs(O.step_flops_per_image(3, 6, 256, 256) / 1e9 - 55.9) < 0.1
+
+
+def test_flop_models_agree():
+    """saragan_b200.costmodel (what bench.py reports `step_tensor_frac` with) against the oracle's count, and the
+    network_dict.py model against a brute-force count over that variant's parameter shapes."""
+    import sys
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        import bench
+    finally:
+        sys.argv = argv
+    from saragan_b200 import costmodel as C
+    for name, cfg in C.CONFIGS.items():
+        assert abs(C.step_flops_per_image(**cfg) - O.step_flops_per_image(cfg["phase"], cfg["num_phases"], cfg["base_dim"],
+                                                                          cfg["latent_dim"])) < 1.0, name
+        ph = cfg["phase"]
+
+        def level(k):
+            if k.startswith("blocks.block_phase_"):
+                return int(k.split("_")[2].split(".")[0])
+            return ph if "_current" in k else ph - 1 if "_prev" in k else 1
+
+        def fwd(params):
+            return sum(2.0 * w.numel() * (1 if w.dim() == 2 else int(np.prod(C.volume(level(k)))))
+                       for k, w in params.items() if k.endswith(".weight"))
+        pg, pd = bench.dict_oracle_state(cfg)
+        assert abs(C.step_flops_per_image_dict(**cfg) - (4 * fwd(pg) + 14 * fwd(pd))) < 1.0, name
