@@ -65,8 +65,8 @@ int sg_act_to_plain(const void* act, float* plain, int dtype, int N, int C, int6
  *   swapped channel roles; dgrad is then sg_conv3d_fprop with Cin/Cout swapped).
  * y = [mask(mask_src) *] [lrelu] (scale * conv(x, wp) + bias)
  *   scale   = the equalized-LR std of network.py:16-23 (applied to the fp32 accumulator)
- *   lrelu   = fuse nn.LeakyReLU(0.2) (network.py:89,159,206,251)
- *   mask_src (nullable, act of y's shape) = multiply by 1 / 0.2 according to its sign:
+ *   lrelu   = fuse nn.LeakyReLU(slope) (network.py:89,159,206,251; slope = sg_get_leaky_slope(), 0.2 by default)
+ *   mask_src (nullable, act of y's shape) = multiply by 1 / slope according to its sign:
  *             LeakyReLU backward fused into the dgrad epilogue. */
 int64_t sg_packed_weight_elems(int Cout, int Cin, int transpose_flip);
 int sg_pack_conv_weight(const float* w, void* dst, int dtype, int Cout, int Cin, int transpose_flip, cudaStream_t stream);
@@ -114,7 +114,7 @@ int sg_pw_wgrad(const void* g, const float* img, float* gw, float* gb, int dtype
  * Input and output element types may differ: the 1x4x4 base level of both networks is kept
  * in fp32 (minibatch-stddev's group centring amplifies bf16 rounding). */
 int sg_down2(const void* x, void* y, int dtype_in, int dtype_out, int vec, int64_t P, int D, int H, int W, float scale, cudaStream_t stream);
-/* mask_ref (nullable, act shaped like y): y *= (mask_ref > 0 ? 1 : 0.2) -- LeakyReLU backward fused
+/* mask_ref (nullable, act shaped like y): y *= (mask_ref > 0 ? 1 : slope) -- LeakyReLU backward fused
  * into the avg-pool backward */
 int sg_up2(const void* x, void* y, const void* mask_ref, int dtype_in, int dtype_out, int vec, int64_t P, int D, int H, int W, float scale, cudaStream_t stream);
 
@@ -122,13 +122,13 @@ int sg_up2(const void* x, void* y, const void* mask_ref, int dtype_in, int dtype
  * y = alpha*a + beta*b (b nullable): fade-in blend (network.py:185,281), instance noise
  * (train.py:144) and the backward scalings. */
 int sg_lincomb(const void* a, const void* b, void* y, int dtype, int64_t n, float alpha, float beta, cudaStream_t stream);
-/* nn.LeakyReLU(0.2) forward, and y = g * (ref > 0 ? 1 : 0.2) for its backward / double backward */
+/* nn.LeakyReLU(slope) forward, and y = g * (ref > 0 ? 1 : slope) for its backward / double backward */
 int sg_lrelu_fwd(const void* x, void* y, int dtype, int64_t n, cudaStream_t stream);
 int sg_mask_mul(const void* g, const void* ref, void* y, int dtype, int64_t n, cudaStream_t stream);
 
 /* ---- ChannelNormalization (network.py:192-197), optionally followed by LeakyReLU */
 int sg_pixelnorm_fwd(const void* x, void* y, int dtype, int N, int C, int64_t V, float eps, int lrelu_after, cudaStream_t stream);
-/* mask_input: x is itself a LeakyReLU output; also multiply gx by (x > 0 ? 1 : 0.2) */
+/* mask_input: x is itself a LeakyReLU output; also multiply gx by (x > 0 ? 1 : slope) */
 int sg_pixelnorm_bwd(const void* x, const void* gy, void* gx, int dtype, int N, int C, int64_t V, float eps, int lrelu_after, int mask_input, cudaStream_t stream);
 
 /* ---- gradient penalty (loss.py:11-13 interpolate, loss.py:25-26 per-sample norm) */
