@@ -3,6 +3,7 @@ the 3D progressive-GAN train step behind the reference's ``pgan_pytorch/network.
 ``loss.py`` / ``train.py`` API.  See DESIGN.md and INTEGRATION.md.
 """
 from . import config  # noqa: F401
+from . import metrics, network_dict  # noqa: F401  (pgan_pytorch/metrics and network_dict.py drop-ins)
 from .config import set_precision, use_precision  # noqa: F401
 from .loss import compute_gradient_penalty, wasserstein_loss  # noqa: F401
 from .network import (ChannelNormalization, Discriminator, DiscriminatorBlock,  # noqa: F401
