@@ -24,6 +24,7 @@ REF = "/root/reference/pgan_pytorch"
 CFG = dict(phase=2, num_phases=3, base_dim=32, latent_dim=32, batch=4, n_batches=3, alpha=0.5, seed=11,
            nonlinearity="leaky_relu", param=0.3)
 BASE_SHAPE = (1, 1, 4, 4)
+TRAIN = dict(mixing_epochs=2, stabilizing_epochs=1)
 
 
 def batches(cfg):
@@ -61,6 +62,22 @@ def main():
                 "ref.g_loss": np.float64(g_loss), "ref.distance": np.float64(dist), "ref.gp": np.float64(gp)})
     out.update({"after.g." + k: v.numpy() for k, v in g.state_dict().items()})
     out.update({"after.d." + k: v.numpy() for k, v in d.state_dict().items()})
+    # the whole train() of train.py:30-123 (alpha schedule 1 -> 0 over the mixing epochs, LambdaLR on G, get_metrics
+    # after every stabilising epoch; writer=None, horovod=False): per-parameter digests of the weights it ends with
+    torch.manual_seed(0)
+    g, d = net.Generator(*args, param=cfg["param"]), net.Discriminator(*args, param=cfg["param"])
+    g_opt = torch.optim.Adam(g.parameters(), lr=1e-3, betas=(0.0, 0.99))
+    d_opt = torch.optim.Adam(d.parameters(), lr=1e-3, betas=(0.0, 0.99))
+    sched = torch.optim.lr_scheduler.LambdaLR(g_opt, lambda epoch: .99 ** epoch)          # main.py:144-145
+    loader = torch.utils.data.DataLoader(torch.cat(batches(cfg)), batch_size=cfg["batch"], shuffle=False)
+    torch.manual_seed(cfg["seed"])
+    ref_train.train(g, d, g_opt, d_opt, sched, loader, TRAIN["mixing_epochs"], TRAIN["stabilizing_epochs"], cfg["phase"], None)
+    for prefix, mod in (("train.g.", g), ("train.d.", d)):
+        for k, v in mod.state_dict().items():
+            out[prefix + k] = np.array([float(v.double().sum()), float(v.double().abs().sum())])
+    out["train.g_lr"] = np.float64(g_opt.param_groups[0]["lr"])
+    out.update({"train." + k: np.int64(v) for k, v in TRAIN.items()})
+    print(f"reference train(): {TRAIN}, final G lr {g_opt.param_groups[0]['lr']:.6g}")
     path = os.path.join(ROOT, "tests", "golden", "dict_epoch.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)")

@@ -63,10 +63,30 @@ def test_unmodified_reference_train_epoch_drives_our_modules(cpu_kernels, monkey
     worst = max(float((v - torch.from_numpy(z[p + k])).abs().max())
                 for p, m in (("after.g.", g), ("after.d.", d)) for k, v in m.state_dict().items())
     assert worst < 3.5e-3, worst
+    # the whole train() (train.py:30-123: alpha from 1 to 0 over the mixing epochs, LambdaLR on G, get_metrics after
+    # every stabilising epoch) on our modules, against the digests of the weights it ends with on the reference's
+    monkeypatch.setattr(our_metrics, "_device", lambda: torch.device("cpu"))
+    with sg.use_precision("fp32"):
+        torch.manual_seed(0)
+        g, d = nd.Generator(*args, param=float(z["param"])), nd.Discriminator(*args, param=float(z["param"]))
+        g_opt = torch.optim.Adam(g.parameters(), lr=1e-3, betas=(0.0, 0.99))
+        d_opt = torch.optim.Adam(d.parameters(), lr=1e-3, betas=(0.0, 0.99))
+        sched = torch.optim.lr_scheduler.LambdaLR(g_opt, lambda epoch: .99 ** epoch)
+        dl = torch.utils.data.DataLoader(torch.cat(loader), batch_size=cfg["batch"], shuffle=False)
+        torch.manual_seed(cfg["seed"])
+        ref_train.train(g, d, g_opt, d_opt, sched, dl, int(z["train.mixing_epochs"]), int(z["train.stabilizing_epochs"]),
+                        cfg["phase"], None)
+    assert abs(g_opt.param_groups[0]["lr"] - float(z["train.g_lr"])) < 1e-12
+    for prefix, mod in (("train.g.", g), ("train.d.", d)):
+        for k, v in mod.state_dict().items():
+            want_sum, want_abs = z[prefix + k]
+            # 9 Adam(beta1 = 0) steps of +-lr per element: digests agree far below one step's worth of change
+            assert abs(float(v.double().abs().sum()) - want_abs) < 1e-4 * want_abs + 1e-6, k
+            assert abs(float(v.double().sum()) - want_sum) < 1e-4 * want_abs + 1e-6, k
+
     # the reference's get_metrics (train.py:12-27) on top of our metrics module, called the way train.py:76,99,120
     # call it (numpy arrays, no generator argument): exact KS distance, the reference's labels
     from tests.test_metrics_oracle_cpu import load_metrics_golden
-    monkeypatch.setattr(our_metrics, "_device", lambda: torch.device("cpu"))
     zm, real, fake, _ = load_metrics_golden("metrics_w64")
     torch.manual_seed(3)
     m = ref_train.get_metrics(real, fake)
