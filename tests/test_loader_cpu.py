@@ -117,3 +117,26 @@ def test_synthetic_pyramid_has_the_reference_layout(tmp_path, no_gpu):
     assert np.array_equal(again, np.load(os.path.join(d, "0000.npy")))             # deterministic per phase
     batches = list(data.VolumeLoader(d, batch_size=3, device="cpu", shuffle=False))
     assert len(batches) == 2 and np.array_equal(batches[1][0].numpy(), v)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/pgan_pytorch/data.py"), reason="reference tree not present")
+def test_loader_agrees_with_the_reference_dataset_class(tmp_path, no_gpu):
+    """The reference's own DatasetFolder + DataLoader (data.py:34-89 with main.py:84-118's loader / transform) and
+    VolumeLoader read the same files in the same order; raw / 1024 (what sg_prepare_real computes without noise)
+    equals the reference's float batches."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("reference_data", "/root/reference/pgan_pytorch/data.py")
+    ref_data = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_data)
+    spec = importlib.util.spec_from_file_location("mk", os.path.join(os.path.dirname(os.path.dirname(__file__)),
+                                                                    "tools", "make_synthetic_volumes.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    d = mk.write_phase(str(tmp_path), 3, 7)
+    dataset = ref_data.DatasetFolder(d, loader=lambda path: torch.from_numpy(np.load(path).astype(np.float32)),
+                                     extensions=(".npy",), transform=lambda x: x.unsqueeze(0) / 1024)     # main.py:84-91
+    ref_batches = list(torch.utils.data.DataLoader(dataset, batch_size=2, shuffle=False, drop_last=True))
+    ours = list(data.VolumeLoader(d, batch_size=2, device="cpu", shuffle=False))
+    assert len(ours) == len(ref_batches) == 3
+    for a, b in zip(ours, ref_batches):
+        assert torch.equal(torch.from_numpy(a.numpy().astype(np.float32))[:, None] / 1024, b)
