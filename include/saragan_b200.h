@@ -70,6 +70,11 @@ int sg_act_to_plain(const void* act, float* plain, int dtype, int N, int C, int6
  *             LeakyReLU backward fused into the dgrad epilogue. */
 int64_t sg_packed_weight_elems(int Cout, int Cin, int transpose_flip);
 int sg_pack_conv_weight(const float* w, void* dst, int dtype, int Cout, int Cin, int transpose_flip, cudaStream_t stream);
+/* every stale packing of a network in ONE launch (after an optimiser step): `jobs` = device array of
+ * { const float* w; void* dst; int Cout, Cin, transpose_flip, dtype; } (32 bytes each); block b packs the tile
+ * (32 output rows from block_r0[b]) x (8-channel K chunk block_kc[b]) x 27 taps of job block_job[b]. */
+int sg_pack_conv_weights_multi(const void* jobs, const int* block_job, const int* block_kc, const int* block_r0,
+                               int n_blocks, cudaStream_t stream);
 int sg_conv3d_fprop(const void* x, const void* wp, const float* bias, const void* mask_src, void* y,
                     int dtype, int N, int Cin, int Cout, int D, int H, int W, float scale, int lrelu,
                     int impl, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
@@ -100,6 +105,10 @@ int sg_conv3d_wgrad(const void* x, const void* gy, float* gw, float* gb, int dty
  * FromRGB (network.py:101-110): y[n][c][v] = lrelu?(scale*w[c]*img[n][v] + bias[c]) */
 int sg_pw_expand(const float* img, const float* w, const float* bias, void* y, int dtype, int N, int C,
                  int64_t V, float scale, int lrelu, cudaStream_t stream);
+/* the same with y *= (mask_ref > 0 ? 1 : slope), mask_ref an act of y's shape: the double backward of the
+ * gradient penalty (loss.py:17-24) expands the image-level gradient and masks it with the sign of FromRGB's output */
+int sg_pw_expand_masked(const float* img, const float* w, const float* bias, const void* mask_ref, void* y, int dtype,
+                        int N, int C, int64_t V, float scale, int lrelu, cudaStream_t stream);
 /* ToRGB (network.py:219-225): img[n][v] = scale*sum_c w[c]*x[n][c][v] + bias[0] */
 int sg_pw_reduce(const void* x, const float* w, const float* bias, float* img, int dtype, int N, int C,
                  int64_t V, float scale, cudaStream_t stream);
@@ -122,6 +131,9 @@ int sg_up2(const void* x, void* y, const void* mask_ref, int dtype_in, int dtype
  * y = alpha*a + beta*b (b nullable): fade-in blend (network.py:185,281), instance noise
  * (train.py:144) and the backward scalings. */
 int sg_lincomb(const void* a, const void* b, void* y, int dtype, int64_t n, float alpha, float beta, cudaStream_t stream);
+/* the same with alpha = coef[0], beta = coef[1] read from DEVICE memory: the fade-in alpha of network.py:185,281 as a
+ * 0-dim tensor (no host sync; a captured CUDA graph follows train.py:33,63's alpha schedule without a re-capture) */
+int sg_lincomb_dev(const void* a, const void* b, void* y, int dtype, int64_t n, const float* coef, cudaStream_t stream);
 /* nn.LeakyReLU(slope) forward, and y = g * (ref > 0 ? 1 : slope) for its backward / double backward */
 int sg_lrelu_fwd(const void* x, void* y, int dtype, int64_t n, cudaStream_t stream);
 int sg_mask_mul(const void* g, const void* ref, void* y, int dtype, int64_t n, cudaStream_t stream);
@@ -155,8 +167,11 @@ int sg_mbstd_bwdbwd(const float* u, const float* gt, const float* out, const flo
  *   struct { float* p; const float* g; float* m; float* v; float* ema; int64_t n; }   (m, ema nullable)
  * block b updates elements [block_offset[b], +1024) of tensor block_tensor[b]; `step` is a device
  * counter holding t-1 (graph-capturable); sg_adam_advance increments it. */
+/* lr_dev (nullable): the learning rate is read from device memory instead of `lr`, so a captured step follows a
+ * LambdaLR schedule (main.py:145) without a re-capture. */
 int sg_adam_step(const void* tensors, const int* block_tensor, const int64_t* block_offset, int n_blocks,
-                 const int* step, float lr, float beta1, float beta2, float eps, float ema_beta, cudaStream_t stream);
+                 const int* step, float lr, const float* lr_dev, float beta1, float beta2, float eps, float ema_beta,
+                 cudaStream_t stream);
 int sg_adam_advance(int* step, cudaStream_t stream);
 
 /* ---- input preparation (main.py:85-87 `np.load -> float32 / 1024`, train.py:144 `+ 0.01*randn`):

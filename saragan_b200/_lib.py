@@ -13,7 +13,8 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsaragan_b200.so")
+# SARAGAN_B200_LIB: load another build of the same library (A/B runs of build-time switches, e.g. SG_TC_WATCHDOG)
+LIB_PATH = os.environ.get("SARAGAN_B200_LIB") or os.path.join(_HERE, "libsaragan_b200.so")
 
 BF16, F32 = 0, 1
 IMPL_AUTO, IMPL_DIRECT, IMPL_TCGEN05 = 0, 1, 2
@@ -30,6 +31,7 @@ SIGNATURES = {
     "sg_act_to_plain": [_c_p, _c_p, _c_int, _c_int, _c_int, _c_i64, _c_p],
     "sg_packed_weight_elems": [_c_int, _c_int, _c_int],
     "sg_pack_conv_weight": [_c_p, _c_p, _c_int, _c_int, _c_int, _c_int, _c_p],
+    "sg_pack_conv_weights_multi": [_c_p, _c_p, _c_p, _c_p, _c_int, _c_p],
     "sg_conv3d_fprop": [_c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                         _c_int, _c_f, _c_int, _c_int, _c_p, _c_i64, _c_p],
     "sg_set_pdl": [_c_int],
@@ -43,11 +45,13 @@ SIGNATURES = {
     "sg_conv3d_wgrad": [_c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                         _c_f, _c_int, _c_p, _c_i64, _c_p],
     "sg_pw_expand": [_c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_i64, _c_f, _c_int, _c_p],
+    "sg_pw_expand_masked": [_c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_i64, _c_f, _c_int, _c_p],
     "sg_pw_reduce": [_c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_i64, _c_f, _c_p],
     "sg_pw_wgrad": [_c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_i64, _c_f, _c_p],
     "sg_down2": [_c_p, _c_p, _c_int, _c_int, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_f, _c_p],
     "sg_up2": [_c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_f, _c_p],
     "sg_lincomb": [_c_p, _c_p, _c_p, _c_int, _c_i64, _c_f, _c_f, _c_p],
+    "sg_lincomb_dev": [_c_p, _c_p, _c_p, _c_int, _c_i64, _c_p, _c_p],
     "sg_lrelu_fwd": [_c_p, _c_p, _c_int, _c_i64, _c_p],
     "sg_mask_mul": [_c_p, _c_p, _c_p, _c_int, _c_i64, _c_p],
     "sg_pixelnorm_fwd": [_c_p, _c_p, _c_int, _c_int, _c_int, _c_i64, _c_f, _c_int, _c_p],
@@ -61,7 +65,7 @@ SIGNATURES = {
     "sg_mbstd_fwd": [_c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _c_p],
     "sg_mbstd_bwd": [_c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_p],
     "sg_mbstd_bwdbwd": [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_p],
-    "sg_adam_step": [_c_p, _c_p, _c_p, _c_int, _c_p, _c_f, _c_f, _c_f, _c_f, _c_f, _c_p],
+    "sg_adam_step": [_c_p, _c_p, _c_p, _c_int, _c_p, _c_f, _c_p, _c_f, _c_f, _c_f, _c_f, _c_p],
     "sg_adam_advance": [_c_p, _c_p],
     "sg_prepare_real": [_c_p, _c_p, _c_p, _c_i64, _c_f, _c_f, _c_p],
     "sg_pyr_down": [_c_p, _c_p, _c_i64, _c_int, _c_int, _c_int, _c_p],
@@ -133,6 +137,13 @@ def call(name: str, *args):
     stream is appended, a non-zero status raises RuntimeError(sg_last_error())."""
     lib = load()
     conv = [(_ptr(a) if (a is None or isinstance(a, torch.Tensor)) else a) for a in args]
+    for a in args:
+        if isinstance(a, torch.Tensor):
+            if a.device.index != torch.cuda.current_device():
+                # launch on the tensors' device (and its current stream), not on whatever device is current
+                with torch.cuda.device(a.device):
+                    return call(name, *args)
+            break
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(torch.cuda.current_stream())

@@ -57,7 +57,7 @@ extern "C" int sg_set_leaky_slope(float slope) {
   g_sg_leak = slope;
   return 0;
 }
-extern "C" int sg_version(void) { return 100; }
+extern "C" int sg_version(void) { return 200; }
 
 // -------------------------------------------------------------------- layout conversion
 // plain [N][C][V] fp32 -> act [N][CC][V][8] (pad channels zero)
@@ -121,10 +121,16 @@ extern "C" int sg_act_to_plain(const void* act, float* plain, int dtype, int N, 
 // ----------------------------------------------------------------------- elementwise
 // y = alpha*a + beta*b   (b may be null).  Fade-in blend (network.py:185,281) and its
 // backward, instance noise (train.py:144), gradient scaling.
+// coef (nullable): alpha = coef[0], beta = coef[1] read from device memory -- the fade-in alpha of a captured CUDA
+// graph follows the schedule (train.py:33,63,82) without a re-capture and a tensor alpha costs no host sync.
 template <typename T>
 __global__ void k_lincomb(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y,
-                          int64_t nvec, int64_t n, float alpha, float beta) {
+                          int64_t nvec, int64_t n, float alpha, float beta, const float* __restrict__ coef) {
   sg_pdl_enter();
+  if (coef) {
+    alpha = __ldg(coef);
+    beta = __ldg(coef + 1);
+  }
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
        i += (int64_t)gridDim.x * blockDim.x) {
     F8 x = ld8(a + i * 8);
@@ -151,9 +157,18 @@ extern "C" int sg_lincomb(const void* a, const void* b, void* y, int dtype, int6
                           float beta, cudaStream_t s) {
   if (n == 0) return 0;
   int64_t nvec = n / 8;
-  SG_DISPATCH(dtype, sg_launch((k_lincomb<T>), sg_grid(nvec > 0 ? nvec : 1, 256), 256, 0, s, 
-                         (const T*)a, (const T*)b, (T*)y, nvec, n, alpha, beta););
+  SG_DISPATCH(dtype, sg_launch((k_lincomb<T>), sg_grid(nvec > 0 ? nvec : 1, 256), 256, 0, s,
+                         (const T*)a, (const T*)b, (T*)y, nvec, n, alpha, beta, (const float*)nullptr););
   return sg_check_launch("sg_lincomb");
+}
+extern "C" int sg_lincomb_dev(const void* a, const void* b, void* y, int dtype, int64_t n, const float* coef,
+                              cudaStream_t s) {
+  SG_REQUIRE(coef != nullptr, "sg_lincomb_dev: coef must point at {alpha, beta} in device memory");
+  if (n == 0) return 0;
+  int64_t nvec = n / 8;
+  SG_DISPATCH(dtype, sg_launch((k_lincomb<T>), sg_grid(nvec > 0 ? nvec : 1, 256), 256, 0, s,
+                         (const T*)a, (const T*)b, (T*)y, nvec, n, 0.f, 0.f, coef););
+  return sg_check_launch("sg_lincomb_dev");
 }
 
 // mode 0: y = lrelu(x)            (network.py:89 etc.)
@@ -449,13 +464,18 @@ extern "C" int sg_pixelnorm_bwd(const void* x, const void* gy, void* gx, int dty
 
 // ------------------------------------------------------------------ 1x1x1 to/from RGB
 // FromRGB (network.py:101-110): y[n][c][v] = act(scale*w[c]*img[n][v] + bias[c])
-// grid.y = (n, chunk): the 8 weights / biases of the chunk live in registers, a thread turns 4 consecutive
-// voxels (one 16-byte image load) into four 16-byte stores -- no index division, no per-element weight loads
-// (the first version spent 16 __ldg and two 64-bit divisions per 16 bytes written: 1.4 TB/s)
+// grid.y = (n, chunk): the 8 weights / biases of the chunk live in registers.  Consecutive LANES own consecutive
+// voxels, so every store instruction of a warp writes one contiguous run (512 B of bf16); four voxels per thread
+// and iteration, 32 voxels apart, keep four stores in flight.  (v2 gave a thread four CONSECUTIVE voxels: each
+// store instruction then touched 32 different 64-byte segments with 16 bytes each -- 1.5 TB/s; v1 spent 16 __ldg
+// and two 64-bit divisions per 16 bytes written.)
+// mask_ref (nullable, shaped like y): y *= (mask_ref > 0 ? 1 : slope) -- the LeakyReLU mask of the gradient
+// penalty's double backward riding in the producer of the masked tensor.
 template <typename T>
-__global__ void k_pw_expand(const float* __restrict__ img, const float* __restrict__ w,
-                            const float* __restrict__ bias, T* __restrict__ y, int N, int C, int CC,
-                            int64_t V, float scale, int lrelu) {
+__global__ void __launch_bounds__(256)
+k_pw_expand(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
+            const T* __restrict__ mask_ref, T* __restrict__ y, int N, int C, int CC, int64_t V, float scale,
+            int lrelu) {
   sg_pdl_enter();
   const int row = blockIdx.y, cc = row % CC, n = row / CC;
   float ws[8], bs[8];
@@ -467,26 +487,31 @@ __global__ void k_pw_expand(const float* __restrict__ img, const float* __restri
   }
   const float* pi = img + (int64_t)n * V;
   T* py = y + (int64_t)row * V * 8;
-  const bool vec = (V & 3) == 0;
-  for (int64_t v = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4; v < V; v += (int64_t)gridDim.x * blockDim.x * 4) {
-    float p[4] = {0.f, 0.f, 0.f, 0.f};
-    const int cnt = V - v < 4 ? (int)(V - v) : 4;
-    if (vec) {
-      const float4 t = *reinterpret_cast<const float4*>(pi + v);
-      p[0] = t.x; p[1] = t.y; p[2] = t.z; p[3] = t.w;
-    } else {
-      for (int q = 0; q < cnt; ++q) p[q] = pi[v + q];
+  const T* pm = mask_ref ? mask_ref + (int64_t)row * V * 8 : nullptr;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t v0 = (int64_t)blockIdx.x * blockDim.x * 4 + threadIdx.x; v0 < V; v0 += step) {
+    float p[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t v = v0 + (int64_t)q * blockDim.x;
+      p[q] = v < V ? __ldg(pi + v) : 0.f;
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      if (q < cnt) {
+      const int64_t v = v0 + (int64_t)q * blockDim.x;
+      if (v < V) {
         F8 r;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float o = fmaf(ws[j], p[q], bs[j]);
           r.v[j] = lrelu ? lrelu02(o) : o;
         }
-        st8(py + (v + q) * 8, r);
+        if (pm) {
+          const F8 m = ld8(pm + v * 8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r.v[j] *= lmask02(m.v[j]);
+        }
+        st8(py + v * 8, r);
       }
     }
   }
@@ -510,44 +535,63 @@ __global__ void k_pw_reduce(const T* __restrict__ x, const float* __restrict__ w
     int64_t n = i / V;
     const T* px = x + (n * CC * V + v) * 8;
     float acc = 0.f;
-    for (int cc = lane; cc < CC; cc += LPV) {
-      F8 r = ld8(px + (int64_t)cc * V * 8);
+    auto dot8 = [&](const F8& r, int cc) {
       const float4 w0 = *reinterpret_cast<const float4*>(w_s + cc * 8), w1 = *reinterpret_cast<const float4*>(w_s + cc * 8 + 4);
-      acc += w0.x * r.v[0] + w0.y * r.v[1] + w0.z * r.v[2] + w0.w * r.v[3] + w1.x * r.v[4] + w1.y * r.v[5] +
+      return w0.x * r.v[0] + w0.y * r.v[1] + w0.z * r.v[2] + w0.w * r.v[3] + w1.x * r.v[4] + w1.y * r.v[5] +
              w1.z * r.v[6] + w1.w * r.v[7];
+    };
+    int cc = lane;
+    // four chunk loads in flight per thread (the chunks of a voxel are V*16 bytes apart: independent requests)
+    for (; cc + 3 * LPV < CC; cc += 4 * LPV) {
+      const F8 r0 = ld8(px + (int64_t)cc * V * 8), r1 = ld8(px + (int64_t)(cc + LPV) * V * 8),
+               r2 = ld8(px + (int64_t)(cc + 2 * LPV) * V * 8), r3 = ld8(px + (int64_t)(cc + 3 * LPV) * V * 8);
+      acc += dot8(r0, cc) + dot8(r1, cc + LPV) + dot8(r2, cc + 2 * LPV) + dot8(r3, cc + 3 * LPV);
     }
+    for (; cc < CC; cc += LPV) acc += dot8(ld8(px + (int64_t)cc * V * 8), cc);
     if (LPV > 1) acc = warp_sum(acc);
     if (lane == 0) img[i] = scale * acc + (bias ? __ldg(bias) : 0.f);
   }
 }
 // gw[c] = scale * sum_{n,v} g[n][c][v]*img[n][v]  (img == null: plain channel sum),
-// gb[c] = sum_{n,v} g[n][c][v].  One block per (chunk, slab); warp-shuffle + one atomic
-// per channel per block.  Outputs must be zeroed by the caller (the entry point does).
+// gb[c] = sum_{n,v} g[n][c][v].  One block per (voxel slab, chunk, sample); four 16-byte loads in flight per
+// thread (one per iteration left the kernel latency-bound at 1.5 TB/s), warp-shuffle + one atomic per channel
+// per block.  Outputs must be zeroed by the caller (the entry point does).
 template <typename T>
-__global__ void k_pw_wgrad(const T* __restrict__ g, const float* __restrict__ img,
-                           float* __restrict__ gw, float* __restrict__ gb, int N, int C, int CC,
-                           int64_t V, float scale, int64_t per_slab) {
+__global__ void __launch_bounds__(256)
+k_pw_wgrad(const T* __restrict__ g, const float* __restrict__ img, float* __restrict__ gw,
+           float* __restrict__ gb, int N, int C, int CC, int64_t V, float scale, int64_t per_slab) {
   sg_pdl_enter();
-  int cc = blockIdx.y;
-  int64_t total = (int64_t)N * V;
-  int64_t lo = blockIdx.x * per_slab;
-  int64_t hi = lo + per_slab < total ? lo + per_slab : total;
+  const int cc = blockIdx.y, n = blockIdx.z;
+  const int64_t lo = blockIdx.x * per_slab;
+  const int64_t hi = lo + per_slab < V ? lo + per_slab : V;
+  const T* pg = g + ((int64_t)n * CC + cc) * V * 8;
+  const float* pi = img ? img + (int64_t)n * V : nullptr;
   float aw[8], ab[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) aw[j] = ab[j] = 0.f;
-  // (n, v) advance with the loop: one division per thread instead of two per element
-  int64_t i0 = lo + threadIdx.x;
-  int64_t n = i0 / V, v = i0 - n * V;
-  for (int64_t i = i0; i < hi; i += blockDim.x) {
-    F8 r = ld8(g + ((n * CC + cc) * V + v) * 8);
-    float p = img ? img[i] : 0.f;
-    v += blockDim.x;
-    while (v >= V) { v -= V; ++n; }
+  const int64_t bd = blockDim.x;
+  for (int64_t v0 = lo + threadIdx.x; v0 < hi; v0 += 4 * bd) {
+    F8 r[4];
+    float p[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      aw[j] += r.v[j] * p;
-      ab[j] += r.v[j];
+    for (int q = 0; q < 4; ++q) {
+      const int64_t v = v0 + q * bd;
+      if (v < hi) {
+        r[q] = ld8(pg + v * 8);
+        p[q] = pi ? __ldg(pi + v) : 0.f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[q].v[j] = 0.f;
+        p[q] = 0.f;
+      }
     }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        aw[j] = fmaf(r[q].v[j], p[q], aw[j]);
+        ab[j] += r[q].v[j];
+      }
   }
   __shared__ float sm[2][8][8];  // [w|b][warp][j]
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -572,19 +616,28 @@ __global__ void k_pw_wgrad(const T* __restrict__ g, const float* __restrict__ im
     }
   }
 }
-extern "C" int sg_pw_expand(const float* img, const float* w, const float* bias, void* y, int dtype,
-                            int N, int C, int64_t V, float scale, int lrelu, cudaStream_t s) {
+static int pw_expand_launch(const float* img, const float* w, const float* bias, const void* mask_ref, void* y,
+                            int dtype, int N, int C, int64_t V, float scale, int lrelu, cudaStream_t s) {
   int CC = sg_chunks(C);
   int64_t total = (int64_t)N * CC * V;
   if (total == 0) return 0;
   SG_REQUIRE((int64_t)N * CC <= 65535, "sg_pw_expand: N * channel chunks = %lld exceeds the grid", (long long)N * CC);
-  const int64_t per_row = (V + 3) / 4;
-  int64_t gx = (per_row + 255) / 256;
+  const int64_t per_row = (V + 1023) / 1024;       // blocks of 256 threads x 4 voxels
+  int64_t gx = per_row;
   const int64_t cap = ((int64_t)sg_num_sms() * 8 + (int64_t)N * CC - 1) / ((int64_t)N * CC);   // ~8 blocks per SM in total
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
-  SG_DISPATCH(dtype, sg_launch((k_pw_expand<T>), dim3((unsigned)gx, (unsigned)(N * CC)), 256, 0, s, img, w, bias, (T*)y, N, C, CC, V, scale, lrelu););
+  SG_DISPATCH(dtype, sg_launch((k_pw_expand<T>), dim3((unsigned)gx, (unsigned)(N * CC)), 256, 0, s, img, w, bias,
+                               (const T*)mask_ref, (T*)y, N, C, CC, V, scale, lrelu););
   return sg_check_launch("sg_pw_expand");
+}
+extern "C" int sg_pw_expand(const float* img, const float* w, const float* bias, void* y, int dtype,
+                            int N, int C, int64_t V, float scale, int lrelu, cudaStream_t s) {
+  return pw_expand_launch(img, w, bias, nullptr, y, dtype, N, C, V, scale, lrelu, s);
+}
+extern "C" int sg_pw_expand_masked(const float* img, const float* w, const float* bias, const void* mask_ref, void* y,
+                                   int dtype, int N, int C, int64_t V, float scale, int lrelu, cudaStream_t s) {
+  return pw_expand_launch(img, w, bias, mask_ref, y, dtype, N, C, V, scale, lrelu, s);
 }
 extern "C" int sg_pw_reduce(const void* x, const float* w, const float* bias, float* img, int dtype,
                             int N, int C, int64_t V, float scale, cudaStream_t s) {
@@ -605,14 +658,15 @@ extern "C" int sg_pw_wgrad(const void* g, const float* img, float* gw, float* gb
   if (gw) cudaMemsetAsync(gw, 0, sizeof(float) * C, s);
   if (gb) cudaMemsetAsync(gb, 0, sizeof(float) * C, s);
   if (total == 0) return 0;
-  // slabs: enough blocks for ~4 waves, at least 2048 voxels per block
-  int64_t want = ((int64_t)sg_num_sms() * 4 + CC - 1) / CC;
-  int64_t slabs = (total + 2047) / 2048;
+  // slabs per sample: enough blocks for ~4 waves, at least 2048 voxels per block
+  SG_REQUIRE(N <= 65535, "sg_pw_wgrad: batch %d exceeds the grid", N);
+  int64_t want = ((int64_t)sg_num_sms() * 4 + (int64_t)CC * N - 1) / ((int64_t)CC * N);
+  int64_t slabs = (V + 2047) / 2048;
   if (slabs > want) slabs = want;
   if (slabs < 1) slabs = 1;
-  int64_t per = (total + slabs - 1) / slabs;
-  slabs = (total + per - 1) / per;
-  dim3 grid((unsigned)slabs, (unsigned)CC);
+  int64_t per = (V + slabs - 1) / slabs;
+  slabs = (V + per - 1) / per;
+  dim3 grid((unsigned)slabs, (unsigned)CC, (unsigned)N);
   SG_DISPATCH(dtype, sg_launch((k_pw_wgrad<T>), grid, 256, 0, s, (const T*)g, img, gw, gb, N, C, CC, V, scale, per););
   return sg_check_launch("sg_pw_wgrad");
 }
@@ -852,42 +906,67 @@ struct SgAdamTensor {
   float* ema;     // may be null
   int64_t n;
 };
-__global__ void k_adam_multi(const SgAdamTensor* __restrict__ tensors, const int* __restrict__ block_tensor,
-                             const int64_t* __restrict__ block_offset, const int* __restrict__ step, float lr,
-                             float beta1, float beta2, float eps, float ema_beta) {
+// lr_dev (nullable): learning rate read from device memory instead of the `lr` argument -- a captured CUDA graph
+// then follows a LambdaLR schedule (main.py:145) without being re-captured.
+__global__ void __launch_bounds__(256)
+k_adam_multi(const SgAdamTensor* __restrict__ tensors, const int* __restrict__ block_tensor,
+             const int64_t* __restrict__ block_offset, const int* __restrict__ step, float lr,
+             const float* __restrict__ lr_dev, float beta1, float beta2, float eps, float ema_beta) {
   sg_pdl_enter();
   const SgAdamTensor t = tensors[block_tensor[blockIdx.x]];
   const int64_t base = block_offset[blockIdx.x];
   const float tt = (float)(*step + 1);
   const float bc1 = beta1 > 0.f ? 1.f - powf(beta1, tt) : 1.f;
   const float bc2_sqrt = sqrtf(1.f - powf(beta2, tt));
+  if (lr_dev) lr = *lr_dev;
   const float step_size = lr / bc1;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int64_t i = base + (int64_t)k * blockDim.x + threadIdx.x;
-    if (i >= t.n) break;
-    const float g = t.g[i];
-    float m = g;
-    if (beta1 > 0.f) {
-      m = beta1 * t.m[i] + (1.f - beta1) * g;
-      t.m[i] = m;
+  auto update = [&](float g, float& m, float& v, float& p, float& e) {
+    m = beta1 > 0.f ? beta1 * m + (1.f - beta1) * g : g;
+    v = beta2 * v + (1.f - beta2) * g * g;
+    p = p - step_size * m / (sqrtf(v) / bc2_sqrt + eps);
+    e = ema_beta * e + (1.f - ema_beta) * p;
+  };
+  // a block owns 1024 consecutive elements; with 16-byte aligned tensors a thread updates four consecutive ones
+  // through float4 accesses (20 B/parameter at beta1 = 0: three 16-byte loads and two stores per thread)
+  const bool vec = ((((uintptr_t)t.p) | ((uintptr_t)t.g) | ((uintptr_t)t.v) | ((uintptr_t)t.m) | ((uintptr_t)t.ema)) & 15) == 0;
+  const int64_t i = base + 4 * (int64_t)threadIdx.x;
+  if (vec && i + 3 < t.n) {
+    const float4 g4 = *reinterpret_cast<const float4*>(t.g + i);
+    float4 v4 = *reinterpret_cast<const float4*>(t.v + i);
+    float4 p4 = *reinterpret_cast<const float4*>(t.p + i);
+    float4 m4 = make_float4(0.f, 0.f, 0.f, 0.f), e4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (beta1 > 0.f) m4 = *reinterpret_cast<const float4*>(t.m + i);
+    if (t.ema) e4 = *reinterpret_cast<const float4*>(t.ema + i);
+    update(g4.x, m4.x, v4.x, p4.x, e4.x);
+    update(g4.y, m4.y, v4.y, p4.y, e4.y);
+    update(g4.z, m4.z, v4.z, p4.z, e4.z);
+    update(g4.w, m4.w, v4.w, p4.w, e4.w);
+    if (beta1 > 0.f) *reinterpret_cast<float4*>(t.m + i) = m4;
+    *reinterpret_cast<float4*>(t.v + i) = v4;
+    *reinterpret_cast<float4*>(t.p + i) = p4;
+    if (t.ema) *reinterpret_cast<float4*>(t.ema + i) = e4;
+  } else {
+    for (int k = 0; k < 4; ++k) {
+      const int64_t e_i = i + k;
+      if (e_i >= t.n) break;
+      float m = beta1 > 0.f ? t.m[e_i] : 0.f, v = t.v[e_i], p = t.p[e_i], e = t.ema ? t.ema[e_i] : 0.f;
+      update(t.g[e_i], m, v, p, e);
+      if (beta1 > 0.f) t.m[e_i] = m;
+      t.v[e_i] = v;
+      t.p[e_i] = p;
+      if (t.ema) t.ema[e_i] = e;
     }
-    const float v = beta2 * t.v[i] + (1.f - beta2) * g * g;
-    t.v[i] = v;
-    const float p = t.p[i] - step_size * m / (sqrtf(v) / bc2_sqrt + eps);
-    t.p[i] = p;
-    if (t.ema) t.ema[i] = ema_beta * t.ema[i] + (1.f - ema_beta) * p;
   }
 }
 __global__ void k_adam_advance(int* step) {
   sg_pdl_enter(); *step += 1; }
 
 extern "C" int sg_adam_step(const void* tensors, const int* block_tensor, const int64_t* block_offset, int n_blocks,
-                            const int* step, float lr, float beta1, float beta2, float eps, float ema_beta,
-                            cudaStream_t s) {
+                            const int* step, float lr, const float* lr_dev, float beta1, float beta2, float eps,
+                            float ema_beta, cudaStream_t s) {
   if (n_blocks == 0) return 0;
   sg_launch((k_adam_multi), (unsigned)n_blocks, 256, 0, s, (const SgAdamTensor*)tensors, block_tensor, block_offset, step, lr,
-                                                  beta1, beta2, eps, ema_beta);
+            lr_dev, beta1, beta2, eps, ema_beta);
   return sg_check_launch("sg_adam_step");
 }
 extern "C" int sg_adam_advance(int* step, cudaStream_t s) {

@@ -31,16 +31,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// Slow path of mbar_wait, kept out of line: the clock read, the time-out and the printf live here, so the
+// fast path (the barrier has already flipped: the common case for a producer running ahead) is ONE try_wait.
+// A protocol bug must fault within ~2 s instead of hanging the GPU.
 #if SG_TC_WATCHDOG
-  long long t0 = clock64();
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {   // ~2 s: a protocol bug must fault, not hang the GPU
+    if (clock64() - t0 > 4000000000LL) {
       printf("conv_tc: mbarrier timeout (block %d,%d,%d thread %d bar %u parity %u)\n", blockIdx.x,
              blockIdx.y, blockIdx.z, threadIdx.x, bar, parity);
       __trap();
     }
   }
+}
+#endif
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#if SG_TC_WATCHDOG
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 #else
   while (!mbar_try_wait(bar, parity)) {
   }

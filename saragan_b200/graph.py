@@ -11,8 +11,9 @@ between them -- see __init__.
 
 Inputs live in static buffers: the real batch, the instance-noise draw, the two latent draws and
 the GP interpolation draw are refreshed outside the graph (`draw()`), then `replay()` runs the
-captured work.  `alpha` is a Python float baked into the kernels' arguments, so a graph is
-captured per alpha value (it changes once per epoch in the reference, train.py:33,63).
+captured work.  `alpha` (train.py:33,63: it changes once per epoch) and the learning rate (main.py:145
+LambdaLR) live in DEVICE scalars the captured kernels read, so one capture serves a whole growth phase:
+`set_alpha()` / the optimisers' `param_groups[...]["lr"]` take effect at the next replay.
 """
 from __future__ import annotations
 
@@ -32,26 +33,69 @@ def make_capturable_optimizers(generator, discriminator, lr: float = 1e-3, world
     lr = lr * float(world_size) ** 0.5
     if fused:
         from .optim import FusedAdam
-        d_optim = FusedAdam(discriminator.parameters(), lr=lr, betas=(0.0, 0.99))
-        g_optim = FusedAdam(generator.parameters(), lr=lr, betas=(0.0, 0.99), ema_beta=ema_beta)
+        d_optim = FusedAdam(discriminator.parameters(), lr=lr, betas=(0.0, 0.99), lr_on_device=True)
+        g_optim = FusedAdam(generator.parameters(), lr=lr, betas=(0.0, 0.99), ema_beta=ema_beta, lr_on_device=True)
     else:
         d_optim = torch.optim.Adam(discriminator.parameters(), lr=lr, betas=(0.0, 0.99), capturable=True)
         g_optim = torch.optim.Adam(generator.parameters(), lr=lr, betas=(0.0, 0.99), capturable=True)
     return g_optim, d_optim
 
 
+def _snapshot(nets, opts):
+    """Copies of every parameter and of every tensor of the optimisers' state (plus FusedAdam's device counter)."""
+    snap = {"p": [(p, p.detach().clone()) for net in nets for p in net.parameters()], "o": []}
+    for opt in opts:
+        st = {p: {k: (v.detach().clone() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+              for p, d in opt.state.items()}
+        snap["o"].append((opt, st, None if getattr(opt, "_step_dev", None) is None else opt._step_dev.clone()))
+    return snap
+
+
+@torch.no_grad()
+def _restore(snap):
+    """Undo the warm-up steps: parameters back to their values, optimiser state back to what it was -- state the
+    warm-up CREATED is kept allocated (a capture must not create it) but reset to its initial value (zeros, step 0,
+    EMA = the weights)."""
+    for p, v in snap["p"]:
+        p.copy_(v)
+        p.grad = None
+    for opt, st, step_dev in snap["o"]:
+        for p, d in opt.state.items():
+            old = st.get(p, {})
+            for k, v in d.items():
+                if not isinstance(v, torch.Tensor):
+                    continue
+                if isinstance(old.get(k), torch.Tensor):
+                    v.copy_(old[k])
+                elif k == "ema":
+                    v.copy_(p)
+                else:
+                    v.zero_()
+        if getattr(opt, "_step_dev", None) is not None:
+            if step_dev is not None:
+                opt._step_dev.copy_(step_dev)
+            else:
+                opt._step_dev.zero_()
+    for p, _ in snap["p"]:
+        torch.autograd.graph.increment_version(p)      # packed-weight caches key on the version counter
+
+
 class GraphedTrainStep:
     def __init__(self, generator, discriminator, g_optim, d_optim, batch: int, volume, alpha: float,
                  warmup: int = 3, seed: Optional[int] = None, grad_sync=None):
+        """The warm-up steps (lazy initialisation, kernel attributes, allocator state, Adam state creation) run on
+        the all-zero static input; weights and optimiser state are restored afterwards, so building the graph does
+        not train on garbage or advance Adam's step count."""
         if warmup < 1:
             # the first optim.step() creates the Adam state; inside a capture that initialisation
             # would be replayed (state reset to zero) on every step
             raise ValueError("GraphedTrainStep needs at least one eager warm-up step before the capture")
         self.grad_sync = grad_sync    # e.g. comm.CapturableAllReduce on several GPUs
         self.g, self.d, self.g_optim, self.d_optim = generator, discriminator, g_optim, d_optim
-        self.alpha = float(alpha)
         dev = discriminator.device
         self.dev = dev
+        # alpha as a device scalar: the blend kernels read it (ops.blend_coef), set_alpha() changes it between replays
+        self.alpha = torch.full((), float(alpha), dtype=torch.float32, device=dev)
         latent = generator.latent_dim
         self.x = torch.zeros((batch, 1, *volume), device=dev)
         self.noise = torch.zeros_like(self.x)
@@ -64,20 +108,25 @@ class GraphedTrainStep:
         self.out: Dict[str, torch.Tensor] = {}
         self.graph = torch.cuda.CUDAGraph()
         # warm-up on a side stream (lazy inits, kernel attributes, allocator state), then capture
+        rng_state = self.rng.get_state()
+        snap = _snapshot((generator, discriminator), (g_optim, d_optim))
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(warmup):
                 self.draw()
                 self._step()
+            _restore(snap)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        # the packed-weight caches hold buffers packed OUTSIDE the graph: drop them so that the
-        # first use of every weight inside the capture re-packs (and the pack kernel is captured)
+        del snap
+        self.rng.set_state(rng_state)
+        # the packings were made OUTSIDE the graph: mark them stale, so that the first `prepack` inside the capture
+        # re-packs every weight (into the same persistent buffers, one captured launch per network)
         for net in (generator, discriminator):
             for m in net.modules():
                 if hasattr(m, "_packed"):
-                    m._packed = type(m._packed)(m.weight, known=m._packed.known)
+                    m._packed._ver = {}
         self.draw()
         for opt in (g_optim, d_optim):
             if hasattr(opt, "reserve_capture_tables"):
@@ -129,6 +178,10 @@ class GraphedTrainStep:
                        z_d=self.z_d, z_g=self.z_g, eps=self.eps, grad_sync=self.grad_sync)
         return {k: o[k] for k in ("d_loss", "gp", "g_loss", "distance", "x_fake")}
 
+    def set_alpha(self, alpha: float) -> None:
+        """New fade-in coefficient for the following replays (train.py:33,63: once per epoch); no re-capture."""
+        self.alpha.fill_(float(alpha))
+
     def draw(self) -> None:
         """Fresh random draws of train.py:144-145,178 and loss.py:11 into the static buffers."""
         self.noise.normal_(generator=self.rng)
@@ -140,6 +193,9 @@ class GraphedTrainStep:
         """x_real: host (pinned) or device batch.  Returns the step's scalars as device tensors
         (valid until the next call)."""
         kernels.ensure_leaky_slope(self._leaky_slope)
+        for opt in (self.g_optim, self.d_optim):
+            if hasattr(opt, "sync_lr"):
+                opt.sync_lr()                  # a scheduler may have changed group["lr"] since the last replay
         self.x.copy_(x_real, non_blocking=True)
         self.draw()
         if self.segments is None:

@@ -87,11 +87,52 @@ def act_to_plain(act: torch.Tensor, c: int) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------- conv
-def pack_conv_weight(w: torch.Tensor, dtype: torch.dtype, flip: bool) -> torch.Tensor:
+def pack_conv_weight(w: torch.Tensor, dtype: torch.dtype, flip: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`out`: a buffer from an earlier call for the same parameter (re-packed in place after an optimiser step)."""
     cout, cin = w.shape[0], w.shape[1]
-    out = torch.empty(_lib.packed_weight_elems(cout, cin, int(flip)), dtype=dtype, device=w.device)
+    if out is None:
+        out = torch.empty(_lib.packed_weight_elems(cout, cin, int(flip)), dtype=dtype, device=w.device)
     call("sg_pack_conv_weight", w, out, _lib.dtype_code(out), cout, cin, int(flip))
     return out
+
+
+_pack_tables = {}
+
+
+def pack_conv_weights_multi(jobs) -> list:
+    """jobs: [(w, dtype, flip, out or None)] -> the packed buffers, all written by ONE launch
+    (sg_pack_conv_weights_multi).  The job / block tables live on the device, cached on the pointers involved; a new
+    table cannot be built while a CUDA graph is being captured (pinned staging), then the jobs run one by one."""
+    outs = []
+    for w, dtype, flip, out in jobs:
+        if out is None:
+            out = torch.empty(_lib.packed_weight_elems(w.shape[0], w.shape[1], int(flip)), dtype=dtype, device=w.device)
+        outs.append(out)
+    key = tuple((w.data_ptr(), o.data_ptr(), int(flip)) for (w, _, flip, _), o in zip(jobs, outs))
+    tab = _pack_tables.get(key)
+    if tab is None:
+        if torch.cuda.is_current_stream_capturing():
+            for (w, dtype, flip, _), o in zip(jobs, outs):
+                pack_conv_weight(w, dtype, flip, o)
+            return outs
+        rows, bj, bk, br = [], [], [], []
+        for ji, ((w, dtype, flip, _), o) in enumerate(zip(jobs, outs)):
+            cout, cin = w.shape[0], w.shape[1]
+            k, r = (cout, cin) if flip else (cin, cout)
+            # struct SgPackJob { const float* w; void* dst; int Cout, Cin, flip, dtype; } as four int64 words
+            rows.append([w.data_ptr(), o.data_ptr(), cout | (cin << 32), int(flip) | (_lib.dtype_code(o) << 32)])
+            for kc in range(chunks(k)):
+                for r0 in range(0, 16 * ((r + 15) // 16), 32):
+                    bj.append(ji), bk.append(kc), br.append(r0)
+        dev = outs[0].device
+        tab = dict(jobs=torch.tensor(rows, dtype=torch.int64).to(dev), n=len(bj),
+                   bj=torch.tensor(bj, dtype=torch.int32).to(dev), bk=torch.tensor(bk, dtype=torch.int32).to(dev),
+                   br=torch.tensor(br, dtype=torch.int32).to(dev))
+        if len(_pack_tables) > 64:
+            _pack_tables.clear()
+        _pack_tables[key] = tab
+    call("sg_pack_conv_weights_multi", tab["jobs"], tab["bj"], tab["bk"], tab["br"], tab["n"])
+    return outs
 
 
 def _workspace(kind: int, x: torch.Tensor, n, cin, cout, d, h, w):
@@ -137,10 +178,15 @@ def conv3d_wgrad(x: torch.Tensor, gy: torch.Tensor, cin: int, cout: int, scale: 
 
 # ----------------------------------------------------------------------------- 1x1x1
 def pw_expand(img: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], dtype: torch.dtype,
-              c: int, scale: float, lrelu: bool) -> torch.Tensor:
+              c: int, scale: float, lrelu: bool, mask_ref: Optional[torch.Tensor] = None) -> torch.Tensor:
     n, _, d, h, wd = img.shape
     y = torch.empty((n, chunks(c), d, h, wd, 8), dtype=dtype, device=img.device)
-    call("sg_pw_expand", img, w, bias, y, _lib.dtype_code(y), n, c, d * h * wd, float(scale), int(lrelu))
+    if mask_ref is None:
+        call("sg_pw_expand", img, w, bias, y, _lib.dtype_code(y), n, c, d * h * wd, float(scale), int(lrelu))
+    else:
+        assert mask_ref.shape == y.shape and mask_ref.dtype == y.dtype
+        call("sg_pw_expand_masked", img, w, bias, mask_ref, y, _lib.dtype_code(y), n, c, d * h * wd, float(scale),
+             int(lrelu))
     return y
 
 
@@ -195,9 +241,15 @@ def up2(x: torch.Tensor, scale: float, out_dtype: Optional[torch.dtype] = None,
 
 
 # ------------------------------------------------------------------------ elementwise
-def lincomb(a: torch.Tensor, b: Optional[torch.Tensor], alpha: float, beta: float) -> torch.Tensor:
+def lincomb(a: torch.Tensor, b: Optional[torch.Tensor], alpha, beta=None) -> torch.Tensor:
+    """y = alpha*a + beta*b.  alpha, beta: Python floats, or `alpha` a 2-element fp32 DEVICE tensor {alpha, beta}
+    (read by the kernel: no host sync, and a captured graph follows the values)."""
     y = torch.empty_like(a)
-    call("sg_lincomb", a, b, y, _lib.dtype_code(a), a.numel(), float(alpha), float(beta))
+    if isinstance(alpha, torch.Tensor):
+        assert alpha.dtype == torch.float32 and alpha.numel() == 2 and alpha.device == a.device
+        call("sg_lincomb_dev", a, b, y, _lib.dtype_code(a), a.numel(), alpha)
+    else:
+        call("sg_lincomb", a, b, y, _lib.dtype_code(a), a.numel(), float(alpha), float(beta))
     return y
 
 

@@ -40,9 +40,6 @@ def _voxels(x: torch.Tensor) -> int:
     return int(x.shape[2] * x.shape[3] * x.shape[4])
 
 
-def _as_float(alpha) -> float:
-    return float(alpha.item()) if isinstance(alpha, torch.Tensor) else float(alpha)
-
 
 class _Blocked:
     """Marker mixin: helpers to enter/leave the blocked layout at module boundaries."""
@@ -103,22 +100,24 @@ class EqualizedConv3d(nn.Module, _Blocked):
             "saragan_b200.EqualizedConv3d covers the PGAN hot path only: 3x3x3/stride 1/pad 1, "
             "and 1x1x1 with one image channel")
 
-    def forward(self, input, lrelu: bool = False, premasked: bool = False, mask_input_grad: bool = False):
-        """lrelu fuses the following LeakyReLU(0.2); premasked / mask_input_grad are the
+    def forward(self, input, lrelu: bool = False, premasked: bool = False, mask_input_grad: bool = False,
+                dd_fuse: bool = False):
+        """lrelu fuses the following LeakyReLU(0.2); premasked / mask_input_grad / dd_fuse are the
         LeakyReLU-backward fusion flags of ops.Conv3x3 (internal wiring of the blocks)."""
         kind = self._kind()
         if kind == "3x3x3":
             plain = not self.is_act(input)
             x = self.enter(input) if plain else input
             if self._packed.weight is not self.weight:  # parameter was re-bound (.to(), load)
-                self._packed = ops.PackedWeight(self.weight)
+                self._packed = ops.PackedWeight(self.weight, known=self._packed.known)
             y = ops.Conv3x3.apply(x, self.weight, self.bias, self._packed, float(self.std), lrelu,
-                                  premasked and not plain, mask_input_grad and not plain)
+                                  premasked and not plain, mask_input_grad and not plain, None,
+                                  dd_fuse and not plain)
             return self.leave(y, self.out_channels) if plain else y
         if kind == "from_rgb":
             return ops.PwExpand.apply(input.float().contiguous(), self.weight.reshape(-1), self.bias,
                                       float(self.std), lrelu, self.out_channels,
-                                      config.act_dtype(_voxels(input)), premasked)
+                                      config.act_dtype(_voxels(input)), premasked, dd_fuse and premasked)
         plain = not self.is_act(input)
         x = self.enter(input) if plain else input
         img = ops.PwReduce.apply(x, self.weight.reshape(-1), self.bias, float(self.std),
@@ -168,15 +167,16 @@ class DiscriminatorBlock(nn.Sequential, _Blocked):
         self.downsampling = nn.AvgPool3d(2)
 
     def forward(self, input, input_is_lrelu: bool = False):
-        """input_is_lrelu: `input` is the LeakyReLU output of a premasked producer (the top-level
-        FromRGB) whose only consumer is this block."""
+        """input_is_lrelu: `input` is the LeakyReLU output of a premasked, dd_fuse-wired producer (the
+        top-level FromRGB) whose only consumer is this block."""
         plain = not self.is_act(input)
         x = self.enter(input) if plain else input
         # LeakyReLU backward masks ride in the consumers' kernels: conv2's dgrad epilogue masks
-        # for conv1, the avg-pool backward masks for conv2
-        x = self.conv1(x, lrelu=True, premasked=True, mask_input_grad=input_is_lrelu and not plain)
-        x = self.conv2(x, lrelu=True, premasked=True, mask_input_grad=True)
-        x = ops.Down2.apply(x, 0.125, config.act_dtype(_voxels(x) // 8), True)
+        # for conv1, the avg-pool backward masks for conv2; in the gradient penalty's double backward
+        # they ride in the producers' epilogues (dd_fuse, ops.Conv3x3)
+        x = self.conv1(x, lrelu=True, premasked=True, mask_input_grad=input_is_lrelu and not plain, dd_fuse=True)
+        x = self.conv2(x, lrelu=True, premasked=True, mask_input_grad=True, dd_fuse=True)
+        x = ops.Down2.apply(x, 0.125, config.act_dtype(_voxels(x) // 8), True, True)
         return self.leave(x, self.filters_out) if plain else x
 
 
@@ -192,7 +192,7 @@ class FromRGB(nn.Sequential):
         )
 
     def forward(self, input, premasked: bool = False):
-        return self.fromrgb[0](input, lrelu=True, premasked=premasked)
+        return self.fromrgb[0](input, lrelu=True, premasked=premasked, dd_fuse=premasked)
 
 
 class MinibatchStandardDeviation(nn.Module):
@@ -257,8 +257,8 @@ class Discriminator(nn.Module):
         axis -- e.g. D(cat(real, fake)) in one pass; minibatch-stddev treats them separately, so the
         result equals the concatenation of the separate calls."""
         kernels.ensure_leaky_slope(LEAKINESS)
-        alpha = _as_float(alpha)
         img = input.to(self.device).float().contiguous()
+        alpha, beta = ops.blend_coef(alpha, img.device)
         # at phase > 1 the top FromRGB feeds only the first block's conv1, whose dgrad epilogue
         # then applies FromRGB's LeakyReLU mask
         x = self.fromrgbs[-self.phase](img, premasked=self.phase > 1)
@@ -266,7 +266,7 @@ class Discriminator(nn.Module):
             x = self.blocks[-i](x, input_is_lrelu=(i == self.phase - 1))
             img = ops.Down2.apply(img, 0.125)
             prev = self.fromrgbs[-i](img)
-            x = ops.Lincomb.apply(prev, x, alpha, 1.0 - alpha)
+            x = ops.Lincomb.apply(prev, x, alpha, beta)
         out = self.discriminator_out
         c = out[1].in_channels - 1
         x = out[0](ops.ToPlain.apply(x, c), sub_batches)
@@ -368,9 +368,9 @@ class Generator(nn.Module):
 
     def forward(self, input, alpha):
         kernels.ensure_leaky_slope(LEAKINESS)
-        alpha = _as_float(alpha)
         gin = self.generator_in
         x = gin[0](input.to(self.device), lrelu=True)
+        alpha, beta = ops.blend_coef(alpha, x.device)
         x = gin[2](x)
         x = ops.ToAct.apply(x, config.act_dtype(_voxels(x)))
         x = gin[3](x, lrelu=True, premasked=True)
@@ -382,6 +382,6 @@ class Generator(nn.Module):
         for i in range(0, self.phase - 1):
             x = self.blocks[i](x)
             img_gen = self.to_rgbs[i + 1](x)
-            images_out = ops.Lincomb.apply(ops.Up2.apply(images_out, 1.0), img_gen, alpha, 1.0 - alpha)
+            images_out = ops.Lincomb.apply(ops.Up2.apply(images_out, 1.0), img_gen, alpha, beta)
             all_out.append(images_out)
         return all_out

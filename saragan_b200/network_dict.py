@@ -24,7 +24,7 @@ from torch.nn.init import calculate_gain
 
 from . import config, kernels, ops
 from . import network as _net
-from .network import ChannelNormalization, Reshape, _as_float, _voxels, num_filters  # noqa: F401
+from .network import ChannelNormalization, Reshape, _voxels, num_filters  # noqa: F401
 
 LEAKINESS = 0.3                                         # network_dict.py:18
 _SLOPES = {"relu": 0.0, "leaky_relu": LEAKINESS}        # network_dict.py:19-23 ('swish': see module docstring)
@@ -177,15 +177,15 @@ class Discriminator(nn.Module):
         """network_dict.py:246-259.  ``sub_batches`` is accepted for the train step's stacked D(real, fake) pass;
         without minibatch-stddev the samples never interact, so it changes nothing."""
         _activate_slope(self.nonlinearity)
-        alpha = _as_float(alpha)
         img = input.to(self.device).float().contiguous()
+        alpha, beta = ops.blend_coef(alpha, img.device)
         # at phase > 1 the top FromRGB feeds only the first block's conv1, whose dgrad epilogue applies its mask
         x = self.fromrgb_current(img, premasked=self.phase > 1)
         for i in reversed(range(2, self.phase + 1)):
             x = self.blocks[f"block_phase_{i}"](x, input_is_lrelu=(i == self.phase))
             if i == self.phase:
                 prev = self.fromrgb_prev(ops.Down2.apply(img, 0.125))
-                x = ops.Lincomb.apply(prev, x, alpha, 1.0 - alpha)
+                x = ops.Lincomb.apply(prev, x, alpha, beta)
         out = self.discriminator_out
         x = out[0](x, lrelu=True)
         x = torch.flatten(ops.ToPlain.apply(x, out[0].out_channels), 1)
@@ -248,9 +248,9 @@ class Generator(nn.Module):
 
     def forward(self, input, alpha):
         _activate_slope(self.nonlinearity)
-        alpha = _as_float(alpha)
         gin = self.generator_in
         x = gin[0](input.to(self.device), lrelu=True)
+        alpha, beta = ops.blend_coef(alpha, x.device)
         x = gin[2](x)
         x = ops.ToAct.apply(x, config.act_dtype(_voxels(x)))
         x = gin[3](x, lrelu=True, premasked=True)
@@ -262,5 +262,5 @@ class Generator(nn.Module):
             x = self.blocks[f"block_phase_{i}"](x)
         images_out = self.torgb_current(x)
         if x_upsample is not None:
-            images_out = ops.Lincomb.apply(x_upsample, images_out, alpha, 1.0 - alpha)
+            images_out = ops.Lincomb.apply(x_upsample, images_out, alpha, beta)
         return images_out

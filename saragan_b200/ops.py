@@ -44,73 +44,111 @@ def _c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 
 
 class PackedWeight:
-    """Per-parameter cache of the two bf16/fp32 packings of a (Cout,Cin,3,3,3) weight; refreshed
-    when the optimiser bumps the parameter's version counter."""
+    """Per-parameter cache of the packings of a (Cout,Cin,3,3,3) weight -- (dtype, flip) -> buffer -- re-packed IN PLACE
+    when the optimiser bumps the parameter's version counter (persistent buffers: stable pointers for captured graphs
+    and for the multi-tensor re-pack of `prepack`)."""
 
     def __init__(self, weight: torch.Tensor, cache: bool = True, known=None):
         self.weight = weight
         self.cache = cache
-        self._key = None
-        self._packs = {}
+        self._bufs = {}
+        self._ver = {}
         self.known = set() if known is None else known   # every (dtype, flip) ever asked for
 
-    def get(self, dtype: torch.dtype, flip: bool) -> torch.Tensor:
+    def _cur(self):
         w = self.weight
-        key = (w._version, w.data_ptr(), w.device)
-        if key != self._key:
-            self._key, self._packs = key, {}
+        return (w._version, w.data_ptr(), w.device)
+
+    def stale(self, k) -> bool:
+        return self._ver.get(k) != self._cur()
+
+    def _reusable(self, k):
+        buf = self._bufs.get(k)
+        return buf if (buf is not None and getattr(buf, "device", None) == self.weight.device) else None
+
+    def get(self, dtype: torch.dtype, flip: bool) -> torch.Tensor:
         k = (dtype, flip)
         self.known.add(k)
-        if k not in self._packs:
-            self._packs[k] = K.pack_conv_weight(w.detach().contiguous(), dtype, flip)
-        return self._packs[k]
+        if self.stale(k):
+            self._bufs[k] = K.pack_conv_weight(self.weight.detach().contiguous(), dtype, flip, self._reusable(k))
+            self._ver[k] = self._cur()
+        return self._bufs[k]
+
+    def stale_jobs(self):
+        return [(k, (self.weight.detach().contiguous(), k[0], k[1], self._reusable(k))) for k in self.known if self.stale(k)]
+
+    def adopt(self, k, buf) -> None:
+        self._bufs[k], self._ver[k] = buf, self._cur()
 
     def prepack(self) -> None:
-        """Refresh every packing used so far on the CURRENT stream (before work forks onto a second stream,
-        where a lazy first use would race with the other stream's)."""
         for k in tuple(self.known):
             self.get(*k)
 
 
-def prepack(net) -> None:
-    """`PackedWeight.prepack` for every conv layer of a network."""
+def prepack(net) -> bool:
+    """Re-pack every stale packing of every conv layer of `net` on the CURRENT stream with ONE launch
+    (`sg_pack_conv_weights_multi`): after an optimiser step, and before work forks onto a second stream (a lazy first
+    packing there would race with the other stream's use of the same buffer).  Returns False when some layer has
+    never been used yet (its packings are unknown: the caller must not fork streams for this pass)."""
+    todo, complete = [], True
     for m in net.modules():
         pw = getattr(m, "_packed", None)
-        if pw is not None:
-            pw.prepack()
+        if pw is None:
+            continue
+        if getattr(pw, "weight", None) is not getattr(m, "weight", None):    # parameter re-bound (.to(), load)
+            pw = m._packed = PackedWeight(m.weight, known=pw.known)
+        if not pw.known:
+            complete = False
+        todo += [(pw, k, job) for k, job in pw.stale_jobs()]
+    if len(todo) == 1:
+        todo[0][0].get(*todo[0][1])
+    elif todo:
+        for (pw, k, _), buf in zip(todo, K.pack_conv_weights_multi([job for _, _, job in todo])):
+            pw.adopt(k, buf)
+    return complete
 
 
 # ================================================================================ conv
 class Conv3x3(Function):
-    """y = [lrelu](std * conv3d(x, w, pad=1) + b)   -- network.py:54-56 (+ :89 etc. fused).
+    """y = [m(out_mask) *] [lrelu](std * conv3d(x, w, pad=1) + b)   -- network.py:54-56 (+ :89 etc. fused).
 
     LeakyReLU-mask fusion (the mask of a layer is the sign of its OUTPUT):
       premasked       -- the consumer of y already multiplied the incoming gradient by m(y)
                          (a following conv's dgrad epilogue, an avg-pool backward, a pixel-norm
                          backward), so this op must not do it again;
       mask_input_grad -- x is the LeakyReLU output of the producing op: multiply the returned
-                         input gradient by m(x) in the dgrad epilogue (the producer is premasked)."""
+                         input gradient by m(x) in the dgrad epilogue (the producer is premasked);
+      dd_fuse         -- the same pairing one order up, for the gradient penalty's double backward: the backward of this
+                         op's dgrad node multiplies what it returns by m(y) in ITS conv epilogue (`out_mask`), and does
+                         not mask what it receives by m(x), because the producer of x -- wired with dd_fuse too --
+                         did.  Without it each of those masks is a stand-alone MaskMul pass over a full-resolution
+                         tensor.  Both sides of a producer/consumer pair must be wired alike (network.py's
+                         Discriminator does so; stand-alone modules leave it off)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, pw: Optional[PackedWeight], std: float, lrelu: bool,
-                premasked: bool = False, mask_input_grad: bool = False):
+                premasked: bool = False, mask_input_grad: bool = False, out_mask=None, dd_fuse: bool = False):
         cout, cin = weight.shape[0], weight.shape[1]
         pw = pw if pw is not None else PackedWeight(weight, cache=False)
-        y = K.conv3d_fprop(x, pw.get(x.dtype, False), bias, None, cin, cout, std, lrelu, IMPL_AUTO)
-        ctx.save_for_backward(x, weight, y if (lrelu and not premasked) else None)
+        y = K.conv3d_fprop(x, pw.get(x.dtype, False), bias, out_mask, cin, cout, std, lrelu, IMPL_AUTO)
+        ctx.save_for_backward(x, weight, y if (lrelu and (dd_fuse or not premasked)) else None, out_mask)
         ctx.pw, ctx.std, ctx.lrelu, ctx.has_bias = pw, std, lrelu, bias is not None
-        ctx.premasked, ctx.mask_input_grad = premasked, mask_input_grad
+        ctx.premasked, ctx.mask_input_grad, ctx.dd_fuse = premasked, mask_input_grad, dd_fuse
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, weight, y = ctx.saved_tensors
+        x, weight, y, out_mask = ctx.saved_tensors
         g = _c(gy)
+        if out_mask is not None:
+            g = MaskMul.apply(g, out_mask)
         if ctx.lrelu and not ctx.premasked:
             g = MaskMul.apply(g, y)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = ConvDgrad.apply(g, weight, ctx.pw, ctx.std, x if ctx.mask_input_grad else None)
+            gx = ConvDgrad.apply(g, weight, ctx.pw, ctx.std, x if ctx.mask_input_grad else None,
+                                 y if (ctx.lrelu and ctx.premasked and ctx.dd_fuse) else None,
+                                 ctx.dd_fuse and ctx.mask_input_grad)
         want_w = ctx.needs_input_grad[1] and _weight_grads_enabled
         want_b = ctx.has_bias and ctx.needs_input_grad[2] and _weight_grads_enabled
         if want_w:
@@ -118,34 +156,38 @@ class Conv3x3(Function):
             gb = gb_ if want_b else None
         elif want_b:
             gb = ChanSum.apply(g, weight.shape[0])
-        return gx, gw, gb, None, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None, None, None
 
 
 class ConvDgrad(Function):
     """gx = [m(mask_ref) *] std * dgrad(g, w): the same implicit GEMM on the flipped/transposed
-    packing; mask_ref fuses the producing layer's LeakyReLU backward into the epilogue."""
+    packing; mask_ref fuses the producing layer's LeakyReLU backward into the epilogue.
+    Double backward (dd_fuse wiring of Conv3x3): g_mask = the output of the layer this node belongs to, whose mask the
+    incoming g already carries -- the gradient w.r.t. g is multiplied by m(g_mask) in the epilogue of the conv that
+    computes it; ggx_premasked = the incoming second-order gradient already carries m(mask_ref)."""
 
     @staticmethod
-    def forward(ctx, g, weight, pw: Optional[PackedWeight], std: float, mask_ref=None):
+    def forward(ctx, g, weight, pw: Optional[PackedWeight], std: float, mask_ref=None, g_mask=None,
+                ggx_premasked: bool = False):
         cout, cin = weight.shape[0], weight.shape[1]
         pw = pw if pw is not None else PackedWeight(weight, cache=False)
         gx = K.conv3d_fprop(g, pw.get(g.dtype, True), None, mask_ref, cout, cin, std, False, IMPL_AUTO)
-        ctx.save_for_backward(g, weight, mask_ref)
-        ctx.pw, ctx.std = pw, std
+        ctx.save_for_backward(g, weight, mask_ref, g_mask)
+        ctx.pw, ctx.std, ctx.ggx_premasked = pw, std, ggx_premasked
         return gx
 
     @staticmethod
     def backward(ctx, ggx):
-        g, weight, mask_ref = ctx.saved_tensors
+        g, weight, mask_ref, g_mask = ctx.saved_tensors
         ggx = _c(ggx)
-        if mask_ref is not None:
+        if mask_ref is not None and not ctx.ggx_premasked:
             ggx = MaskMul.apply(ggx, mask_ref)
         gg = gw = None
         if ctx.needs_input_grad[0]:
-            gg = Conv3x3.apply(ggx, weight, None, ctx.pw, ctx.std, False)
+            gg = Conv3x3.apply(ggx, weight, None, ctx.pw, ctx.std, False, False, False, g_mask)
         if ctx.needs_input_grad[1] and _weight_grads_enabled:
             gw, _ = ConvWgrad.apply(ggx, g, ctx.std, weight.shape[1], weight.shape[0], False)
-        return gg, gw, None, None, None
+        return gg, gw, None, None, None, None, None
 
 
 class ConvWgrad(Function):
@@ -222,25 +264,28 @@ class Down2(Function):
     """y = scale * (2x2x2 block sum): AvgPool3d(2) with scale 1/8 (network.py:90,154)."""
 
     @staticmethod
-    def forward(ctx, x, scale: float, out_dtype: Optional[torch.dtype] = None, premask: bool = False):
+    def forward(ctx, x, scale: float, out_dtype: Optional[torch.dtype] = None, premask: bool = False,
+                dd_fuse: bool = False):
         """premask: x is the LeakyReLU output of a (premasked) conv; fold that conv's mask into
-        this op's backward (the up-sampling kernel multiplies by m(x))."""
-        ctx.scale, ctx.in_dtype = scale, x.dtype
+        this op's backward (the up-sampling kernel multiplies by m(x)).  dd_fuse: see Conv3x3."""
+        ctx.scale, ctx.in_dtype, ctx.dd_fuse = scale, x.dtype, dd_fuse
         ctx.save_for_backward(x if premask else None)
         return K.down2(x, scale, out_dtype)
 
     @staticmethod
     def backward(ctx, gy):
         (ref,) = ctx.saved_tensors
-        return Up2.apply(_c(gy), ctx.scale, ctx.in_dtype, ref), None, None, None
+        return Up2.apply(_c(gy), ctx.scale, ctx.in_dtype, ref, ctx.dd_fuse and ref is not None), None, None, None, None
 
 
 class Up2(Function):
-    """y[child] = scale * x[parent]: nearest Upsample(2) with scale 1 (network.py:203,265)."""
+    """y[child] = scale * x[parent]: nearest Upsample(2) with scale 1 (network.py:203,265).
+    gy_premasked: the gradient arriving in backward already carries m(mask_ref) (dd_fuse wiring of Conv3x3)."""
 
     @staticmethod
-    def forward(ctx, x, scale: float, out_dtype: Optional[torch.dtype] = None, mask_ref=None):
-        ctx.scale, ctx.in_dtype = scale, x.dtype
+    def forward(ctx, x, scale: float, out_dtype: Optional[torch.dtype] = None, mask_ref=None,
+                gy_premasked: bool = False):
+        ctx.scale, ctx.in_dtype, ctx.gy_premasked = scale, x.dtype, gy_premasked
         ctx.save_for_backward(mask_ref)
         return K.up2(x, scale, out_dtype, mask_ref)
 
@@ -248,79 +293,98 @@ class Up2(Function):
     def backward(ctx, gy):
         (ref,) = ctx.saved_tensors
         gy = _c(gy)
-        if ref is not None:
+        if ref is not None and not ctx.gy_premasked:
             gy = MaskMul.apply(gy, ref)
-        return Down2.apply(gy, ctx.scale, ctx.in_dtype), None, None, None
+        return Down2.apply(gy, ctx.scale, ctx.in_dtype), None, None, None, None
 
 
 class Lincomb(Function):
-    """y = alpha*a + beta*b: the fade-in blend (network.py:185,281)."""
+    """y = alpha*a + beta*b: the fade-in blend (network.py:185,281).  alpha, beta are Python floats, or -- for a tensor
+    alpha -- `alpha` = the device pair {alpha, beta} and `beta` = the swapped pair {beta, alpha} (`blend_coef`)."""
 
     @staticmethod
-    def forward(ctx, a, b, alpha: float, beta: float):
+    def forward(ctx, a, b, alpha, beta):
         ctx.alpha, ctx.beta, ctx.has_b = alpha, beta, b is not None
         return K.lincomb(a, b, alpha, beta)
 
     @staticmethod
     def backward(ctx, gy):
         gy = _c(gy)
-        ga = Lincomb.apply(gy, None, ctx.alpha, 0.0) if ctx.needs_input_grad[0] else None
-        gb = Lincomb.apply(gy, None, ctx.beta, 0.0) if ctx.has_b and ctx.needs_input_grad[1] else None
+        dev = isinstance(ctx.alpha, torch.Tensor)
+        ga = gb = None
+        if ctx.needs_input_grad[0]:
+            ga = Lincomb.apply(gy, None, ctx.alpha, ctx.beta if dev else 0.0)
+        if ctx.has_b and ctx.needs_input_grad[1]:
+            gb = Lincomb.apply(gy, None, ctx.beta, ctx.alpha if dev else 0.0)
         return ga, gb, None, None
+
+
+def blend_coef(alpha, device):
+    """(alpha, 1 - alpha) as the arguments of Lincomb: floats for a Python number, device pairs for a tensor alpha
+    (no `.item()` host sync; inside a captured graph the kernels then read the current value on every replay)."""
+    if isinstance(alpha, torch.Tensor):
+        a = alpha.detach().to(device=device, dtype=torch.float32).reshape(())
+        pair = torch.stack([a, 1.0 - a])
+        return pair, pair.flip(0)
+    return float(alpha), 1.0 - float(alpha)
 
 
 # =============================================================================== 1x1x1
 class PwExpand(Function):
-    """FromRGB (network.py:101-110): y[n,c,v] = [lrelu](std*w[c]*img[n,v] + b[c])."""
+    """FromRGB (network.py:101-110): y[n,c,v] = [m(out_mask) *] [lrelu](std*w[c]*img[n,v] + b[c]).
+    premasked / dd_fuse: as in Conv3x3 (the consumer is the top block's conv1)."""
 
     @staticmethod
     def forward(ctx, img, w, bias, std: float, lrelu: bool, c: int, dtype: torch.dtype,
-                premasked: bool = False):
-        y = K.pw_expand(img, w, bias, dtype, c, std, lrelu)
-        ctx.save_for_backward(img, w, y if (lrelu and not premasked) else None)
-        ctx.std, ctx.lrelu, ctx.c, ctx.has_bias, ctx.premasked = std, lrelu, c, bias is not None, premasked
+                premasked: bool = False, dd_fuse: bool = False, out_mask=None):
+        y = K.pw_expand(img, w, bias, dtype, c, std, lrelu, out_mask)
+        ctx.save_for_backward(img, w, y if (lrelu and (dd_fuse or not premasked)) else None, out_mask)
+        ctx.std, ctx.lrelu, ctx.c, ctx.has_bias, ctx.premasked, ctx.dd_fuse = std, lrelu, c, bias is not None, premasked, dd_fuse
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        img, w, y = ctx.saved_tensors
+        img, w, y, out_mask = ctx.saved_tensors
         g = _c(gy)
+        if out_mask is not None:
+            g = MaskMul.apply(g, out_mask)
         if ctx.lrelu and not ctx.premasked:
             g = MaskMul.apply(g, y)
         gimg = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gimg = PwReduce.apply(g, w, None, ctx.std, ctx.c)
+            gimg = PwReduce.apply(g, w, None, ctx.std, ctx.c, y if (ctx.lrelu and ctx.premasked and ctx.dd_fuse) else None)
         want_w = ctx.needs_input_grad[1] and _weight_grads_enabled
         want_b = ctx.has_bias and ctx.needs_input_grad[2] and _weight_grads_enabled
         if want_w or want_b:
             gw_, gb_ = PwWgrad.apply(g, img, ctx.std, ctx.c)
             gw = gw_ if want_w else None
             gb = gb_ if want_b else None
-        return gimg, gw, gb, None, None, None, None, None
+        return gimg, gw, gb, None, None, None, None, None, None, None
 
 
 class PwReduce(Function):
-    """ToRGB (network.py:219-225): img[n,v] = std*sum_c w[c]*x[n,c,v] + b."""
+    """ToRGB (network.py:219-225): img[n,v] = std*sum_c w[c]*x[n,c,v] + b.
+    x_mask (dd_fuse wiring): x already carries m(x_mask); the gradient w.r.t. x is masked by it where it is computed."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, std: float, c: int):
+    def forward(ctx, x, w, bias, std: float, c: int, x_mask=None):
         img = K.pw_reduce(x, w, bias, c, std)
-        ctx.save_for_backward(x, w)
+        ctx.save_for_backward(x, w, x_mask)
         ctx.std, ctx.c, ctx.has_bias = std, c, bias is not None
         return img
 
     @staticmethod
     def backward(ctx, gimg):
-        x, w = ctx.saved_tensors
+        x, w, x_mask = ctx.saved_tensors
         gimg = _c(gimg)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = PwExpand.apply(gimg, w, None, ctx.std, False, ctx.c, x.dtype)
+            gx = PwExpand.apply(gimg, w, None, ctx.std, False, ctx.c, x.dtype, False, False, x_mask)
         if ctx.needs_input_grad[1] and _weight_grads_enabled:
             gw, _ = PwWgrad.apply(x, gimg, ctx.std, ctx.c)
         if ctx.has_bias and ctx.needs_input_grad[2] and _weight_grads_enabled:
             gb = gimg.sum().reshape(1)
-        return gx, gw, gb, None, None
+        return gx, gw, gb, None, None, None
 
 
 class PwWgrad(Function):

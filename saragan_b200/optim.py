@@ -19,9 +19,15 @@ _CHUNK = 1024   # elements per block (256 threads x 4)
 
 class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr: float = 1e-3, betas=(0.0, 0.99), eps: float = 1e-8,
-                 ema_beta: Optional[float] = None):
+                 ema_beta: Optional[float] = None, lr_on_device: bool = False):
+        """lr_on_device: the kernel reads each group's learning rate from a device scalar that `step()` refreshes
+        from `group["lr"]` OUTSIDE any capture (`sync_lr()`): a CUDA graph that captured `step()` then follows an
+        LR scheduler (main.py:145 LambdaLR) without being re-captured."""
         super().__init__(params, dict(lr=lr, betas=tuple(float(b) for b in betas), eps=eps))
         self.ema_beta = ema_beta
+        self.lr_on_device = lr_on_device
+        self._lr_dev: Dict[int, torch.Tensor] = {}
+        self._lr_host: Dict[int, float] = {}
         self._step_dev: Optional[torch.Tensor] = None
         self._tables: Dict[int, dict] = {}
         self._spare: Dict[int, dict] = {}
@@ -82,6 +88,24 @@ class FusedAdam(torch.optim.Optimizer):
         self._tables[gi] = tab
         return tab
 
+    def sync_lr(self) -> None:
+        """Copy every group's current `lr` into its device scalar (lr_on_device); call between graph replays after
+        a scheduler step.  `step()` does it itself when it is not being captured."""
+        for gi, group in enumerate(self.param_groups):
+            dev_t = self._lr_dev.get(gi)
+            if dev_t is not None and self._lr_host.get(gi) != float(group["lr"]):
+                dev_t.fill_(float(group["lr"]))
+                self._lr_host[gi] = float(group["lr"])
+
+    def init_state(self, params=None) -> None:
+        """Create the Adam state (and the device step counter) without taking a step -- before a CUDA-graph capture,
+        where a lazy creation would be recorded and replayed (state reset on every replay)."""
+        for group in self.param_groups:
+            for p in (group["params"] if params is None else params):
+                self._state_for(p, group["betas"][0])
+                if self._step_dev is None:
+                    self._step_dev = torch.zeros(4, dtype=torch.int32, device=p.device)
+
     @torch.no_grad()
     def step(self, closure=None):
         assert closure is None
@@ -92,16 +116,47 @@ class FusedAdam(torch.optim.Optimizer):
                 continue
             first = params[0]
             if self._step_dev is None:
-                self._step_dev = torch.zeros(4, dtype=torch.int32, device=first.device)
+                self._step_dev = torch.full((4,), int(getattr(self, "_pending_step", 0)), dtype=torch.int32,
+                                            device=first.device)
             beta1, beta2 = group["betas"]
             tab = self._table(gi, params, beta1)
+            lr_dev = None
+            if self.lr_on_device:
+                if gi not in self._lr_dev:
+                    if torch.cuda.is_current_stream_capturing():
+                        raise RuntimeError("FusedAdam(lr_on_device): take one eager step (or call init_state + sync_lr) "
+                                           "before capturing")
+                    self._lr_dev[gi] = torch.zeros(4, dtype=torch.float32, device=first.device)
+                if not torch.cuda.is_current_stream_capturing():
+                    self.sync_lr()
+                lr_dev = self._lr_dev[gi]
             call("sg_adam_step", tab["t"], tab["bt"], tab["bo"], tab["n_blocks"], self._step_dev, float(group["lr"]),
-                 float(beta1), float(beta2), float(group["eps"]), float(self.ema_beta or 0.0))
+                 lr_dev, float(beta1), float(beta2), float(group["eps"]), float(self.ema_beta or 0.0))
             # the kernel wrote the parameters through raw pointers: tell torch (the packed-weight caches of the conv
             # layers key on the version counter -- without this they kept serving the weights of the first step)
             torch.autograd.graph.increment_version(params)
         if first is not None:
             call("sg_adam_advance", self._step_dev)
+
+    def state_dict(self):
+        """torch's layout plus the device-side step counter (`fused_step`), so that a resumed run continues the bias
+        correction where it stopped.  The counter is shared by all parameters: like main.py:141-145, create one
+        optimiser per growth phase (a parameter that first gets a gradient later would inherit the global t)."""
+        sd = super().state_dict()
+        sd["fused_step"] = int(self._step_dev[0]) if self._step_dev is not None else 0
+        return sd
+
+    def load_state_dict(self, state_dict):
+        sd = dict(state_dict)
+        step = int(sd.pop("fused_step", 0))
+        super().load_state_dict(sd)
+        self._tables.clear()          # the state tensors were replaced
+        for st in self.state.values():
+            if "exp_avg_sq" in st and self._step_dev is None:
+                self._step_dev = torch.zeros(4, dtype=torch.int32, device=st["exp_avg_sq"].device)
+        if self._step_dev is not None:
+            self._step_dev.fill_(step)
+        self._pending_step = step     # applied when the counter is created by the first step()
 
     def ema_state(self) -> Dict[torch.Tensor, torch.Tensor]:
         """parameter -> its EMA shadow (for evaluation/checkpoints, cf. ExtendedEMA.py:27-58)."""

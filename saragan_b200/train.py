@@ -53,6 +53,9 @@ def d_phase(x_real: torch.Tensor, generator, discriminator, discriminator_optim,
     _set_requires_grad(generator, False)
     _set_requires_grad(discriminator, True)
 
+    # every stale weight packing of both networks in one launch each (the optimiser steps of the previous iteration
+    # bumped the parameters' versions); False = some conv layer has never run yet, its packings are unknown
+    packs_known = ops.prepack(generator) & ops.prepack(discriminator)
     x_real = x_real.to(dev, non_blocking=True).float().contiguous()
     if noise is None:
         noise = torch.randn_like(x_real)
@@ -67,10 +70,12 @@ def d_phase(x_real: torch.Tensor, generator, discriminator, discriminator_optim,
     # the gradient sum.  The low-resolution levels of either chain occupy a fraction of the SMs, which the
     # other chain's kernels fill.  (Hook-based gradient sync fires per accumulated gradient, so it keeps
     # the single-stream order.)
-    two_streams = overlap_gp and x_real.is_cuda and grad_sync is None
+    # (A layer's FIRST packing happens lazily at its first use and is cached: on a fresh network -- first step,
+    # after grow() -- that would be on whichever stream gets there first while the other stream reads the same
+    # buffer un-ordered, so that one pass stays on a single stream.)
+    two_streams = overlap_gp and x_real.is_cuda and grad_sync is None and packs_known
     if two_streams:
         d_params = [p for p in discriminator.parameters() if p.requires_grad]
-        ops.prepack(discriminator)            # a lazy first packing on one stream would race with the other
         main, side = torch.cuda.current_stream(dev), _side_stream(dev)
         side.wait_stream(main)
         with torch.cuda.stream(side):
@@ -115,6 +120,7 @@ def g_phase(batch: int, generator, discriminator, generator_optim, alpha, *,
     discriminator.eval()
     _set_requires_grad(generator, True)
     _set_requires_grad(discriminator, False)
+    ops.prepack(discriminator)                # the D update just changed its weights
     if x_fake is None:
         if z_g is None:
             z_g = torch.randn(batch, generator.latent_dim)

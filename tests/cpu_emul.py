@@ -48,8 +48,12 @@ class _Packed:
         self.flip = flip
 
 
-def pack_conv_weight(w, dtype, flip):
+def pack_conv_weight(w, dtype, flip, out=None):
     return _Packed(w, dtype, flip)
+
+
+def pack_conv_weights_multi(jobs):
+    return [_Packed(w, dtype, flip) for w, dtype, flip, _ in jobs]
 
 
 def _mask(ref):
@@ -81,13 +85,16 @@ def conv3d_wgrad(x, gy, cin, cout, scale, want_bias, impl=0):
     return gw.contiguous(), gb
 
 
-def pw_expand(img, w, bias, dtype, c, scale, lrelu):
+def pw_expand(img, w, bias, dtype, c, scale, lrelu, mask_ref=None):
     y = img * (w.view(1, -1, 1, 1, 1) * scale)
     if bias is not None:
         y = y + bias.view(1, -1, 1, 1, 1)
     if lrelu:
         y = F.leaky_relu(y, LEAK)
-    return plain_to_act(y, dtype)
+    out = plain_to_act(y, dtype)
+    if mask_ref is not None:
+        out = (out.float() * _mask(mask_ref)).to(dtype)
+    return out
 
 
 def pw_reduce(x, w, bias, c, scale):
@@ -132,7 +139,9 @@ def up2(x, scale, out_dtype=None, mask_ref=None):
     return out
 
 
-def lincomb(a, b, alpha, beta):
+def lincomb(a, b, alpha, beta=None):
+    if isinstance(alpha, torch.Tensor):      # device pair {alpha, beta} (sg_lincomb_dev)
+        alpha, beta = float(alpha[0]), float(alpha[1])
     y = a.float() * alpha
     if b is not None:
         y = y + b.float() * beta
