@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import os
 import threading
-from queue import Queue
+from queue import Full, Queue
 from typing import Iterator, List, Optional
 
 import numpy as np
@@ -45,63 +45,101 @@ def prepare_real(raw_u16: torch.Tensor, noise: Optional[torch.Tensor] = None, sc
 
 class VolumeLoader:
     """Batches of raw uint16 volumes, prefetched by a host thread into pinned buffers and copied to
-    the device on a side stream (double buffered).  Rank r of `world` takes files r, r+world, ...
-    (the reference's DistributedSampler without shuffling when `shuffle=False`)."""
+    the device on a side stream (double buffered).
+
+    Sharding follows torch's DistributedSampler as the reference uses it (main.py:106-107, `set_epoch` per epoch):
+    the file list is shuffled GLOBALLY with a generator seeded by (seed, epoch) -- the same on every rank --, padded by
+    wrapping around to a multiple of `world`, and rank r takes entries r, r + world, ...  Every rank therefore sees
+    the same number of batches (a rank with one batch more would block forever in the per-step gradient
+    all-reduce) and a different subset every epoch."""
 
     def __init__(self, root: str, batch_size: int, device, rank: int = 0, world: int = 1, shuffle: bool = True,
                  seed: int = 0, extension: str = ".npy", drop_last: bool = True):
-        self.files = list_volumes(root, extension)[rank::world]
-        if not self.files:
+        self.all_files = list_volumes(root, extension)
+        if not self.all_files:
             raise FileNotFoundError(f"no {extension} volumes under {root}")
+        self.rank, self.world, self.seed, self.epoch = rank, world, seed, 0
+        self.per_rank = (len(self.all_files) + world - 1) // world
         self.batch_size, self.device, self.shuffle, self.drop_last = batch_size, torch.device(device), shuffle, drop_last
-        self.rng = np.random.default_rng(seed + rank)
         self.stream = torch.cuda.Stream(device=self.device)
-        # per staging slot: `_free` is set by the consumer once the copy out of the slot has been ENQUEUED, `_copied`
-        # is the CUDA event recorded right behind that copy; the producer re-fills a slot only after both
-        self._free = [threading.Event(), threading.Event()]
-        self._copied = [None, None]
+
+    def set_epoch(self, epoch: int) -> None:
+        """Reshuffle for the next pass (DistributedSampler.set_epoch)."""
+        self.epoch = int(epoch)
+
+    def indices(self) -> np.ndarray:
+        """This rank's file indices for the current epoch."""
+        n = len(self.all_files)
+        order = np.random.default_rng([self.seed, self.epoch]).permutation(n) if self.shuffle else np.arange(n)
+        total = self.per_rank * self.world
+        if total > n:
+            order = np.concatenate([order, np.resize(order, total - n)])       # wrap around, like DistributedSampler
+        return order[self.rank:total:self.world]
+
+    @property
+    def files(self) -> List[str]:
+        return [self.all_files[i] for i in self.indices()]
 
     def __len__(self):
-        n = len(self.files) // self.batch_size
-        return n if self.drop_last or len(self.files) % self.batch_size == 0 else n + 1
+        n = self.per_rank // self.batch_size
+        return n if self.drop_last or self.per_rank % self.batch_size == 0 else n + 1
 
-    def _host_batches(self, q: Queue):
-        order = self.rng.permutation(len(self.files)) if self.shuffle else np.arange(len(self.files))
+    def _host_batches(self, q: Queue, st: dict):
+        """Producer thread of ONE pass; `st` holds that pass's staging-slot hand-over state.  A staging slot is
+        re-filled only after (a) the consumer has enqueued the copy out of it (`free`) and (b) that copy has
+        finished (`copied`, a CUDA event)."""
+        files = self.files
         pinned = [None, None]
-        for bi in range(len(self)):
-            idx = order[bi * self.batch_size:(bi + 1) * self.batch_size]
-            vols = [np.load(self.files[i]) for i in idx]
-            arr = np.stack(vols).astype(np.uint16, copy=False)
-            slot = bi & 1
-            if pinned[slot] is None or pinned[slot].shape != arr.shape:
-                pinned[slot] = torch.empty(arr.shape, dtype=torch.uint16).pin_memory()
-            self._free[slot].wait()
-            self._free[slot].clear()
-            if self._copied[slot] is not None:
-                self._copied[slot].synchronize()     # the asynchronous copy out of this slot has finished
-            pinned[slot].numpy()[...] = arr
-            q.put((slot, pinned[slot]))
-        q.put(None)
+        try:
+            for bi in range(len(self)):
+                vols = [np.load(f) for f in files[bi * self.batch_size:(bi + 1) * self.batch_size]]
+                arr = np.stack(vols).astype(np.uint16, copy=False)
+                slot = bi & 1
+                if pinned[slot] is None or pinned[slot].shape != arr.shape:
+                    pinned[slot] = torch.empty(arr.shape, dtype=torch.uint16).pin_memory()
+                while not st["free"][slot].wait(timeout=0.1):
+                    if st["stop"].is_set():
+                        return
+                st["free"][slot].clear()
+                if st["copied"][slot] is not None:
+                    st["copied"][slot].synchronize()     # the asynchronous copy out of this slot has finished
+                pinned[slot].numpy()[...] = arr
+                while True:
+                    if st["stop"].is_set():
+                        return
+                    try:
+                        q.put((slot, pinned[slot]), timeout=0.1)
+                        break
+                    except Full:
+                        continue
+        finally:
+            if not st["stop"].is_set():
+                q.put(None)
 
     def __iter__(self) -> Iterator[torch.Tensor]:
         q: Queue = Queue(maxsize=1)      # one batch being filled while one is in flight
-        for f in self._free:
+        st = dict(free=[threading.Event(), threading.Event()], copied=[None, None], stop=threading.Event())
+        for f in st["free"]:
             f.set()
-        self._copied = [None, None]
-        t = threading.Thread(target=self._host_batches, args=(q,), daemon=True)
+        t = threading.Thread(target=self._host_batches, args=(q, st), daemon=True)
         t.start()
-        while True:
-            item = q.get()
-            if item is None:
-                break
-            slot, host = item
-            with torch.cuda.stream(self.stream):
-                dev = host.to(self.device, non_blocking=True)
-                done = torch.cuda.Event()
-                done.record(self.stream)
-            self._copied[slot] = done
-            self._free[slot].set()
-            torch.cuda.current_stream(self.device).wait_stream(self.stream)
-            dev.record_stream(torch.cuda.current_stream(self.device))
-            yield dev
-        t.join()
+        try:
+            while True:
+                item = q.get()
+                if item is None:
+                    break
+                slot, host = item
+                with torch.cuda.stream(self.stream):
+                    dev = host.to(self.device, non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(self.stream)
+                st["copied"][slot] = done
+                st["free"][slot].set()
+                torch.cuda.current_stream(self.device).wait_stream(self.stream)
+                dev.record_stream(torch.cuda.current_stream(self.device))
+                yield dev
+        finally:
+            # the consumer may abandon the pass early (break, exception): release the producer and wait for it, so
+            # that nothing of this pass is still running when the next one starts
+            st["stop"].set()
+            t.join()

@@ -73,13 +73,50 @@ def test_loader_order_sharding_and_slots(tmp_path, no_gpu):
     seen = []
     for rank in range(2):
         loader = data.VolumeLoader(str(tmp_path), batch_size=2, device="cpu", rank=rank, world=2, shuffle=False)
-        assert len(loader) == (3 if rank == 0 else 2)            # 6 and 5 files, drop_last
+        # 11 files over 2 ranks: padded by wrapping to 12 like DistributedSampler, so BOTH ranks run 3 batches (a
+        # rank with one batch more would block in the per-step gradient all-reduce)
+        assert len(loader) == 3
         batches = [b.clone() for b in loader]
         assert all(b.dtype == torch.uint16 and tuple(b.shape) == (2, 2, 4, 4) for b in batches)
         seen.append([int(b[i, 0, 0, 0]) for b in batches for i in range(2)])
-    assert seen == [[0, 2, 4, 6, 8, 10], [1, 3, 5, 7]]            # rank r takes files r, r + world, ...
+    assert seen == [[0, 2, 4, 6, 8, 10], [1, 3, 5, 7, 9, 0]]      # rank r takes entries r, r + world, ... of the padded list
     # a staging slot is re-filled only after the copy out of it was waited for: every refill of a used slot syncs
-    assert _Event.log.count("record") == 5 and _Event.log.count("sync") >= 1
+    assert _Event.log.count("record") == 6 and _Event.log.count("sync") >= 1
+
+
+def test_loader_matches_distributed_sampler_semantics(tmp_path, no_gpu):
+    """Same contract as torch.utils.data.DistributedSampler (main.py:106-107): one GLOBAL permutation per (seed, epoch)
+    shared by the ranks, padded by wrap-around, strided by rank; set_epoch reshuffles; equal length on every rank."""
+    _dataset(tmp_path, 10)
+    world = 4
+    loaders = [data.VolumeLoader(str(tmp_path), 1, "cpu", rank=r, world=world, seed=5) for r in range(world)]
+    per_epoch = []
+    for epoch in range(2):
+        for ld in loaders:
+            ld.set_epoch(epoch)
+        idx = [list(ld.indices()) for ld in loaders]
+        assert {len(i) for i in idx} == {3} and {len(ld) for ld in loaders} == {3}
+        merged = [idx[r][k] for k in range(3) for r in range(world)]          # undo the stride
+        assert sorted(merged[:10]) == list(range(10)) and merged[10:] == merged[:2]   # a permutation + wrap-around pad
+        ref = torch.utils.data.DistributedSampler(list(range(10)), num_replicas=world, rank=1, shuffle=True, seed=5)
+        ref.set_epoch(epoch)
+        assert len(list(ref)) == len(idx[1])                                  # same per-rank count as torch's sampler
+        per_epoch.append(merged)
+    assert per_epoch[0] != per_epoch[1]                                       # set_epoch reshuffles
+
+
+def test_loader_survives_an_abandoned_pass(tmp_path, no_gpu):
+    """Breaking out of a pass stops its producer thread; the next pass starts clean (own slot state per pass)."""
+    import threading
+    _dataset(tmp_path, 12)
+    loader = data.VolumeLoader(str(tmp_path), 2, "cpu", shuffle=False)
+    n_threads = threading.active_count()
+    it = iter(loader)
+    first = next(it)
+    it.close()                                                                # consumer walks away after one batch
+    assert threading.active_count() == n_threads
+    again = [int(b[0, 0, 0, 0]) for b in loader]
+    assert int(first[0, 0, 0, 0]) == 0 and again == [0, 2, 4, 6, 8, 10]
 
 
 def test_loader_keeps_the_last_partial_batch_on_request(tmp_path, no_gpu):
