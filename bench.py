@@ -11,10 +11,17 @@ configuration the metric is quoted on, it fits one GPU).  Synthetic CT-like volu
 weights.
 
 Prints ONE JSON line (rank 0).  `value` = images/s with the inputs already resident in HBM;
-`e2e` = the same metric through the public API with host (pinned) inputs, H2D copy and a D2H
-read of the losses inside the timed region; `roofline` = the dominant conv kernel timed with
-CUDA events inside the timed region against the measured bf16 peak; `cpu_baseline` = the
-oracle (port of the reference step) timed on this box's host cores.
+`e2e` = the same metric through the public API from HOST memory: the raw uint16 volumes in pinned
+memory -> H2D -> sg_prepare_real (cast, /1024) -> step -> D2H read of the losses, every step;
+`roofline` = the kernel (entry point + shape) with the largest share of the step, timed with CUDA
+events on its launching stream in two EAGER passes of the same step right after the timed region (a
+graph replay cannot carry per-kernel events), against the measured BURST peaks (a single kernel timed
+alone between events); `roofline_more` = the other convolution variants of that layer and the
+memory-bound kernels with the largest shares against the measured HBM peak; `traffic` = dram bytes
+of that launch from the committed `ncu --set full` capture (profiles/ncu_traffic.json, null if the
+launch is not in it); `parity_check` = one step on seeded inputs against the stored fp32 oracle
+losses (tests/golden/fullsize_*.json, oracle/pin_fullsize.py) -- the run aborts if it fails;
+`cpu_baseline` = the oracle (port of the reference step) timed on this box's host cores.
 `--impl reference` times the reference's CPU implementation of the path (oracle port; the
 reference itself is Python/torch and /root/reference does not exist on the GPU box).
 """
@@ -41,37 +48,33 @@ def parse():
     ap.add_argument("--config", default="cfg3")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
     ap.add_argument("--alpha", type=float, default=0.5)
     ap.add_argument("--network", default="network", choices=["network", "network_dict"],
                     help="network: the pgan_pytorch/network.py API (BASELINE north star); network_dict: the network_dict.py "
                          "variant main.py imports (LeakyReLU 0.3, He gain, no minibatch-stddev, top-level fade-in; SURVEY 8f row 3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-batch", type=int, default=2)
+    ap.add_argument("--cpu-batch", type=int, default=0, help="batch of the CPU arm (default: the per-GPU batch)")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as CUDA graph(s) (on several GPUs: three "
                     "segments with the NCCL all-reduce between them); 0: eager with the bucketed, overlapped all-reduce")
     return ap.parse_args()
 
 
 def peaks():
+    """Measured peaks (driver-written MEASURED_PEAKS.json): burst = a kernel timed alone, sustained = inside a long
+    step; fallback = the figures of B200_PROFILING.md."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
             p = json.load(f)
-        return dict(bf16=p.get("bf16_tflops_sustained", p.get("bf16_tflops")), hbm=p.get("hbm_gbs"),
-                    src="measured (MEASURED_PEAKS.json, sustained bf16)")
-    return dict(bf16=1590.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+        return dict(bf16_burst=p.get("bf16_tflops"), bf16_sustained=p.get("bf16_tflops_sustained", p.get("bf16_tflops")),
+                    hbm=p.get("hbm_gbs"), src="measured (MEASURED_PEAKS.json)")
+    return dict(bf16_burst=1590.0, bf16_sustained=1590.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
 
 
 def smooth_volumes(n, vol, seed):
-    """Synthetic CT-like reals: clip(1024 + 350*smooth(N(0,1)), 0, 3072)/1024."""
-    gen = torch.Generator().manual_seed(seed)
-    x = torch.randn(n, 1, *vol, generator=gen)
-    k = torch.ones(1, 1, 3, 3, 3) / 27
-    for _ in range(2):
-        x = torch.nn.functional.conv3d(x, k, padding=1)
-    x = x / x.std()
-    return (torch.clamp(1024 + 350 * x, 0, 3072) / 1024).contiguous()
+    from saragan_b200.data import synthetic_reals
+    return synthetic_reals(n, vol, seed)
 
 
 class ClockSampler:
@@ -179,17 +182,124 @@ def cpu_step_rate(cfg, batch, steps, warmup, alpha, threads=None, network="netwo
 def run_reference(args, cfg, rank):
     if rank != 0:
         return
-    b = args.cpu_batch
+    b = args.cpu_batch or cfg["batch"]
     rate, t, threads = cpu_step_rate(cfg, b, args.steps, args.warmup, args.alpha, network=args.network)
     sample = (f"{args.steps} full train steps (after {args.warmup} warm-up) at batch {b} of {args.config} "
               f"({args.network}.py), fp32, torch CPU")
     line = {"impl": "reference", "metric": "G+D train images/s", "value": rate, "unit": "img/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["desc"], "per_gpu_batch": b, "name": args.config, "network": args.network + ".py"},
+            "config": {"workload": cfg["desc"].rsplit(", B=", 1)[0] + f", B={b}", "per_gpu_batch": b, "name": args.config,
+                       "network": args.network + ".py"},
             "cpu_baseline": {"value": rate, "unit": "img/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def parity_check(args, cfg, g, d, g_opt, d_opt, dev):
+    """One train step (no optimiser update) on the seeded inputs of tests/golden/fullsize_<cfg>_b<B>.json against the
+    fp32 oracle losses stored there (oracle/pin_fullsize.py).  Aborts the run when the CUDA path disagrees."""
+    import saragan_b200 as sg
+    from saragan_b200 import costmodel as C
+    from saragan_b200.data import step_draws, synthetic_reals
+    path = os.path.join(ROOT, "tests", "golden", f"fullsize_{args.config}_b{cfg['batch']}.json")
+    if args.network != "network" or not os.path.exists(path):
+        return None
+    with open(path) as f:
+        ref = json.load(f)
+    vol = C.volume(cfg["phase"])
+    x = synthetic_reals(cfg["batch"], vol, ref["x_seed"])
+    dr = step_draws(cfg["batch"], vol, cfg["latent_dim"], ref["draw_seed"])
+    out = sg.train_step(x, g, d, g_opt, d_opt, ref["alpha"], apply=False, **dr)
+    got = {k: float(out[k]) for k in ("d_loss", "gp", "g_loss")}
+    tol = {"bf16": 2e-3, "tf32": 1e-3, "fp32": 1e-4}[args.precision]
+    err = {k: abs(got[k] - ref["losses"][k]) / max(abs(ref["losses"][k]), 1.0 if k == "g_loss" else 1e-12) for k in got}
+    for net in (g, d):
+        for p in net.parameters():
+            p.grad = None
+    res = {"fixture": os.path.relpath(path, ROOT), "cuda": got, "oracle": ref["losses"], "rel_err": err, "tol": tol,
+           "ok": all(e < tol for e in err.values())}
+    if not res["ok"]:
+        print(json.dumps({"parity_check": res}), file=sys.stderr, flush=True)
+        raise SystemExit("bench.py: the CUDA step disagrees with the stored oracle losses -- not benchmarking a wrong kernel")
+    return res
+
+
+def _dt(code):
+    return 2 if code == 0 else 4       # element size of SG_BF16 / SG_F32
+
+
+def launch_work(name, ints, flags):
+    """(bound, algorithmic flops or bytes, label) of one ABI call from its integer arguments (include/saragan_b200.h;
+    DESIGN.md lists the per-unit figures), or None for calls that are not reported."""
+    if name == "sg_conv3d_fprop":
+        dt, n, ci, co, d, h, w = ints[:7]
+        return "tensor", 2.0 * n * d * h * w * ci * co * 27, f"conv3d fprop/dgrad {ci}->{co} @{d}x{h}x{w} B={n} ({'bf16' if dt == 0 else 'fp32 storage'})"
+    if name == "sg_conv3d_wgrad":
+        dt, n, ci, co, d, h, w = ints[:7]
+        return "tensor", 2.0 * n * d * h * w * ci * co * 27, f"conv3d wgrad {ci}->{co} @{d}x{h}x{w} B={n} ({'bf16' if dt == 0 else 'fp32 storage'})"
+    if name == "sg_up2":
+        di, do, vec, p, d, h, w = ints[:7]
+        v = p * d * h * w * vec
+        has_mask = len(flags) > 2 and flags[2]
+        return "hbm", v * _dt(di) + 8 * v * _dt(do) * (2 if has_mask else 1), f"up2{'+mask' if has_mask else ''} [{p}]x{d}x{h}x{w}x{vec}"
+    if name == "sg_down2":
+        di, do, vec, p, d, h, w = ints[:7]
+        v = p * d * h * w * vec
+        return "hbm", v * _dt(di) + v // 8 * _dt(do), f"down2 [{p}]x{d}x{h}x{w}x{vec}"
+    if name in ("sg_pw_expand", "sg_pw_expand_masked"):
+        dt, n, c, v = ints[:4]
+        cp = 16 * ((c + 15) // 16)
+        return "hbm", n * v * (4 + cp * _dt(dt) * (2 if name.endswith("masked") else 1)), f"FromRGB 1->{c} B={n} V={v}"
+    if name == "sg_pw_reduce":
+        dt, n, c, v = ints[:4]
+        return "hbm", n * v * (16 * ((c + 15) // 16) * _dt(dt) + 4), f"ToRGB {c}->1 B={n} V={v}"
+    if name == "sg_pw_wgrad":
+        dt, n, c, v = ints[:4]
+        return "hbm", n * v * (16 * ((c + 15) // 16) * _dt(dt) + (4 if flags[1] else 0)), f"1x1x1 wgrad C={c} B={n} V={v}"
+    if name == "sg_mask_mul":
+        dt, n = ints[:2]
+        return "hbm", 3 * n * _dt(dt), f"mask_mul n={n}"
+    if name == "sg_lincomb":
+        dt, n = ints[:2]
+        return "hbm", (3 if flags[1] else 2) * n * _dt(dt), f"lincomb n={n}"
+    if name in ("sg_pixelnorm_fwd", "sg_pixelnorm_bwd"):
+        dt, n, c, v = ints[:4]
+        cp = 16 * ((c + 15) // 16)
+        return "hbm", n * v * cp * _dt(dt) * (2 if name.endswith("fwd") else 3), f"{name[3:]} C={c} B={n} V={v}"
+    return None
+
+
+def roofline_entries(table, pk, n_passes):
+    """table: (entry point, int args, pointer flags) -> [ms per launch].  First entry = the launch shape with the
+    largest time share of the step (always a convolution), then the other conv variants with the next shares and the
+    memory-bound kernels with the largest shares."""
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f)
+    rows = []
+    for (name, ints, flags), ms in table.items():
+        wk = launch_work(name, ints, flags)
+        if wk is None:
+            continue
+        bound, work, label = wk
+        dur = float(np.mean(ms)) * 1e-3
+        peak = pk["bf16_burst"] if bound == "tensor" else pk["hbm"]
+        ach = work / dur / (1e12 if bound == "tensor" else 1e9)
+        key = name + ":" + ",".join(map(str, ints[:7]))
+        rows.append({"bound": bound, "kernel": f"{name}: {label}", "achieved": ach, "peak": peak,
+                     "unit": "TFLOP/s" if bound == "tensor" else "GB/s", "frac": ach / peak,
+                     "traffic": traffic.get(key, {}).get("dram_bytes"), "launches_per_step": len(ms) / n_passes,
+                     "ms_per_launch": dur * 1e3, "ms_per_step": float(np.sum(ms)) / n_passes,
+                     ("flop_per_launch" if bound == "tensor" else "bytes_per_launch"): work,
+                     "peak_source": pk["src"] + (", burst bf16 (kernel timed alone between events)" if bound == "tensor" else ", copy bandwidth"),
+                     "timed": "CUDA events on the launching stream, eager single-stream passes after the timed region"})
+    rows.sort(key=lambda r: -r["ms_per_step"])
+    conv = [r for r in rows if r["bound"] == "tensor"]
+    mem = [r for r in rows if r["bound"] == "hbm"]
+    return conv[:4] + mem[:6]
 
 
 def main():
@@ -207,7 +317,7 @@ def main():
 
     import torch.distributed as dist
     import saragan_b200 as sg
-    from saragan_b200 import _lib, comm, kernels
+    from saragan_b200 import _lib, comm, data
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -237,9 +347,14 @@ def main():
     else:
         dp = None
 
+    # ---- parity gate: one step (no optimiser update) on seeded inputs against the stored fp32 oracle losses
+    parity = parity_check(args, cfg, g, d, g_opt, d_opt, dev) if rank == 0 else None
+
     n_pool = 4
-    host_pool = [smooth_volumes(B, vol, seed=1234 + 17 * rank + i).pin_memory() for i in range(n_pool)]
-    dev_pool = [x.to(dev) for x in host_pool]
+    host_pool = [smooth_volumes(B, vol, seed=1234 + 17 * rank + i) for i in range(n_pool)]
+    # the dataset's raw form: uint16 voxels (create_lidc_idri_dataset.py:185-212), value*1024 -- what e2e feeds
+    host_raw = [(x * 1024).round().to(torch.uint16).pin_memory() for x in host_pool]
+    dev_pool = [r.to(dev).float().div_(1024).reshape(B, 1, *vol) for r in host_raw]
     rng = torch.Generator(device=dev).manual_seed(1000 + rank)
 
     def draws():
@@ -258,6 +373,8 @@ def main():
             return graphed(x)
     else:
         def step(x):
+            if x.dtype == torch.uint16:
+                x = data.prepare_real(x.to(dev, non_blocking=True), None)
             return sg.train_step(x, g, d, g_opt, d_opt, alpha, grad_sync=dp, **draws())
 
     def barrier():
@@ -265,22 +382,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # kernels reported against the roofline: the top D block's convolutions (the launch shapes with
-    # the largest time shares in profiles/): wgrad of conv2 (k_wgrad_tc is the kernel with the largest
-    # share of the step), fprop of conv2, and conv2's dgrad
-    layers = C.conv_layers("d", cfg["phase"], cfg["num_phases"], cfg["base_dim"])
-    name, ci, co, v = max(layers, key=lambda l: l[1] * l[2] * int(np.prod(l[3])))
-    flops_per_launch = 2.0 * B * int(np.prod(v)) * ci * co * 27
-    probe_keys = {"wgrad": ("wgrad", B, ci, co, *v), "fprop": ("fprop", B, ci, co, *v), "dgrad": ("fprop", B, co, ci, *v)}
-    probe = kernels.ConvProbe(probe_keys.values())
-    # dram__bytes_read+write per launch from the committed `ncu --set full` capture (profiles/), cfg3 only
-    ncu_traffic = {"wgrad": 407.1e6, "fprop": 349.9e6, "dgrad": 381.5e6} if (args.config == "cfg3" and B == 4) else {}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     try:
         for i in range(args.warmup):
             step(dev_pool[i % n_pool])
         barrier()
-        kernels.conv_probe = probe
         launches0 = _lib.launch_count()
         t_region0 = time.perf_counter()
         e0.record()
@@ -291,21 +397,6 @@ def main():
         t_region1 = time.perf_counter()
     finally:
         clocks.__exit__(None, None, None)
-    if os.environ.get("SARAGAN_BENCH_DEBUG") and rank == 0:
-        print("debug: losses after the timed region", [float(out[k]) for k in ("d_loss", "g_loss", "gp")], file=sys.stderr)
-    kernels.conv_probe = None
-    if use_graph:
-        # a graph replay cannot carry per-kernel events: time the dominant kernel in two eager
-        # passes of the same step (same shapes, same in-step cache state) right after the timed region
-        kernels.conv_probe = probe
-        for i in range(2):
-            # single-stream order: with the gradient-penalty chain on its second stream the events around a launch
-            # would also time whatever the other stream runs meanwhile
-            sg.train_step(dev_pool[i % n_pool], g, d, g_opt, d_opt, alpha, grad_sync=dp, overlap_gp=False, **draws())
-        barrier()
-        kernels.conv_probe = None
-        if os.environ.get("SARAGAN_BENCH_DEBUG") and rank == 0:
-            print("debug: eager probe steps done", file=sys.stderr)
     launches = graphed.launches_per_step * args.steps if use_graph else _lib.launch_count() - launches0
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
@@ -313,18 +404,14 @@ def main():
     ms_step = float(ms) / args.steps
     value = world * B / (ms_step * 1e-3)
 
-    # end-to-end: pinned host batch -> H2D -> step -> D2H of the three losses, every step
-    def e2e_step(i):
-        # graph mode copies the pinned host batch straight into the graph's static input buffer
-        return step(host_pool[i % n_pool] if use_graph else host_pool[i % n_pool].to(dev, non_blocking=True))
-
+    # ---- end-to-end: pinned uint16 host batch -> H2D -> sg_prepare_real -> step -> D2H of the three losses, every step
     for i in range(2):
-        e2e_step(i)
+        step(host_raw[i % n_pool])
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for i in range(args.steps):
-        o = e2e_step(i)
+        o = step(host_raw[i % n_pool])
         losses = torch.stack([o["d_loss"], o["g_loss"], o["gp"]]).cpu()
     f1.record()
     barrier()
@@ -333,47 +420,52 @@ def main():
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e = world * B / (float(ms2) / args.steps * 1e-3)
 
+    # ---- per-kernel roofline: two eager, single-stream passes of the same step (same shapes, same in-step cache
+    # state) with CUDA events around every ABI call on its launching stream (with the gradient-penalty chain on its
+    # second stream the events around a launch would also time whatever the other stream runs meanwhile)
+    table = {}
+    if rank == 0 or world > 1:
+        _lib.PROFILE = []
+        for i in range(2):
+            sg.train_step(dev_pool[i % n_pool], g, d, g_opt, d_opt, alpha, grad_sync=dp, overlap_gp=False, **draws())
+        barrier()
+        prof, _lib.PROFILE = _lib.PROFILE, None
+        for name, ints, a, b, flags in prof:
+            table.setdefault((name, ints, flags), []).append(a.elapsed_time(b))
+
     if rank == 0:
         pk = peaks()
         step_flops = (C.step_flops_per_image_dict if args.network == "network_dict" else C.step_flops_per_image)(**cfg)
         line = {
             "metric": "G+D train images/s", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": cfg["desc"], "name": args.config, "network": args.network + ".py",
-                       "per_gpu_batch": B, "global_batch": B * world,
+            "vs_baseline": None, "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[args.precision], "data": "synthetic",
+            "config": {"workload": cfg["desc"].rsplit(", B=", 1)[0] + f", B={B}", "name": args.config,
+                       "network": args.network + ".py", "per_gpu_batch": B, "global_batch": B * world,
                        "alpha": alpha, "parallelism": f"dp{world}",
-                       "launch": ("cuda-graph replay of the whole step" if world == 1 else
-                                  "4 cuda-graph segments + eager NCCL all-reduce (D-gradient all-reduce overlapped with the generator forward)") if use_graph else "eager",
+                       "precision_policy": sg.config.describe(),
+                       "launch": ("cuda-graph replay of the whole step" if world == 1 else graphed.launch_desc) if use_graph else "eager",
                        "l2": "per-step working set (GBs of activations) >> 126 MB L2; 4 rotating input batches",
                        "step_gflop_per_image": step_flops / 1e9,
-                       "step_tensor_frac": step_flops * value / world / (pk["bf16"] * 1e12)},
-            "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": B * int(np.prod(vol)) * 4,
-                    "d2h_bytes_per_step": 12},
+                       "step_tensor_frac_of_burst": step_flops * value / world / (pk["bf16_burst"] * 1e12),
+                       "step_tensor_frac_of_sustained": step_flops * value / world / (pk["bf16_sustained"] * 1e12)},
+            "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": B * int(np.prod(vol)) * 2,
+                    "d2h_bytes_per_step": 12, "input": "raw uint16 volumes in pinned host memory (data.prepare_real on the device)"},
             "gpu_launches": int(launches),
             "cuda_core_conv_fallbacks_per_step": graphed.cuda_core_conv_fallbacks if use_graph else None,
             "clocks": clocks.summary(t_region0, t_region1),
             "losses": [float(v) for v in losses],
+            "parity_check": parity,
         }
-        def roof(kind, label):
-            kd_ = probe.durations_ms(probe_keys[kind])
-            if not kd_:
-                return None
-            dur = float(np.mean(kd_)) * 1e-3
-            ach = flops_per_launch / dur / 1e12
-            return {"bound": "tensor", "kernel": label, "achieved": ach, "peak": pk["bf16"], "unit": "TFLOP/s",
-                    "frac": ach / pk["bf16"], "traffic": ncu_traffic.get(kind), "launches_timed": len(kd_),
-                    "ms_per_launch": dur * 1e3, "flop_per_launch": flops_per_launch, "peak_source": pk["src"]}
-        shape = f"{ci}->{co} @{'x'.join(map(str, v))} B={B}"
-        r = roof("wgrad", f"k_wgrad_tc: conv3d wgrad {name} {shape}")
-        if r:
-            line["roofline"] = r
-            line["roofline_more"] = [x for x in (roof("fprop", f"k_conv_tc_res: conv3d fprop {name} {shape}"),
-                                                 roof("dgrad", f"k_conv_tc_res: conv3d dgrad {name} {shape}")) if x]
+        roofs = roofline_entries(table, pk, n_passes=2)
+        if roofs:
+            line["roofline"] = roofs[0]
+            line["roofline_more"] = roofs[1:]
         if world == 1 and not args.no_cpu_baseline:
-            rate, t, threads = cpu_step_rate(cfg, args.cpu_batch, 1, 0, alpha, network=args.network)
+            cb = args.cpu_batch or B
+            rate, t, threads = cpu_step_rate(cfg, cb, 1, 0, alpha, network=args.network)
             line["cpu_baseline"] = {"value": rate, "unit": "img/s", "cores": threads, "kind": "port",
-                                    "sample": f"1 full train step at batch {args.cpu_batch} of {args.config} "
+                                    "sample": f"1 full train step at batch {cb} of {args.config} "
                                               f"({t:.1f} s), fp32 torch CPU oracle"}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -127,8 +127,9 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-# tools/profile_step.py sets this to a list to collect (name, int-args, start event, end event)
-# for every ABI call (CUDA events on the launching stream; no effect when None).
+# tools/profile_step.py / bench.py set this to a list to collect (name, int-args, start event, end event, pointer
+# flags) for every ABI call (CUDA events on the launching stream; no effect when None); pointer flags = which of the
+# tensor arguments were non-null (e.g. whether an up-sampling call carried a mask).
 PROFILE = None
 
 
@@ -149,7 +150,8 @@ def call(name: str, *args):
         e0.record(torch.cuda.current_stream())
         rc = getattr(lib, name)(*conv, _stream())
         e1.record(torch.cuda.current_stream())
-        PROFILE.append((name, tuple(a for a in args if isinstance(a, (int, bool))), e0, e1))
+        PROFILE.append((name, tuple(a for a in args if isinstance(a, (int, bool))), e0, e1,
+                        tuple(a is not None for a in args if a is None or isinstance(a, torch.Tensor))))
     else:
         rc = getattr(lib, name)(*conv, _stream())
     if rc != 0:

@@ -35,6 +35,14 @@ def act_dtype(voxels: int = 1 << 30) -> torch.dtype:
     return torch.bfloat16
 
 
+def describe() -> str:
+    """One line for logs / bench.py: which storage and arithmetic each level uses under the current policy."""
+    if _precision == "fp32":
+        return "fp32 storage, CUDA-core fp32 convolutions at every level"
+    return (f"bf16 storage + tcgen05 kind::f16 (fp32 accumulate) above {FP32_MAX_VOXELS} voxels; "
+            f"fp32 storage + fp32 CUDA-core kernels at <= {FP32_MAX_VOXELS} voxels (1x4x4 base level, minibatch-stddev)")
+
+
 @contextlib.contextmanager
 def use_precision(name: str):
     old = _precision

@@ -143,3 +143,23 @@ class VolumeLoader:
             # that nothing of this pass is still running when the next one starts
             st["stop"].set()
             t.join()
+
+
+def synthetic_reals(n: int, volume, seed: int, passes: int = 2) -> torch.Tensor:
+    """Synthetic CT-like reals of SURVEY.md 8(d): clip(1024 + 350*smooth(N(0,1)), 0, 3072) / 1024 as (n,1,D,H,W) fp32
+    on the host, deterministic per seed (box-filtered white noise; bench.py, the full-size parity fixtures)."""
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, 1, *volume, generator=gen)
+    k = torch.ones(1, 1, 3, 3, 3) / 27
+    for _ in range(passes):
+        x = torch.nn.functional.conv3d(x, k, padding=1)
+    x = x / x.std()
+    return (torch.clamp(1024 + 350 * x, 0, 3072) / 1024).contiguous()
+
+
+def step_draws(batch: int, volume, latent_dim: int, seed: int):
+    """The random draws of one train step (train.py:144-145,178, loss.py:11) from a host generator: a step can be
+    replayed bit-for-bit on another implementation (oracle/pin_fullsize.py, bench.py's parity check)."""
+    gen = torch.Generator().manual_seed(seed)
+    return dict(noise=torch.randn(batch, 1, *volume, generator=gen), z_d=torch.randn(batch, latent_dim, generator=gen),
+                z_g=torch.randn(batch, latent_dim, generator=gen), eps=torch.rand(batch, 1, 1, 1, 1, generator=gen))

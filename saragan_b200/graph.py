@@ -106,6 +106,8 @@ class GraphedTrainStep:
         if seed is not None:
             self.rng.manual_seed(seed)
         self.out: Dict[str, torch.Tensor] = {}
+        self._raw = None
+        self.launch_desc = "cuda-graph replay of the whole step"
         self.graph = torch.cuda.CUDAGraph()
         # warm-up on a side stream (lazy inits, kernel attributes, allocator state), then capture
         rng_state = self.rng.get_state()
@@ -164,6 +166,8 @@ class GraphedTrainStep:
             with torch.cuda.graph(g3, pool=g1.pool()):
                 self.g_optim.step()
             self.segments = (g1, g2a, g2b, g3)
+            self.launch_desc = ("4 cuda-graph segments + eager NCCL all-reduce (D-gradient all-reduce overlapped with "
+                                "the generator forward)")
             self._comm_stream = torch.cuda.Stream(device=dev)
             self.out = {"d_loss": od["d_loss"], "gp": od["gp"], "g_loss": og["g_loss"], "distance": dist_,
                         "x_fake": og["x_fake"]}
@@ -196,7 +200,16 @@ class GraphedTrainStep:
         for opt in (self.g_optim, self.d_optim):
             if hasattr(opt, "sync_lr"):
                 opt.sync_lr()                  # a scheduler may have changed group["lr"] since the last replay
-        self.x.copy_(x_real, non_blocking=True)
+        if x_real.dtype == torch.uint16:
+            # raw dataset voxels (data.VolumeLoader batches / pinned host memory): H2D of 2 bytes per voxel, then
+            # cast and 1/1024 scale in one kernel straight into the graph's input buffer (main.py:85-87)
+            from .data import prepare_real
+            if self._raw is None or self._raw.shape != x_real.shape:
+                self._raw = torch.empty(x_real.shape, dtype=torch.uint16, device=self.dev)
+            self._raw.copy_(x_real, non_blocking=True)
+            prepare_real(self._raw, None, out=self.x)
+        else:
+            self.x.copy_(x_real, non_blocking=True)
         self.draw()
         if self.segments is None:
             self.graph.replay()

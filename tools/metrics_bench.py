@@ -56,7 +56,7 @@ def main():
     M.get_metrics(real, fake)
     torch.cuda.synchronize()
     per = {}
-    for name, _, a, b in _lib.PROFILE:
+    for name, _, a, b, *_r in _lib.PROFILE:
         t = per.setdefault(name, [0, 0.0])
         t[0] += 1
         t[1] += a.elapsed_time(b)
