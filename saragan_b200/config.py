@@ -35,6 +35,11 @@ def act_dtype(voxels: int = 1 << 30) -> torch.dtype:
     return torch.bfloat16
 
 
+def policy_key():
+    """Everything that decides which storage types (hence which weight packings) a pass uses."""
+    return (_precision, FP32_MAX_VOXELS)
+
+
 def describe() -> str:
     """One line for logs / bench.py: which storage and arithmetic each level uses under the current policy."""
     if _precision == "fp32":

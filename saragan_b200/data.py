@@ -159,7 +159,7 @@ def synthetic_reals(n: int, volume, seed: int, passes: int = 2) -> torch.Tensor:
 
 def step_draws(batch: int, volume, latent_dim: int, seed: int):
     """The random draws of one train step (train.py:144-145,178, loss.py:11) from a host generator: a step can be
-    replayed bit-for-bit on another implementation (oracle/pin_fullsize.py, bench.py's parity check)."""
+    replayed bit-for-bit on another implementation (the full-size parity fixtures, bench.py's parity check)."""
     gen = torch.Generator().manual_seed(seed)
     return dict(noise=torch.randn(batch, 1, *volume, generator=gen), z_d=torch.randn(batch, latent_dim, generator=gen),
                 z_g=torch.randn(batch, latent_dim, generator=gen), eps=torch.rand(batch, 1, 1, 1, 1, generator=gen))

@@ -18,6 +18,7 @@ import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
+from . import config
 from . import kernels as K
 from ._lib import IMPL_AUTO
 
@@ -85,27 +86,35 @@ class PackedWeight:
             self.get(*k)
 
 
-def prepack(net) -> bool:
+def prepack(net) -> None:
     """Re-pack every stale packing of every conv layer of `net` on the CURRENT stream with ONE launch
-    (`sg_pack_conv_weights_multi`): after an optimiser step, and before work forks onto a second stream (a lazy first
-    packing there would race with the other stream's use of the same buffer).  Returns False when some layer has
-    never been used yet (its packings are unknown: the caller must not fork streams for this pass)."""
-    todo, complete = [], True
+    (`sg_pack_conv_weights_multi`): after an optimiser step, and before work forks onto a second stream."""
+    todo = []
     for m in net.modules():
         pw = getattr(m, "_packed", None)
         if pw is None:
             continue
         if getattr(pw, "weight", None) is not getattr(m, "weight", None):    # parameter re-bound (.to(), load)
             pw = m._packed = PackedWeight(m.weight, known=pw.known)
-        if not pw.known:
-            complete = False
         todo += [(pw, k, job) for k, job in pw.stale_jobs()]
     if len(todo) == 1:
         todo[0][0].get(*todo[0][1])
     elif todo:
         for (pw, k, _), buf in zip(todo, K.pack_conv_weights_multi([job for _, _, job in todo])):
             pw.adopt(k, buf)
-    return complete
+
+
+def packs_settled(net) -> bool:
+    """True once `net` has run a complete pass at its current phase, i.e. every packing the pass needs exists and
+    `prepack` refreshes it.  A layer's FIRST packing is made lazily at its first use and then cached; with the D
+    phase forked onto two streams that first use would be on whichever stream gets there first while the other
+    stream reads the same buffer un-ordered -- train.d_phase keeps such a pass (first step, after grow() or a
+    change of `.phase`) on one stream."""
+    return getattr(net, "_packs_phase", None) == (getattr(net, "phase", None), id(net), config.policy_key())
+
+
+def mark_packs_settled(net) -> None:
+    net._packs_phase = (getattr(net, "phase", None), id(net), config.policy_key())
 
 
 # ================================================================================ conv

@@ -54,8 +54,9 @@ def d_phase(x_real: torch.Tensor, generator, discriminator, discriminator_optim,
     _set_requires_grad(discriminator, True)
 
     # every stale weight packing of both networks in one launch each (the optimiser steps of the previous iteration
-    # bumped the parameters' versions); False = some conv layer has never run yet, its packings are unknown
-    packs_known = ops.prepack(generator) & ops.prepack(discriminator)
+    # bumped the parameters' versions)
+    ops.prepack(generator)
+    ops.prepack(discriminator)
     x_real = x_real.to(dev, non_blocking=True).float().contiguous()
     if noise is None:
         noise = torch.randn_like(x_real)
@@ -73,7 +74,7 @@ def d_phase(x_real: torch.Tensor, generator, discriminator, discriminator_optim,
     # (A layer's FIRST packing happens lazily at its first use and is cached: on a fresh network -- first step,
     # after grow() -- that would be on whichever stream gets there first while the other stream reads the same
     # buffer un-ordered, so that one pass stays on a single stream.)
-    two_streams = overlap_gp and x_real.is_cuda and grad_sync is None and packs_known
+    two_streams = overlap_gp and x_real.is_cuda and grad_sync is None and ops.packs_settled(discriminator)
     if two_streams:
         d_params = [p for p in discriminator.parameters() if p.requires_grad]
         main, side = torch.cuda.current_stream(dev), _side_stream(dev)
@@ -106,6 +107,7 @@ def d_phase(x_real: torch.Tensor, generator, discriminator, discriminator_optim,
         if grad_sync is not None:
             grad_sync.arm(discriminator)
         d_loss.backward()
+    ops.mark_packs_settled(discriminator)
     return {"d_loss": d_loss.detach(), "gp": gp_loss.detach(), "d_real_mean": real_loss.detach(),
             "x_real": x_real}
 
