@@ -36,6 +36,10 @@ typedef struct CUstream_st* cudaStream_t;
 #define SG_IMPL_AUTO 0    /* tcgen05 when the shape is covered, else direct */
 #define SG_IMPL_DIRECT 1  /* CUDA-core kernel (fp32 mode, odd shapes, on-device cross-check) */
 #define SG_IMPL_TCGEN05 2 /* tcgen05/TMEM/TMA implicit GEMM; error if the shape is not covered */
+#define SG_IMPL_TF32 3    /* fp32 tensors through tcgen05 kind::tf32 (10-bit mantissa operands rounded to nearest, fp32
+                             accumulate): fprop/dgrad need the SG_TF32 packing and fail (-5) on an uncovered shape;
+                             wgrad falls back to the fp32 CUDA-core kernel */
+#define SG_TF32 2         /* dtype code of sg_pack_conv_weight only: fp32 [tap][K/4][rows][4], rounded to tf32 */
 
 int sg_version(void);
 /* 1: kernels are launched with programmatic dependent launch (each starts with
@@ -78,6 +82,8 @@ int sg_pack_conv_weights_multi(const void* jobs, const int* block_job, const int
 int sg_conv3d_fprop(const void* x, const void* wp, const float* bias, const void* mask_src, void* y,
                     int dtype, int N, int Cin, int Cout, int D, int H, int W, float scale, int lrelu,
                     int impl, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+/* 1 when impl = SG_IMPL_TF32 covers this fprop/dgrad shape (W % 8 == 0, H a multiple of min(H, 16) >= 8, ...) */
+int sg_conv3d_tf32_supported(int N, int Cin, int Cout, int D, int H, int W);
 /* bytes of caller-provided scratch the conv entry points need for this shape; kind 0 = fprop/dgrad
  * (split-K partial sums [N*V][CoutP] fp32), 1 = wgrad (tap-major sums [27][Cout][CinP] fp32 that the
  * finishing kernel transposes into gw).  The library never allocates. */

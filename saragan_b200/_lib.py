@@ -16,8 +16,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # SARAGAN_B200_LIB: load another build of the same library (A/B runs of build-time switches, e.g. SG_TC_WATCHDOG)
 LIB_PATH = os.environ.get("SARAGAN_B200_LIB") or os.path.join(_HERE, "libsaragan_b200.so")
 
-BF16, F32 = 0, 1
-IMPL_AUTO, IMPL_DIRECT, IMPL_TCGEN05 = 0, 1, 2
+BF16, F32, TF32_PACK = 0, 1, 2
+IMPL_AUTO, IMPL_DIRECT, IMPL_TCGEN05, IMPL_TF32 = 0, 1, 2, 3
 
 _c_int, _c_i64, _c_f, _c_p = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
 
@@ -41,6 +41,7 @@ SIGNATURES = {
     "sg_tc_res_zs_mode": [_c_int],
     "sg_tc_force_plan": [_c_int, _c_int, _c_int, _c_int],
     "sg_tc_plan_debug": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, ctypes.POINTER(ctypes.c_int)],
+    "sg_conv3d_tf32_supported": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int],
     "sg_conv3d_workspace_bytes": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int],
     "sg_conv3d_wgrad": [_c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                         _c_f, _c_int, _c_p, _c_i64, _c_p],

@@ -4,14 +4,19 @@ import contextlib
 import torch
 
 _precision = "bf16"
+PRECISIONS = ("bf16", "tf32", "fp32")
 
 
 def set_precision(name: str) -> None:
-    """'bf16': bf16 activations/gradients, fp32 accumulation (tcgen05 kind::f16 convolutions).
-    'fp32': fp32 storage and CUDA-core convolutions -- the tight-tolerance verification mode."""
+    """'bf16': bf16 activations/gradients + tcgen05 kind::f16 convolutions (fp32 accumulation) at the levels above
+            TF32_MAX_VOXELS voxels; fp32 storage + tcgen05 kind::tf32 at the levels up to TF32_MAX_VOXELS; plain fp32
+            (CUDA cores) at the base level (<= FP32_MAX_VOXELS).  The benchmarked policy.
+    'tf32': fp32 storage everywhere, tcgen05 kind::tf32 convolutions (operands rounded to nearest to 10 mantissa bits,
+            fp32 accumulation) above the base level -- the <= 1e-3 tier of BASELINE.json on tensor cores.
+    'fp32': fp32 storage and CUDA-core fp32 convolutions everywhere -- the exact verification mode."""
     global _precision
-    if name not in ("bf16", "fp32"):
-        raise ValueError("precision must be 'bf16' or 'fp32'")
+    if name not in PRECISIONS:
+        raise ValueError(f"precision must be one of {PRECISIONS}")
     _precision = name
 
 
@@ -20,32 +25,64 @@ def precision() -> str:
 
 
 # Levels with at most this many voxels (the 1x4x4 base level) keep fp32 activations and
-# gradients even in bf16 mode: MinibatchStandardDeviation subtracts the group mean there, in
+# gradients AND exact fp32 arithmetic in every mode: MinibatchStandardDeviation subtracts the group mean there, in
 # the forward AND (through autograd) in the backward pass, and early in training the samples
 # of a group are nearly identical, so the centred values are small differences of large
 # numbers -- bf16 rounding before the subtraction costs 10-30 % relative gradient error
 # (measured); fp32 there brings it to ~1 %.  The base level is < 0.2 % of the FLOPs.
 FP32_MAX_VOXELS = 16
 
+# bf16 mode: levels with at most this many voxels (up to 4x16x16: < 9 % of the step's FLOPs, all of them latency- and
+# weight-stream-bound) keep fp32 storage and run their convolutions as TF32 on the tensor cores.  Their pre-activations
+# feed the deepest part of the gradient chain (and the minibatch-stddev statistics); at TF32 the whole-step parameter
+# gradients of the golden configurations sit at 1.4 % median against the fp32 reference (bf16 there: 5 %).
+TF32_MAX_VOXELS = 1024
+
 
 def act_dtype(voxels: int = 1 << 30) -> torch.dtype:
     """Storage type of an activation / gradient tensor at a level with `voxels` = D*H*W."""
-    if _precision == "fp32" or voxels <= FP32_MAX_VOXELS:
+    if _precision != "bf16" or voxels <= max(FP32_MAX_VOXELS, TF32_MAX_VOXELS):
         return torch.float32
     return torch.bfloat16
 
 
+def conv_route(x: torch.Tensor, cin: int, cout: int):
+    """(impl code, packed-weight kind) of a 3x3x3 convolution on the blocked activation `x` under the current policy:
+    bf16 tensors -> tcgen05 kind::f16; fp32 tensors above the base level -> tcgen05 kind::tf32 (modes 'bf16', 'tf32')
+    when the kernel covers the shape; everything else -> the fp32 CUDA-core kernels."""
+    from . import _lib
+    if x.dtype == torch.float32 and _precision != "fp32":
+        n, _, d, h, w, _ = x.shape
+        if d * h * w > FP32_MAX_VOXELS and tf32_supported(n, cin, cout, d, h, w):
+            return _lib.IMPL_TF32, "tf32"
+    return _lib.IMPL_AUTO, x.dtype
+
+
+_tf32_ok = {}
+
+
+def tf32_supported(n, cin, cout, d, h, w) -> bool:
+    key = (n, cin, cout, d, h, w)
+    if key not in _tf32_ok:
+        from . import kernels
+        _tf32_ok[key] = kernels.conv_tf32_supported(*key)
+    return _tf32_ok[key]
+
+
 def policy_key():
     """Everything that decides which storage types (hence which weight packings) a pass uses."""
-    return (_precision, FP32_MAX_VOXELS)
+    return (_precision, FP32_MAX_VOXELS, TF32_MAX_VOXELS)
 
 
 def describe() -> str:
     """One line for logs / bench.py: which storage and arithmetic each level uses under the current policy."""
+    base = f"fp32 storage + fp32 CUDA-core kernels at <= {FP32_MAX_VOXELS} voxels (1x4x4 base level, minibatch-stddev)"
     if _precision == "fp32":
         return "fp32 storage, CUDA-core fp32 convolutions at every level"
-    return (f"bf16 storage + tcgen05 kind::f16 (fp32 accumulate) above {FP32_MAX_VOXELS} voxels; "
-            f"fp32 storage + fp32 CUDA-core kernels at <= {FP32_MAX_VOXELS} voxels (1x4x4 base level, minibatch-stddev)")
+    if _precision == "tf32":
+        return f"fp32 storage + tcgen05 kind::tf32 (rounded to nearest, fp32 accumulate) above {FP32_MAX_VOXELS} voxels; " + base
+    return (f"bf16 storage + tcgen05 kind::f16 (fp32 accumulate) above {TF32_MAX_VOXELS} voxels; fp32 storage + tcgen05 "
+            f"kind::tf32 from {FP32_MAX_VOXELS + 1} to {TF32_MAX_VOXELS} voxels; " + base)
 
 
 @contextlib.contextmanager

@@ -14,6 +14,7 @@
 
 #define SG_DTYPE_BF16 0
 #define SG_DTYPE_F32 1
+#define SG_DTYPE_TF32 2   /* packed-weight flavour only: fp32 [tap][K/4][RP][4], values rounded to tf32 */
 
 // error plumbing ------------------------------------------------------------------------
 void sg_set_error(const char* fmt, ...);

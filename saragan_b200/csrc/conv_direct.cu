@@ -12,11 +12,11 @@ SG_DEFINE_LEAK_SETTER(sg_set_leak_conv_direct)
 // fall through to the direct kernel, 0 on success, <0 / cudaError on failure.
 int sg_tc_fprop(const void* x, const void* wp, const float* bias, const void* mask_src, void* y,
                 int N, int Cin, int Cout, int D, int H, int W, float scale, int lrelu,
-                void* workspace, int64_t workspace_bytes, cudaStream_t s);
+                void* workspace, int64_t workspace_bytes, cudaStream_t s, int tf32);
 int sg_tc_wgrad(const void* x, const void* gy, float* gw, float* gb, int N, int Cin, int Cout,
                 int D, int H, int W, float scale, void* workspace, int64_t workspace_bytes,
-                cudaStream_t s);
-int64_t sg_tc_workspace_bytes(int kind, int N, int Cin, int Cout, int D, int H, int W);
+                cudaStream_t s, int tf32);
+int64_t sg_tc_workspace_bytes(int kind, int N, int Cin, int Cout, int D, int H, int W, int tf32);
 int sg_wgrad_finish(const float* ws, float* gw, int Cout, int Cin, int CinP, float scale, cudaStream_t s);
 
 // bf16 convolutions that the tcgen05 planners declined and the CUDA-core kernels ran instead
@@ -38,7 +38,7 @@ extern "C" int64_t sg_cuda_core_fallbacks(int reset) {
 // the fp32 reads (runs of 216 / 864 consecutive floats of the parameter) and the packed writes (runs of 256
 // consecutive elements per tap) are coalesced.  (The first version gathered one 4-byte element per thread, 108
 // bytes apart: 8x read amplification, 0.5 ms per step for the 44 packings of the cfg3 networks.)
-template <typename T>
+template <typename T, bool TF32 = false>
 __device__ __forceinline__ void pack_tile(const float* __restrict__ w, T* __restrict__ dst, int Cout, int Cin,
                                           int transpose_flip, int kc, int r0, float* s /* [32][8][27] */) {
   const int K = transpose_flip ? Cout : Cin;     // contraction channels
@@ -65,16 +65,26 @@ __device__ __forceinline__ void pack_tile(const float* __restrict__ w, T* __rest
   __syncthreads();
   for (int idx = threadIdx.x; idx < 27 * 256; idx += blockDim.x) {
     const int tap = idx >> 8, e = idx & 255;
-    const int r = e >> 3, j = e & 7;
-    if (r0 + r < RP) st1(dst + (((int64_t)tap * KC + kc) * RP + r0 + r) * 8 + j, s[(r * 8 + j) * 27 + tap]);
+    if (TF32) {
+      // SG_TF32 packing [tap][K/4][RP][4] fp32, rounded to tf32: the 8-channel chunk is two 16-byte K chunks
+      const int h = e >> 7, r = (e >> 2) & 31, j4 = e & 3;
+      if (r0 + r < RP) {
+        uint32_t t;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(s[(r * 8 + h * 4 + j4) * 27 + tap]));
+        st1(dst + (((int64_t)tap * 2 * KC + 2 * kc + h) * RP + r0 + r) * 4 + j4, __uint_as_float(t));
+      }
+    } else {
+      const int r = e >> 3, j = e & 7;
+      if (r0 + r < RP) st1(dst + (((int64_t)tap * KC + kc) * RP + r0 + r) * 8 + j, s[(r * 8 + j) * 27 + tap]);
+    }
   }
 }
-template <typename T>
+template <typename T, bool TF32>
 __global__ void __launch_bounds__(256)
 k_pack_conv_weight(const float* __restrict__ w, T* __restrict__ dst, int Cout, int Cin, int transpose_flip) {
   sg_pdl_enter();
   __shared__ float s[32 * 8 * 27];
-  pack_tile<T>(w, dst, Cout, Cin, transpose_flip, blockIdx.y, blockIdx.x * 32, s);
+  pack_tile<T, TF32>(w, dst, Cout, Cin, transpose_flip, blockIdx.y, blockIdx.x * 32, s);
 }
 // every stale packing of a network in ONE launch: table row = one (weight, packing), block -> (row, kc, r tile)
 struct SgPackJob {
@@ -90,6 +100,8 @@ k_pack_conv_weights_multi(const SgPackJob* __restrict__ jobs, const int* __restr
   const SgPackJob jb = jobs[block_job[blockIdx.x]];
   if (jb.dtype == SG_DTYPE_BF16)
     pack_tile<__nv_bfloat16>(jb.w, (__nv_bfloat16*)jb.dst, jb.Cout, jb.Cin, jb.flip, block_kc[blockIdx.x], block_r0[blockIdx.x], s);
+  else if (jb.dtype == SG_DTYPE_TF32)
+    pack_tile<float, true>(jb.w, (float*)jb.dst, jb.Cout, jb.Cin, jb.flip, block_kc[blockIdx.x], block_r0[blockIdx.x], s);
   else
     pack_tile<float>(jb.w, (float*)jb.dst, jb.Cout, jb.Cin, jb.flip, block_kc[blockIdx.x], block_r0[blockIdx.x], s);
 }
@@ -102,7 +114,11 @@ extern "C" int sg_pack_conv_weight(const float* w, void* dst, int dtype, int Cou
                                    int transpose_flip, cudaStream_t s) {
   const int K = transpose_flip ? Cout : Cin, R = transpose_flip ? Cin : Cout;
   dim3 grid((unsigned)((16 * ((R + 15) / 16) + 31) / 32), (unsigned)(2 * ((K + 15) / 16)));
-  SG_DISPATCH(dtype, sg_launch((k_pack_conv_weight<T>), grid, 256, 0, s, w, (T*)dst, Cout, Cin, transpose_flip););
+  if (dtype == SG_DTYPE_TF32) {
+    sg_launch((k_pack_conv_weight<float, true>), grid, 256, 0, s, w, (float*)dst, Cout, Cin, transpose_flip);
+  } else {
+    SG_DISPATCH(dtype, sg_launch((k_pack_conv_weight<T, false>), grid, 256, 0, s, w, (T*)dst, Cout, Cin, transpose_flip););
+  }
   return sg_check_launch("sg_pack_conv_weight");
 }
 extern "C" int sg_pack_conv_weights_multi(const void* jobs, const int* block_job, const int* block_kc,
@@ -357,6 +373,15 @@ int sg_conv_finish_bf16(const float* acc, const float* bias, const void* mask_sr
   return sg_check_launch("sg_conv_finish");
 }
 
+int sg_conv_finish_f32(const float* acc, const float* bias, const void* mask_src, void* y, int N,
+                       int Cout, int64_t V, float scale, int lrelu, cudaStream_t s) {
+  int CCout = sg_chunks(Cout), CoutP = 16 * ((Cout + 15) / 16);
+  int64_t total = (int64_t)N * CCout * V;
+  sg_launch((k_conv_finish<float, 1>), sg_grid(total, 256), 256, 0, s,
+      acc, bias, (const float*)mask_src, (float*)y, N, Cout, CCout, CoutP, V, scale, lrelu, 1);
+  return sg_check_launch("sg_conv_finish");
+}
+
 static bool small_f32_applies(int dtype, int N, int D, int H, int W) {
   return dtype == SG_DTYPE_F32 && (int64_t)D * H * W <= 128 && (int64_t)N * D * H * W <= 8192;
 }
@@ -395,10 +420,9 @@ extern "C" int64_t sg_conv3d_workspace_bytes(int kind, int dtype, int N, int Cin
   }
   if (kind == 1 && small_f32_applies(dtype, N, D, H, W))
     need = (int64_t)27 * Cout * (16 * ((Cin + 15) / 16)) * (int64_t)sizeof(float);
-  if (dtype == SG_DTYPE_BF16) {
-    int64_t t = sg_tc_workspace_bytes(kind, N, Cin, Cout, D, H, W);
-    if (t > need) need = t;
-  }
+  // fp32 tensors may take the TF32 tensor-core path (impl = SG_IMPL_TF32): size for whichever needs more
+  int64_t t = sg_tc_workspace_bytes(kind, N, Cin, Cout, D, H, W, dtype == SG_DTYPE_F32);
+  if (t > need) need = t;
   return need;
 }
 
@@ -420,10 +444,16 @@ extern "C" int sg_conv3d_fprop(const void* x, const void* wp, const float* bias,
                                int D, int H, int W, float scale, int lrelu, int impl, void* ws,
                                int64_t ws_bytes, cudaStream_t s) {
   SG_REQUIRE(N >= 0 && Cin > 0 && Cout > 0 && D > 0 && H > 0 && W > 0, "sg_conv3d_fprop: bad shape");
-  SG_REQUIRE(impl >= 0 && impl <= 2, "sg_conv3d_fprop: impl must be 0 (auto), 1 (direct), 2 (tcgen05)");
+  SG_REQUIRE(impl >= 0 && impl <= 3, "sg_conv3d_fprop: impl must be 0 (auto), 1 (direct), 2 (tcgen05), 3 (tcgen05 tf32)");
   if (N == 0) return 0;
+  if (impl == SG_IMPL_TF32) {
+    SG_REQUIRE(dtype == SG_DTYPE_F32, "sg_conv3d_fprop: the TF32 path takes fp32 activations (and the SG_TF32 packing)");
+    int rc = sg_tc_fprop(x, wp, bias, mask_src, y, N, Cin, Cout, D, H, W, scale, lrelu, ws, ws_bytes, s, 1);
+    if (rc == 1) sg_set_error("sg_conv3d_fprop: shape not covered by the tcgen05 tf32 kernel");
+    return rc == 1 ? -5 : rc;     // no fallback: the packing differs from the CUDA-core kernels' (caller decides)
+  }
   if (impl != SG_IMPL_DIRECT && dtype == SG_DTYPE_BF16) {
-    int rc = sg_tc_fprop(x, wp, bias, mask_src, y, N, Cin, Cout, D, H, W, scale, lrelu, ws, ws_bytes, s);
+    int rc = sg_tc_fprop(x, wp, bias, mask_src, y, N, Cin, Cout, D, H, W, scale, lrelu, ws, ws_bytes, s, 0);
     if (rc != 1) return rc;
     SG_REQUIRE(impl != SG_IMPL_TCGEN05, "sg_conv3d_fprop: shape not covered by the tcgen05 kernel");
     if (impl == SG_IMPL_AUTO) ++g_cuda_core_fallbacks;
@@ -578,9 +608,16 @@ extern "C" int sg_conv3d_wgrad(const void* x, const void* gy, float* gw, float* 
                                int N, int Cin, int Cout, int D, int H, int W, float scale, int impl,
                                void* ws, int64_t ws_bytes, cudaStream_t s) {
   SG_REQUIRE(N >= 0 && Cin > 0 && Cout > 0 && D > 0 && H > 0 && W > 0, "sg_conv3d_wgrad: bad shape");
-  SG_REQUIRE(impl >= 0 && impl <= 2, "sg_conv3d_wgrad: impl must be 0 (auto), 1 (direct), 2 (tcgen05)");
+  SG_REQUIRE(impl >= 0 && impl <= 3, "sg_conv3d_wgrad: impl must be 0 (auto), 1 (direct), 2 (tcgen05), 3 (tcgen05 tf32)");
+  if (impl == SG_IMPL_TF32 && N > 0) {
+    SG_REQUIRE(dtype == SG_DTYPE_F32, "sg_conv3d_wgrad: the TF32 path takes fp32 activations");
+    int rc = sg_tc_wgrad(x, gy, gw, gb, N, Cin, Cout, D, H, W, scale, ws, ws_bytes, s, 1);
+    if (rc != 1) return rc;
+    ++g_cuda_core_fallbacks;      // shape not covered: the fp32 CUDA-core kernels below take the same operands
+    impl = SG_IMPL_AUTO;
+  }
   if (impl != SG_IMPL_DIRECT && dtype == SG_DTYPE_BF16 && N > 0) {
-    int rc = sg_tc_wgrad(x, gy, gw, gb, N, Cin, Cout, D, H, W, scale, ws, ws_bytes, s);
+    int rc = sg_tc_wgrad(x, gy, gw, gb, N, Cin, Cout, D, H, W, scale, ws, ws_bytes, s, 0);
     if (rc != 1) return rc;
     SG_REQUIRE(impl != SG_IMPL_TCGEN05, "sg_conv3d_wgrad: shape not covered by the tcgen05 kernel");
     if (impl == SG_IMPL_AUTO) ++g_cuda_core_fallbacks;

@@ -25,6 +25,7 @@
 #include <array>
 #include <map>
 #include <mutex>
+#include <type_traits>
 
 #include "../../include/saragan_b200.h"
 #include "common.cuh"
@@ -40,13 +41,14 @@ namespace {
 constexpr int kThreads = 192;
 
 struct TcParams {
-  const __nv_bfloat16* wp;   // packed weights [27][CCin][CoutP][8]
+  const void* wp;            // packed weights [27][CCin][CoutP][16 bytes]
   const float* bias;         // nullable
-  const __nv_bfloat16* mask; // nullable
-  __nv_bfloat16* y;          // output act (splits == 1)
+  const void* mask;          // nullable, act of y's type
+  void* y;                   // output act (splits == 1): bf16, or fp32 for the TF32 kernel
   float* ws;                 // fp32 [N*V][CoutP] (splits > 1)
   int N, D, H, W;
-  int CCin, Cout, CoutP, CCout;
+  int CCin;                  // 16-byte K chunks of the input: 8 bf16 channels, or 4 fp32 channels (TF32)
+  int Cout, CoutP, CCout;    // CCout: 8-channel chunks of the output tensor (both types)
   int td, th, tn;            // tile extents in output voxels (tw == 8)
   int tiles_w, tiles_h, tiles_d, tiles_n;
   int halo_w, halo_h, halo_d;
@@ -95,21 +97,29 @@ constexpr CoverCE cover_ce(int tn, int td, int th) {
 // weight stage -- so that every descriptor offset of the 27 x n_sub MMAs of a K block is a constant and
 // the fully unrolled issue loop costs one uniform add per MMA (the generic loop costs the single issuing
 // warp ~200 cycles per tap plus ~100 per MMA: more than the MMAs themselves).
-template <int NT, int TD, int TH, int TN>
+// TF32: fp32 activations (the 8-blocked fp32 layout, read through TWO tensor maps -- one per 16-byte half of a
+// voxel's 32-byte chunk -- so that a shared-memory voxel is again one 16-byte core-matrix row, now of 4 channels),
+// fp32 packed weights [27][C/4][CoutP][4] pre-rounded to tf32, kind::tf32 MMAs (K = 8 = two 16-byte chunks, exactly
+// the bf16 kernel's byte geometry), fp32 output.  The tensor core would TRUNCATE the fp32 activations to tf32: the
+// four epilogue warps, idle during the main loop, round every landed halo block in place (tf32_rna) and hand it to
+// the MMA issuer through the ROUND_A barriers.
+template <int NT, int TD, int TH, int TN, bool TF32>
 __global__ void __launch_bounds__(kThreads)
-k_conv_tc(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap,
-          const __grid_constant__ TcParams p) {
+k_conv_tc(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap xmap1,
+          const __grid_constant__ CUtensorMap wmap, const __grid_constant__ TcParams p) {
+  using T = typename std::conditional<TF32, float, __nv_bfloat16>::type;
   extern __shared__ __align__(128) uint8_t smem[];
   sg_pdl_trigger();
   // carve-up: [A halo block][weight ring][barriers][tmem base]
   uint8_t* a_smem = smem;
   uint8_t* w_smem = smem + p.a_stages * p.a_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + p.sw * p.w_stage_bytes);
-  // bars: [0,1] full_a, [2,3] empty_a, [4] acc_full, [5 .. 5+sw) full_w, [5+sw .. 5+2sw) empty_w   (sw <= 8)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  // bars: [0,1] full_a, [2,3] empty_a, [4] acc_full, [5 .. 5+sw) full_w, [5+sw .. 5+2sw) empty_w   (sw <= 8),
+  //       [22,23] round_a (TF32)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-  const int FULL_A = 0, EMPTY_A = 2, ACC_FULL = 4, FULL_W = 5, EMPTY_W = 5 + p.sw;
+  const int FULL_A = 0, EMPTY_A = 2, ACC_FULL = 4, FULL_W = 5, EMPTY_W = 5 + p.sw, ROUND_A = 22;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -125,10 +135,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUte
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+    if constexpr (TF32) asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap1) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
     for (int i = 0; i < 2; ++i) {
       mbar_init(BAR(FULL_A + i), 1);
       mbar_init(BAR(EMPTY_A + i), 1);
+      mbar_init(BAR(ROUND_A + i), 128);   // every thread of the four epilogue warps
     }
     mbar_init(BAR(ACC_FULL), 1);
     for (int i = 0; i < p.sw; ++i) {
@@ -164,9 +176,17 @@ k_conv_tc(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUte
         mbar_wait(BAR(EMPTY_A + sa), ((kb / p.a_stages) & 1) ^ 1);
         const int chunk0 = (kb0 + kb) * p.kb_chunks;
         mbar_expect_tx(BAR(FULL_A + sa), a_tx);
-        for (int c = 0; c < p.kb_chunks; ++c)
-          tma_load_5d(a_addr + sa * p.a_bytes + c * p.chunk_bytes, &xmap, BAR(FULL_A + sa), (w0 - 1) * 8, h0 - 1, d0 - 1,
-                      chunk0 + c, n0);
+        for (int c = 0; c < p.kb_chunks; ++c) {
+          if constexpr (TF32) {
+            // fp32 tensor as [4 | W | H | D | N*CC8] (voxel pitch 32 bytes), one map per 16-byte half: tn == 1
+            const int q = chunk0 + c;
+            tma_load_5d(a_addr + sa * p.a_bytes + c * p.chunk_bytes, (q & 1) ? &xmap1 : &xmap, BAR(FULL_A + sa), 0, w0 - 1,
+                        h0 - 1, d0 - 1, n0 * (p.CCin >> 1) + (q >> 1));
+          } else {
+            tma_load_5d(a_addr + sa * p.a_bytes + c * p.chunk_bytes, &xmap, BAR(FULL_A + sa), (w0 - 1) * 8, h0 - 1, d0 - 1,
+                        chunk0 + c, n0);
+          }
+        }
         for (int g = 0; g < groups; ++g, ++it) {
           const int s = it % p.sw;
           mbar_wait(BAR(EMPTY_W + s), ((it / p.sw) & 1) ^ 1);
@@ -180,8 +200,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUte
     // ================================ MMA issuer ================================
     {
       const uint32_t leader = elect_one();   // all lanes run the loops; one issues
-      // instruction descriptor: D=f32, A=B=bf16, both K-major, N = NT, M = 128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+      // instruction descriptor: D=f32, A=B=bf16 (tf32), both K-major, N = NT, M = 128
+      const uint32_t idesc = idesc_formats(TF32) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+      const int A_READY = TF32 ? ROUND_A : FULL_A;   // TF32: the halo block is usable once it has been rounded
       const uint32_t line_pitch = (uint32_t)p.halo_w * 16u;
       // hoisted descriptor pieces (16-byte units): the first valid line sits (halo_h + 1) lines into
       // the block, which is also the most negative tap offset, so both offset families are >= 0
@@ -204,7 +225,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUte
         constexpr uint32_t W_TAP16 = 2u * NT;   // one tap of a stage: 2 chunks x NT rows x 16 B
         for (int kb = 0; kb < p.kblocks_per_split; ++kb) {
           const int sa = kb % p.a_stages;
-          mbar_wait(BAR(FULL_A + sa), (kb / p.a_stages) & 1);
+          mbar_wait(BAR(A_READY + sa), (kb / p.a_stages) & 1);
           const uint64_t a_kb = a_desc0 + (uint64_t)((uint32_t)(sa * p.a_bytes) >> 4);
           const uint32_t acc0 = kb != 0;
 #pragma unroll
@@ -222,8 +243,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUte
               const uint32_t tap_off = (uint32_t)((((tap / 9) - 1) * HALO_H + ((tap / 3) % 3 - 1)) * HALO_W + BIAS_VOX + tap % 3);
 #pragma unroll
               for (int sub = 0; sub < cov.n; ++sub)
-                tc_mma(tmem_base + sub * NT, a_kb + (uint64_t)(tap_off + (uint32_t)(cov.line[sub] * HALO_W - BIAS_VOX)),
-                       b_stage + (uint64_t)(t9 * W_TAP16), idesc, tap ? 1u : acc0, leader);
+                tc_mma_t<TF32>(tmem_base + sub * NT, a_kb + (uint64_t)(tap_off + (uint32_t)(cov.line[sub] * HALO_W - BIAS_VOX)),
+                               b_stage + (uint64_t)(t9 * W_TAP16), idesc, tap ? 1u : acc0, leader);
             }
             tc_commit(BAR(EMPTY_W + s), leader);
             if (++s == sw) { s = 0; ph ^= 1; }
@@ -233,7 +254,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUte
       } else {
       for (int kb = 0; kb < p.kblocks_per_split; ++kb) {
         const int sa = kb % p.a_stages;
-        mbar_wait(BAR(FULL_A + sa), (kb / p.a_stages) & 1);
+        mbar_wait(BAR(A_READY + sa), (kb / p.a_stages) & 1);
         const uint64_t a_desc_kb = a_desc0 + (uint64_t)((uint32_t)(sa * p.a_bytes) >> 4);
         int tap = 0;
         for (int kd = 0; kd < 3; ++kd)
@@ -244,7 +265,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUte
                 mbar_wait(BAR(FULL_W + s), ph);
                 tc_fence_after();
               }
-              issue_tap<NT>(tmem_base, a_desc_kb + (uint64_t)(uint32_t)(row_off + kw),
+              issue_tap<NT, TF32>(tmem_base, a_desc_kb + (uint64_t)(uint32_t)(row_off + kw),
                             w_desc0 + (uint64_t)(s * w_stage16 + tl * w_tap16), sub_off, n_sub, kpairs, kk_a, idesc,
                             (kb | tap) != 0, leader);
               if (++tl == tps) {
@@ -265,11 +286,20 @@ k_conv_tc(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUte
     const int row = quad * 32 + lane;       // accumulator row == TMEM lane
     const float scale = p.scale;
     const int lrelu = p.lrelu;
-    const __nv_bfloat16* mask = p.mask;
-    __nv_bfloat16* yout = p.y;
-    float* s_bias = reinterpret_cast<float*>(bars + 24);   // NT floats, 16-byte aligned, after the barriers
+    const T* mask = reinterpret_cast<const T*>(p.mask);
+    T* yout = reinterpret_cast<T*>(p.y);
+    float* s_bias = reinterpret_cast<float*>(bars + 26);   // NT floats, 16-byte aligned, after the barriers
     for (int i = row; i < NT; i += 128) s_bias[i] = (p.bias && co0 + i < p.Cout) ? p.bias[co0 + i] : 0.f;
     asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+    if constexpr (TF32) {
+      // main loop duty of these warps: round every landed halo block to tf32 in place, then release it to the issuer
+      for (int kb = 0; kb < p.kblocks_per_split; ++kb) {
+        const int sa = kb % p.a_stages;
+        mbar_wait(BAR(FULL_A + sa), (kb / p.a_stages) & 1);
+        round_tile_tf32(a_smem + sa * p.a_bytes, p.kb_chunks * p.chunk_bytes, row, 128);
+        mbar_arrive(BAR(ROUND_A + sa));
+      }
+    }
     mbar_wait(BAR(ACC_FULL), 0);
     tc_fence_after();
     const int64_t V = (int64_t)p.D * p.H * p.W;
@@ -291,9 +321,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUte
         const int64_t o = (((int64_t)n * p.CCout + (co0 + c0) / 8) * V + vox) * 8;
         // the LeakyReLU-mask vectors of these columns are fetched before the accumulator round trip
         uint4 mk[CB / 8];
-        if (direct && mask) {
+        if constexpr (!TF32) {
+          if (direct && mask) {
 #pragma unroll
-          for (int q = 0; q < CB / 8; ++q) mk[q] = __ldg(reinterpret_cast<const uint4*>(mask + o + (int64_t)q * V * 8));
+            for (int q = 0; q < CB / 8; ++q) mk[q] = __ldg(reinterpret_cast<const uint4*>(mask + o + (int64_t)q * V * 8));
+          }
         }
         float v[CB];
         __syncwarp();   // tcgen05.ld is .sync.aligned: the warp must be converged here
@@ -307,9 +339,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUte
           for (int q = 0; q < CB / 4; ++q) red_add_v4(dst + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         } else {
 #pragma unroll
-          for (int j = 0; j < CB / 16; ++j)
-            epilogue16_regmask(v + 16 * j, s_bias + c0 + 16 * j, scale, lrelu, mask != nullptr, mk[2 * j], mk[2 * j + 1],
-                               yout + o + (int64_t)(2 * j) * V * 8, V * 8);
+          for (int j = 0; j < CB / 16; ++j) {
+            if constexpr (TF32)
+              epilogue16<float>(v + 16 * j, s_bias + c0 + 16 * j, scale, lrelu, mask ? mask + o + (int64_t)(2 * j) * V * 8 : nullptr,
+                                yout + o + (int64_t)(2 * j) * V * 8, V * 8);
+            else
+              epilogue16_regmask(v + 16 * j, s_bias + c0 + 16 * j, scale, lrelu, mask != nullptr, mk[2 * j], mk[2 * j + 1],
+                                 yout + o + (int64_t)(2 * j) * V * 8, V * 8);
+          }
         }
       }
     }
@@ -366,11 +403,13 @@ int cover_lines(int tn, int td, int th, int halo_d, int halo_h, int* out) {
 // One candidate tiling of the streaming kernel.  `big` = sized for ONE CTA per SM (<= 512 TMEM columns,
 // ~200 KB of shared memory) instead of two (<= 256 columns, ~110 KB each); NT = output channels per CTA;
 // td_max caps the planes per tile; splits = split-K factor (must divide the K-block count).
-Plan make_plan_cfg(int N, int Cin, int Cout, int D, int H, int W, int NT, bool big, int td_max, int splits) {
+Plan make_plan_cfg(int N, int Cin, int Cout, int D, int H, int W, int NT, bool big, int td_max, int splits,
+                   bool tf32 = false) {
   Plan pl;
   TcParams& p = pl.p;
   if (W % 8 != 0 || H < 8) return pl;
-  const int CCin = sg_chunks(Cin), CoutP = 16 * ((Cout + 15) / 16);
+  // 16-byte K chunks: 8 bf16 channels, or 4 fp32 channels (TF32) -- from here on the geometry is in bytes and equal
+  const int CCin = sg_chunks(Cin) * (tf32 ? 2 : 1), CoutP = 16 * ((Cout + 15) / 16);
   if (CoutP % NT != 0) return pl;
   const int tmem_budget = big ? 512 : 256;
   const int max_sub = tmem_budget / NT < kMaxSub ? tmem_budget / NT : kMaxSub;
@@ -383,6 +422,7 @@ Plan make_plan_cfg(int N, int Cin, int Cout, int D, int H, int W, int NT, bool b
     if (D % td) continue;
     for (int tn = 1; tn <= N && tn <= 8; ++tn) {
       if (td < D && tn > 1) continue;   // span samples only when a tile already holds a whole volume
+      if (tf32 && tn > 1) continue;     // the fp32 tensor maps merge (sample, chunk) into one dimension
       if (tn > 1 && tn * td > td_max) continue;
       int lines[kMaxSub];
       int ns = cover_lines(tn, td, th, td + 2, th + 2, lines);
@@ -448,11 +488,11 @@ Plan make_plan_cfg(int N, int Cin, int Cout, int D, int H, int W, int NT, bool b
   const int64_t ctas = (int64_t)p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n * (CoutP / NT);
   pl.NT = NT;
   pl.big = big;
-  pl.smem = (size_t)p.a_stages * p.a_bytes + (size_t)p.sw * p.w_stage_bytes + 8 * 24 + 4 * 128 + 16;
+  pl.smem = (size_t)p.a_stages * p.a_bytes + (size_t)p.sw * p.w_stage_bytes + 8 * 26 + 4 * 128 + 16;
   pl.grid = dim3((unsigned)(p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n), (unsigned)(CoutP / NT), (unsigned)splits);
   pl.ok = true;
   // ---- estimated cycles (constants fitted to tools/plan_sweep.py measurements)
-  const double mma_cyc = NT == 128 ? 64.0 : NT == 64 ? 48.0 : 45.5;
+  const double mma_cyc = (NT == 128 ? 64.0 : NT == 64 ? 48.0 : 45.5) * (tf32 ? 2.0 : 1.0);
   const int co_res = (big || pl.smem > 112 * 1024 || p.tmem_cols > 256) ? 1 : 2;
   const double n_cta = (double)ctas * splits;
   const double slots = (double)sg_num_sms() * co_res;
@@ -488,28 +528,28 @@ Plan make_plan_cfg(int N, int Cin, int Cout, int D, int H, int W, int NT, bool b
 // test / tuning hook: NT, big, td_max, splits (0 = choose by estimated cost)
 int g_force_plan[4] = {0, 0, 0, 0};
 
-Plan make_plan(int N, int Cin, int Cout, int D, int H, int W) {
+Plan make_plan(int N, int Cin, int Cout, int D, int H, int W, bool tf32 = false) {
   if (g_force_plan[0] > 0)
     return make_plan_cfg(N, Cin, Cout, D, H, W, g_force_plan[0], g_force_plan[1] != 0, g_force_plan[2] > 0 ? g_force_plan[2] : 8,
-                         g_force_plan[3] > 0 ? g_force_plan[3] : 1);
+                         g_force_plan[3] > 0 ? g_force_plan[3] : 1, tf32);
   // the search walks ~1000 candidates: remember the winner per shape (launch-time cost matters in eager mode)
   static std::mutex mu;
-  static std::map<std::array<int, 6>, Plan> cache;
-  const std::array<int, 6> key = {N, Cin, Cout, D, H, W};
+  static std::map<std::array<int, 7>, Plan> cache;
+  const std::array<int, 7> key = {N, Cin, Cout, D, H, W, tf32 ? 1 : 0};
   {
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
   }
   Plan best;
-  const int CCin = sg_chunks(Cin);
+  const int CCin = sg_chunks(Cin) * (tf32 ? 2 : 1);
   static const int nts[4] = {128, 64, 32, 16};
   for (int ni = 0; ni < 4; ++ni)
     for (int big = 0; big < 2; ++big)
       for (int td_max = 8; td_max >= 1; td_max /= 2)
         for (int splits = 1; splits <= CCin / 2; ++splits) {
           if ((CCin / 2) % splits && (CCin / 4 == 0 || (CCin / 4) % splits)) continue;
-          Plan c = make_plan_cfg(N, Cin, Cout, D, H, W, nts[ni], big != 0, td_max, splits);
+          Plan c = make_plan_cfg(N, Cin, Cout, D, H, W, nts[ni], big != 0, td_max, splits, tf32);
           if (c.ok && (!best.ok || c.cost < best.cost)) best = c;
         }
   {
@@ -519,31 +559,32 @@ Plan make_plan(int N, int Cin, int Cout, int D, int H, int W) {
   return best;
 }
 
-template <int NT, int TD, int TH, int TN>
-int launch(const Plan& pl, const CUtensorMap& map, const CUtensorMap& wmap, cudaStream_t s) {
+template <int NT, int TD, int TH, int TN, bool TF32 = false>
+int launch(const Plan& pl, const CUtensorMap& map, const CUtensorMap& map1, const CUtensorMap& wmap, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_tc<NT, TD, TH, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_conv_tc<NT, TD, TH, TN, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
     if (e != cudaSuccess) {
       sg_set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return (int)e;
     }
     attr_set = true;
   }
-  sg_launch((k_conv_tc<NT, TD, TH, TN>), pl.grid, kThreads, pl.smem, s, map, wmap, pl.p);
-  return sg_check_launch("sg_conv3d_fprop(tcgen05)");
+  sg_launch((k_conv_tc<NT, TD, TH, TN, TF32>), pl.grid, kThreads, pl.smem, s, map, map1, wmap, pl.p);
+  return sg_check_launch(TF32 ? "sg_conv3d_fprop(tcgen05 tf32)" : "sg_conv3d_fprop(tcgen05)");
 }
 
-template <int NT>
-int launch_spec(const Plan& pl, const CUtensorMap& map, const CUtensorMap& wmap, cudaStream_t s) {
+template <int NT, bool TF32 = false>
+int launch_spec(const Plan& pl, const CUtensorMap& map, const CUtensorMap& map1, const CUtensorMap& wmap, cudaStream_t s) {
   const TcParams& p = pl.p;
   if (p.th == 16 && p.tn == 1) {
-    if (p.td == 1) return launch<NT, 1, 16, 1>(pl, map, wmap, s);
-    if (p.td == 2) return launch<NT, 2, 16, 1>(pl, map, wmap, s);
-    if (p.td == 4) return launch<NT, 4, 16, 1>(pl, map, wmap, s);
+    if (p.td == 1) return launch<NT, 1, 16, 1, TF32>(pl, map, map1, wmap, s);
+    if (p.td == 2) return launch<NT, 2, 16, 1, TF32>(pl, map, map1, wmap, s);
+    if (p.td == 4) return launch<NT, 4, 16, 1, TF32>(pl, map, map1, wmap, s);
   } else if (p.th == 8 && p.td == 2) {
-    if (p.tn == 1) return launch<NT, 2, 8, 1>(pl, map, wmap, s);
-    if (p.tn == 2) return launch<NT, 2, 8, 2>(pl, map, wmap, s);
+    if (p.tn == 1) return launch<NT, 2, 8, 1, TF32>(pl, map, map1, wmap, s);
+    if constexpr (!TF32)
+      if (p.tn == 2) return launch<NT, 2, 8, 2, false>(pl, map, map1, wmap, s);
   }
   sg_set_error("conv_tc: no specialised kernel for tile %dx%dx%d", p.tn, p.td, p.th);
   return -4;
@@ -588,20 +629,54 @@ extern "C" void sg_tc_force_plan(int nt, int big, int td_max, int splits) {
   g_force_plan[0] = nt; g_force_plan[1] = big; g_force_plan[2] = td_max; g_force_plan[3] = splits;
 }
 
-int64_t sg_tc_wgrad_workspace_bytes(int N, int Cin, int Cout, int D, int H, int W);
+int64_t sg_tc_wgrad_workspace_bytes(int N, int Cin, int Cout, int D, int H, int W, int tf32);
 
-int64_t sg_tc_workspace_bytes(int kind, int N, int Cin, int Cout, int D, int H, int W) {
-  if (kind == 1) return sg_tc_wgrad_workspace_bytes(N, Cin, Cout, D, H, W);
+int sg_conv_finish_f32(const float* acc, const float* bias, const void* mask_src, void* y, int N,
+                       int Cout, int64_t V, float scale, int lrelu, cudaStream_t s);
+
+int64_t sg_tc_workspace_bytes(int kind, int N, int Cin, int Cout, int D, int H, int W, int tf32) {
+  if (kind == 1) return sg_tc_wgrad_workspace_bytes(N, Cin, Cout, D, H, W, tf32);
   if (kind != 0) return 0;
-  if (g_force_streaming != 1 && make_res_plan(N, Cin, Cout, D, H, W, g_force_streaming == 2).ok) return 0;
-  Plan pl = make_plan(N, Cin, Cout, D, H, W);
+  if (!tf32 && g_force_streaming != 1 && make_res_plan(N, Cin, Cout, D, H, W, g_force_streaming == 2).ok) return 0;
+  Plan pl = make_plan(N, Cin, Cout, D, H, W, tf32 != 0);
   if (!pl.ok || pl.p.splits == 1) return 0;
   return (int64_t)N * D * H * W * pl.p.CoutP * (int64_t)sizeof(float);
 }
 
+namespace {
+// fp32 activations [N][CC8][D][H][W][8] as the 5-D tensor [4 | W | H | D | N*CC8] (voxel pitch 32 bytes) starting at the
+// `half`-th 16 bytes of the voxels: box = one 4-channel halo block, which lands as [d][h][w][16 bytes]
+int encode_f32_half_map(CUtensorMap* map, const void* x, int half, int N, int CC8, int D, int H, int W, int box_w,
+                        int box_h, int box_d, int box_c) {
+  EncodeTiledFn encode = get_encode();
+  if (!encode) {
+    sg_set_error("conv_tc: cuTensorMapEncodeTiled not available");
+    return -2;
+  }
+  cuuint64_t dims[5] = {4, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N * CC8};
+  cuuint64_t strides[4] = {32, (cuuint64_t)W * 32, (cuuint64_t)H * W * 32, (cuuint64_t)D * H * W * 32};
+  cuuint32_t box[5] = {4, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_d, (cuuint32_t)box_c};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)((const char*)x + 16 * half), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    sg_set_error("conv_tc: cuTensorMapEncodeTiled (fp32 half map) failed (%d)", (int)r);
+    return -3;
+  }
+  return 0;
+}
+}  // namespace
+int sg_encode_f32_half_map(CUtensorMap* map, const void* x, int half, int N, int CC8, int D, int H, int W, int box_w,
+                           int box_h, int box_d, int box_c) {
+  return encode_f32_half_map(map, x, half, N, CC8, D, H, W, box_w, box_h, box_d, box_c);
+}
+
+// tf32 != 0: x, y, mask_src are fp32 acts, wp is the SG_TF32 packing; the streaming kernel with kind::tf32
 int sg_tc_fprop(const void* x, const void* wp, const float* bias, const void* mask_src, void* y, int N, int Cin,
-                int Cout, int D, int H, int W, float scale, int lrelu, void* ws, int64_t ws_bytes, cudaStream_t s) {
-  if (g_force_streaming != 1) {
+                int Cout, int D, int H, int W, float scale, int lrelu, void* ws, int64_t ws_bytes, cudaStream_t s,
+                int tf32) {
+  if (!tf32 && g_force_streaming != 1) {
     ResPlan rp = make_res_plan(N, Cin, Cout, D, H, W, g_force_streaming == 2);
     if (rp.ok) {
       ResParams& q = rp.p;
@@ -621,7 +696,7 @@ int sg_tc_fprop(const void* x, const void* wp, const float* bias, const void* ma
       }
     }
   }
-  Plan pl = make_plan(N, Cin, Cout, D, H, W);
+  Plan pl = make_plan(N, Cin, Cout, D, H, W, tf32 != 0);
   if (!pl.ok) return 1;
   EncodeTiledFn encode = get_encode();
   if (!encode) {
@@ -629,10 +704,10 @@ int sg_tc_fprop(const void* x, const void* wp, const float* bias, const void* ma
     return -2;
   }
   TcParams& p = pl.p;
-  p.wp = (const __nv_bfloat16*)wp;
+  p.wp = wp;
   p.bias = bias;
-  p.mask = (const __nv_bfloat16*)mask_src;
-  p.y = (__nv_bfloat16*)y;
+  p.mask = mask_src;
+  p.y = y;
   p.ws = (float*)ws;
   p.scale = scale;
   p.lrelu = lrelu;
@@ -642,29 +717,38 @@ int sg_tc_fprop(const void* x, const void* wp, const float* bias, const void* ma
                (long long)ws_bytes, (long long)need);
     cudaMemsetAsync(ws, 0, (size_t)need, s);
   }
-  // activations as a 5-D tensor [W*8 | H | D | CC | N] of bf16; box = one 8-channel halo block
-  CUtensorMap map;
-  cuuint64_t dims[5] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)p.CCin, (cuuint64_t)N};
-  cuuint64_t strides[4] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16,
-                           (cuuint64_t)p.CCin * D * H * W * 16};
-  cuuint32_t box[5] = {(cuuint32_t)p.halo_w * 8, (cuuint32_t)p.halo_h, (cuuint32_t)p.halo_d, 1, (cuuint32_t)p.tn};
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    sg_set_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
-    return -3;
+  CUtensorMap map, map1;
+  CUresult r;
+  if (tf32) {
+    int rc = encode_f32_half_map(&map, x, 0, N, p.CCin / 2, D, H, W, p.halo_w, p.halo_h, p.halo_d, 1);
+    if (!rc) rc = encode_f32_half_map(&map1, x, 1, N, p.CCin / 2, D, H, W, p.halo_w, p.halo_h, p.halo_d, 1);
+    if (rc) return rc;
+  } else {
+    // activations as a 5-D tensor [W*8 | H | D | CC | N] of bf16; box = one 8-channel halo block
+    cuuint64_t dims[5] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)p.CCin, (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16,
+                             (cuuint64_t)p.CCin * D * H * W * 16};
+    cuuint32_t box[5] = {(cuuint32_t)p.halo_w * 8, (cuuint32_t)p.halo_h, (cuuint32_t)p.halo_d, 1, (cuuint32_t)p.tn};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      sg_set_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+      return -3;
+    }
+    map1 = map;
   }
-  // packed weights [27][CCin][CoutP][8] as a 4-D tensor [64 = 8 co x 8 ci | CoutP/8 | CCin | 27]; box = one stage
+  // packed weights [27][CCin][CoutP][16 B] as a 4-D tensor [128 B = 8 co x 16 B | CoutP/8 | CCin | 27]; box = one stage
   CUtensorMap wmap;
   {
-    cuuint64_t wd[4] = {64, (cuuint64_t)p.CoutP / 8, (cuuint64_t)p.CCin, 27};
+    const cuuint64_t inner = tf32 ? 32 : 64;   // elements per 128 bytes
+    cuuint64_t wd[4] = {inner, (cuuint64_t)p.CoutP / 8, (cuuint64_t)p.CCin, 27};
     cuuint64_t wst[3] = {128, (cuuint64_t)p.CoutP * 16, (cuuint64_t)p.CCin * p.CoutP * 16};
-    cuuint32_t wbox[4] = {64, (cuuint32_t)pl.NT / 8, (cuuint32_t)p.kb_chunks, (cuuint32_t)p.tps};
+    cuuint32_t wbox[4] = {(cuuint32_t)inner, (cuuint32_t)pl.NT / 8, (cuuint32_t)p.kb_chunks, (cuuint32_t)p.tps};
     cuuint32_t we[4] = {1, 1, 1, 1};
-    r = encode(&wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(wp), wd, wst, wbox, we,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    r = encode(&wmap, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(wp), wd,
+               wst, wbox, we, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       sg_set_error("conv_tc: cuTensorMapEncodeTiled (weights) failed (%d)", (int)r);
@@ -672,20 +756,38 @@ int sg_tc_fprop(const void* x, const void* wp, const float* bias, const void* ma
     }
   }
   int rc;
-  if (pl.spec) {
-    rc = pl.NT == 128 ? launch_spec<128>(pl, map, wmap, s) : launch_spec<64>(pl, map, wmap, s);
+  if (tf32) {
+    if (pl.spec) {
+      rc = pl.NT == 128 ? launch_spec<128, true>(pl, map, map1, wmap, s) : launch_spec<64, true>(pl, map, map1, wmap, s);
+    } else {
+      switch (pl.NT) {
+        case 16: rc = launch<16, 0, 0, 0, true>(pl, map, map1, wmap, s); break;
+        case 32: rc = launch<32, 0, 0, 0, true>(pl, map, map1, wmap, s); break;
+        case 64: rc = launch<64, 0, 0, 0, true>(pl, map, map1, wmap, s); break;
+        default: rc = launch<128, 0, 0, 0, true>(pl, map, map1, wmap, s); break;
+      }
+    }
+  } else if (pl.spec) {
+    rc = pl.NT == 128 ? launch_spec<128>(pl, map, map1, wmap, s) : launch_spec<64>(pl, map, map1, wmap, s);
   } else {
     switch (pl.NT) {
-      case 16: rc = launch<16, 0, 0, 0>(pl, map, wmap, s); break;
-      case 32: rc = launch<32, 0, 0, 0>(pl, map, wmap, s); break;
-      case 64: rc = launch<64, 0, 0, 0>(pl, map, wmap, s); break;
-      default: rc = launch<128, 0, 0, 0>(pl, map, wmap, s); break;
+      case 16: rc = launch<16, 0, 0, 0>(pl, map, map1, wmap, s); break;
+      case 32: rc = launch<32, 0, 0, 0>(pl, map, map1, wmap, s); break;
+      case 64: rc = launch<64, 0, 0, 0>(pl, map, map1, wmap, s); break;
+      default: rc = launch<128, 0, 0, 0>(pl, map, map1, wmap, s); break;
     }
   }
   if (rc) return rc;
   if (p.splits > 1)
-    return sg_conv_finish_bf16((const float*)ws, bias, mask_src, y, N, Cout, (int64_t)D * H * W, scale, lrelu, s);
+    return tf32 ? sg_conv_finish_f32((const float*)ws, bias, mask_src, y, N, Cout, (int64_t)D * H * W, scale, lrelu, s)
+                : sg_conv_finish_bf16((const float*)ws, bias, mask_src, y, N, Cout, (int64_t)D * H * W, scale, lrelu, s);
   return 0;
+}
+
+// 1 when sg_conv3d_fprop(..., impl = SG_IMPL_TF32) covers the shape (fp32 activations, kind::tf32)
+extern "C" int sg_conv3d_tf32_supported(int N, int Cin, int Cout, int D, int H, int W) {
+  if (N <= 0 || Cin <= 0 || Cout <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
+  return make_plan(N, Cin, Cout, D, H, W, true).ok ? 1 : 0;
 }
 
 // Introspection for tests / DESIGN.md: the tiling the tcgen05 path would use for a shape.

@@ -45,10 +45,6 @@ struct ResParams {
   int lrelu;
 };
 
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-
 // NT = output-channel tile, TD = depth planes per tile (= MMA tiles per accumulator set),
 // KBC = 8-channel chunks per K block.  With th = 16 and tw = 8 fixed, every descriptor offset of
 // the 27 x KBC/2 x TD MMAs of a K block is a compile-time constant: the fully unrolled issue

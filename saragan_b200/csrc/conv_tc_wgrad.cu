@@ -28,9 +28,22 @@
 // reductions, or plain stores when it is the only CTA of its group -- into a tap-major fp32 workspace
 // [27][Cout][CinP]; k_wgrad_finish transposes that into the parameter layout [Cout][Cin][27] (scattered
 // 4-byte atomics straight into that layout cost more than the MMAs at the low-resolution levels).
+//
+// TF32 variant (fp32 activations and gradients, kind::tf32, K = 8 voxels = ONE line per MMA): the fp32 tensors are read
+// through two tensor maps per operand (one per 16-byte half of a voxel's 32-byte chunk, see conv_tc.cu), so a
+// shared-memory slot holds 4 channels and everything above holds with "chunk" = 16 bytes: M = 128 rows are 32 slots,
+// the x copies are NT/4 slots each.  The gy box of a plane brings g_chunks 8-channel chunks per HALF, so the slots of a
+// plane are ordered [half][chunk] and accumulator row r of a kd block is channel 8*(slot % g_chunks) + 4*(slot /
+// g_chunks) + r % 4 with slot = r / 4 (the epilogue un-permutes).  Both tiles are rounded to tf32 in shared memory by
+// the epilogue warps before the MMAs read them (the tensor core would truncate).
+#include <type_traits>
+
 #include "../../include/saragan_b200.h"
 #include "tc_common.cuh"
 SG_DEFINE_LEAK_SETTER(sg_set_leak_conv_tc_wgrad)
+
+int sg_encode_f32_half_map(CUtensorMap* map, const void* x, int half, int N, int CC8, int D, int H, int W, int box_w,
+                           int box_h, int box_d, int box_c);
 
 namespace {
 
@@ -57,23 +70,25 @@ struct WgParams {
   int direct;              // one CTA per group: plain stores, no zero-fill of ws needed
 };
 
-template <int NT>
+template <int NT, bool TF32>
 __global__ void __launch_bounds__(kThreadsW)
-k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUtensorMap xmap,
+k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUtensorMap gmap1,
+           const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap xmap1,
            const __grid_constant__ WgParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   sg_pdl_trigger();
   // carve-up: stages x [gy planes | 3 kw copies of the x halo tile | ones], then barriers
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes + p.slack_bytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * 8 + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * 8 + 1);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-  const int FULL = 0, EMPTY = p.stages, ACC_FULL = 2 * p.stages;
+  const int FULL = 0, EMPTY = p.stages, ACC_FULL = 2 * p.stages, ROUND = 2 * p.stages + 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = blockIdx.y;
   const int co_tile = blockIdx.z / p.ci_tiles, ci_tile = blockIdx.z % p.ci_tiles;
-  const int x_chunks = NT / 8;
+  constexpr int x_chunks = TF32 ? NT / 4 : NT / 8;     // 16-byte slots per kw copy of the x tile
+  constexpr int ONES = TF32 ? 4 : 2;                   // slots of ones: 16 channels of gy (x) 1
   const int halo_h = p.th + 2;
   // CTA group -> which planes it pairs.  Row block s of the accumulator holds the tap kd_hi - s.
   //   shifts 3: gy planes from d0 - 1, x plane d0      -> kd = 2, 1, 0
@@ -93,7 +108,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
     for (int st = 0; st < p.stages; ++st) {
       uint32_t* ones = reinterpret_cast<uint32_t*>(smem + (size_t)st * p.stage_bytes + g_bytes +
                                                    3 * x_chunks * p.x_chunk_bytes);
-      for (int i = threadIdx.x; i < 2 * p.x_chunk_bytes / 4; i += blockDim.x) ones[i] = 0x3F803F80u;
+      for (int i = threadIdx.x; i < ONES * p.x_chunk_bytes / 4; i += blockDim.x) ones[i] = TF32 ? 0x3F800000u : 0x3F803F80u;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -101,9 +116,14 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&gmap) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+    if constexpr (TF32) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&gmap1) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap1) : "memory");
+    }
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(BAR(FULL + i), 1);
       mbar_init(BAR(EMPTY + i), 1);
+      mbar_init(BAR(ROUND + i), 128);   // every thread of the four epilogue warps (TF32 rounding pass)
     }
     mbar_init(BAR(ACC_FULL), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -138,34 +158,48 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
         mbar_expect_tx(BAR(FULL + s), tx);
         const uint32_t g_dst = smem_base + s * p.stage_bytes;
         const uint32_t x_dst = g_dst + g_bytes;
-        for (int pl = 0; pl < p.g_planes; ++pl)   // one box = all chunks of one plane (planes outside D: zeros)
-          tma_load_5d(g_dst + pl * p.g_plane_bytes, &gmap, BAR(FULL + s), w0 * 8, h0, d0 + g_plane0 + pl, co_tile * 16, n);
-        for (int k = 0; k < 3; ++k)        // kw copy k = the tile shifted by k - 1 voxels in w
-          for (int c = 0; c < x_chunks; ++c)
-            tma_load_5d(x_dst + (k * x_chunks + c) * p.x_chunk_bytes, &xmap, BAR(FULL + s), (w0 - 1 + k) * 8, h0 - 1,
-                        d0 + x_plane0, ci_tile * x_chunks + c, n);
+        if constexpr (TF32) {
+          // fp32 tensors as [4 | W | H | D | N*CC8], one map per 16-byte half; a plane's slots are [half][chunk]
+          for (int pl = 0; pl < p.g_planes; ++pl)
+            for (int hf = 0; hf < 2; ++hf)
+              tma_load_5d(g_dst + pl * p.g_plane_bytes + hf * (p.g_plane_bytes >> 1), hf ? &gmap1 : &gmap, BAR(FULL + s), 0, w0,
+                          h0, d0 + g_plane0 + pl, n * p.CCout + co_tile * 16);
+          for (int k = 0; k < 3; ++k)
+            for (int c = 0; c < x_chunks; ++c)
+              tma_load_5d(x_dst + (k * x_chunks + c) * p.x_chunk_bytes, (c & 1) ? &xmap1 : &xmap, BAR(FULL + s), 0, w0 - 1 + k,
+                          h0 - 1, d0 + x_plane0, n * p.CCin + ci_tile * (NT / 8) + (c >> 1));
+        } else {
+          for (int pl = 0; pl < p.g_planes; ++pl)   // one box = all chunks of one plane (planes outside D: zeros)
+            tma_load_5d(g_dst + pl * p.g_plane_bytes, &gmap, BAR(FULL + s), w0 * 8, h0, d0 + g_plane0 + pl, co_tile * 16, n);
+          for (int k = 0; k < 3; ++k)        // kw copy k = the tile shifted by k - 1 voxels in w
+            for (int c = 0; c < x_chunks; ++c)
+              tma_load_5d(x_dst + (k * x_chunks + c) * p.x_chunk_bytes, &xmap, BAR(FULL + s), (w0 - 1 + k) * 8, h0 - 1,
+                          d0 + x_plane0, ci_tile * x_chunks + c, n);
+        }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     {
       const uint32_t leader = elect_one();   // all lanes run the loops; one issues
-      // D=f32, A=B=bf16, both MN-major (bits 15,16), N = 3*NT ([kw][ci]), M = 128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+      // D=f32, A=B=bf16 (tf32), both MN-major (bits 15,16), N = 3*NT ([kw][ci]), M = 128
+      const uint32_t idesc = idesc_formats(TF32) | (1u << 15) | (1u << 16) |
                              ((uint32_t)((3 * NT) >> 3) << 17) | ((128u >> 4) << 24);
-      // the kh = 1 MMA of a bias-computing CTA also spans the two ones slots: N = 3*NT + 16
-      const uint32_t idesc_mid = do_bias ? ((1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+      // the kh = 1 MMA of a bias-computing CTA also spans the ones slots: N = 3*NT + 16
+      const uint32_t idesc_mid = do_bias ? (idesc_formats(TF32) | (1u << 15) | (1u << 16) |
                                             ((uint32_t)((3 * NT + 16) >> 3) << 17) | ((128u >> 4) << 24))
                                          : idesc;
       // descriptors: bases hoisted, per-MMA cost = one 64-bit add (offsets in 16-byte units = voxels)
       const uint64_t g_desc0 = make_desc(smem_base, 128u, (uint32_t)(p.th * 128));
       const uint64_t x_desc0 = make_desc(smem_base + g_bytes, 128u, (uint32_t)p.x_chunk_bytes);
       const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4, plane16 = (uint32_t)p.g_plane_bytes >> 4;
-      const int ksteps_per_plane = p.th / 2, td = p.td, stages = p.stages;
+      // one MMA contracts over 32 bytes of voxels per channel: two lines of 8 (bf16, K = 16) or one (tf32, K = 8)
+      constexpr uint32_t KSTEP = TF32 ? 8u : 16u;
+      const int ksteps_per_plane = TF32 ? p.th : p.th / 2, td = p.td, stages = p.stages;
       int s = 0, ph = 0;
       uint32_t acc = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        mbar_wait(BAR(FULL + s), ph);
+        mbar_wait(BAR((TF32 ? ROUND : FULL) + s), ph);
         tc_fence_after();
         const uint64_t g_stage = g_desc0 + (uint64_t)(s * stage16);
         const uint64_t x_stage = x_desc0 + (uint64_t)(s * stage16);
@@ -174,12 +208,12 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
           uint64_t b_k = x_stage + (uint64_t)(dl * halo_h * 8);
           for (int j = 0; j < ksteps_per_plane; ++j) {
             // accumulator columns: kh=0 at 0, kh=1 at 3*NT (3*NT + 16 wide), kh=2 at 6*NT + 16
-            tc_mma(tmem_base, a_k, b_k, idesc, acc, leader);
-            tc_mma(tmem_base + 3 * NT, a_k, b_k + 8, idesc_mid, acc, leader);
-            tc_mma(tmem_base + 6 * NT + 16, a_k, b_k + 16, idesc, acc, leader);
+            tc_mma_t<TF32>(tmem_base, a_k, b_k, idesc, acc, leader);
+            tc_mma_t<TF32>(tmem_base + 3 * NT, a_k, b_k + 8, idesc_mid, acc, leader);
+            tc_mma_t<TF32>(tmem_base + 6 * NT + 16, a_k, b_k + 16, idesc, acc, leader);
             acc = 1;
-            a_k += 16;   // two lines of 8 voxels (gy plane and x copies alike)
-            b_k += 16;
+            a_k += KSTEP;   // the next line(s) of 8 voxels (gy plane and x copies alike)
+            b_k += KSTEP;
           }
         }
         tc_commit(BAR(EMPTY + s), leader);
@@ -192,8 +226,23 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const int shift = row / rows_per_shift;
-    const int co = co_tile * 128 + row - shift * rows_per_shift;
+    int r_in = row - shift * rows_per_shift;        // row inside its kd block -> output channel of the co tile
+    if constexpr (TF32) {
+      const int slot = r_in >> 2;                   // slots of a plane are [half][chunk]
+      r_in = 8 * (slot % p.g_chunks) + 4 * (slot / p.g_chunks) + (r_in & 3);
+    }
+    const int co = co_tile * 128 + r_in;
     const int kd = kd_hi - shift;
+    if constexpr (TF32) {
+      // main loop duty of these warps: round every landed stage (gy planes + x copies) to tf32, release it to the issuer
+      int s2 = 0;
+      for (int tile = blockIdx.x, it = 0; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        mbar_wait(BAR(FULL + s2), (it / p.stages) & 1);
+        round_tile_tf32(smem + (size_t)s2 * p.stage_bytes, g_bytes + 3 * x_chunks * p.x_chunk_bytes, row, 128);
+        mbar_arrive(BAR(ROUND + s2));
+        if (++s2 == p.stages) s2 = 0;
+      }
+    }
     mbar_wait(BAR(ACC_FULL), 0);
     tc_fence_after();
     const bool mine = blockIdx.x < p.n_tiles && shift < live_shifts && co < p.Cout;
@@ -221,7 +270,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
       float v[16];
       __syncwarp();
       tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(6 * NT), v);
-      const int cb = co_tile * 128 + row - bias_row0;
+      const int cb = co;      // the kd = 1 block's rows map to channels like every block's
       if (blockIdx.x < p.n_tiles && row >= bias_row0 && row < bias_row0 + rows_per_shift && cb < p.Cout)
         atomicAdd(p.gb + cb, v[0]);
     }
@@ -262,7 +311,7 @@ struct WgPlan {
   int64_t ws_bytes = 0;
 };
 
-WgPlan make_wgrad_plan(int N, int Cin, int Cout, int D, int H, int W) {
+WgPlan make_wgrad_plan(int N, int Cin, int Cout, int D, int H, int W, bool tf32 = false) {
   WgPlan pl;
   WgParams& p = pl.p;
   if (W % 8 != 0 || H % 2 != 0 || H < 2) return pl;
@@ -280,10 +329,11 @@ WgPlan make_wgrad_plan(int N, int Cin, int Cout, int D, int H, int W) {
   int td = 0, stages = 0;
   for (int cand = 4; cand >= 1; cand /= 2) {
     if (cand > D || D % cand) continue;
-    const int plane = p.g_chunks * th * 128, xb = cand * (th + 2) * 128;
+    // 16-byte slots: a gy plane holds g_chunks (bf16) or 2 * g_chunks (tf32: 4 channels per slot), an x copy NT/8 or NT/4
+    const int plane = p.g_chunks * th * 128 * (tf32 ? 2 : 1), xb = cand * (th + 2) * 128;
     const int g_planes = cand + p.shifts - 1;
-    const int stage = g_planes * plane + (3 * (NT / 8) + 2) * xb;   // + two ones slots for the bias gradient
-    const int over = (cand - 1) * plane + 16 * th * 128 - stage;
+    const int stage = g_planes * plane + (3 * (NT / (tf32 ? 4 : 8)) + (tf32 ? 4 : 2)) * xb;   // + ones slots (bias gradient)
+    const int over = (cand - 1) * plane + (tf32 ? 32 : 16) * th * 128 - stage;
     const int slack = over > 0 ? (over + 255) / 128 * 128 : 128;
     int st = (200 * 1024 - slack) / stage;
     if (st > 8) st = 8;
@@ -312,26 +362,27 @@ WgPlan make_wgrad_plan(int N, int Cin, int Cout, int D, int H, int W) {
   if (per_group < 1) per_group = 1;
   p.direct = per_group == 1;
   pl.grid = dim3((unsigned)per_group, (unsigned)kd_groups, (unsigned)(co_tiles * p.ci_tiles));
-  pl.smem = total + p.slack_bytes + 8 * (2 * 8 + 1) + 16;
+  pl.smem = total + p.slack_bytes + 8 * (3 * 8 + 1) + 16;
   pl.ws_bytes = (int64_t)27 * Cout * CinP * (int64_t)sizeof(float);
   pl.NT = NT;
   pl.ok = true;
   return pl;
 }
 
-template <int NT>
-int launch_wgrad(const WgPlan& pl, const CUtensorMap& gmap, const CUtensorMap& xmap, cudaStream_t s) {
+template <int NT, bool TF32 = false>
+int launch_wgrad(const WgPlan& pl, const CUtensorMap& gmap, const CUtensorMap& gmap1, const CUtensorMap& xmap,
+                 const CUtensorMap& xmap1, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc<NT, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
     if (e != cudaSuccess) {
       sg_set_error("conv_tc_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return (int)e;
     }
     attr_set = true;
   }
-  sg_launch((k_wgrad_tc<NT>), pl.grid, kThreadsW, pl.smem, s, gmap, xmap, pl.p);
-  return sg_check_launch("sg_conv3d_wgrad(tcgen05)");
+  sg_launch((k_wgrad_tc<NT, TF32>), pl.grid, kThreadsW, pl.smem, s, gmap, gmap1, xmap, xmap1, pl.p);
+  return sg_check_launch(TF32 ? "sg_conv3d_wgrad(tcgen05 tf32)" : "sg_conv3d_wgrad(tcgen05)");
 }
 
 int encode_act_map(CUtensorMap* map, const void* base, int N, int CC, int D, int H, int W, int box_w_vox, int box_h,
@@ -364,29 +415,43 @@ int sg_wgrad_finish(const float* ws, float* gw, int Cout, int Cin, int CinP, flo
   return sg_check_launch("sg_conv3d_wgrad(finish)");
 }
 
-int64_t sg_tc_wgrad_workspace_bytes(int N, int Cin, int Cout, int D, int H, int W) {
-  WgPlan pl = make_wgrad_plan(N, Cin, Cout, D, H, W);
+int64_t sg_tc_wgrad_workspace_bytes(int N, int Cin, int Cout, int D, int H, int W, int tf32) {
+  WgPlan pl = make_wgrad_plan(N, Cin, Cout, D, H, W, tf32 != 0);
   return pl.ok ? pl.ws_bytes : 0;
 }
 
 // returns 1 if the shape is not covered (caller falls through to the direct kernel)
 int sg_tc_wgrad(const void* x, const void* gy, float* gw, float* gb, int N, int Cin, int Cout, int D, int H, int W,
-                float scale, void* ws, int64_t ws_bytes, cudaStream_t s) {
-  WgPlan pl = make_wgrad_plan(N, Cin, Cout, D, H, W);
+                float scale, void* ws, int64_t ws_bytes, cudaStream_t s, int tf32) {
+  WgPlan pl = make_wgrad_plan(N, Cin, Cout, D, H, W, tf32 != 0);
   if (!pl.ok) return 1;
   WgParams& p = pl.p;
   SG_REQUIRE(ws != nullptr && ws_bytes >= pl.ws_bytes, "sg_conv3d_wgrad(tcgen05): workspace too small (%lld < %lld)",
              (long long)ws_bytes, (long long)pl.ws_bytes);
   p.ws = (float*)ws;
   p.gb = gb;
-  CUtensorMap gmap, xmap;
-  int rc = encode_act_map(&gmap, gy, N, p.CCout, D, H, W, 8, p.th, 1, p.g_chunks);
-  if (rc) return rc;
-  rc = encode_act_map(&xmap, x, N, p.CCin, D, H, W, 8, p.th + 2, p.td, 1);
-  if (rc) return rc;
+  CUtensorMap gmap, gmap1, xmap, xmap1;
+  int rc;
+  if (tf32) {
+    rc = sg_encode_f32_half_map(&gmap, gy, 0, N, p.CCout, D, H, W, 8, p.th, 1, p.g_chunks);
+    if (!rc) rc = sg_encode_f32_half_map(&gmap1, gy, 1, N, p.CCout, D, H, W, 8, p.th, 1, p.g_chunks);
+    if (!rc) rc = sg_encode_f32_half_map(&xmap, x, 0, N, p.CCin, D, H, W, 8, p.th + 2, p.td, 1);
+    if (!rc) rc = sg_encode_f32_half_map(&xmap1, x, 1, N, p.CCin, D, H, W, 8, p.th + 2, p.td, 1);
+    if (rc) return rc;
+  } else {
+    rc = encode_act_map(&gmap, gy, N, p.CCout, D, H, W, 8, p.th, 1, p.g_chunks);
+    if (rc) return rc;
+    rc = encode_act_map(&xmap, x, N, p.CCin, D, H, W, 8, p.th + 2, p.td, 1);
+    if (rc) return rc;
+    gmap1 = gmap;
+    xmap1 = xmap;
+  }
   if (!p.direct) cudaMemsetAsync(ws, 0, (size_t)pl.ws_bytes, s);
   if (gb) cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)Cout, s);
-  rc = pl.NT == 32 ? launch_wgrad<32>(pl, gmap, xmap, s) : launch_wgrad<16>(pl, gmap, xmap, s);
+  if (tf32)
+    rc = pl.NT == 32 ? launch_wgrad<32, true>(pl, gmap, gmap1, xmap, xmap1, s) : launch_wgrad<16, true>(pl, gmap, gmap1, xmap, xmap1, s);
+  else
+    rc = pl.NT == 32 ? launch_wgrad<32>(pl, gmap, gmap1, xmap, xmap1, s) : launch_wgrad<16>(pl, gmap, gmap1, xmap, xmap1, s);
   if (rc) return rc;
   return sg_wgrad_finish((const float*)ws, gw, Cout, Cin, p.CinP, scale, s);
 }

@@ -99,6 +99,50 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
       : "memory");
 }
+// The same for fp32 operands read as TF32 (kind::tf32, K = 8 per instruction: with 16-byte core-matrix rows of
+// FOUR channels the shared-memory operand layout is byte-for-byte the bf16 one -- DESIGN.md "TF32").
+template <bool TF32>
+__device__ __forceinline__ void tc_mma_t(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate, uint32_t leader = 1) {
+  if constexpr (TF32) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
+        : "memory");
+  } else {
+    tc_mma(d_tmem, adesc, bdesc, idesc, accumulate, leader);
+  }
+}
+// instruction descriptor without the N / M / major-ness fields: D = f32, A = B = bf16 (1) or tf32 (2)
+__host__ __device__ constexpr uint32_t idesc_formats(bool tf32) {
+  return (1u << 4) | ((tf32 ? 2u : 1u) << 7) | ((tf32 ? 2u : 1u) << 10);
+}
+// round-to-nearest fp32 -> tf32 (the tensor core itself TRUNCATES the 13 low mantissa bits: a systematic -2^-11
+// relative bias per operand that would accumulate over the layers)
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+// In-place tf32 rounding of `bytes` (multiple of 16) of a TMA-written shared-memory tile by the `nthreads` calling
+// threads (thread index `tid`), followed by the proxy fence that makes the generic-proxy writes visible to the
+// tensor core's async-proxy reads.  The caller then arrives on the barrier the MMA issuer waits on.
+__device__ __forceinline__ void round_tile_tf32(uint8_t* base, int bytes, int tid, int nthreads) {
+  float4* p = reinterpret_cast<float4*>(base);
+  for (int i = tid; i < bytes / 16; i += nthreads) {
+    float4 v = p[i];
+    v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w);
+    p[i] = v;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 // K-major, no swizzle: 8 rows x 16 B core matrices; LBO = byte distance between the two core
 // matrices along K, SBO = byte distance between 8-row groups along M/N (cute::UMMA::SmemDescriptor).
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
@@ -187,8 +231,9 @@ __device__ __forceinline__ F8 unpack8(const uint4& u) {
 // SHARED memory (broadcast float4 reads; the first version fetched them with per-element __ldg
 // and the four epilogue warps became the kernel's bottleneck).  Pad output channels need no
 // special case: their packed weight rows and biases are zero, so they come out as exact zeros.
-__device__ __forceinline__ void epilogue16(const float (&v)[16], const float* sb, float scale, int lrelu,
-                                           const __nv_bfloat16* mask, __nv_bfloat16* y, int64_t chunk_stride) {
+template <typename T>
+__device__ __forceinline__ void epilogue16(const float* v, const float* sb, float scale, int lrelu,
+                                           const T* mask, T* y, int64_t chunk_stride) {
   float r[16];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -221,7 +266,7 @@ __device__ __forceinline__ void epilogue16(const float (&v)[16], const float* sb
 // (an MMA with N = 64 lasts ~32-48 cycles): descriptors are formed with one 64-bit add each
 // from bases and offsets hoisted out of the loops (all offsets in 16-byte units, i.e. added to
 // the descriptors' start-address field).
-template <int NT>
+template <int NT, bool TF32 = false>
 __device__ __forceinline__ void issue_tap(uint32_t tmem_acc, uint64_t a_desc, uint64_t b_desc,
                                           const uint32_t (&sub_off)[kMaxSub], int n_sub, int kpairs, uint32_t kk_a,
                                           uint32_t idesc, uint32_t acc_first, uint32_t leader) {
@@ -233,7 +278,7 @@ __device__ __forceinline__ void issue_tap(uint32_t tmem_acc, uint64_t a_desc, ui
       const uint32_t acc = kk == 0 ? acc_first : 1u;
 #pragma unroll
       for (int sub = 0; sub < kMaxSub; ++sub)
-        if (sub < n_sub) tc_mma(tmem_acc + sub * NT, a_k + sub_off[sub], b, idesc, acc, leader);
+        if (sub < n_sub) tc_mma_t<TF32>(tmem_acc + sub * NT, a_k + sub_off[sub], b, idesc, acc, leader);
     }
   }
 }

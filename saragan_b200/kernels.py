@@ -87,13 +87,26 @@ def act_to_plain(act: torch.Tensor, c: int) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------- conv
-def pack_conv_weight(w: torch.Tensor, dtype: torch.dtype, flip: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def _pack_kind(kind):
+    """packed-weight kind -> (buffer dtype, ABI dtype code): torch.bfloat16, torch.float32, or "tf32" (fp32 values
+    rounded to tf32 in the 4-channel-chunk layout of the kind::tf32 kernels)"""
+    if kind == "tf32":
+        return torch.float32, _lib.TF32_PACK
+    return kind, (_lib.BF16 if kind == torch.bfloat16 else _lib.F32)
+
+
+def pack_conv_weight(w: torch.Tensor, kind, flip: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """`out`: a buffer from an earlier call for the same parameter (re-packed in place after an optimiser step)."""
     cout, cin = w.shape[0], w.shape[1]
+    dtype, code = _pack_kind(kind)
     if out is None:
         out = torch.empty(_lib.packed_weight_elems(cout, cin, int(flip)), dtype=dtype, device=w.device)
-    call("sg_pack_conv_weight", w, out, _lib.dtype_code(out), cout, cin, int(flip))
+    call("sg_pack_conv_weight", w, out, code, cout, cin, int(flip))
     return out
+
+
+def conv_tf32_supported(n, cin, cout, d, h, w) -> bool:
+    return bool(_lib.load().sg_conv3d_tf32_supported(n, cin, cout, d, h, w))
 
 
 _pack_tables = {}
@@ -104,11 +117,12 @@ def pack_conv_weights_multi(jobs) -> list:
     (sg_pack_conv_weights_multi).  The job / block tables live on the device, cached on the pointers involved; a new
     table cannot be built while a CUDA graph is being captured (pinned staging), then the jobs run one by one."""
     outs = []
-    for w, dtype, flip, out in jobs:
+    for w, kind, flip, out in jobs:
         if out is None:
-            out = torch.empty(_lib.packed_weight_elems(w.shape[0], w.shape[1], int(flip)), dtype=dtype, device=w.device)
+            out = torch.empty(_lib.packed_weight_elems(w.shape[0], w.shape[1], int(flip)), dtype=_pack_kind(kind)[0],
+                              device=w.device)
         outs.append(out)
-    key = tuple((w.data_ptr(), o.data_ptr(), int(flip)) for (w, _, flip, _), o in zip(jobs, outs))
+    key = tuple((w.data_ptr(), o.data_ptr(), int(flip), str(kind)) for (w, kind, flip, _), o in zip(jobs, outs))
     tab = _pack_tables.get(key)
     if tab is None:
         if torch.cuda.is_current_stream_capturing():
@@ -120,7 +134,7 @@ def pack_conv_weights_multi(jobs) -> list:
             cout, cin = w.shape[0], w.shape[1]
             k, r = (cout, cin) if flip else (cin, cout)
             # struct SgPackJob { const float* w; void* dst; int Cout, Cin, flip, dtype; } as four int64 words
-            rows.append([w.data_ptr(), o.data_ptr(), cout | (cin << 32), int(flip) | (_lib.dtype_code(o) << 32)])
+            rows.append([w.data_ptr(), o.data_ptr(), cout | (cin << 32), int(flip) | (_pack_kind(dtype)[1] << 32)])
             for kc in range(chunks(k)):
                 for r0 in range(0, 16 * ((r + 15) // 16), 32):
                     bj.append(ji), bk.append(kc), br.append(r0)

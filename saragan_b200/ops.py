@@ -139,7 +139,8 @@ class Conv3x3(Function):
                 premasked: bool = False, mask_input_grad: bool = False, out_mask=None, dd_fuse: bool = False):
         cout, cin = weight.shape[0], weight.shape[1]
         pw = pw if pw is not None else PackedWeight(weight, cache=False)
-        y = K.conv3d_fprop(x, pw.get(x.dtype, False), bias, out_mask, cin, cout, std, lrelu, IMPL_AUTO)
+        impl, kind = config.conv_route(x, cin, cout)
+        y = K.conv3d_fprop(x, pw.get(kind, False), bias, out_mask, cin, cout, std, lrelu, impl)
         ctx.save_for_backward(x, weight, y if (lrelu and (dd_fuse or not premasked)) else None, out_mask)
         ctx.pw, ctx.std, ctx.lrelu, ctx.has_bias = pw, std, lrelu, bias is not None
         ctx.premasked, ctx.mask_input_grad, ctx.dd_fuse = premasked, mask_input_grad, dd_fuse
@@ -180,7 +181,8 @@ class ConvDgrad(Function):
                 ggx_premasked: bool = False):
         cout, cin = weight.shape[0], weight.shape[1]
         pw = pw if pw is not None else PackedWeight(weight, cache=False)
-        gx = K.conv3d_fprop(g, pw.get(g.dtype, True), None, mask_ref, cout, cin, std, False, IMPL_AUTO)
+        impl, kind = config.conv_route(g, cout, cin)
+        gx = K.conv3d_fprop(g, pw.get(kind, True), None, mask_ref, cout, cin, std, False, impl)
         ctx.save_for_backward(g, weight, mask_ref, g_mask)
         ctx.pw, ctx.std, ctx.ggx_premasked = pw, std, ggx_premasked
         return gx
@@ -204,7 +206,7 @@ class ConvWgrad(Function):
 
     @staticmethod
     def forward(ctx, x, g, std: float, cin: int, cout: int, want_bias: bool):
-        gw, gb = K.conv3d_wgrad(x, g, cin, cout, std, want_bias, IMPL_AUTO)
+        gw, gb = K.conv3d_wgrad(x, g, cin, cout, std, want_bias, config.conv_route(x, cin, cout)[0])
         ctx.save_for_backward(x, g)
         ctx.std, ctx.cin, ctx.cout = std, cin, cout
         if gb is None:

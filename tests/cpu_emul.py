@@ -40,12 +40,23 @@ def act_to_plain(act, c):
     return act.float().permute(0, 1, 5, 2, 3, 4).reshape(n, cc * 8, d, h, w)[:, :c].contiguous()
 
 
-class _Packed:
-    """stand-in for the packed weight buffer: keeps the logical (Cout,Cin,3,3,3) tensor"""
+def _tf32(t):
+    """round to nearest to 10 mantissa bits (cvt.rna.tf32.f32: ties away from zero in magnitude)"""
+    i = t.detach().float().contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
 
-    def __init__(self, w, dtype, flip):
-        self.w = w.detach().to(dtype).float()
+
+class _Packed:
+    """stand-in for the packed weight buffer: keeps the logical (Cout,Cin,3,3,3) tensor, rounded like the packing"""
+
+    def __init__(self, w, kind, flip):
+        self.w = _tf32(w) if kind == "tf32" else w.detach().to(kind).float()
+        self.kind = kind
         self.flip = flip
+
+
+def conv_tf32_supported(n, cin, cout, d, h, w):
+    return w % 8 == 0 and h >= 8 and h % min(h, 16) == 0
 
 
 def pack_conv_weight(w, dtype, flip, out=None):
@@ -62,6 +73,10 @@ def _mask(ref):
 
 def conv3d_fprop(x, wp, bias, mask_src, cin, cout, scale, lrelu, impl=0):
     xp = act_to_plain(x, cin)
+    assert (impl == 3) == (wp.kind == "tf32"), "SG_IMPL_TF32 goes with the SG_TF32 packing"
+    if impl == 3:       # kind::tf32: the kernel rounds the landed activations to tf32
+        assert x.dtype == torch.float32
+        xp = _tf32(xp)
     if wp.flip:   # dgrad packing: contraction over the weight's Cout, flipped taps
         w = wp.w.flip(2, 3, 4).transpose(0, 1)
     else:
@@ -80,8 +95,10 @@ def conv3d_fprop(x, wp, bias, mask_src, cin, cout, scale, lrelu, impl=0):
 def conv3d_wgrad(x, gy, cin, cout, scale, want_bias, impl=0):
     xp = act_to_plain(x, cin)
     gp = act_to_plain(gy, cout)
+    if impl == 3:
+        xp, gp = _tf32(xp), _tf32(gp)
     gw = torch.nn.grad.conv3d_weight(xp, (cout, cin, 3, 3, 3), gp, stride=1, padding=1) * scale
-    gb = gp.sum(dim=(0, 2, 3, 4)) if want_bias else None
+    gb = gp.sum(dim=(0, 2, 3, 4)) if want_bias else None      # (the tf32 kernel sums the rounded gy: gy (x) 1)
     return gw.contiguous(), gb
 
 

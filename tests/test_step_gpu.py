@@ -1,13 +1,16 @@
 """Parity of the CUDA train step (through saragan_b200's public API, i.e. through the C ABI)
 against the golden fixtures minted from the unmodified reference and against the CPU oracle.
 
-Tolerances (BASELINE.json north_star): fp32 mode <= 1e-3 everywhere (TF32 tier); bf16 mode
-<= 2e-2 per layer, checked LAYER-LOCALLY (each block fed the oracle's input and upstream
-gradient).  End-to-end bf16 gradients of the whole step are additionally checked against a
-looser, explicitly stated bound: minibatch-stddev's group centring (network.py:127) turns the
-0.3 % activation rounding of the bf16 levels into several % of gradient error when the samples
-of a group are nearly identical, as they are for white-noise inputs at initialisation
-(DESIGN.md "Precision").
+Tolerances (BASELINE.json north_star): per-layer activation and gradient relative error <= 1e-3 for TF32
+and <= 2e-2 for BF16; the exact fp32 mode is held to 1e-3 on everything, elementwise.
+
+What "per layer" can mean for gradients (DESIGN.md "Precision", measured with tests/cpu_emul.py, i.e. independent of
+the CUDA kernels): every LINEAR layer (conv fprop / dgrad / wgrad, linear, 1x1x1, pool, up-sampling) meets the bound
+elementwise.  A LeakyReLU behind a reduced-precision convolution does not, for ANY implementation: a pre-activation
+within the forward rounding error of zero changes sign and its gradient changes 5x (slope 1 <-> 0.2) -- 0.24 % of the
+elements at bf16 (4-5 % norm-wise), 0.03 % at TF32 (1.4 %).  The layer-local test therefore checks blocks against the
+oracle evaluated AT THE CUDA PATH'S OWN MASKS (arithmetic: must meet the bound) and bounds the fraction of flipped masks
+separately; whole-step gradients are bounded as measured (median <= 2e-2 under the benchmarked policy).
 """
 import numpy as np
 import pytest
@@ -15,6 +18,7 @@ import torch
 
 import saragan_b200 as sg
 from oracle import pgan_oracle as O
+from saragan_b200 import ops
 from tests.util import build_pair, draw_inputs, golden_tensors, load_golden, rel_err, run_step
 
 pytestmark = pytest.mark.gpu
@@ -56,10 +60,15 @@ def test_golden_step_fp32(name):
             assert rel_err(got[k], v) < tol, (kind, k, rel_err(got[k], v))
 
 
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
 @pytest.mark.parametrize("name", ["tiny_p3", "tiny_p2_b8", "tiny_p1"])
-def test_golden_step_bf16(name):
+def test_golden_step_reduced_precision(name, precision):
+    """The benchmarked policy ('bf16': bf16 above 4x16x16, TF32 tensor cores up to there, exact fp32 at the base level)
+    and the all-TF32 mode against the reference goldens: losses to 2e-3, every parameter gradient elementwise --
+    median <= 2e-2 (north star), worst tensor <= 8e-2 (white-noise reals at initialisation: mask flips plus the
+    real/fake cancellation in d_loss; CPU emulation of the same rounding points: 1.4e-2 / 3.9e-2)."""
     z, cfg = load_golden(name)
-    with sg.use_precision("bf16"):
+    with sg.use_precision(precision):
         g, d = build_pair(cfg)
         out = run_step(g, d, _golden_inputs(z), cfg["alpha"])
     for k, tol in (("d_loss", 2e-3), ("gp", 2e-3)):
@@ -75,12 +84,12 @@ def test_golden_step_bf16(name):
             errs.append(rel_err(got, v))
             if v.numel() > 1:
                 coss.append(cosine(got, v))
-    # white-noise reals at init: the worst case for the mbstd amplification (see module doc)
-    assert np.median(errs) < 0.15 and max(errs) < 0.4, (np.median(errs), max(errs))
-    assert min(coss) > 0.95, min(coss)
+    print(f"\n[golden {name} {precision}] parameter gradients vs reference: median {np.median(errs):.3e} max {max(errs):.3e}")
+    assert np.median(errs) < 2e-2 and max(errs) < 8e-2, (np.median(errs), max(errs))
+    assert min(coss) > 0.995, min(coss)
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 0.35)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("tf32", 5e-2), ("bf16", 5e-2)])
 def test_cfg1_against_reference_scalars(precision, tol):
     """BASELINE cfg1 (xs, phase 3 of 6, 4x16x16, B=4): losses and every parameter-gradient norm
     of the reference run, weights re-drawn from the reference's RNG stream (seed 0)."""
@@ -155,8 +164,11 @@ def _layer_local(block_fn_oracle, module, x, c_out, precision, tol, gtol=None):
         params_c = [dict(module.named_parameters())[n] for n in block_fn_oracle.names]
         grads_c = torch.autograd.grad(yc, [xc] + params_c, gy.cuda())
     assert rel_err(yc, yo) < tol, ("activation", rel_err(yc, yo))
+    worst = 0.0
     for name, a, b in zip(["input"] + block_fn_oracle.names, grads_c, grads_o):
         assert rel_err(a, b) < gtol, (name, rel_err(a, b))
+        worst = max(worst, rel_err(a, b))
+    return rel_err(yc, yo), worst
 
 
 class _OracleBlock:
@@ -170,35 +182,76 @@ class _OracleBlock:
         return self.fn(self.sd, x)
 
 
-@pytest.mark.parametrize("precision,tol,gtol", [("fp32", 1e-3, 1e-3), ("bf16", 2e-2, 8e-2)])
-def test_layer_local_parity(precision, tol, gtol):
-    """BASELINE tolerance, per layer: activation and gradient relative error <= 1e-3 in fp32
-    (TF32 tier); bf16 activations <= 2e-2.  bf16 GRADIENTS of a block with LeakyReLU are bounded
-    by mask flips, not by arithmetic: a pre-activation within the 0.4 % bf16 forward error of
-    zero changes sign, which changes that element's gradient by 5x (slope 1 vs 0.2).  ~0.3 % of
-    the elements flip, giving sqrt(0.003)*0.8 = 4-5 % norm-wise error against an fp32 oracle for
-    ANY bf16 implementation (measured 4.9 % here); the bound is therefore 8e-2, and the
-    arithmetic itself is pinned to 3e-3 by the same-input kernel tests and by
-    test_step_bf16_matches_bf16_emulation."""
+def _masked_lrelu(a, y_cuda, flips):
+    """LeakyReLU of the oracle evaluated at the CUDA path's mask: a * m(sign of the CUDA activation); records the
+    fraction of elements whose mask differs from the oracle's own."""
+    m = torch.where(y_cuda > 0, 1.0, 0.2)
+    flips.append(float(((y_cuda > 0) != (a.detach() > 0)).float().mean()))
+    return a * m
+
+
+# precision, activation / gradient tolerance (north star), bound on the fraction of flipped LeakyReLU masks per layer
+@pytest.mark.parametrize("precision,tol,flip_max", [("fp32", 1e-3, 1e-5), ("tf32", 1e-3, 1.5e-3), ("bf16", 2e-2, 1e-2)])
+def test_layer_local_parity(precision, tol, flip_max):
+    """BASELINE tolerance per layer: activation and gradient relative error <= 1e-3 (TF32; also the exact fp32 mode)
+    and <= 2e-2 (bf16), each block fed the oracle's input and upstream gradient, at shapes above 4x16x16 so that the
+    'bf16' arm really runs the bf16 kernels.  Blocks with LeakyReLUs are compared against the oracle evaluated at the
+    CUDA path's own masks (see the module docstring); the masks themselves may differ from the oracle's only where
+    the pre-activation is within rounding of zero: their fraction is bounded per layer."""
+    torch.manual_seed(5)
+    names = ["conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias"]
+    report = {}
+
+    # ---- discriminator block 32 -> 64 at 8x16x16 (conv, lrelu, conv, lrelu, avg-pool)
+    dblk = sg.DiscriminatorBlock(32, 64).cuda()
+    x = torch.randn(2, 32, 8, 16, 16)
+    with sg.use_precision(precision), torch.no_grad():
+        xa = dblk.enter(x.cuda())
+        y1 = dblk.conv1(xa, lrelu=True)
+        y2 = dblk.conv2(y1, lrelu=True)
+        y1, y2 = dblk.leave(y1, 32).cpu(), dblk.leave(y2, 64).cpu()
+    flips = []
+    o = _OracleBlock(dblk, lambda p, x: O.pool2(_masked_lrelu(O.eq_conv3d(_masked_lrelu(O.eq_conv3d(
+        x, p["conv1.weight"], p["conv1.bias"], 1), y1, flips), p["conv2.weight"], p["conv2.bias"], 1), y2, flips)), names)
+    report["D block"] = _layer_local(o, dblk, x, 64, precision, tol) + (max(flips),)
+    assert max(flips) < flip_max, flips
+
+    # ---- generator block 64 -> 32 from 4x8x8 (up, conv, lrelu, pixel-norm, conv, pixel-norm, lrelu)
+    gblk = sg.GeneratorBlock(64, 32).cuda()
+    x = torch.randn(2, 64, 4, 8, 8)
+    with sg.use_precision(precision), torch.no_grad():
+        xa = ops.Up2.apply(gblk.enter(x.cuda()), 1.0, sg.config.act_dtype(8 * 16 * 16))
+        y1a = gblk.conv1(xa, lrelu=True)
+        y2a = gblk.cn(gblk.conv2(gblk.cn(y1a, channels=32)), channels=32)       # sign of what the last lrelu sees
+        y1, y2 = gblk.leave(y1a, 32).cpu(), gblk.leave(y2a, 32).cpu()
+    flips = []
+    o = _OracleBlock(gblk, lambda p, x: _masked_lrelu(O.pixel_norm(O.eq_conv3d(O.pixel_norm(_masked_lrelu(O.eq_conv3d(
+        O.up2(x), p["conv1.weight"], p["conv1.bias"], 1), y1, flips)), p["conv2.weight"], p["conv2.bias"], 1)), y2, flips), names)
+    report["G block"] = _layer_local(o, gblk, x, 32, precision, tol) + (max(flips),)
+    assert max(flips) < flip_max, flips
+
+    # ---- a bare convolution (linear: no masks involved) and a linear layer
+    conv = sg.EqualizedConv3d(48, 16, 3, padding=1).cuda()
+    o = _OracleBlock(conv, lambda p, x: O.eq_conv3d(x, p["weight"], p["bias"], 1), ["weight", "bias"])
+    report["conv 48->16"] = _layer_local(o, conv, torch.randn(1, 48, 4, 16, 32), 16, precision, tol)
+
+    lin = sg.EqualizedLinear(512, 64).cuda()
+    o = _OracleBlock(lin, lambda p, x: O.eq_linear(x, p["weight"], p["bias"]), ["weight", "bias"])
+    report["linear"] = _layer_local(o, lin, torch.randn(4, 512), 64, "fp32", 1e-3)
+    print(f"\n[layer-local {precision}] (activation err, worst gradient err[, flipped-mask fraction]): {report}")
+
+
+def test_own_mask_gap_is_the_mask_flips():
+    """The same D block against the PURE fp32 oracle (its own masks): the bf16 gradient error is the 4-5 % that mask
+    flips predict and sits far above the arithmetic error measured at equal masks -- kept as a measured fact."""
     torch.manual_seed(5)
     names = ["conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias"]
     dblk = sg.DiscriminatorBlock(32, 64).cuda()
     o = _OracleBlock(dblk, lambda p, x: O.pool2(O.lrelu(O.eq_conv3d(O.lrelu(O.eq_conv3d(
         x, p["conv1.weight"], p["conv1.bias"], 1)), p["conv2.weight"], p["conv2.bias"], 1))), names)
-    _layer_local(o, dblk, torch.randn(2, 32, 4, 16, 16), 64, precision, tol, gtol)
-
-    gblk = sg.GeneratorBlock(64, 32).cuda()
-    o = _OracleBlock(gblk, lambda p, x: O.lrelu(O.pixel_norm(O.eq_conv3d(O.pixel_norm(O.lrelu(O.eq_conv3d(
-        O.up2(x), p["conv1.weight"], p["conv1.bias"], 1))), p["conv2.weight"], p["conv2.bias"], 1))), names)
-    _layer_local(o, gblk, torch.randn(2, 64, 2, 8, 8), 32, precision, tol, gtol)
-
-    conv = sg.EqualizedConv3d(48, 16, 3, padding=1).cuda()
-    o = _OracleBlock(conv, lambda p, x: O.eq_conv3d(x, p["weight"], p["bias"], 1), ["weight", "bias"])
-    _layer_local(o, conv, torch.randn(3, 48, 2, 8, 16), 16, precision, tol)
-
-    lin = sg.EqualizedLinear(512, 64).cuda()
-    o = _OracleBlock(lin, lambda p, x: O.eq_linear(x, p["weight"], p["bias"]), ["weight", "bias"])
-    _layer_local(o, lin, torch.randn(4, 512), 64, "fp32", 1e-3)
+    act, worst = _layer_local(o, dblk, torch.randn(2, 32, 8, 16, 16), 64, "bf16", 2e-2, 8e-2)
+    print(f"\n[D block bf16 vs pure fp32 oracle] activation {act:.3e}, worst gradient {worst:.3e}")
+    assert worst > 1e-2
 
 
 def test_step_bf16_matches_bf16_emulation(monkeypatch):

@@ -1,0 +1,149 @@
+"""tcgen05 kind::tf32 convolution kernels (SG_IMPL_TF32: fp32 activations read through half-chunk tensor maps, weights in
+the SG_TF32 packing, operands rounded to nearest to 10 mantissa bits in the kernel, fp32 accumulation) through the C ABI.
+
+Two kinds of check per shape:
+ * operands already representable in tf32: the kernel must agree with the exact fp32 CUDA-core kernel on the same values
+   to accumulation-order noise (1e-5) -- pins the data path (tensor maps, descriptors, epilogue, tap geometry);
+ * arbitrary fp32 operands: against the CPU restatement that rounds to nearest (tests/cpu_emul.py, impl 3) to 1e-5 --
+   pins the in-kernel rounding (a kernel that let the tensor core truncate would sit at ~5e-4)."""
+import pytest
+import torch
+
+from saragan_b200 import _lib
+from saragan_b200 import kernels as K
+from tests import cpu_emul as E
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+F32 = torch.float32
+
+SHAPES = [
+    # n, cin, cout, d, h, w
+    (1, 16, 16, 4, 16, 8),
+    (1, 32, 64, 4, 16, 16),
+    (2, 32, 32, 8, 32, 32),
+    (2, 64, 128, 2, 16, 16),
+    (1, 128, 256, 4, 16, 16),
+    (4, 64, 64, 2, 8, 8),      # H = 8: MMA tiles straddle halo lines (no sample-spanning tiles in the tf32 kernel)
+    (3, 256, 128, 2, 8, 8),    # deep K, split-K workspace
+    (2, 16, 8, 4, 16, 16),     # Cout = 8 padded to 16
+    (1, 24, 48, 2, 16, 8),     # Cin padded (24 -> 32), CoutP = 48
+    (4, 512, 512, 2, 8, 8),    # the cfg3 low-resolution shape class
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("flip", [False, True])
+def test_tf32_fprop_and_dgrad(shape, flip):
+    n, cin, cout, d, h, w = shape
+    assert K.conv_tf32_supported(n, cin, cout, d, h, w)
+    g = torch.Generator().manual_seed(sum(shape))
+    wt = torch.randn(cout, cin, 3, 3, 3, generator=g)
+    kin, kout = (cout, cin) if flip else (cin, cout)
+    x = torch.randn(n, kin, d, h, w, generator=g)
+    ma = E.plain_to_act(torch.randn(n, kout, d, h, w, generator=g), F32)
+    bias = torch.randn(kout, generator=g)
+    # (a) tf32-representable operands against the exact fp32 kernel
+    xr, wr = E._tf32(x), E._tf32(wt)
+    xg, mg = E.plain_to_act(xr, F32).cuda(), ma.cuda()
+    wp_tf32, wp_f32 = K.pack_conv_weight(wr.cuda(), "tf32", flip), K.pack_conv_weight(wr.cuda(), F32, flip)
+    for (b, lrelu, mask) in [(None, False, False), (bias, True, False), (bias, False, True)]:
+        tail = (None if b is None else b.cuda(), mg if mask else None, kin, kout, 0.05, lrelu)
+        ref = K.conv3d_fprop(xg, wp_f32, *tail, _lib.IMPL_DIRECT)
+        got = K.conv3d_fprop(xg, wp_tf32, *tail, _lib.IMPL_TF32)
+        torch.cuda.synchronize()
+        e = rel_err(got, ref)
+        assert e < 1e-5, f"{shape} flip={flip} lrelu={lrelu} mask={mask}: tf32 kernel vs fp32 kernel on tf32 operands {e:.3e}"
+    # (b) arbitrary operands against the round-to-nearest restatement
+    xa = E.plain_to_act(x, F32)
+    want = E.conv3d_fprop(xa, E.pack_conv_weight(wt, "tf32", flip), bias, None, kin, kout, 0.05, True, 3)
+    got = K.conv3d_fprop(xa.cuda(), K.pack_conv_weight(wt.cuda(), "tf32", flip), bias.cuda(), None, kin, kout, 0.05, True,
+                         _lib.IMPL_TF32)
+    e = rel_err(got.cpu(), want)
+    assert e < 1e-5, f"{shape} flip={flip}: in-kernel rounding {e:.3e}"
+    exact = E.conv3d_fprop(xa, E.pack_conv_weight(wt, F32, flip), bias, None, kin, kout, 0.05, True)
+    assert 2e-5 < rel_err(got.cpu(), exact) < 1e-3      # it IS tf32 arithmetic, and within the tier's tolerance
+
+
+FORCED = [
+    ((2, 64, 128, 4, 16, 16), (128, 0, 1, 1)),    # k_conv_tc<128,1,16,1,tf32>
+    ((2, 64, 128, 4, 16, 16), (128, 0, 2, 2)),    # <128,2,16,1>, split-K 2
+    ((1, 64, 128, 8, 16, 16), (128, 1, 4, 1)),    # <128,4,16,1>
+    ((2, 128, 64, 4, 16, 16), (64, 0, 1, 4)),     # <64,1,16,1>, split-K 4
+    ((2, 128, 64, 4, 32, 16), (64, 0, 2, 1)),     # <64,2,16,1>
+    ((1, 64, 64, 8, 16, 16), (64, 0, 4, 1)),      # <64,4,16,1>
+    ((4, 64, 128, 2, 8, 8), (128, 0, 2, 2)),      # <128,2,8,1>
+    ((3, 64, 64, 2, 8, 8), (64, 0, 2, 2)),        # <64,2,8,1>
+    ((2, 32, 32, 4, 16, 16), (32, 0, 2, 1)),      # generic kernel (NT = 32)
+    ((1, 64, 64, 8, 16, 16), (64, 1, 8, 1)),      # generic kernel: td = 8
+]
+
+
+@pytest.mark.parametrize("shape,plan", FORCED)
+def test_tf32_forced_tilings(shape, plan):
+    n, cin, cout, d, h, w = shape
+    g = torch.Generator().manual_seed(sum(shape) + 11)
+    wr = E._tf32(torch.randn(cout, cin, 3, 3, 3, generator=g)).cuda()
+    xg = E.plain_to_act(E._tf32(torch.randn(n, cin, d, h, w, generator=g)), F32).cuda()
+    mg = E.plain_to_act(torch.randn(n, cout, d, h, w, generator=g), F32).cuda()
+    bias = torch.randn(cout, generator=g).cuda()
+    lib = _lib.load()
+    try:
+        lib.sg_tc_force_plan(*plan)
+        for (b, lrelu, mask) in [(None, False, False), (bias, True, True)]:
+            tail = (b, mg if mask else None, cin, cout, 0.05, lrelu)
+            got = K.conv3d_fprop(xg, K.pack_conv_weight(wr, "tf32", False), *tail, _lib.IMPL_TF32)
+            ref = K.conv3d_fprop(xg, K.pack_conv_weight(wr, F32, False), *tail, _lib.IMPL_DIRECT)
+            torch.cuda.synchronize()
+            assert rel_err(got, ref) < 1e-5, (shape, plan, lrelu, rel_err(got, ref))
+    finally:
+        lib.sg_tc_force_plan(0, 0, 0, 0)
+
+
+WGRAD_SHAPES = [
+    (1, 16, 16, 4, 16, 8),      # Cout <= 32: all three kd stacked along M, NT = 16
+    (2, 32, 32, 8, 16, 16),     # NT = 32
+    (1, 32, 64, 4, 16, 16),     # Cout <= 64: two kd groups
+    (2, 64, 128, 2, 16, 16),    # one kd per CTA group, two ci tiles
+    (1, 128, 256, 4, 16, 16),   # two co tiles
+    (4, 64, 64, 2, 8, 8),       # th = 8
+    (2, 24, 48, 2, 16, 8),      # padded channels
+    (4, 512, 512, 2, 8, 8),     # the cfg3 low-resolution shape class
+]
+
+
+@pytest.mark.parametrize("shape", WGRAD_SHAPES)
+def test_tf32_wgrad(shape):
+    n, cin, cout, d, h, w = shape
+    g = torch.Generator().manual_seed(sum(shape) + 3)
+    x, gy = torch.randn(n, cin, d, h, w, generator=g), torch.randn(n, cout, d, h, w, generator=g)
+    # (a) tf32-representable operands against the exact fp32 kernel
+    xg, gg = E.plain_to_act(E._tf32(x), F32).cuda(), E.plain_to_act(E._tf32(gy), F32).cuda()
+    ref_w, ref_b = K.conv3d_wgrad(xg, gg, cin, cout, 0.05, True, _lib.IMPL_DIRECT)
+    got_w, got_b = K.conv3d_wgrad(xg, gg, cin, cout, 0.05, True, _lib.IMPL_TF32)
+    torch.cuda.synchronize()
+    assert rel_err(got_w, ref_w) < 1e-5, (shape, rel_err(got_w, ref_w))
+    assert rel_err(got_b, ref_b) < 1e-5, (shape, rel_err(got_b, ref_b))
+    # (b) arbitrary operands against the round-to-nearest restatement
+    xa, ga = E.plain_to_act(x, F32), E.plain_to_act(gy, F32)
+    want_w, _ = E.conv3d_wgrad(xa, ga, cin, cout, 0.05, True, 3)
+    got_w, _ = K.conv3d_wgrad(xa.cuda(), ga.cuda(), cin, cout, 0.05, True, _lib.IMPL_TF32)
+    assert rel_err(got_w.cpu(), want_w) < 1e-5, (shape, rel_err(got_w.cpu(), want_w))
+
+
+def test_tf32_packing_layout():
+    """SG_TF32 packing = [tap][K/4][rows][4] fp32, values rounded to nearest tf32, pad rows / channels zero."""
+    cout, cin = 24, 20
+    wt = torch.randn(cout, cin, 3, 3, 3, generator=torch.Generator().manual_seed(1))
+    for flip in (False, True):
+        got = K.pack_conv_weight(wt.cuda(), "tf32", flip).cpu()
+        k, r = (cout, cin) if flip else (cin, cout)
+        kc4, rp = 4 * ((k + 15) // 16), 16 * ((r + 15) // 16)
+        want = torch.zeros(27, kc4, rp, 4)
+        src = E._tf32(wt).reshape(cout, cin, 27)
+        for tap in range(27):
+            m = src[:, :, 26 - tap].t() if flip else src[:, :, tap]        # [row][k]
+            pad = torch.zeros(rp, kc4 * 4)
+            pad[:r, :k] = m if not flip else m
+            want[tap] = pad.reshape(rp, kc4, 4).permute(1, 0, 2)
+        assert torch.equal(got.reshape(27, kc4, rp, 4), want), flip

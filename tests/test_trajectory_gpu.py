@@ -20,7 +20,9 @@ from tests import trajectory as T
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("precision,worst,median", [("fp32", 1e-4, 1e-5), ("bf16", 8e-2, 3e-2)])
+# teacher-forced bounds: north star "within 1 %" for the benchmarked policy and the TF32 mode (at 4x16x16 both run
+# TF32 tensor cores + the exact base level); the exact fp32 mode reproduces the oracle to rounding
+@pytest.mark.parametrize("precision,worst,median", [("fp32", 1e-4, 1e-5), ("tf32", 1e-2, 3e-3), ("bf16", 1e-2, 3e-3)])
 def test_100_step_trajectory(precision, worst, median):
     s = T.summarize(*T.run(precision, steps=100))
     print(precision, s)
@@ -30,3 +32,15 @@ def test_100_step_trajectory(precision, worst, median):
         assert v["free_running_range_norm"] < 0.3 and v["free_running_last10_range_norm"] < 0.15, (k, v)
     # the trajectory actually goes somewhere (a frozen model would pass everything above)
     assert s["gp"]["oracle_range"] > 2.0 and abs(s["g_loss"]["oracle_last"] - s["g_loss"]["oracle_first"]) > 1.0
+
+
+def test_100_step_trajectory_with_a_bf16_level():
+    """The same protocol one growth phase up (phase 4 of 4: 8x32x32, 16 -> 32 channels at the top), where the top
+    level of both networks runs the bf16 kernels under the benchmarked policy: teacher-forced, all three losses within
+    1 % at every one of the 100 steps."""
+    cfg = dict(T.CFG, phase=4)
+    s = T.summarize(*T.run("bf16", steps=100, cfg=cfg))
+    print("bf16 phase 4", s)
+    for k, v in s.items():
+        assert v["teacher_forced_rel"] < 1e-2 and v["teacher_forced_median_rel"] < 3e-3, (k, v)
+        assert v["free_running_range_norm"] < 0.3, (k, v)
