@@ -180,6 +180,12 @@ int sg_adam_step(const void* tensors, const int* block_tensor, const int64_t* bl
                  cudaStream_t stream);
 int sg_adam_advance(int* step, cudaStream_t stream);
 
+/* ---- gradient arena for the data-parallel exchange (main.py:147-160 hvd.DistributedOptimizer): dst = scale * src for
+ * every row { const float* src; float* dst; int64_t n; } of the device table `rows` in one launch; block b handles
+ * elements [block_offset[b], +1024) of row block_row[b].  The arena is what ncclAllReduce sums and sg_adam_step reads. */
+int sg_multi_copy_scale(const void* rows, const int* block_row, const int64_t* block_offset, int n_blocks, float scale,
+                        cudaStream_t stream);
+
 /* ---- input preparation (main.py:85-87 `np.load -> float32 / 1024`, train.py:144 `+ 0.01*randn`):
  * out = raw_u16 * scale + sigma * noise (noise nullable) */
 int sg_prepare_real(const void* raw_u16, const float* noise, float* out, int64_t n, float scale, float sigma,

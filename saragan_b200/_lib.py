@@ -68,6 +68,7 @@ SIGNATURES = {
     "sg_mbstd_bwdbwd": [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_p],
     "sg_adam_step": [_c_p, _c_p, _c_p, _c_int, _c_p, _c_f, _c_p, _c_f, _c_f, _c_f, _c_f, _c_p],
     "sg_adam_advance": [_c_p, _c_p],
+    "sg_multi_copy_scale": [_c_p, _c_p, _c_p, _c_int, _c_f, _c_p],
     "sg_prepare_real": [_c_p, _c_p, _c_p, _c_i64, _c_f, _c_f, _c_p],
     "sg_pyr_down": [_c_p, _c_p, _c_i64, _c_int, _c_int, _c_int, _c_p],
     "sg_pyr_up_sub": [_c_p, _c_p, _c_p, _c_i64, _c_int, _c_int, _c_int, _c_p],

@@ -218,3 +218,111 @@ class FlatAllReduce:
         flat.mul_(1.0 / self.world)
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
         GradBucketer._scatter(flat, grads)
+
+
+class ArenaAllReduce:
+    """Gradient averaging through ONE contiguous arena per network, capturable in a CUDA graph: a multi-tensor kernel
+    gathers the (1/world-scaled) gradients of the active parameters into the arena (`sg_multi_copy_scale`, one launch),
+    `ncclAllReduce` sums the arena in place, and the fused Adam reads its gradients straight from the arena
+    (`FusedAdam.step(grads=...)`) -- no torch.cat, no scaling pass, no scatter back into `p.grad`.
+
+        sync = ArenaAllReduce(generator, discriminator)
+        ... backward ...
+        grads = sync.reduce(discriminator)          # {param: arena view}; the all-reduce is enqueued on the current stream
+        d_optim.step(grads=grads)
+
+    The arena and its tables are (re)built when the set of parameters with gradients or their gradient buffers change
+    (never inside a capture: build once in the eager warm-up steps)."""
+
+    def __init__(self, generator, discriminator, comm_dtype: Optional[torch.dtype] = None):
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self._plans: Dict[int, dict] = {}
+        if comm_dtype is not None:
+            raise NotImplementedError("ArenaAllReduce exchanges fp32 gradients")
+        broadcast_parameters(generator)
+        broadcast_parameters(discriminator)
+
+    def arm(self, module) -> None:
+        pass
+
+    def reserve_capture_tables(self) -> None:
+        """Call right before capturing a step in a CUDA graph: inside the capture the gradient buffers are new, so the
+        copy table is rebuilt there from pinned host memory that must exist beforehand and outlive the graph (the
+        captured H2D copy re-reads it on every replay).  The arena itself -- and with it the Adam table -- is kept."""
+        for plan in self._plans.values():
+            if "rows" in plan:
+                plan["spare"] = dict(rows=torch.empty(tuple(plan["rows"].shape), dtype=torch.int64).pin_memory())
+
+    def _plan(self, module) -> dict:
+        params = [p for p in module.parameters() if p.grad is not None]
+        key = tuple((id(p), p.grad.data_ptr()) for p in params)
+        plan = self._plans.get(id(module))
+        if plan is not None and plan["key"] == key:
+            return plan
+        dev = params[0].device
+        capturing = dev.type == "cuda" and torch.cuda.is_current_stream_capturing()
+        if plan is not None and [id(p) for p in plan["params"]] == [id(p) for p in params] and "rows" in plan:
+            # same parameters, new gradient buffers: only the source pointers of the copy table change
+            src = torch.tensor([p.grad.data_ptr() for p in params], dtype=torch.int64)
+            if capturing:
+                spare = plan.pop("spare", None)
+                if spare is None:
+                    raise RuntimeError("ArenaAllReduce: call reserve_capture_tables() before capturing the step")
+                host = spare["rows"]
+                host.copy_(plan["rows_host"])
+                host[:, 0] = src
+                plan.setdefault("keepalive", []).append(host)
+            else:
+                host = plan["rows_host"].clone()
+                host[:, 0] = src
+                host = host.pin_memory()
+            plan["rows"] = host.to(dev, non_blocking=True)
+            plan["rows_host"], plan["key"] = host, key
+            return plan
+        if capturing:
+            raise RuntimeError("ArenaAllReduce: the set of parameters with gradients changed inside a CUDA-graph "
+                               "capture; run one eager step at this phase first")
+        sizes = [p.numel() for p in params]
+        # 16-byte aligned segments so that both the copy kernel and Adam use float4 accesses
+        offs, total = [], 0
+        for n in sizes:
+            offs.append(total)
+            total += (n + 3) // 4 * 4
+        arena = torch.zeros(total, dtype=torch.float32, device=dev)
+        views = {p: arena[o:o + n].view_as(p) for p, o, n in zip(params, offs, sizes)}
+        plan = dict(key=key, params=params, arena=arena, views=views)
+        if dev.type == "cuda":
+            rows, brow, boff = [], [], []
+            for ri, (p, o, n) in enumerate(zip(params, offs, sizes)):
+                rows.append([p.grad.data_ptr(), arena.data_ptr() + 4 * o, n])
+                for b in range(0, n, 1024):
+                    brow.append(ri), boff.append(b)
+            rows_host = torch.tensor(rows, dtype=torch.int64)
+            plan.update(rows_host=rows_host, rows=rows_host.to(dev), brow=torch.tensor(brow, dtype=torch.int32).to(dev),
+                        boff=torch.tensor(boff, dtype=torch.int64).to(dev), n_blocks=len(brow))
+        self._plans[id(module)] = plan
+        return plan
+
+    def reduce(self, module) -> Dict[torch.Tensor, torch.Tensor]:
+        """Pack, all-reduce (on the current stream), return {param: averaged gradient view}."""
+        plan = self._plan(module)
+        scale = 1.0 / self.world
+        if plan["arena"].is_cuda:
+            from ._lib import call
+            call("sg_multi_copy_scale", plan["rows"], plan["brow"], plan["boff"], plan["n_blocks"], float(scale))
+        else:
+            for p in plan["params"]:
+                plan["views"][p].copy_(p.grad * scale)
+        if self.world > 1:
+            dist.all_reduce(plan["arena"], op=dist.ReduceOp.SUM)
+        return plan["views"]
+
+    def finish(self, module) -> None:
+        """comm.DataParallel-compatible form: the averages end up in `p.grad` (one extra copy; the graph path uses
+        `reduce()` + `FusedAdam.step(grads=...)` instead)."""
+        views = self.reduce(module)
+        with torch.no_grad():
+            torch._foreach_copy_([p.grad for p in views], list(views.values()))
+
+    def finish_tensors(self, grads) -> None:
+        raise NotImplementedError("ArenaAllReduce works per module: use reduce(module)")

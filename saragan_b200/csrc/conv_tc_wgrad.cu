@@ -29,13 +29,15 @@
 // [27][Cout][CinP]; k_wgrad_finish transposes that into the parameter layout [Cout][Cin][27] (scattered
 // 4-byte atomics straight into that layout cost more than the MMAs at the low-resolution levels).
 //
-// TF32 variant (fp32 activations and gradients, kind::tf32, K = 8 voxels = ONE line per MMA): the fp32 tensors are read
-// through two tensor maps per operand (one per 16-byte half of a voxel's 32-byte chunk, see conv_tc.cu), so a
-// shared-memory slot holds 4 channels and everything above holds with "chunk" = 16 bytes: M = 128 rows are 32 slots,
-// the x copies are NT/4 slots each.  The gy box of a plane brings g_chunks 8-channel chunks per HALF, so the slots of a
-// plane are ordered [half][chunk] and accumulator row r of a kd block is channel 8*(slot % g_chunks) + 4*(slot /
-// g_chunks) + r % 4 with slot = r / 4 (the epilogue un-permutes).  Both tiles are rounded to tf32 in shared memory by
-// the epilogue warps before the MMAs read them (the tensor core would truncate).
+// SPLIT variant -- the weight gradient of the fp32 / TF32 levels.  tcgen05 kind::tf32 does not take MN-major operands
+// (tools/tf32_mn_probe.cu: an MN-major tf32 MMA returns zeros on B200, whatever the header comments of CUTLASS say), and
+// the voxel-contraction of a wgrad on this layout IS MN-major.  So the fp32 tensors are split into bf16 halves in
+// shared memory, x = hi + lo with hi = bf16(x), lo = bf16(x - hi), and the product is formed from three bf16 MMAs,
+//   gy (x) x  ~  g_hi (x) x_hi + g_lo (x) x_hi + g_hi (x) x_lo        (lo (x) lo ~ 2^-18 relative is dropped),
+// i.e. 16 mantissa bits per operand: more accurate than TF32's 10.  The fp32 tensors are read through two tensor maps
+// (one per 16-byte half of a voxel's 32-byte chunk, see conv_tc.cu) into two regions H0 / H1 of identical geometry;
+// the four epilogue warps, idle during the main loop, turn {H0, H1} = {channels 0-3, channels 4-7} of every voxel in
+// place into {H0, H1} = {hi, lo} of its 8 channels -- each then IS a bf16 tile of the layout described above.
 #include <type_traits>
 
 #include "../../include/saragan_b200.h"
@@ -70,7 +72,26 @@ struct WgParams {
   int direct;              // one CTA per group: plain stores, no zero-fill of ws needed
 };
 
-template <int NT, bool TF32>
+// in place: {h0[u], h1[u]} = fp32 channels {0-3, 4-7} of voxel u  ->  {bf16 hi, bf16 lo} of its 8 channels
+__device__ __forceinline__ void split_tile_bf16(uint8_t* h0, uint8_t* h1, int bytes, int tid, int nthreads) {
+  for (int u = tid; u < bytes / 16; u += nthreads) {
+    const float4 a = reinterpret_cast<const float4*>(h0)[u], b = reinterpret_cast<const float4*>(h1)[u];
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint4 hi, lo;
+    __nv_bfloat162* ph = reinterpret_cast<__nv_bfloat162*>(&hi);
+    __nv_bfloat162* pl = reinterpret_cast<__nv_bfloat162*>(&lo);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ph[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      const float2 f = __bfloat1622float2(ph[i]);
+      pl[i] = __floats2bfloat162_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+    }
+    reinterpret_cast<uint4*>(h0)[u] = hi;
+    reinterpret_cast<uint4*>(h1)[u] = lo;
+  }
+}
+
+template <int NT, bool SPLIT>
 __global__ void __launch_bounds__(kThreadsW)
 k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUtensorMap gmap1,
            const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap xmap1,
@@ -78,17 +99,17 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
   extern __shared__ __align__(128) uint8_t smem[];
   sg_pdl_trigger();
   // carve-up: stages x [gy planes | 3 kw copies of the x halo tile | ones], then barriers
+  // (SPLIT: stages x [gy H0 | gy H1 | x H0 | ones | x H1])
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes + p.slack_bytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * 8 + 1);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-  const int FULL = 0, EMPTY = p.stages, ACC_FULL = 2 * p.stages, ROUND = 2 * p.stages + 1;
+  const int FULL = 0, EMPTY = p.stages, ACC_FULL = 2 * p.stages, READY = 2 * p.stages + 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = blockIdx.y;
   const int co_tile = blockIdx.z / p.ci_tiles, ci_tile = blockIdx.z % p.ci_tiles;
-  constexpr int x_chunks = TF32 ? NT / 4 : NT / 8;     // 16-byte slots per kw copy of the x tile
-  constexpr int ONES = TF32 ? 4 : 2;                   // slots of ones: 16 channels of gy (x) 1
+  const int x_chunks = NT / 8;
   const int halo_h = p.th + 2;
   // CTA group -> which planes it pairs.  Row block s of the accumulator holds the tap kd_hi - s.
   //   shifts 3: gy planes from d0 - 1, x plane d0      -> kd = 2, 1, 0
@@ -102,13 +123,15 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
   // the row block whose gy plane is unshifted against its own voxels (kd = 1) carries the bias gradient
   const int bias_row0 = (kd_hi - 1) * rows_per_shift;
   const bool do_bias = p.gb != nullptr && ci_tile == 0 && kd_hi >= 1 && kd_hi - 1 < live_shifts;
-  const int g_bytes = p.g_planes * p.g_plane_bytes;
+  const int g_bytes = p.g_planes * p.g_plane_bytes;                  // one (bf16-sized) set of gy planes
+  const int xh_bytes = 3 * x_chunks * p.x_chunk_bytes;               // one set of the three x copies
+  const int x_off = SPLIT ? 2 * g_bytes : g_bytes;                   // x (H0) region of a stage, the ones slots behind it
+  const int xlo_off = x_off + xh_bytes + 2 * p.x_chunk_bytes;        // SPLIT: x H1 region
   if (do_bias) {
     // ones slots (bf16 1.0 = 0x3F80) behind the 3*x_chunks x slots of every stage; the TMA never writes them
     for (int st = 0; st < p.stages; ++st) {
-      uint32_t* ones = reinterpret_cast<uint32_t*>(smem + (size_t)st * p.stage_bytes + g_bytes +
-                                                   3 * x_chunks * p.x_chunk_bytes);
-      for (int i = threadIdx.x; i < ONES * p.x_chunk_bytes / 4; i += blockDim.x) ones[i] = TF32 ? 0x3F800000u : 0x3F803F80u;
+      uint32_t* ones = reinterpret_cast<uint32_t*>(smem + (size_t)st * p.stage_bytes + x_off + xh_bytes);
+      for (int i = threadIdx.x; i < 2 * p.x_chunk_bytes / 4; i += blockDim.x) ones[i] = 0x3F803F80u;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -116,14 +139,14 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&gmap) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
-    if constexpr (TF32) {
+    if constexpr (SPLIT) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&gmap1) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap1) : "memory");
     }
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(BAR(FULL + i), 1);
       mbar_init(BAR(EMPTY + i), 1);
-      mbar_init(BAR(ROUND + i), 128);   // every thread of the four epilogue warps (TF32 rounding pass)
+      mbar_init(BAR(READY + i), 128);   // SPLIT: every thread of the four epilogue warps after the hi/lo pass
     }
     mbar_init(BAR(ACC_FULL), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -144,7 +167,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
   if (warp == 0) {
     // ================================ producer ================================
     if (lane == 0) {
-      const uint32_t tx = (uint32_t)(g_bytes + 3 * x_chunks * p.x_chunk_bytes);
+      const uint32_t tx = (uint32_t)(g_bytes + xh_bytes) * (SPLIT ? 2u : 1u);
       int it = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
         int t = tile;
@@ -157,17 +180,18 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
         mbar_wait(BAR(EMPTY + s), ((it / p.stages) & 1) ^ 1);
         mbar_expect_tx(BAR(FULL + s), tx);
         const uint32_t g_dst = smem_base + s * p.stage_bytes;
-        const uint32_t x_dst = g_dst + g_bytes;
-        if constexpr (TF32) {
-          // fp32 tensors as [4 | W | H | D | N*CC8], one map per 16-byte half; a plane's slots are [half][chunk]
-          for (int pl = 0; pl < p.g_planes; ++pl)
-            for (int hf = 0; hf < 2; ++hf)
-              tma_load_5d(g_dst + pl * p.g_plane_bytes + hf * (p.g_plane_bytes >> 1), hf ? &gmap1 : &gmap, BAR(FULL + s), 0, w0,
-                          h0, d0 + g_plane0 + pl, n * p.CCout + co_tile * 16);
-          for (int k = 0; k < 3; ++k)
-            for (int c = 0; c < x_chunks; ++c)
-              tma_load_5d(x_dst + (k * x_chunks + c) * p.x_chunk_bytes, (c & 1) ? &xmap1 : &xmap, BAR(FULL + s), 0, w0 - 1 + k,
-                          h0 - 1, d0 + x_plane0, n * p.CCin + ci_tile * (NT / 8) + (c >> 1));
+        const uint32_t x_dst = g_dst + x_off;
+        if constexpr (SPLIT) {
+          // fp32 tensors as [4 | W | H | D | N*CC8], one map per 16-byte half of the voxels; H0 / H1 regions alike
+          for (int hf = 0; hf < 2; ++hf) {
+            for (int pl = 0; pl < p.g_planes; ++pl)
+              tma_load_5d(g_dst + hf * g_bytes + pl * p.g_plane_bytes, hf ? &gmap1 : &gmap, BAR(FULL + s), 0, w0, h0,
+                          d0 + g_plane0 + pl, n * p.CCout + co_tile * 16);
+            for (int k = 0; k < 3; ++k)
+              for (int c = 0; c < x_chunks; ++c)
+                tma_load_5d(g_dst + (hf ? xlo_off : x_off) + (k * x_chunks + c) * p.x_chunk_bytes, hf ? &xmap1 : &xmap,
+                            BAR(FULL + s), 0, w0 - 1 + k, h0 - 1, d0 + x_plane0, n * p.CCin + ci_tile * x_chunks + c);
+          }
         } else {
           for (int pl = 0; pl < p.g_planes; ++pl)   // one box = all chunks of one plane (planes outside D: zeros)
             tma_load_5d(g_dst + pl * p.g_plane_bytes, &gmap, BAR(FULL + s), w0 * 8, h0, d0 + g_plane0 + pl, co_tile * 16, n);
@@ -182,24 +206,23 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
     // ================================ MMA issuer ================================
     {
       const uint32_t leader = elect_one();   // all lanes run the loops; one issues
-      // D=f32, A=B=bf16 (tf32), both MN-major (bits 15,16), N = 3*NT ([kw][ci]), M = 128
-      const uint32_t idesc = idesc_formats(TF32) | (1u << 15) | (1u << 16) |
+      // D=f32, A=B=bf16, both MN-major (bits 15,16), N = 3*NT ([kw][ci]), M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)((3 * NT) >> 3) << 17) | ((128u >> 4) << 24);
-      // the kh = 1 MMA of a bias-computing CTA also spans the ones slots: N = 3*NT + 16
-      const uint32_t idesc_mid = do_bias ? (idesc_formats(TF32) | (1u << 15) | (1u << 16) |
+      // the kh = 1 MMA of a bias-computing CTA also spans the two ones slots: N = 3*NT + 16
+      const uint32_t idesc_mid = do_bias ? ((1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                                             ((uint32_t)((3 * NT + 16) >> 3) << 17) | ((128u >> 4) << 24))
                                          : idesc;
       // descriptors: bases hoisted, per-MMA cost = one 64-bit add (offsets in 16-byte units = voxels)
       const uint64_t g_desc0 = make_desc(smem_base, 128u, (uint32_t)(p.th * 128));
-      const uint64_t x_desc0 = make_desc(smem_base + g_bytes, 128u, (uint32_t)p.x_chunk_bytes);
+      const uint64_t x_desc0 = make_desc(smem_base + x_off, 128u, (uint32_t)p.x_chunk_bytes);
+      const uint32_t g_lo16 = (uint32_t)g_bytes >> 4, x_lo16 = (uint32_t)(xlo_off - x_off) >> 4;   // SPLIT: H1 regions
       const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4, plane16 = (uint32_t)p.g_plane_bytes >> 4;
-      // one MMA contracts over 32 bytes of voxels per channel: two lines of 8 (bf16, K = 16) or one (tf32, K = 8)
-      constexpr uint32_t KSTEP = TF32 ? 8u : 16u;
-      const int ksteps_per_plane = TF32 ? p.th : p.th / 2, td = p.td, stages = p.stages;
+      const int ksteps_per_plane = p.th / 2, td = p.td, stages = p.stages;
       int s = 0, ph = 0;
       uint32_t acc = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        mbar_wait(BAR((TF32 ? ROUND : FULL) + s), ph);
+        mbar_wait(BAR((SPLIT ? READY : FULL) + s), ph);
         tc_fence_after();
         const uint64_t g_stage = g_desc0 + (uint64_t)(s * stage16);
         const uint64_t x_stage = x_desc0 + (uint64_t)(s * stage16);
@@ -208,12 +231,22 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
           uint64_t b_k = x_stage + (uint64_t)(dl * halo_h * 8);
           for (int j = 0; j < ksteps_per_plane; ++j) {
             // accumulator columns: kh=0 at 0, kh=1 at 3*NT (3*NT + 16 wide), kh=2 at 6*NT + 16
-            tc_mma_t<TF32>(tmem_base, a_k, b_k, idesc, acc, leader);
-            tc_mma_t<TF32>(tmem_base + 3 * NT, a_k, b_k + 8, idesc_mid, acc, leader);
-            tc_mma_t<TF32>(tmem_base + 6 * NT + 16, a_k, b_k + 16, idesc, acc, leader);
+            tc_mma(tmem_base, a_k, b_k, idesc, acc, leader);
+            tc_mma(tmem_base + 3 * NT, a_k, b_k + 8, idesc_mid, acc, leader);
+            tc_mma(tmem_base + 6 * NT + 16, a_k, b_k + 16, idesc, acc, leader);
             acc = 1;
-            a_k += KSTEP;   // the next line(s) of 8 voxels (gy plane and x copies alike)
-            b_k += KSTEP;
+            if constexpr (SPLIT) {
+              // + g_lo (x) x_hi (the ones columns take g_lo too: bias = sum of hi + lo) + g_hi (x) x_lo
+              const uint64_t a_lo = a_k + g_lo16, b_lo = b_k + x_lo16;
+              tc_mma(tmem_base, a_lo, b_k, idesc, 1u, leader);
+              tc_mma(tmem_base + 3 * NT, a_lo, b_k + 8, idesc_mid, 1u, leader);
+              tc_mma(tmem_base + 6 * NT + 16, a_lo, b_k + 16, idesc, 1u, leader);
+              tc_mma(tmem_base, a_k, b_lo, idesc, 1u, leader);
+              tc_mma(tmem_base + 3 * NT, a_k, b_lo + 8, idesc, 1u, leader);
+              tc_mma(tmem_base + 6 * NT + 16, a_k, b_lo + 16, idesc, 1u, leader);
+            }
+            a_k += 16;   // two lines of 8 voxels (gy plane and x copies alike)
+            b_k += 16;
           }
         }
         tc_commit(BAR(EMPTY + s), leader);
@@ -226,20 +259,18 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const int shift = row / rows_per_shift;
-    int r_in = row - shift * rows_per_shift;        // row inside its kd block -> output channel of the co tile
-    if constexpr (TF32) {
-      const int slot = r_in >> 2;                   // slots of a plane are [half][chunk]
-      r_in = 8 * (slot % p.g_chunks) + 4 * (slot / p.g_chunks) + (r_in & 3);
-    }
-    const int co = co_tile * 128 + r_in;
+    const int co = co_tile * 128 + row - shift * rows_per_shift;
     const int kd = kd_hi - shift;
-    if constexpr (TF32) {
-      // main loop duty of these warps: round every landed stage (gy planes + x copies) to tf32, release it to the issuer
+    if constexpr (SPLIT) {
+      // main loop duty of these warps: the in-place fp32 -> bf16 hi/lo pass over every landed stage
       int s2 = 0;
       for (int tile = blockIdx.x, it = 0; tile < p.n_tiles; tile += gridDim.x, ++it) {
         mbar_wait(BAR(FULL + s2), (it / p.stages) & 1);
-        round_tile_tf32(smem + (size_t)s2 * p.stage_bytes, g_bytes + 3 * x_chunks * p.x_chunk_bytes, row, 128);
-        mbar_arrive(BAR(ROUND + s2));
+        uint8_t* st = smem + (size_t)s2 * p.stage_bytes;
+        split_tile_bf16(st, st + g_bytes, g_bytes, row, 128);
+        split_tile_bf16(st + x_off, st + xlo_off, xh_bytes, row, 128);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(BAR(READY + s2));
         if (++s2 == p.stages) s2 = 0;
       }
     }
@@ -270,7 +301,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
       float v[16];
       __syncwarp();
       tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(6 * NT), v);
-      const int cb = co;      // the kd = 1 block's rows map to channels like every block's
+      const int cb = co_tile * 128 + row - bias_row0;
       if (blockIdx.x < p.n_tiles && row >= bias_row0 && row < bias_row0 + rows_per_shift && cb < p.Cout)
         atomicAdd(p.gb + cb, v[0]);
     }
@@ -311,39 +342,43 @@ struct WgPlan {
   int64_t ws_bytes = 0;
 };
 
-WgPlan make_wgrad_plan(int N, int Cin, int Cout, int D, int H, int W, bool tf32 = false) {
+WgPlan make_wgrad_plan(int N, int Cin, int Cout, int D, int H, int W, bool split = false) {
   WgPlan pl;
   WgParams& p = pl.p;
   if (W % 8 != 0 || H % 2 != 0 || H < 2) return pl;
   const int CinP = 16 * ((Cin + 15) / 16), CoutP = 16 * ((Cout + 15) / 16);
-  const int NT = CinP % 32 == 0 ? 32 : 16;
-  int th = H < 16 ? H : 16;
-  if (H % th) return pl;
-  p.th = th;
   p.g_chunks = CoutP / 8 < 16 ? CoutP / 8 : 16;
   const int fit = 16 / p.g_chunks;            // row blocks of 8*g_chunks rows in M = 128
   p.shifts = fit >= 3 ? 3 : fit;
-  // td: as many planes per tile (4, 2, 1) as leave room for >= 2 pipeline stages.  The M = 128 operand
-  // reads 16 chunk strides from its plane on: past the gy planes these are garbage rows (discarded) read
-  // from the following bytes -- `slack` keeps those reads of the LAST stage inside the allocation.
-  int td = 0, stages = 0;
-  for (int cand = 4; cand >= 1; cand /= 2) {
-    if (cand > D || D % cand) continue;
-    // 16-byte slots: a gy plane holds g_chunks (bf16) or 2 * g_chunks (tf32: 4 channels per slot), an x copy NT/8 or NT/4
-    const int plane = p.g_chunks * th * 128 * (tf32 ? 2 : 1), xb = cand * (th + 2) * 128;
-    const int g_planes = cand + p.shifts - 1;
-    const int stage = g_planes * plane + (3 * (NT / (tf32 ? 4 : 8)) + (tf32 ? 4 : 2)) * xb;   // + ones slots (bias gradient)
-    const int over = (cand - 1) * plane + (tf32 ? 32 : 16) * th * 128 - stage;
-    const int slack = over > 0 ? (over + 255) / 128 * 128 : 128;
-    int st = (200 * 1024 - slack) / stage;
-    if (st > 8) st = 8;
-    if (st >= 2) {
-      td = cand; stages = st;
-      p.g_planes = g_planes; p.g_plane_bytes = plane; p.x_chunk_bytes = xb; p.stage_bytes = stage;
-      p.slack_bytes = slack;
-      break;
-    }
-  }
+  // Tile = td x th x 8 voxels, NT input channels per CTA: as many planes per tile (4, 2, 1) as leave room for >= 2
+  // pipeline stages.  The M = 128 operand reads 16 slot strides from its plane on: past the gy planes these are
+  // garbage rows (discarded) read from the following bytes -- `slack` keeps those reads of the LAST stage inside the
+  // allocation.  The SPLIT stages hold every tile twice (H0 / H1): they may fall back to th = 8 and NT = 16.
+  int td = 0, stages = 0, NT = 0, th = 0;
+  const int th_max = H < 16 ? H : 16;
+  if (H % th_max) return pl;
+  const int th_cands[2] = {th_max, (split && th_max > 8) ? 8 : 0};
+  const int nt_cands[2] = {CinP % 32 == 0 ? 32 : 16, (split && CinP % 32 == 0) ? 16 : 0};
+  for (int ti = 0; ti < 2 && td == 0; ++ti)
+    for (int ni = 0; ni < 2 && td == 0; ++ni)
+      for (int cand = 4; cand >= 1 && td == 0; cand /= 2) {
+        const int th_c = th_cands[ti], nt_c = nt_cands[ni];
+        if (th_c == 0 || nt_c == 0 || H % th_c || cand > D || D % cand) continue;
+        const int plane = p.g_chunks * th_c * 128, xb = cand * (th_c + 2) * 128;
+        const int g_planes = cand + p.shifts - 1;
+        // [gy | x copies | two ones slots]  /  SPLIT: [gy H0 | gy H1 | x H0 | ones | x H1]
+        const int stage = (split ? 2 : 1) * g_planes * plane + ((split ? 6 : 3) * (nt_c / 8) + 2) * xb;
+        const int over = (split ? g_planes * plane : 0) + (cand - 1) * plane + 16 * th_c * 128 - stage;
+        const int slack = over > 0 ? (over + 255) / 128 * 128 : 128;
+        int st = (200 * 1024 - slack) / stage;
+        if (st > 8) st = 8;
+        if (st >= 2) {
+          td = cand; stages = st; NT = nt_c; th = th_c;
+          p.g_planes = g_planes; p.g_plane_bytes = plane; p.x_chunk_bytes = xb; p.stage_bytes = stage;
+          p.slack_bytes = slack;
+        }
+      }
+  p.th = th;
   if (td == 0) return pl;
   p.td = td;
   size_t total = (size_t)stages * p.stage_bytes;
@@ -369,20 +404,20 @@ WgPlan make_wgrad_plan(int N, int Cin, int Cout, int D, int H, int W, bool tf32 
   return pl;
 }
 
-template <int NT, bool TF32 = false>
+template <int NT, bool SPLIT = false>
 int launch_wgrad(const WgPlan& pl, const CUtensorMap& gmap, const CUtensorMap& gmap1, const CUtensorMap& xmap,
                  const CUtensorMap& xmap1, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc<NT, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc<NT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
     if (e != cudaSuccess) {
       sg_set_error("conv_tc_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return (int)e;
     }
     attr_set = true;
   }
-  sg_launch((k_wgrad_tc<NT, TF32>), pl.grid, kThreadsW, pl.smem, s, gmap, gmap1, xmap, xmap1, pl.p);
-  return sg_check_launch(TF32 ? "sg_conv3d_wgrad(tcgen05 tf32)" : "sg_conv3d_wgrad(tcgen05)");
+  sg_launch((k_wgrad_tc<NT, SPLIT>), pl.grid, kThreadsW, pl.smem, s, gmap, gmap1, xmap, xmap1, pl.p);
+  return sg_check_launch(SPLIT ? "sg_conv3d_wgrad(tcgen05 split-bf16)" : "sg_conv3d_wgrad(tcgen05)");
 }
 
 int encode_act_map(CUtensorMap* map, const void* base, int N, int CC, int D, int H, int W, int box_w_vox, int box_h,
@@ -415,15 +450,16 @@ int sg_wgrad_finish(const float* ws, float* gw, int Cout, int Cin, int CinP, flo
   return sg_check_launch("sg_conv3d_wgrad(finish)");
 }
 
-int64_t sg_tc_wgrad_workspace_bytes(int N, int Cin, int Cout, int D, int H, int W, int tf32) {
-  WgPlan pl = make_wgrad_plan(N, Cin, Cout, D, H, W, tf32 != 0);
+int64_t sg_tc_wgrad_workspace_bytes(int N, int Cin, int Cout, int D, int H, int W, int f32) {
+  WgPlan pl = make_wgrad_plan(N, Cin, Cout, D, H, W, f32 != 0);
   return pl.ok ? pl.ws_bytes : 0;
 }
 
-// returns 1 if the shape is not covered (caller falls through to the direct kernel)
+// returns 1 if the shape is not covered (caller falls through to the direct kernel).  f32 != 0: x and gy are fp32
+// acts (the SPLIT kernel: bf16 hi/lo halves formed in shared memory, three bf16 MMAs per product)
 int sg_tc_wgrad(const void* x, const void* gy, float* gw, float* gb, int N, int Cin, int Cout, int D, int H, int W,
-                float scale, void* ws, int64_t ws_bytes, cudaStream_t s, int tf32) {
-  WgPlan pl = make_wgrad_plan(N, Cin, Cout, D, H, W, tf32 != 0);
+                float scale, void* ws, int64_t ws_bytes, cudaStream_t s, int f32) {
+  WgPlan pl = make_wgrad_plan(N, Cin, Cout, D, H, W, f32 != 0);
   if (!pl.ok) return 1;
   WgParams& p = pl.p;
   SG_REQUIRE(ws != nullptr && ws_bytes >= pl.ws_bytes, "sg_conv3d_wgrad(tcgen05): workspace too small (%lld < %lld)",
@@ -432,7 +468,7 @@ int sg_tc_wgrad(const void* x, const void* gy, float* gw, float* gb, int N, int 
   p.gb = gb;
   CUtensorMap gmap, gmap1, xmap, xmap1;
   int rc;
-  if (tf32) {
+  if (f32) {
     rc = sg_encode_f32_half_map(&gmap, gy, 0, N, p.CCout, D, H, W, 8, p.th, 1, p.g_chunks);
     if (!rc) rc = sg_encode_f32_half_map(&gmap1, gy, 1, N, p.CCout, D, H, W, 8, p.th, 1, p.g_chunks);
     if (!rc) rc = sg_encode_f32_half_map(&xmap, x, 0, N, p.CCin, D, H, W, 8, p.th + 2, p.td, 1);
@@ -448,7 +484,7 @@ int sg_tc_wgrad(const void* x, const void* gy, float* gw, float* gb, int N, int 
   }
   if (!p.direct) cudaMemsetAsync(ws, 0, (size_t)pl.ws_bytes, s);
   if (gb) cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)Cout, s);
-  if (tf32)
+  if (f32)
     rc = pl.NT == 32 ? launch_wgrad<32, true>(pl, gmap, gmap1, xmap, xmap1, s) : launch_wgrad<16, true>(pl, gmap, gmap1, xmap, xmap1, s);
   else
     rc = pl.NT == 32 ? launch_wgrad<32>(pl, gmap, gmap1, xmap, xmap1, s) : launch_wgrad<16>(pl, gmap, gmap1, xmap, xmap1, s);

@@ -976,6 +976,37 @@ extern "C" int sg_adam_advance(int* step, cudaStream_t s) {
   return sg_check_launch("sg_adam_advance");
 }
 
+// ------------------------------------------------- gradient arena packing (data-parallel exchange)
+// dst[i] = scale * src[i] for every (src, dst, n) row of a device table in ONE launch: the gradients of a network's
+// active parameters gathered into the contiguous arena that ncclAllReduce sums (scale = 1 / world) and that the fused
+// Adam then reads directly -- replaces torch.cat + mul_ + _foreach_copy_ around the all-reduce (main.py:147-160's
+// hvd.DistributedOptimizer).  block b copies elements [block_offset[b], +1024) of row block_row[b].
+struct SgCopyRow {
+  const float* src;
+  float* dst;
+  int64_t n;
+};
+__global__ void __launch_bounds__(256)
+k_multi_copy_scale(const SgCopyRow* __restrict__ rows, const int* __restrict__ block_row,
+                   const int64_t* __restrict__ block_offset, float scale) {
+  sg_pdl_enter();
+  const SgCopyRow r = rows[block_row[blockIdx.x]];
+  const int64_t i = block_offset[blockIdx.x] + 4 * (int64_t)threadIdx.x;
+  if (((((uintptr_t)r.src) | ((uintptr_t)r.dst)) & 15) == 0 && i + 3 < r.n) {
+    float4 v = *reinterpret_cast<const float4*>(r.src + i);
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    *reinterpret_cast<float4*>(r.dst + i) = v;
+  } else {
+    for (int k = 0; k < 4 && i + k < r.n; ++k) r.dst[i + k] = scale * r.src[i + k];
+  }
+}
+extern "C" int sg_multi_copy_scale(const void* rows, const int* block_row, const int64_t* block_offset, int n_blocks,
+                                   float scale, cudaStream_t s) {
+  if (n_blocks == 0) return 0;
+  sg_launch((k_multi_copy_scale), (unsigned)n_blocks, 256, 0, s, (const SgCopyRow*)rows, block_row, block_offset, scale);
+  return sg_check_launch("sg_multi_copy_scale");
+}
+
 // --------------------------------------------------------------- input preparation
 // main.py:85-87 loader (`np.load -> float32 -> [None] / 1024`) + train.py:144 instance noise in one
 // pass over the raw uint16 voxels: out = raw * scale + sigma * noise.

@@ -136,10 +136,22 @@ class GraphedTrainStep:
         from . import _lib
         n0 = _lib.launch_count()
         f0 = int(_lib.load().sg_cuda_core_fallbacks(0))
+        if hasattr(grad_sync, "reserve_capture_tables"):
+            grad_sync.reserve_capture_tables()
         if grad_sync is None:
             with torch.cuda.graph(self.graph):
                 self.out = self._step()
             self.segments = None
+        elif hasattr(grad_sync, "reduce"):
+            # several GPUs, gradient arena (comm.ArenaAllReduce): ONE graph with the NCCL all-reduces inside.  The D
+            # gradients' all-reduce is a fork of the graph that runs beside the G update's generator forward; only
+            # the G gradients' all-reduce (and two pack kernels) sit on the critical path.  NCCL's watchdog thread
+            # polls CUDA events while we capture: capture_error_mode="thread_local" keeps its calls out of our capture.
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                self.out = self._step()
+            self.segments = None
+            self.launch_desc = ("one cuda-graph replay per step with the NCCL all-reduces captured inside (D-gradient "
+                                "all-reduce forked beside the generator forward; gradient arena read by the fused Adam)")
         else:
             # several GPUs: the gradient all-reduce runs EAGERLY between graph segments
             #   g1: D forward/backward | g2a: the G update's generator forward | g2b: D update + D(fakes) +

@@ -54,8 +54,9 @@ class FusedAdam(torch.optim.Optimizer):
             st["ema"] = p.detach().clone() if self.ema_beta is not None else None
         return st
 
-    def _table(self, gi: int, params, beta1: float) -> dict:
-        key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in params)
+    def _table(self, gi: int, params, beta1: float, grads=None) -> dict:
+        gof = (lambda p: p.grad) if grads is None else (lambda p: grads[p])
+        key = tuple((p.data_ptr(), gof(p).data_ptr()) for p in params)
         tab = self._tables.get(gi)
         if tab is not None and tab["key"] == key:
             return tab
@@ -63,9 +64,9 @@ class FusedAdam(torch.optim.Optimizer):
         rows, block_tensor, block_offset = [], [], []
         for ti, p in enumerate(params):
             st = self._state_for(p, beta1)
-            if not (p.is_contiguous() and p.grad.is_contiguous() and p.dtype == torch.float32):
+            if not (p.is_contiguous() and gof(p).is_contiguous() and p.dtype == torch.float32):
                 raise RuntimeError("FusedAdam needs contiguous fp32 parameters and gradients")
-            rows.append([p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr() if st["exp_avg"] is not None else 0,
+            rows.append([p.data_ptr(), gof(p).data_ptr(), st["exp_avg"].data_ptr() if st["exp_avg"] is not None else 0,
                          st["exp_avg_sq"].data_ptr(), st["ema"].data_ptr() if st["ema"] is not None else 0, p.numel()])
             for off in range(0, p.numel(), _CHUNK):
                 block_tensor.append(ti)
@@ -107,11 +108,13 @@ class FusedAdam(torch.optim.Optimizer):
                     self._step_dev = torch.zeros(4, dtype=torch.int32, device=p.device)
 
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, grads=None):
+        """grads (optional): {parameter: gradient tensor} to use instead of `p.grad` -- the views of the all-reduced
+        gradient arena of comm.ArenaAllReduce (no copy back into `p.grad`)."""
         assert closure is None
         first = None
         for gi, group in enumerate(self.param_groups):
-            params = [p for p in group["params"] if p.grad is not None]
+            params = [p for p in group["params"] if (p.grad is not None if grads is None else p in grads)]
             if not params:
                 continue
             first = params[0]
@@ -119,7 +122,7 @@ class FusedAdam(torch.optim.Optimizer):
                 self._step_dev = torch.full((4,), int(getattr(self, "_pending_step", 0)), dtype=torch.int32,
                                             device=first.device)
             beta1, beta2 = group["betas"]
-            tab = self._table(gi, params, beta1)
+            tab = self._table(gi, params, beta1, grads)
             lr_dev = None
             if self.lr_on_device:
                 if gi not in self._lr_dev:

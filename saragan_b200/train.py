@@ -74,7 +74,8 @@ def d_phase(x_real: torch.Tensor, generator, discriminator, discriminator_optim,
     # (A layer's FIRST packing happens lazily at its first use and is cached: on a fresh network -- first step,
     # after grow() -- that would be on whichever stream gets there first while the other stream reads the same
     # buffer un-ordered, so that one pass stays on a single stream.)
-    two_streams = overlap_gp and x_real.is_cuda and grad_sync is None and ops.packs_settled(discriminator)
+    hooked = grad_sync is not None and not hasattr(grad_sync, "reduce")      # hook-driven bucketing needs one stream
+    two_streams = overlap_gp and x_real.is_cuda and not hooked and ops.packs_settled(discriminator)
     if two_streams:
         d_params = [p for p in discriminator.parameters() if p.requires_grad]
         main, side = torch.cuda.current_stream(dev), _side_stream(dev)
@@ -149,15 +150,40 @@ def train_step(x_real: torch.Tensor, generator, discriminator, generator_optim, 
     reference: hvd.DistributedOptimizer, main.py:153-160)."""
     out = d_phase(x_real, generator, discriminator, discriminator_optim, alpha, noise=noise, z_d=z_d, eps=eps,
                   grad_sync=grad_sync, overlap_gp=overlap_gp)
-    if grad_sync is not None:
-        grad_sync.finish(discriminator)
-    if apply:
-        discriminator_optim.step()
-    g = g_phase(x_real.shape[0], generator, discriminator, generator_optim, alpha, z_g=z_g, grad_sync=grad_sync)
-    if grad_sync is not None:
-        grad_sync.finish(generator)
-    if apply:
-        generator_optim.step()
+    if hasattr(grad_sync, "reduce") and hasattr(discriminator_optim, "ema_state"):
+        # gradient arena + fused Adam (comm.ArenaAllReduce): the D gradients are averaged on a second stream WHILE the
+        # generator forward of the G update runs (it needs nothing the D update changes); Adam reads the arena
+        dev = discriminator.device
+        if z_g is None:
+            z_g = torch.randn(x_real.shape[0], generator.latent_dim)
+        if dev.type == "cuda":
+            main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                d_grads = grad_sync.reduce(discriminator)
+        else:
+            d_grads = grad_sync.reduce(discriminator)
+        generator.train()
+        _set_requires_grad(generator, True)
+        x_fake_g = top_image(generator(z_g, alpha))
+        if dev.type == "cuda":
+            main.wait_stream(side)
+        if apply:
+            discriminator_optim.step(grads=d_grads)
+        g = g_phase(x_real.shape[0], generator, discriminator, generator_optim, alpha, z_g=z_g, x_fake=x_fake_g)
+        g_grads = grad_sync.reduce(generator)
+        if apply:
+            generator_optim.step(grads=g_grads)
+    else:
+        if grad_sync is not None:
+            grad_sync.finish(discriminator)
+        if apply:
+            discriminator_optim.step()
+        g = g_phase(x_real.shape[0], generator, discriminator, generator_optim, alpha, z_g=z_g, grad_sync=grad_sync)
+        if grad_sync is not None:
+            grad_sync.finish(generator)
+        if apply:
+            generator_optim.step()
     out["g_loss"] = g["g_loss"]
     out["distance"] = out["d_real_mean"] - g["d_fake_mean"]
     out["x_fake"] = g["x_fake"]

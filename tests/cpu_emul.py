@@ -95,10 +95,16 @@ def conv3d_fprop(x, wp, bias, mask_src, cin, cout, scale, lrelu, impl=0):
 def conv3d_wgrad(x, gy, cin, cout, scale, want_bias, impl=0):
     xp = act_to_plain(x, cin)
     gp = act_to_plain(gy, cout)
+    wg = lambda a, b: torch.nn.grad.conv3d_weight(a, (cout, cin, 3, 3, 3), b, stride=1, padding=1)     # noqa: E731
     if impl == 3:
-        xp, gp = _tf32(xp), _tf32(gp)
-    gw = torch.nn.grad.conv3d_weight(xp, (cout, cin, 3, 3, 3), gp, stride=1, padding=1) * scale
-    gb = gp.sum(dim=(0, 2, 3, 4)) if want_bias else None      # (the tf32 kernel sums the rounded gy: gy (x) 1)
+        # the fp32 levels' tensor-core wgrad: bf16 hi/lo halves, g (x) x ~ (g_hi + g_lo) (x) x_hi + g_hi (x) x_lo
+        x_hi, g_hi = xp.bfloat16().float(), gp.bfloat16().float()
+        x_lo, g_lo = (xp - x_hi).bfloat16().float(), (gp - g_hi).bfloat16().float()
+        gw = (wg(x_hi, g_hi + g_lo) + wg(x_lo, g_hi)) * scale
+        gp = g_hi + g_lo
+    else:
+        gw = wg(xp, gp) * scale
+    gb = gp.sum(dim=(0, 2, 3, 4)) if want_bias else None
     return gw.contiguous(), gb
 
 

@@ -44,6 +44,8 @@ def _worker(rank, world, port, variant, sync, grow, q):
     g, d = _build(variant, seed=100 + rank)               # different init per rank: the broadcast must fix it
     if sync == "flat":
         dp = comm.FlatAllReduce(g, d)
+    elif sync == "arena":      # the gradient arena of the single-graph multi-GPU step
+        dp = comm.ArenaAllReduce(g, d)
     else:       # "buckets_bf16": bf16 payload, the analogue of hvd.Compression.fp16 (main.py:149-150)
         dp = comm.DataParallel(g, d, bucket_bytes=1 << 16, comm_dtype=torch.bfloat16 if sync == "buckets_bf16" else None)
     opts = sg.make_optimizers(g, d)
@@ -93,7 +95,8 @@ def _worker(rank, world, port, variant, sync, grow, q):
 @pytest.mark.parametrize("variant,sync,grow", [("network", "buckets", False), ("network", "flat", False),
                                                ("network_dict", "buckets", False), ("network", "buckets_bf16", False),
                                                ("network", "buckets", True),
-                                               ("network_dict", "buckets", True)])
+                                               ("network_dict", "buckets", True),
+                                               ("network", "arena", False), ("network", "arena", True)])
 def test_train_step_two_ranks_gloo(variant, sync, grow):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

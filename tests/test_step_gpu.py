@@ -52,7 +52,10 @@ def test_golden_step_fp32(name):
             # gradient error 3.6e-6 over 120 runs.  (With atomics in those two kernels one mask flipped in ~10 %
             # of the runs and moved fromrgbs.0's bias gradient by 2.7e-3.)  Bias gradients are signed sums over
             # every voxel of a level (|sum| << sum of |terms|), hence the looser bound.
-            tol = 5e-3 if k.endswith(".bias") else 1e-3
+            # (2e-3 on weights: the base-level finishing kernel adds its partial sums in a fixed tree order since round
+            # 2 -- another rounding than round 1's sequential order, and in tiny_p3 ONE mask of blocks.0.conv2's
+            # input sits within that rounding of zero: 1.27e-3 on a gradient of magnitude 1e-6.)
+            tol = 5e-3 if k.endswith(".bias") else 2e-3
             if v.numel() == 1:
                 # the last linear's bias gradient is sum(-1/B ... +1/B ...) + drift ~ 1e-5: a cancelling sum of
                 # O(1) terms, so fp32 summation order moves it by ~1e-7 absolute (D(real), D(fake) are one batch)

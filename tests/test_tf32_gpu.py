@@ -113,22 +113,26 @@ WGRAD_SHAPES = [
 
 
 @pytest.mark.parametrize("shape", WGRAD_SHAPES)
-def test_tf32_wgrad(shape):
+def test_fp32_level_wgrad_split_bf16(shape):
+    """wgrad of the fp32 / TF32 levels (SG_IMPL_TF32 on fp32 tensors): tcgen05 kind::tf32 has no MN-major operands
+    (tools/tf32_mn_probe.cu), so the kernel splits the fp32 tiles into bf16 hi + lo halves in shared memory and forms
+    the product from three bf16 MMAs -- 16 mantissa bits per operand.  Against the exact fp32 CUDA-core kernel on the
+    same operands: 5e-5 (TF32 would sit at 3e-4); against the CPU restatement of the same split: 1e-5."""
     n, cin, cout, d, h, w = shape
     g = torch.Generator().manual_seed(sum(shape) + 3)
     x, gy = torch.randn(n, cin, d, h, w, generator=g), torch.randn(n, cout, d, h, w, generator=g)
-    # (a) tf32-representable operands against the exact fp32 kernel
-    xg, gg = E.plain_to_act(E._tf32(x), F32).cuda(), E.plain_to_act(E._tf32(gy), F32).cuda()
+    xa, ga = E.plain_to_act(x, F32), E.plain_to_act(gy, F32)
+    xg, gg = xa.cuda(), ga.cuda()
     ref_w, ref_b = K.conv3d_wgrad(xg, gg, cin, cout, 0.05, True, _lib.IMPL_DIRECT)
+    f0 = int(_lib.load().sg_cuda_core_fallbacks(0))
     got_w, got_b = K.conv3d_wgrad(xg, gg, cin, cout, 0.05, True, _lib.IMPL_TF32)
     torch.cuda.synchronize()
-    assert rel_err(got_w, ref_w) < 1e-5, (shape, rel_err(got_w, ref_w))
-    assert rel_err(got_b, ref_b) < 1e-5, (shape, rel_err(got_b, ref_b))
-    # (b) arbitrary operands against the round-to-nearest restatement
-    xa, ga = E.plain_to_act(x, F32), E.plain_to_act(gy, F32)
-    want_w, _ = E.conv3d_wgrad(xa, ga, cin, cout, 0.05, True, 3)
-    got_w, _ = K.conv3d_wgrad(xa.cuda(), ga.cuda(), cin, cout, 0.05, True, _lib.IMPL_TF32)
+    assert int(_lib.load().sg_cuda_core_fallbacks(0)) == f0, "the tensor-core wgrad declined this shape"
+    assert rel_err(got_w, ref_w) < 5e-5, (shape, rel_err(got_w, ref_w))
+    assert rel_err(got_b, ref_b) < 5e-5, (shape, rel_err(got_b, ref_b))
+    want_w, want_b = E.conv3d_wgrad(xa, ga, cin, cout, 0.05, True, 3)
     assert rel_err(got_w.cpu(), want_w) < 1e-5, (shape, rel_err(got_w.cpu(), want_w))
+    assert rel_err(got_b.cpu(), want_b) < 1e-5, (shape, rel_err(got_b.cpu(), want_b))
 
 
 def test_tf32_packing_layout():
