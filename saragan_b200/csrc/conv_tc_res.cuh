@@ -9,15 +9,21 @@
 //   * two TMEM accumulator sets: the epilogue of tile i overlaps the MMAs of tile i+1.
 // Geometry, operand descriptors and epilogue are those of k_conv_tc.
 //
-// ZS ("z-stacked") variant for NT <= 32.  An M = 128 MMA costs ~45 cycles for any N <= 32 (the A operand read
-// bounds it, tools/mma_bench.cu), so a 32-channel layer reaches half the tensor rate of a 64-channel one.
-// Instead of accumulating y[p] += x[p + kd - 1] * W[kd] (three MMAs with three different A operands per
-// output plane), the ZS kernel computes Z[q][kd] = x[q] * W[kd] for every INPUT plane q of the halo tile with
-// the kd taps stacked along N (one MMA, A = plane q, N up to 3*NT: 56 cycles for N = 96), and the epilogue
-// forms y[p] = Z[p-1][0] + Z[p][1] + Z[p+1][2] -- the three terms sit in the SAME accumulator row (TMEM lane)
-// of three different column blocks, so the sum costs the epilogue thread two adds per value.  Per (kh, kw,
-// K step) that is TD + 2 MMAs instead of 3 * TD, each at least as wide: 1.46x fewer tensor cycles at
-// NT = 32, TD = 2 and 2x at NT = 16, TD = 4.  Input plane q only needs the kd with 0 <= q - kd + 1 < TD.
+// ZS ("z-stacked") form.  An M = 128, K = 16 MMA costs max(N / 2, ~46) cycles (tools/mma_bench.cu; the floor is per
+// instruction -- the A-operand collector does not lift it, tools/mma_collector_bench.cu), so an MMA with N = 32 or 64
+// runs the tensor pipe at 35 % / 67 %.  Instead of y[p] += x[p + kd - 1] * W[kd] (three MMAs with three different A
+// operands per output plane), the ZS loop walks the INPUT planes q of the halo tile and issues ONE MMA per plane with
+// the kd taps stacked along N in DESCENDING order, B = [W[kd=2]; W[kd=1]; W[kd=0]] (3*NT rows), whose accumulator is
+// the block of THREE ADJACENT output-plane accumulators starting at plane q - 1:
+//     columns [acc[q-1] | acc[q] | acc[q+1]]  +=  x[q] * [W[2] | W[1] | W[0]]
+// -- every term lands where it belongs, the tensor core's own accumulate does the sum over kd, and TMEM holds TD * NT
+// columns per set like the plain form.  The two planes at either end of the halo use the sub-ranges of B that fall
+// inside the tile (N = NT, 2*NT).  Per (kh, kw, K step) that is TD + 2 MMAs of N up to 3*NT instead of 3 * TD of N = NT:
+// NT = 64, TD = 4: 416 cycles for 384 cycles of work (92 % against 67 %); NT = 32, TD = 4: 64 % against 35 %.
+// One instruction has one accumulate flag for all its columns, so the very first (kh, kw, K step) of a tile is issued
+// tap by tap (each accumulator is first touched by its kd = 0 tap, with the flag off); everything after it is stacked.
+// (Round 1 stacked kd into SEPARATE accumulators Z[q][kd] and summed three of them per output in the epilogue: three
+// times the TMEM columns, which capped TD at 2 for NT = 32.)
 #pragma once
 
 namespace {
@@ -49,28 +55,10 @@ struct ResParams {
 // KBC = 8-channel chunks per K block.  With th = 16 and tw = 8 fixed, every descriptor offset of
 // the 27 x KBC/2 x TD MMAs of a K block is a compile-time constant: the fully unrolled issue
 // loop costs one uniform-datapath add per MMA.
-// columns of one ZS accumulator set: input plane j - 1 (j = 0 .. TD+1) holds the kd range [kd0(j), kd1(j)]
-struct ZsMap {
-  int col[8], kd0[8], cnt[8], total;
-};
-constexpr ZsMap zs_map(int td, int nt) {
-  ZsMap m{};
-  int c = 0;
-  for (int j = 0; j < td + 2; ++j) {
-    const int q = j - 1;
-    const int lo = q + 2 - td > 0 ? q + 2 - td : 0, hi = q + 1 < 2 ? q + 1 : 2;
-    m.col[j] = c; m.kd0[j] = lo; m.cnt[j] = hi - lo + 1;
-    c += (hi - lo + 1) * nt;
-  }
-  m.total = c;
-  return m;
-}
-
 template <int NT, int TD, int KBC, bool ZS>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ ResParams p) {
   constexpr int HALO_H = 18, HALO_W = 10;
-  constexpr ZsMap ZM = zs_map(TD, NT);
   constexpr int CHUNK_BYTES = ((TD + 2) * HALO_H * HALO_W * 16 + 127) / 128 * 128;
   constexpr uint32_t KK_A = (2u * CHUNK_BYTES) >> 4;
   constexpr uint32_t PLANE = HALO_H * HALO_W;   // voxels (16-byte units) per halo plane
@@ -113,7 +101,7 @@ k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   sg_pdl_wait();   // everything above touched only shared / tensor memory and kernel parameters
-  const int acc_cols = ZS ? ZM.total : p.n_sub * NT;      // columns of one accumulator set
+  const int acc_cols = p.n_sub * NT;                     // columns of one accumulator set
   float* s_bias = reinterpret_cast<float*>(bars + 16);   // NT floats, 16-byte aligned, after the barriers
 
   if (warp == 0) {
@@ -124,9 +112,9 @@ k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
       mbar_expect_tx(BAR(W_FULL), (uint32_t)p.w_bytes);
       for (int i = 0; i < 27 * p.CCin; ++i) {
         uint32_t dst = w_addr + i * NT * 16;
-        if (ZS) {   // [kh][kw][chunk][kd][co][8]: the three kd taps of a (kh, kw, chunk) are consecutive N rows
+        if (ZS) {   // [kh][kw][chunk][kd = 2, 1, 0][co][8]: the three kd taps of a (kh, kw, chunk) are consecutive N rows
           const int tap = i / p.CCin, chunk = i - tap * p.CCin;
-          dst = w_addr + ((((tap % 9) * p.CCin + chunk) * 3 + tap / 9) * NT) * 16;
+          dst = w_addr + ((((tap % 9) * p.CCin + chunk) * 3 + (2 - tap / 9)) * NT) * 16;
         }
         bulk_load(dst, p.wp + ((int64_t)i * p.CoutP + co0) * 8, NT * 16u, BAR(W_FULL));
       }
@@ -175,7 +163,7 @@ k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
           const uint64_t a_stage = a_desc0 + (uint64_t)(s * stage16);
           const uint32_t acc0 = kb != 0;
           if constexpr (ZS) {
-            // B rows [kd][co] of a (kh, kw, chunk): chunk stride (LBO) = 3*NT rows
+            // B rows [kd = 2, 1, 0][co] of a (kh, kw, chunk): chunk stride (LBO) = 3*NT rows
             uint64_t b_khw = wz_desc0 + (uint64_t)(kb * (KBC * 3 * NT));
 #pragma unroll
             for (int khw = 0; khw < 9; ++khw) {
@@ -184,10 +172,26 @@ k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
               for (int kk = 0; kk < KBC / 2; ++kk)
 #pragma unroll
                 for (int j = 0; j < TD + 2; ++j) {
-                  const uint32_t idz = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((ZM.cnt[j] * NT) >> 3) << 17) |
+                  // input plane q = j - 1 feeds output planes q + 1 - kd, kd in [kd_lo, kd_hi]
+                  constexpr int dummy = 0;
+                  (void)dummy;
+                  const int q = j - 1;
+                  const int kd_hi = q + 1 < 2 ? q + 1 : 2, kd_lo = q + 2 - TD > 0 ? q + 2 - TD : 0;
+                  const uint64_t a = a_stage + (uint64_t)(a_off + j * PLANE + kk * KK_A);
+                  const uint64_t b = b_khw + (uint64_t)(kk * 2 * 3 * NT);
+                  if ((khw | kk) == 0) {
+                    // first K step of a K block: tap by tap; in the tile's first K block the kd = 0 tap of every
+                    // output plane (its first touch) overwrites
+                    if (kb == 0) {
+#pragma unroll
+                      for (int kd = kd_lo; kd <= kd_hi; ++kd)
+                        tc_mma(d_tmem + (q + 1 - kd) * NT, a, b + (uint64_t)((2 - kd) * NT), idesc, kd != 0, leader);
+                      continue;
+                    }
+                  }
+                  const uint32_t idz = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(((kd_hi - kd_lo + 1) * NT) >> 3) << 17) |
                                        ((128u >> 4) << 24);
-                  tc_mma(d_tmem + ZM.col[j], a_stage + (uint64_t)(a_off + j * PLANE + kk * KK_A),
-                         b_khw + (uint64_t)(kk * 2 * 3 * NT + ZM.kd0[j] * NT), idz, (khw | kk) ? 1u : acc0, leader);
+                  tc_mma(d_tmem + (q + 1 - kd_hi) * NT, a, b + (uint64_t)((2 - kd_hi) * NT), idz, 1u, leader);
                 }
               b_khw += wz_khw16;
             }
@@ -254,17 +258,7 @@ k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
           float v[16];
           __syncwarp();
           const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * acc_cols);
-          if constexpr (ZS) {
-            // y[plane sub] = Z[sub-1][kd 0] + Z[sub][kd 1] + Z[sub+1][kd 2]: same lane, three column blocks
-            float z[48];
-            tmem_ld3x16(trow + (uint32_t)(ZM.col[sub] + (0 - ZM.kd0[sub]) * NT + c0),
-                        trow + (uint32_t)(ZM.col[sub + 1] + (1 - ZM.kd0[sub + 1]) * NT + c0),
-                        trow + (uint32_t)(ZM.col[sub + 2] + (2 - ZM.kd0[sub + 2]) * NT + c0), z);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = z[i] + z[16 + i] + z[32 + i];
-          } else {
-            tmem_ld16(trow + (uint32_t)(sub * NT + c0), v);
-          }
+          tmem_ld16(trow + (uint32_t)(sub * NT + c0), v);
           epilogue16_regmask(v, s_bias + c0, scale, lrelu, mask != nullptr, mk[sub][c0 / 8], mk[sub][c0 / 8 + 1],
                              yout + obase0 + sub * plane8 + (int64_t)(c0 / 8) * V * 8, V * 8);
         }
@@ -313,32 +307,27 @@ ResPlan make_res_plan(int N, int Cin, int Cout, int D, int H, int W, bool for_te
   p.w_bytes = 27 * CCin * NT * 16;
   p.th = 16;
   p.halo_w = 10; p.halo_h = 18;
-  p.kb_chunks = CCin % 4 == 0 ? 4 : 2;
-  p.n_kblocks = CCin / p.kb_chunks;
-  // td: two accumulator sets of td MMA tiles must fit TMEM; >= 2 stages must fit shared memory.  NT <= 32
-  // prefers the z-stacked form, whose accumulator set is 3*td*NT columns wide (td = 2 at NT = 32, 4 at 16).
-  int best_td = 0;
+  // (td, K block): two accumulator sets of td MMA tiles must fit TMEM, >= 2 halo stages must fit shared memory.
+  // The z-stacked form (td >= 2) gains with every extra plane per tile ((td + 2) wide MMAs instead of 3 * td narrow
+  // ones), so the largest td wins; a K block of 4 chunks halves the barrier rounds when it still leaves 2 stages.
+  int best_td = 0, best_kb = 0;
   bool zs = false;
-  if (NT <= 32 && g_res_zs_mode != 1) {
-    for (int td = 1; td <= D && td <= 4; td *= 2) {
-      if (D % td || td == 1) continue;
-      if (2 * 3 * td * NT > 512) continue;
-      int chunk = ((td + 2) * 18 * 10 * 16 + 127) / 128 * 128;
-      int stage = p.kb_chunks * chunk;
-      if (p.w_bytes + 2 * stage + 4096 + 512 > budget) continue;
-      best_td = td;
-      zs = true;
+  for (int td = 8; td >= 1 && best_td == 0; td /= 2) {
+    if (td > D || D % td) continue;
+    if (2 * td * NT > 512) continue;
+    const bool this_zs = td >= 2 && g_res_zs_mode != 1;
+    if (!this_zs && td > 4) continue;                 // the plain form is instantiated up to td = 4
+    for (int kb : {4, 2}) {
+      if (CCin % kb) continue;
+      const int chunk = ((td + 2) * 18 * 10 * 16 + 127) / 128 * 128;
+      if (p.w_bytes + 2 * kb * chunk + 4096 + 512 > budget) continue;
+      best_td = td; best_kb = kb; zs = this_zs;
+      break;
     }
   }
-  for (int td = 1; td <= D && td <= 4 && !zs; td *= 2) {
-    if (D % td) continue;
-    if (2 * td * NT > 512) continue;
-    int chunk = ((td + 2) * 18 * 10 * 16 + 127) / 128 * 128;
-    int stage = p.kb_chunks * chunk;
-    if (p.w_bytes + 2 * stage + 4096 + 512 > budget) continue;
-    best_td = td;
-  }
   if (best_td == 0) return pl;
+  p.kb_chunks = best_kb;
+  p.n_kblocks = CCin / p.kb_chunks;
   p.td = best_td;
   p.halo_d = p.td + 2;
   p.chunk_tx_bytes = p.halo_d * p.halo_h * p.halo_w * 16;
@@ -353,7 +342,7 @@ ResPlan make_res_plan(int N, int Cin, int Cout, int D, int H, int W, bool for_te
   p.n_tiles = p.tiles_w * p.tiles_h * p.tiles_d * N;
   p.N = N; p.D = D; p.H = H; p.W = W;
   p.CCin = CCin; p.Cout = Cout; p.CoutP = CoutP; p.CCout = sg_chunks(Cout);
-  p.tmem_cols = round_pow2_cols(2 * (zs ? 3 : 1) * p.n_sub * NT);
+  p.tmem_cols = round_pow2_cols(2 * p.n_sub * NT);
   pl.zs = zs;
   const int n_ntiles = CoutP / NT;
   int ctas = sg_num_sms() / n_ntiles;
@@ -391,18 +380,20 @@ int launch_res_inst(const ResPlan& pl, const CUtensorMap& map, cudaStream_t s) {
 template <int NT>
 int launch_res(const ResPlan& pl, const CUtensorMap& map, cudaStream_t s) {
   const int td = pl.p.td, kbc = pl.p.kb_chunks;
-  if constexpr (NT <= 32) {
-    if (pl.zs) {
-      if (kbc == 4) {
-        if (td == 2) return launch_res_inst<NT, 2, 4, true>(pl, map, s);
-        if (td == 4 && NT == 16) return launch_res_inst<NT == 16 ? 16 : 32, NT == 16 ? 4 : 2, 4, true>(pl, map, s);
-      } else {
-        if (td == 2) return launch_res_inst<NT, 2, 2, true>(pl, map, s);
-        if (td == 4 && NT == 16) return launch_res_inst<NT == 16 ? 16 : 32, NT == 16 ? 4 : 2, 2, true>(pl, map, s);
-      }
-      sg_set_error("conv_tc_res: no z-stacked instantiation for td=%d kb_chunks=%d", td, kbc);
-      return -4;
+  if (pl.zs) {
+    if (kbc == 4) {
+      if (td == 2) return launch_res_inst<NT, 2, 4, true>(pl, map, s);
+      if (td == 4) return launch_res_inst<NT, 4, 4, true>(pl, map, s);
+      if constexpr (NT <= 32)
+        if (td == 8) return launch_res_inst<NT, 8, 4, true>(pl, map, s);
+    } else {
+      if (td == 2) return launch_res_inst<NT, 2, 2, true>(pl, map, s);
+      if (td == 4) return launch_res_inst<NT, 4, 2, true>(pl, map, s);
+      if constexpr (NT <= 32)
+        if (td == 8) return launch_res_inst<NT, 8, 2, true>(pl, map, s);
     }
+    sg_set_error("conv_tc_res: no z-stacked instantiation for td=%d kb_chunks=%d", td, kbc);
+    return -4;
   }
   if (kbc == 4) {
     if (td == 1) return launch_res_inst<NT, 1, 4, false>(pl, map, s);

@@ -39,31 +39,33 @@ def _run(precision, name="cfg3", batch=2):
     return ref, out, g, d
 
 
-# loss tolerance / bound on |norm - oracle norm| / oracle norm of every parameter gradient (median, max).  The
-# per-element gradient error of a reduced-precision step against an fp32 run is dominated by LeakyReLU mask flips
-# and the real/fake cancellation at initialisation (DESIGN.md "Precision": even TF32 operands everywhere give
-# 1.7 % median), so the NORMS are what a whole-step check can pin; elementwise parity is checked layer-locally.
-# One-element gradients (the ToRGB biases: a signed sum over the whole image gradient) cancel heavily and get 4x
-# the bound (measured on B200, bf16: median 3.6e-2, max 0.13 on tensors, 0.32 on the ToRGB biases).
-@pytest.mark.parametrize("precision,ltol,med,mx", [("bf16", 2e-3, 6e-2, 0.2), ("tf32", 1e-3, 2e-2, 0.1)])
-def test_cfg3_shaped_step_against_oracle(precision, ltol, med, mx):
+# loss tolerance / bounds on |norm - oracle norm| / oracle norm of every parameter gradient: median and maximum over
+# the weight / bias tensors, maximum over the one-element gradients.  The per-element gradient error of a
+# reduced-precision step against an fp32 run is dominated by LeakyReLU mask flips and the real/fake cancellation at
+# initialisation (DESIGN.md "Precision": even TF32 operands everywhere give 1.4 % median), so the NORMS are what a
+# whole-step check can pin; elementwise parity is checked layer-locally.  One-element gradients (the ToRGB biases: a
+# signed sum over the whole image gradient) cancel heavily.  Measured on B200: bf16 policy median 1.7e-2, worst tensor
+# 4.3e-2, ToRGB biases 0.27; tf32 mode 1.4e-2 / 3.3e-2 / 0.14.
+@pytest.mark.parametrize("precision,ltol,med,mx,mx1", [("bf16", 2e-3, 3e-2, 0.1, 0.5), ("tf32", 1e-3, 2e-2, 0.08, 0.3)])
+def test_cfg3_shaped_step_against_oracle(precision, ltol, med, mx, mx1):
     _need(precision)
     ref, out, g, d = _run(precision)
     for k in ("d_loss", "gp"):
         want = ref["losses"][k]
         assert abs(float(out[k]) - want) < ltol * abs(want), (k, float(out[k]), want)
     assert abs(float(out["g_loss"]) - ref["losses"]["g_loss"]) < ltol, float(out["g_loss"])
-    errs = {}
+    errs, errs1 = {}, {}
     for mod, key in ((d, "d_grad_norms"), (g, "g_grad_norms")):
         got = {k: p.grad for k, p in mod.named_parameters() if p.grad is not None}
         assert set(got) == set(ref[key]), key                      # exactly the active levels' parameters have gradients
         for k, want in ref[key].items():
             assert torch.isfinite(got[k]).all(), k
-            errs[key[0] + "." + k] = abs(float(got[k].double().norm()) - want) / want
+            (errs1 if got[k].numel() == 1 else errs)[key[0] + "." + k] = abs(float(got[k].double().norm()) - want) / want
     e = np.array(list(errs.values()))
-    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
-    print(f"\n[fullsize cfg3 B=2 {precision}] gradient-norm error: median {np.median(e):.3e} max {e.max():.3e}; worst {worst}")
-    assert np.median(e) < med and e.max() < mx, (np.median(e), e.max(), worst)
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:3]
+    print(f"\n[fullsize cfg3 B=2 {precision}] gradient-norm error over {len(e)} tensors: median {np.median(e):.3e} max {e.max():.3e} "
+          f"{worst}; one-element gradients: max {max(errs1.values()):.3e}")
+    assert np.median(e) < med and e.max() < mx and max(errs1.values()) < mx1, (np.median(e), e.max(), worst, errs1)
 
 
 @pytest.mark.parametrize("precision,tol", [("bf16", 2e-2), ("tf32", 1e-3)])
