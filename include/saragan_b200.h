@@ -39,6 +39,9 @@ typedef struct CUstream_st* cudaStream_t;
 #define SG_IMPL_TF32 3    /* fp32 tensors through tcgen05 kind::tf32 (10-bit mantissa operands rounded to nearest, fp32
                              accumulate): fprop/dgrad need the SG_TF32 packing and fail (-5) on an uncovered shape;
                              wgrad falls back to the fp32 CUDA-core kernel */
+#define SG_IMPL_F32_AS_BF16 4 /* sg_conv3d_wgrad only: fp32 tensors, operands rounded to bf16 in shared memory (the weight
+                             gradient of the fp32-storage levels under the bf16 policy; impl 3 there = split-bf16,
+                             three MMAs per product, ~16 mantissa bits) */
 #define SG_TF32 2         /* dtype code of sg_pack_conv_weight only: fp32 [tap][K/4][rows][4], rounded to tf32 */
 
 int sg_version(void);

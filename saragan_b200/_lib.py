@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SARAGAN_B200_LIB") or os.path.join(_HERE, "libsaragan_b200.so")
 
 BF16, F32, TF32_PACK = 0, 1, 2
-IMPL_AUTO, IMPL_DIRECT, IMPL_TCGEN05, IMPL_TF32 = 0, 1, 2, 3
+IMPL_AUTO, IMPL_DIRECT, IMPL_TCGEN05, IMPL_TF32, IMPL_F32_AS_BF16 = 0, 1, 2, 3, 4
 
 _c_int, _c_i64, _c_f, _c_p = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
 

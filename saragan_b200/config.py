@@ -58,6 +58,17 @@ def conv_route(x: torch.Tensor, cin: int, cout: int):
     return _lib.IMPL_AUTO, x.dtype
 
 
+def wgrad_impl(x: torch.Tensor, cin: int, cout: int) -> int:
+    """impl code of the weight gradient: like conv_route, except that under the 'bf16' policy the fp32-storage levels
+    round the wgrad operands to bf16 (one MMA per product instead of the split's three): 3e-3 of noise on a weight
+    gradient, no mask involved -- the accuracy the bf16 levels' weight gradients have anyway."""
+    from . import _lib
+    impl = conv_route(x, cin, cout)[0]
+    if impl == _lib.IMPL_TF32 and _precision == "bf16":
+        return _lib.IMPL_F32_AS_BF16
+    return impl
+
+
 _tf32_ok = {}
 
 

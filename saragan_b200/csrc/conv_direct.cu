@@ -410,6 +410,18 @@ static int launch_small_f32(const void* x, const void* wp, const float* bias, co
   return sg_check_launch("sg_conv3d_fprop(small f32 finish)");
 }
 
+// bytes of a bf16 copy of an fp32 act (256-byte aligned): impl = SG_IMPL_F32_AS_BF16 casts both wgrad operands once and
+// runs the bf16 kernel on them (the fp32 tensors' half-chunk tensor maps move 16 bytes per TMA row: a wgrad, which
+// reads every voxel once per launch, is bound by that; a 3x3x3 fprop re-uses its halo tile 27 times and is not)
+static int64_t bf16_copy_bytes(int N, int C, int D, int H, int W) {
+  return ((int64_t)N * sg_chunks(C) * D * H * W * 8 * 2 + 255) / 256 * 256;
+}
+__global__ void k_cast_f32_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t nvec) {
+  sg_pdl_enter();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x)
+    st8(dst + i * 8, ld8(src + i * 8));
+}
+
 extern "C" int64_t sg_conv3d_workspace_bytes(int kind, int dtype, int N, int Cin, int Cout, int D,
                                              int H, int W) {
   int64_t need = 0;
@@ -420,8 +432,16 @@ extern "C" int64_t sg_conv3d_workspace_bytes(int kind, int dtype, int N, int Cin
   }
   if (kind == 1 && small_f32_applies(dtype, N, D, H, W))
     need = (int64_t)27 * Cout * (16 * ((Cin + 15) / 16)) * (int64_t)sizeof(float);
-  // fp32 tensors may take the TF32 tensor-core path (impl = SG_IMPL_TF32): size for whichever needs more
+  // fp32 tensors may take the tensor-core paths (impl = SG_IMPL_TF32 / SG_IMPL_F32_AS_BF16): size for whichever needs
+  // more; the wgrad of impl 4 also keeps bf16 copies of both operands in the workspace
   int64_t t = sg_tc_workspace_bytes(kind, N, Cin, Cout, D, H, W, dtype == SG_DTYPE_F32);
+  if (kind == 1 && dtype == SG_DTYPE_F32) {
+    const int64_t tb = sg_tc_workspace_bytes(1, N, Cin, Cout, D, H, W, 0);      // the bf16 kernel behind impl 4
+    if (tb > 0) {
+      if (tb > t) t = tb;
+      t += bf16_copy_bytes(N, Cin, D, H, W) + bf16_copy_bytes(N, Cout, D, H, W);
+    }
+  }
   if (t > need) need = t;
   return need;
 }
@@ -608,10 +628,28 @@ extern "C" int sg_conv3d_wgrad(const void* x, const void* gy, float* gw, float* 
                                int N, int Cin, int Cout, int D, int H, int W, float scale, int impl,
                                void* ws, int64_t ws_bytes, cudaStream_t s) {
   SG_REQUIRE(N >= 0 && Cin > 0 && Cout > 0 && D > 0 && H > 0 && W > 0, "sg_conv3d_wgrad: bad shape");
-  SG_REQUIRE(impl >= 0 && impl <= 3, "sg_conv3d_wgrad: impl must be 0 (auto), 1 (direct), 2 (tcgen05), 3 (tcgen05 tf32)");
-  if (impl == SG_IMPL_TF32 && N > 0) {
-    SG_REQUIRE(dtype == SG_DTYPE_F32, "sg_conv3d_wgrad: the TF32 path takes fp32 activations");
-    int rc = sg_tc_wgrad(x, gy, gw, gb, N, Cin, Cout, D, H, W, scale, ws, ws_bytes, s, 1);
+  SG_REQUIRE(impl >= 0 && impl <= 4, "sg_conv3d_wgrad: impl must be 0 (auto), 1 (direct), 2 (tcgen05), 3 (fp32 tensors, "
+             "split-bf16 tensor cores), 4 (fp32 tensors, bf16 operands)");
+  if (impl == SG_IMPL_F32_AS_BF16 && N > 0 && sg_tc_workspace_bytes(1, N, Cin, Cout, D, H, W, 0) > 0) {
+    // fp32 tensors, bf16 operands: cast both once into the workspace, then the bf16 tensor-core kernel
+    SG_REQUIRE(dtype == SG_DTYPE_F32, "sg_conv3d_wgrad: impl 4 takes fp32 activations");
+    const int64_t xb = bf16_copy_bytes(N, Cin, D, H, W), gyb = bf16_copy_bytes(N, Cout, D, H, W);
+    SG_REQUIRE(ws != nullptr && ws_bytes >= xb + gyb, "sg_conv3d_wgrad(impl 4): workspace too small");
+    const int64_t nx = (int64_t)N * sg_chunks(Cin) * D * H * W, ng = (int64_t)N * sg_chunks(Cout) * D * H * W;
+    sg_launch((k_cast_f32_bf16), sg_grid(nx, 256), 256, 0, s, (const float*)x, (__nv_bfloat16*)ws, nx);
+    int rc = sg_check_launch("sg_conv3d_wgrad(cast x)");
+    if (rc) return rc;
+    sg_launch((k_cast_f32_bf16), sg_grid(ng, 256), 256, 0, s, (const float*)gy, (__nv_bfloat16*)((char*)ws + xb), ng);
+    rc = sg_check_launch("sg_conv3d_wgrad(cast gy)");
+    if (rc) return rc;
+    rc = sg_tc_wgrad(ws, (char*)ws + xb, gw, gb, N, Cin, Cout, D, H, W, scale, (char*)ws + xb + gyb, ws_bytes - xb - gyb, s, 0);
+    if (rc != 1) return rc;
+    ++g_cuda_core_fallbacks;
+    impl = SG_IMPL_AUTO;
+  }
+  if ((impl == SG_IMPL_TF32 || impl == SG_IMPL_F32_AS_BF16) && N > 0) {
+    SG_REQUIRE(dtype == SG_DTYPE_F32, "sg_conv3d_wgrad: impl 3 / 4 take fp32 activations");
+    int rc = sg_tc_wgrad(x, gy, gw, gb, N, Cin, Cout, D, H, W, scale, ws, ws_bytes, s, impl == SG_IMPL_TF32 ? 1 : 2);
     if (rc != 1) return rc;
     ++g_cuda_core_fallbacks;      // shape not covered: the fp32 CUDA-core kernels below take the same operands
     impl = SG_IMPL_AUTO;

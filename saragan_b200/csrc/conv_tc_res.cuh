@@ -163,37 +163,39 @@ k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
           const uint64_t a_stage = a_desc0 + (uint64_t)(s * stage16);
           const uint32_t acc0 = kb != 0;
           if constexpr (ZS) {
-            // B rows [kd = 2, 1, 0][co] of a (kh, kw, chunk): chunk stride (LBO) = 3*NT rows
-            uint64_t b_khw = wz_desc0 + (uint64_t)(kb * (KBC * 3 * NT));
+            // B rows [kd = 2, 1, 0][co] of a (kh, kw, chunk): chunk stride (LBO) = 3*NT rows.
+            // PLANE-OUTER order: all 9 * KBC/2 MMAs of an input plane go to the SAME accumulator columns back to back
+            // (a dependent chain on identical columns runs at full rate, tools/mma_overlap_bench.cu); the tap-outer
+            // order made every MMA overlap its predecessor's columns shifted by NT, which serialises them.
+            uint64_t b_khw[9];
+            b_khw[0] = wz_desc0 + (uint64_t)(kb * (KBC * 3 * NT));
 #pragma unroll
-            for (int khw = 0; khw < 9; ++khw) {
-              const uint32_t a_off = (uint32_t)((khw / 3) * HALO_W + khw % 3);
+            for (int khw = 1; khw < 9; ++khw) b_khw[khw] = b_khw[khw - 1] + wz_khw16;
 #pragma unroll
-              for (int kk = 0; kk < KBC / 2; ++kk)
+            for (int j = 0; j < TD + 2; ++j) {
+              // input plane q = j - 1 feeds output planes q + 1 - kd, kd in [kd_lo, kd_hi]
+              const int q = j - 1;
+              const int kd_hi = q + 1 < 2 ? q + 1 : 2, kd_lo = q + 2 - TD > 0 ? q + 2 - TD : 0;
+              const uint32_t idz = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(((kd_hi - kd_lo + 1) * NT) >> 3) << 17) |
+                                   ((128u >> 4) << 24);
 #pragma unroll
-                for (int j = 0; j < TD + 2; ++j) {
-                  // input plane q = j - 1 feeds output planes q + 1 - kd, kd in [kd_lo, kd_hi]
-                  constexpr int dummy = 0;
-                  (void)dummy;
-                  const int q = j - 1;
-                  const int kd_hi = q + 1 < 2 ? q + 1 : 2, kd_lo = q + 2 - TD > 0 ? q + 2 - TD : 0;
+              for (int khw = 0; khw < 9; ++khw) {
+                const uint32_t a_off = (uint32_t)((khw / 3) * HALO_W + khw % 3);
+#pragma unroll
+                for (int kk = 0; kk < KBC / 2; ++kk) {
                   const uint64_t a = a_stage + (uint64_t)(a_off + j * PLANE + kk * KK_A);
-                  const uint64_t b = b_khw + (uint64_t)(kk * 2 * 3 * NT);
-                  if ((khw | kk) == 0) {
-                    // first K step of a K block: tap by tap; in the tile's first K block the kd = 0 tap of every
-                    // output plane (its first touch) overwrites
-                    if (kb == 0) {
+                  const uint64_t b = b_khw[khw] + (uint64_t)(kk * 2 * 3 * NT);
+                  if ((khw | kk) == 0 && kb == 0) {
+                    // first K step of the tile for this plane: tap by tap, the kd = 0 tap (first touch of output
+                    // plane q + 1) overwrites -- one instruction has one accumulate flag for all its columns
 #pragma unroll
-                      for (int kd = kd_lo; kd <= kd_hi; ++kd)
-                        tc_mma(d_tmem + (q + 1 - kd) * NT, a, b + (uint64_t)((2 - kd) * NT), idesc, kd != 0, leader);
-                      continue;
-                    }
+                    for (int kd = kd_lo; kd <= kd_hi; ++kd)
+                      tc_mma(d_tmem + (q + 1 - kd) * NT, a, b + (uint64_t)((2 - kd) * NT), idesc, kd != 0, leader);
+                  } else {
+                    tc_mma(d_tmem + (q + 1 - kd_hi) * NT, a, b + (uint64_t)((2 - kd_hi) * NT), idz, 1u, leader);
                   }
-                  const uint32_t idz = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(((kd_hi - kd_lo + 1) * NT) >> 3) << 17) |
-                                       ((128u >> 4) << 24);
-                  tc_mma(d_tmem + (q + 1 - kd_hi) * NT, a, b + (uint64_t)((2 - kd_hi) * NT), idz, 1u, leader);
                 }
-              b_khw += wz_khw16;
+              }
             }
           } else {
           uint64_t b_tap = w_desc0 + (uint64_t)(kb * (KBC * NT));

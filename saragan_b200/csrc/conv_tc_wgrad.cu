@@ -73,6 +73,8 @@ struct WgParams {
 };
 
 // in place: {h0[u], h1[u]} = fp32 channels {0-3, 4-7} of voxel u  ->  {bf16 hi, bf16 lo} of its 8 channels
+// (WANT_LO = false: only the hi half is formed -- plain bf16 operands, SPLIT == 2)
+template <bool WANT_LO>
 __device__ __forceinline__ void split_tile_bf16(uint8_t* h0, uint8_t* h1, int bytes, int tid, int nthreads) {
   for (int u = tid; u < bytes / 16; u += nthreads) {
     const float4 a = reinterpret_cast<const float4*>(h0)[u], b = reinterpret_cast<const float4*>(h1)[u];
@@ -87,11 +89,14 @@ __device__ __forceinline__ void split_tile_bf16(uint8_t* h0, uint8_t* h1, int by
       pl[i] = __floats2bfloat162_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
     }
     reinterpret_cast<uint4*>(h0)[u] = hi;
-    reinterpret_cast<uint4*>(h1)[u] = lo;
+    if (WANT_LO) reinterpret_cast<uint4*>(h1)[u] = lo;
   }
 }
 
-template <int NT, bool SPLIT>
+// SPLIT: 0 = bf16 tensors; 1 = fp32 tensors, three bf16 MMAs per product (hi/lo split, ~16 mantissa bits);
+//        2 = fp32 tensors, bf16 operands (hi halves only) -- the weight gradient of the fp32-storage levels under the
+//            bf16 policy: rounding its operands to bf16 adds 3e-3 of noise to a weight gradient and flips no mask
+template <int NT, int SPLIT>
 __global__ void __launch_bounds__(kThreadsW)
 k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUtensorMap gmap1,
            const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap xmap1,
@@ -235,7 +240,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
             tc_mma(tmem_base + 3 * NT, a_k, b_k + 8, idesc_mid, acc, leader);
             tc_mma(tmem_base + 6 * NT + 16, a_k, b_k + 16, idesc, acc, leader);
             acc = 1;
-            if constexpr (SPLIT) {
+            if constexpr (SPLIT == 1) {
               // + g_lo (x) x_hi (the ones columns take g_lo too: bias = sum of hi + lo) + g_hi (x) x_lo
               const uint64_t a_lo = a_k + g_lo16, b_lo = b_k + x_lo16;
               tc_mma(tmem_base, a_lo, b_k, idesc, 1u, leader);
@@ -267,8 +272,8 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUt
       for (int tile = blockIdx.x, it = 0; tile < p.n_tiles; tile += gridDim.x, ++it) {
         mbar_wait(BAR(FULL + s2), (it / p.stages) & 1);
         uint8_t* st = smem + (size_t)s2 * p.stage_bytes;
-        split_tile_bf16(st, st + g_bytes, g_bytes, row, 128);
-        split_tile_bf16(st + x_off, st + xlo_off, xh_bytes, row, 128);
+        split_tile_bf16<SPLIT == 1>(st, st + g_bytes, g_bytes, row, 128);
+        split_tile_bf16<SPLIT == 1>(st + x_off, st + xlo_off, xh_bytes, row, 128);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(BAR(READY + s2));
         if (++s2 == p.stages) s2 = 0;
@@ -404,7 +409,7 @@ WgPlan make_wgrad_plan(int N, int Cin, int Cout, int D, int H, int W, bool split
   return pl;
 }
 
-template <int NT, bool SPLIT = false>
+template <int NT, int SPLIT = 0>
 int launch_wgrad(const WgPlan& pl, const CUtensorMap& gmap, const CUtensorMap& gmap1, const CUtensorMap& xmap,
                  const CUtensorMap& xmap1, cudaStream_t s) {
   static bool attr_set = false;
@@ -456,7 +461,8 @@ int64_t sg_tc_wgrad_workspace_bytes(int N, int Cin, int Cout, int D, int H, int 
 }
 
 // returns 1 if the shape is not covered (caller falls through to the direct kernel).  f32 != 0: x and gy are fp32
-// acts (the SPLIT kernel: bf16 hi/lo halves formed in shared memory, three bf16 MMAs per product)
+// acts: 1 = the SPLIT kernel (bf16 hi/lo halves formed in shared memory, three bf16 MMAs per product), 2 = bf16
+// operands (hi halves only)
 int sg_tc_wgrad(const void* x, const void* gy, float* gw, float* gb, int N, int Cin, int Cout, int D, int H, int W,
                 float scale, void* ws, int64_t ws_bytes, cudaStream_t s, int f32) {
   WgPlan pl = make_wgrad_plan(N, Cin, Cout, D, H, W, f32 != 0);
@@ -484,8 +490,10 @@ int sg_tc_wgrad(const void* x, const void* gy, float* gw, float* gb, int N, int 
   }
   if (!p.direct) cudaMemsetAsync(ws, 0, (size_t)pl.ws_bytes, s);
   if (gb) cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)Cout, s);
-  if (f32)
-    rc = pl.NT == 32 ? launch_wgrad<32, true>(pl, gmap, gmap1, xmap, xmap1, s) : launch_wgrad<16, true>(pl, gmap, gmap1, xmap, xmap1, s);
+  if (f32 == 2)
+    rc = pl.NT == 32 ? launch_wgrad<32, 2>(pl, gmap, gmap1, xmap, xmap1, s) : launch_wgrad<16, 2>(pl, gmap, gmap1, xmap, xmap1, s);
+  else if (f32)
+    rc = pl.NT == 32 ? launch_wgrad<32, 1>(pl, gmap, gmap1, xmap, xmap1, s) : launch_wgrad<16, 1>(pl, gmap, gmap1, xmap, xmap1, s);
   else
     rc = pl.NT == 32 ? launch_wgrad<32>(pl, gmap, gmap1, xmap, xmap1, s) : launch_wgrad<16>(pl, gmap, gmap1, xmap, xmap1, s);
   if (rc) return rc;

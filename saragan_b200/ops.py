@@ -206,7 +206,7 @@ class ConvWgrad(Function):
 
     @staticmethod
     def forward(ctx, x, g, std: float, cin: int, cout: int, want_bias: bool):
-        gw, gb = K.conv3d_wgrad(x, g, cin, cout, std, want_bias, config.conv_route(x, cin, cout)[0])
+        gw, gb = K.conv3d_wgrad(x, g, cin, cout, std, want_bias, config.wgrad_impl(x, cin, cout))
         ctx.save_for_backward(x, g)
         ctx.std, ctx.cin, ctx.cout = std, cin, cout
         if gb is None:

@@ -102,6 +102,9 @@ def conv3d_wgrad(x, gy, cin, cout, scale, want_bias, impl=0):
         x_lo, g_lo = (xp - x_hi).bfloat16().float(), (gp - g_hi).bfloat16().float()
         gw = (wg(x_hi, g_hi + g_lo) + wg(x_lo, g_hi)) * scale
         gp = g_hi + g_lo
+    elif impl == 4:
+        gp = gp.bfloat16().float()      # fp32 tensors, bf16 operands (the bias gradient sums the rounded gy)
+        gw = wg(xp.bfloat16().float(), gp) * scale
     else:
         gw = wg(xp, gp) * scale
     gb = gp.sum(dim=(0, 2, 3, 4)) if want_bias else None

@@ -135,6 +135,24 @@ def test_fp32_level_wgrad_split_bf16(shape):
     assert rel_err(got_b.cpu(), want_b) < 1e-5, (shape, rel_err(got_b.cpu(), want_b))
 
 
+@pytest.mark.parametrize("shape", WGRAD_SHAPES[1:6])
+def test_fp32_level_wgrad_bf16_operands(shape):
+    """SG_IMPL_F32_AS_BF16: the same kernel forming only the hi halves (what the bf16 policy uses for the weight
+    gradients of its fp32-storage levels) against the restatement that rounds both operands to bf16."""
+    n, cin, cout, d, h, w = shape
+    g = torch.Generator().manual_seed(sum(shape) + 5)
+    xa = E.plain_to_act(torch.randn(n, cin, d, h, w, generator=g), F32)
+    ga = E.plain_to_act(torch.randn(n, cout, d, h, w, generator=g), F32)
+    f0 = int(_lib.load().sg_cuda_core_fallbacks(0))
+    got_w, got_b = K.conv3d_wgrad(xa.cuda(), ga.cuda(), cin, cout, 0.05, True, _lib.IMPL_F32_AS_BF16)
+    torch.cuda.synchronize()
+    assert int(_lib.load().sg_cuda_core_fallbacks(0)) == f0
+    want_w, want_b = E.conv3d_wgrad(xa, ga, cin, cout, 0.05, True, 4)
+    assert rel_err(got_w.cpu(), want_w) < 1e-5 and rel_err(got_b.cpu(), want_b) < 1e-5, shape
+    exact_w, _ = E.conv3d_wgrad(xa, ga, cin, cout, 0.05, True)
+    assert rel_err(got_w.cpu(), exact_w) < 6e-3
+
+
 def test_tf32_packing_layout():
     """SG_TF32 packing = [tap][K/4][rows][4] fp32, values rounded to nearest tf32, pad rows / channels zero."""
     cout, cin = 24, 20
