@@ -3,8 +3,9 @@
 Checks, on a small PGAN (phase 3 of 4, 4x16x16, per-rank batch 4, different reals and draws per rank):
  1. ONE step's averaged gradients of the eager bucketed/overlapped path (comm.DataParallel) and of the flat all-reduce
     (comm.FlatAllReduce) equal the mean over ranks of the gradients each rank computes alone;
- 2. K optimiser steps through the eager bucketed path and through the segmented CUDA-graph path leave the replicas
-    BIT-IDENTICAL across ranks, and the two paths agree with each other to the run-to-run noise of the step.
+ 2. K optimiser steps through the eager bucketed path, through the segmented CUDA-graph path (flat all-reduce between
+    four graph segments) and through the SINGLE-graph path (gradient arena, NCCL captured inside the graph) leave the
+    replicas BIT-IDENTICAL across ranks, and the paths agree with each other to the run-to-run noise of the step.
 Prints one JSON line on rank 0; exit code 1 on any violation."""
 import json
 import os
@@ -83,7 +84,7 @@ def main():
 
     # ---- 2. K steps: eager bucketed vs segmented graph; replicas bit-identical
     finals = {}
-    for mode in ("eager_bucketed", "graph_segments"):
+    for mode in ("eager_bucketed", "graph_segments", "graph_arena"):
         g, d = build()
         g_opt, d_opt = make_capturable_optimizers(g, d, world_size=world)
         if mode == "eager_bucketed":
@@ -91,7 +92,7 @@ def main():
             for i in range(K):
                 o = sg.train_step(reals(rank, i, dev), g, d, g_opt, d_opt, ALPHA, grad_sync=dp, **draws(rank, i, dev))
         else:
-            dp = comm.FlatAllReduce(g, d)
+            dp = comm.FlatAllReduce(g, d) if mode == "graph_segments" else comm.ArenaAllReduce(g, d)
             graphed = GraphedTrainStep(g, d, g_opt, d_opt, B, VOL, ALPHA, warmup=2, seed=1, grad_sync=dp)
             for i in range(K):
                 dr = draws(rank, i, dev)
@@ -104,14 +105,15 @@ def main():
         ok &= same
         finals[mode] = flat
         res[f"losses.{mode}"] = [float(o[k]) for k in ("d_loss", "gp", "g_loss")]
-    diff = float((finals["eager_bucketed"] - finals["graph_segments"]).abs().mean())
-    res["mean_abs_weight_diff_eager_vs_graph"] = diff
-    # Adam with beta1 = 0 turns rounding-level gradient differences into +-lr steps: after K steps the two paths may
-    # differ by a fraction of K*lr per weight, never by more
-    ok &= diff < 0.25 * K * 1e-3 * world ** 0.5
-    for k in range(3):
-        a, b = res["losses.eager_bucketed"][k], res["losses.graph_segments"][k]
-        ok &= abs(a - b) < 2e-2 * max(1.0, abs(a))
+    for other in ("graph_segments", "graph_arena"):
+        diff = float((finals["eager_bucketed"] - finals[other]).abs().mean())
+        res[f"mean_abs_weight_diff_eager_vs_{other}"] = diff
+        # Adam with beta1 = 0 turns rounding-level gradient differences into +-lr steps: after K steps the two paths
+        # may differ by a fraction of K*lr per weight, never by more
+        ok &= diff < 0.25 * K * 1e-3 * world ** 0.5
+        for k in range(3):
+            a, b = res["losses.eager_bucketed"][k], res[f"losses.{other}"][k]
+            ok &= abs(a - b) < 2e-2 * max(1.0, abs(a))
     res["ok"] = bool(ok)
     if rank == 0:
         print("MGPU_RESULT " + json.dumps(res), flush=True)

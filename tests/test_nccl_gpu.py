@@ -24,3 +24,4 @@ def test_two_rank_nccl_step():
     print(json.dumps(res, indent=1))
     assert r.returncode == 0 and res["ok"], res
     assert res["replicas_bit_identical.eager_bucketed"] and res["replicas_bit_identical.graph_segments"]
+    assert res["replicas_bit_identical.graph_arena"]
