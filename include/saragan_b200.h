@@ -99,6 +99,9 @@ void sg_tc_force_streaming(int mode);
 /* test hook for the weight-resident kernel: 0 = z-stacked form (kd taps stacked along the MMA N dimension)
  * whenever NT <= 32 allows it; 1 = never */
 void sg_tc_res_zs_mode(int mode);
+/* tuning hook for the weight-resident kernel: planes per tile (1, 2, 4, 8) and 8-channel chunks per K block (2, 4);
+ * 0 = automatic.  A combination that does not fit shared / tensor memory falls back to the streaming kernel. */
+void sg_tc_res_force(int td, int kb_chunks);
 /* test / tuning hook for the streaming kernel: force the tiling (output channels per CTA nt in
  * {128,64,32,16}; big = tiles for one CTA per SM; td_max = planes per tile cap; splits = split-K
  * factor) instead of choosing by estimated cost; nt = 0 restores the automatic choice */

@@ -39,6 +39,7 @@ SIGNATURES = {
     "sg_get_leaky_slope": [],
     "sg_tc_force_streaming": [_c_int],
     "sg_tc_res_zs_mode": [_c_int],
+    "sg_tc_res_force": [_c_int, _c_int],
     "sg_tc_force_plan": [_c_int, _c_int, _c_int, _c_int],
     "sg_tc_plan_debug": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, ctypes.POINTER(ctypes.c_int)],
     "sg_conv3d_tf32_supported": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int],
@@ -79,7 +80,7 @@ SIGNATURES = {
 }
 _RESTYPES = {"sg_last_error": ctypes.c_char_p, "sg_packed_weight_elems": ctypes.c_int64,
              "sg_conv3d_workspace_bytes": ctypes.c_int64, "sg_launch_count": ctypes.c_int64, "sg_cuda_core_fallbacks": ctypes.c_int64,
-             "sg_set_pdl": None, "sg_get_leaky_slope": ctypes.c_float, "sg_tc_force_streaming": None, "sg_tc_res_zs_mode": None, "sg_tc_force_plan": None}
+             "sg_set_pdl": None, "sg_get_leaky_slope": ctypes.c_float, "sg_tc_force_streaming": None, "sg_tc_res_zs_mode": None, "sg_tc_res_force": None, "sg_tc_force_plan": None}
 
 _lib = None
 

@@ -625,6 +625,7 @@ int encode_halo_map(CUtensorMap* map, const void* x, int N, int CC, int D, int H
 
 extern "C" void sg_tc_force_streaming(int on) { g_force_streaming = on; }
 extern "C" void sg_tc_res_zs_mode(int mode) { g_res_zs_mode = mode; }
+extern "C" void sg_tc_res_force(int td, int kb_chunks) { g_res_force_td = td; g_res_force_kb = kb_chunks; }
 extern "C" void sg_tc_force_plan(int nt, int big, int td_max, int splits) {
   g_force_plan[0] = nt; g_force_plan[1] = big; g_force_plan[2] = td_max; g_force_plan[3] = splits;
 }

@@ -55,6 +55,47 @@ struct ResParams {
 // KBC = 8-channel chunks per K block.  With th = 16 and tw = 8 fixed, every descriptor offset of
 // the 27 x KBC/2 x TD MMAs of a K block is a compile-time constant: the fully unrolled issue
 // loop costs one uniform-datapath add per MMA.
+// The MMAs of one K block of the z-stacked form.  B rows [kd = 2, 1, 0][co] of a (kh, kw, chunk): chunk stride (LBO) =
+// 3*NT rows.  PLANE-OUTER order: the 9 * KBC/2 MMAs of an input plane go to the same accumulator columns back to back.
+// FIRST (the tile's first K block): the first K step of every plane is issued tap by tap, the kd = 0 tap (first touch
+// of output plane q + 1) with the accumulate flag off -- one instruction has one flag for all its columns.  Every
+// descriptor offset is a compile-time constant or a running uniform add.
+template <int NT, int TD, int KBC, bool FIRST>
+__device__ __forceinline__ void zs_issue_kblock(uint32_t d_tmem, uint64_t a_stage, uint64_t b_kb, uint32_t wz_khw16,
+                                                uint32_t leader) {
+  constexpr int HALO_H = 18, HALO_W = 10;
+  constexpr int CHUNK_BYTES = ((TD + 2) * HALO_H * HALO_W * 16 + 127) / 128 * 128;
+  constexpr uint32_t KK_A = (2u * CHUNK_BYTES) >> 4;
+  constexpr uint32_t PLANE = HALO_H * HALO_W;
+  constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+#pragma unroll
+  for (int j = 0; j < TD + 2; ++j) {
+    // input plane q = j - 1 feeds output planes q + 1 - kd, kd in [kd_lo, kd_hi]
+    const int q = j - 1;
+    const int kd_hi = q + 1 < 2 ? q + 1 : 2, kd_lo = q + 2 - TD > 0 ? q + 2 - TD : 0;
+    const uint32_t idz = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(((kd_hi - kd_lo + 1) * NT) >> 3) << 17) |
+                         ((128u >> 4) << 24);
+    const uint64_t a_plane = a_stage + (uint64_t)(j * PLANE);
+    uint64_t b_run = b_kb + (uint64_t)((2 - kd_hi) * NT);
+#pragma unroll
+    for (int khw = 0; khw < 9; ++khw) {
+      const uint32_t a_off = (uint32_t)((khw / 3) * HALO_W + khw % 3);
+#pragma unroll
+      for (int kk = 0; kk < KBC / 2; ++kk) {
+        const uint64_t a = a_plane + (uint64_t)(a_off + kk * KK_A);
+        if (FIRST && (khw | kk) == 0) {
+#pragma unroll
+          for (int kd = kd_lo; kd <= kd_hi; ++kd)
+            tc_mma(d_tmem + (q + 1 - kd) * NT, a, b_run + (uint64_t)((kd_hi - kd) * NT), idesc, kd != 0, leader);
+        } else {
+          tc_mma(d_tmem + (q + 1 - kd_hi) * NT, a, b_run + (uint64_t)(kk * 2 * 3 * NT), idz, 1u, leader);
+        }
+      }
+      b_run += wz_khw16;
+    }
+  }
+}
+
 template <int NT, int TD, int KBC, bool ZS>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ ResParams p) {
@@ -163,40 +204,9 @@ k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
           const uint64_t a_stage = a_desc0 + (uint64_t)(s * stage16);
           const uint32_t acc0 = kb != 0;
           if constexpr (ZS) {
-            // B rows [kd = 2, 1, 0][co] of a (kh, kw, chunk): chunk stride (LBO) = 3*NT rows.
-            // PLANE-OUTER order: all 9 * KBC/2 MMAs of an input plane go to the SAME accumulator columns back to back
-            // (a dependent chain on identical columns runs at full rate, tools/mma_overlap_bench.cu); the tap-outer
-            // order made every MMA overlap its predecessor's columns shifted by NT, which serialises them.
-            uint64_t b_khw[9];
-            b_khw[0] = wz_desc0 + (uint64_t)(kb * (KBC * 3 * NT));
-#pragma unroll
-            for (int khw = 1; khw < 9; ++khw) b_khw[khw] = b_khw[khw - 1] + wz_khw16;
-#pragma unroll
-            for (int j = 0; j < TD + 2; ++j) {
-              // input plane q = j - 1 feeds output planes q + 1 - kd, kd in [kd_lo, kd_hi]
-              const int q = j - 1;
-              const int kd_hi = q + 1 < 2 ? q + 1 : 2, kd_lo = q + 2 - TD > 0 ? q + 2 - TD : 0;
-              const uint32_t idz = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(((kd_hi - kd_lo + 1) * NT) >> 3) << 17) |
-                                   ((128u >> 4) << 24);
-#pragma unroll
-              for (int khw = 0; khw < 9; ++khw) {
-                const uint32_t a_off = (uint32_t)((khw / 3) * HALO_W + khw % 3);
-#pragma unroll
-                for (int kk = 0; kk < KBC / 2; ++kk) {
-                  const uint64_t a = a_stage + (uint64_t)(a_off + j * PLANE + kk * KK_A);
-                  const uint64_t b = b_khw[khw] + (uint64_t)(kk * 2 * 3 * NT);
-                  if ((khw | kk) == 0 && kb == 0) {
-                    // first K step of the tile for this plane: tap by tap, the kd = 0 tap (first touch of output
-                    // plane q + 1) overwrites -- one instruction has one accumulate flag for all its columns
-#pragma unroll
-                    for (int kd = kd_lo; kd <= kd_hi; ++kd)
-                      tc_mma(d_tmem + (q + 1 - kd) * NT, a, b + (uint64_t)((2 - kd) * NT), idesc, kd != 0, leader);
-                  } else {
-                    tc_mma(d_tmem + (q + 1 - kd_hi) * NT, a, b + (uint64_t)((2 - kd_hi) * NT), idz, 1u, leader);
-                  }
-                }
-              }
-            }
+            const uint64_t b_kb = wz_desc0 + (uint64_t)(kb * (KBC * 3 * NT));
+            if (kb == 0) zs_issue_kblock<NT, TD, KBC, true>(d_tmem, a_stage, b_kb, wz_khw16, leader);
+            else zs_issue_kblock<NT, TD, KBC, false>(d_tmem, a_stage, b_kb, wz_khw16, leader);
           } else {
           uint64_t b_tap = w_desc0 + (uint64_t)(kb * (KBC * NT));
 #pragma unroll
@@ -290,6 +300,7 @@ struct ResPlan {
 };
 
 int g_res_zs_mode = 0;   // test hook: 0 = auto, 1 = never z-stack, 2 = z-stack whenever possible
+int g_res_force_td = 0, g_res_force_kb = 0;   // tuning hook (sg_tc_res_force): planes per tile / chunks per K block, 0 = auto
 
 // Applies when H >= 16, W % 8 == 0 and the weight slice of one N tile fits next to >= 2 halo stages.
 ResPlan make_res_plan(int N, int Cin, int Cout, int D, int H, int W, bool for_test = false) {
@@ -305,7 +316,8 @@ ResPlan make_res_plan(int N, int Cin, int Cout, int D, int H, int W, bool for_te
     if (27 * CCin * cand * 16 <= 120 * 1024) { NT = cand; break; }
   }
   if (NT == 0) return pl;
-  if (CoutP / NT > 2) return pl;           // more N tiles would re-read the halo too often: stream instead
+  if (CoutP / NT > 1) return pl;           // a second N tile re-reads every halo tile: the streaming kernel wins
+                                           // (64->64 @16x64x64: 69.5 us streamed, 79.9 us resident with two N tiles)
   p.w_bytes = 27 * CCin * NT * 16;
   p.th = 16;
   p.halo_w = 10; p.halo_h = 18;
@@ -317,10 +329,12 @@ ResPlan make_res_plan(int N, int Cin, int Cout, int D, int H, int W, bool for_te
   for (int td = 8; td >= 1 && best_td == 0; td /= 2) {
     if (td > D || D % td) continue;
     if (2 * td * NT > 512) continue;
+    if (g_res_force_td && td != g_res_force_td) continue;
     const bool this_zs = td >= 2 && g_res_zs_mode != 1;
     if (!this_zs && td > 4) continue;                 // the plain form is instantiated up to td = 4
     for (int kb : {4, 2}) {
       if (CCin % kb) continue;
+      if (g_res_force_kb && kb != g_res_force_kb) continue;
       const int chunk = ((td + 2) * 18 * 10 * 16 + 127) / 128 * 128;
       if (p.w_bytes + 2 * kb * chunk + 4096 + 512 > budget) continue;
       best_td = td; best_kb = kb; zs = this_zs;
