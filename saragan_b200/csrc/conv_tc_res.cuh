@@ -252,11 +252,15 @@ k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
       const int64_t plane8 = (int64_t)p.H * p.W * 8;
       const int64_t obase0 =
           (((int64_t)n * p.CCout + co0 / 8) * V + ((int64_t)d0 * p.H + h0 + (row >> 3)) * p.W + w0 + (row & 7)) * 8;
-      // prefetch the LeakyReLU-mask vectors of the whole tile before waiting for the MMAs
-      uint4 mk[TD][NT / 8];
+      // The LeakyReLU-mask vectors are prefetched before the accumulators are waited for: those of the whole tile when
+      // they fit 16 registers x 4 (TD * NT <= 128), else those of one plane at a time (a whole 4 x 64 tile is 128
+      // registers: the NT = 64 kernel with a mask ran 227 us against 171 us without).
+      constexpr bool PREFETCH_TILE = TD * NT <= 128;
+      constexpr int MK_SUB = PREFETCH_TILE ? TD : 1;
+      uint4 mk[MK_SUB][NT / 8];
       if (mask) {
 #pragma unroll
-        for (int sub = 0; sub < TD; ++sub)
+        for (int sub = 0; sub < MK_SUB; ++sub)
 #pragma unroll
           for (int c = 0; c < NT / 8; ++c)
             mk[sub][c] = __ldg(reinterpret_cast<const uint4*>(mask + obase0 + sub * plane8 + (int64_t)c * V * 8));
@@ -265,14 +269,25 @@ k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
       tc_fence_after();
 #pragma unroll
       for (int sub = 0; sub < TD; ++sub) {
+        uint4 mn[NT / 8];      // !PREFETCH_TILE: the next plane's masks, in flight during this plane's epilogue
+        if (!PREFETCH_TILE && mask && sub + 1 < TD) {
+#pragma unroll
+          for (int c = 0; c < NT / 8; ++c)
+            mn[c] = __ldg(reinterpret_cast<const uint4*>(mask + obase0 + (sub + 1) * plane8 + (int64_t)c * V * 8));
+        }
 #pragma unroll
         for (int c0 = 0; c0 < NT; c0 += 16) {
           float v[16];
           __syncwarp();
           const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * acc_cols);
           tmem_ld16(trow + (uint32_t)(sub * NT + c0), v);
-          epilogue16_regmask(v, s_bias + c0, scale, lrelu, mask != nullptr, mk[sub][c0 / 8], mk[sub][c0 / 8 + 1],
+          const int ms = PREFETCH_TILE ? sub : 0;
+          epilogue16_regmask(v, s_bias + c0, scale, lrelu, mask != nullptr, mk[ms][c0 / 8], mk[ms][c0 / 8 + 1],
                              yout + obase0 + sub * plane8 + (int64_t)(c0 / 8) * V * 8, V * 8);
+        }
+        if (!PREFETCH_TILE && mask && sub + 1 < TD) {
+#pragma unroll
+          for (int c = 0; c < NT / 8; ++c) mk[0][c] = mn[c];
         }
       }
       // this warp is done reading the accumulator set: hand it back to the MMA issuer
@@ -330,6 +345,9 @@ ResPlan make_res_plan(int N, int Cin, int Cout, int D, int H, int W, bool for_te
     if (td > D || D % td) continue;
     if (2 * td * NT > 512) continue;
     if (g_res_force_td && td != g_res_force_td) continue;
+    // measured (tools/res_sweep.py): 16 -> 32 @64x256x256 runs 236 us at td = 4 against 277 us at td = 8 (one K block
+    // of two chunks per tile: the epilogue of 8 planes outlasts the 90 MMAs that produce them)
+    if (!g_res_force_td && td == 8 && NT == 32 && CCin == 2 && D % 4 == 0) continue;
     const bool this_zs = td >= 2 && g_res_zs_mode != 1;
     if (!this_zs && td > 4) continue;                 // the plain form is instantiated up to td = 4
     for (int kb : {4, 2}) {
