@@ -85,6 +85,22 @@ int sg_pack_conv_weights_multi(const void* jobs, const int* block_job, const int
 int sg_conv3d_fprop(const void* x, const void* wp, const float* bias, const void* mask_src, void* y,
                     int dtype, int N, int Cin, int Cout, int D, int H, int W, float scale, int lrelu,
                     int impl, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+/* conv3d + ChannelNormalization (network.py:204-216, GeneratorBlock: conv1 -> lrelu -> pixel-norm, conv2 -> pixel-norm ->
+ * lrelu) in ONE tcgen05 kernel: the epilogue thread of a voxel holds all its output channels, normalises them and
+ * writes y = [lrelu](scale*conv + bias) (kept for the backward) and y_norm = [lrelu_after](y * rsqrt(mean_c y^2 + eps)).
+ * bf16, shapes with sg_conv3d_pixelnorm_supported() == 1 (weight-resident kernel, all channels in one N tile);
+ * -6 otherwise. */
+int sg_conv3d_pixelnorm_supported(int N, int Cin, int Cout, int D, int H, int W);
+int sg_conv3d_fprop_pixelnorm(const void* x, const void* wp, const float* bias, void* y, void* y_norm, int dtype, int N,
+                              int Cin, int Cout, int D, int H, int W, float scale, int lrelu, int lrelu_after, float eps,
+                              cudaStream_t stream);
+/* conv3d + nn.AvgPool3d(2) (network.py:88-90, DiscriminatorBlock: conv2 -> lrelu -> avg-pool) in ONE tcgen05 kernel:
+ * y = [lrelu](scale*conv + bias) is still written (its sign is the LeakyReLU mask of the backward pass) and
+ * y_pool[N][CC][D/2][H/2][W/2][8] = pool_scale * (2x2x2 block sums of y) (pool_scale = 1/8).  bf16, shapes with
+ * sg_conv3d_pool_supported() == 1 (weight-resident kernel, even planes per tile); -6 otherwise. */
+int sg_conv3d_pool_supported(int N, int Cin, int Cout, int D, int H, int W);
+int sg_conv3d_fprop_pool(const void* x, const void* wp, const float* bias, void* y, void* y_pool, int dtype, int N, int Cin,
+                         int Cout, int D, int H, int W, float scale, int lrelu, float pool_scale, cudaStream_t stream);
 /* 1 when impl = SG_IMPL_TF32 covers this fprop/dgrad shape (W % 8 == 0, H a multiple of min(H, 16) >= 8, ...) */
 int sg_conv3d_tf32_supported(int N, int Cin, int Cout, int D, int H, int W);
 /* bytes of caller-provided scratch the conv entry points need for this shape; kind 0 = fprop/dgrad

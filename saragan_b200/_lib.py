@@ -42,6 +42,12 @@ SIGNATURES = {
     "sg_tc_res_force": [_c_int, _c_int],
     "sg_tc_force_plan": [_c_int, _c_int, _c_int, _c_int],
     "sg_tc_plan_debug": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, ctypes.POINTER(ctypes.c_int)],
+    "sg_conv3d_pixelnorm_supported": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int],
+    "sg_conv3d_fprop_pixelnorm": [_c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f,
+                                  _c_int, _c_int, _c_f, _c_p],
+    "sg_conv3d_pool_supported": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int],
+    "sg_conv3d_fprop_pool": [_c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f,
+                             _c_int, _c_f, _c_p],
     "sg_conv3d_tf32_supported": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int],
     "sg_conv3d_workspace_bytes": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int],
     "sg_conv3d_wgrad": [_c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,

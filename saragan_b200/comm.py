@@ -234,9 +234,12 @@ class ArenaAllReduce:
     The arena and its tables are (re)built when the set of parameters with gradients or their gradient buffers change
     (never inside a capture: build once in the eager warm-up steps)."""
 
-    def __init__(self, generator, discriminator, comm_dtype: Optional[torch.dtype] = None):
+    def __init__(self, generator, discriminator, comm_dtype: Optional[torch.dtype] = None, dedicated_group: bool = True):
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self._plans: Dict[int, dict] = {}
+        # the all-reduces that end up inside a captured graph get their own communicator: eager collectives of the
+        # application (barriers, metric reductions) keep using the default group
+        self.group = dist.new_group() if (self.world > 1 and dedicated_group) else None
         if comm_dtype is not None:
             raise NotImplementedError("ArenaAllReduce exchanges fp32 gradients")
         broadcast_parameters(generator)
@@ -271,7 +274,10 @@ class ArenaAllReduce:
                 host = spare["rows"]
                 host.copy_(plan["rows_host"])
                 host[:, 0] = src
-                plan.setdefault("keepalive", []).append(host)
+                # nothing pinned may be RELEASED while the stream captures (the host allocator would record its
+                # reuse event inside the capture and later query it: cudaErrorInvalidValue at the next pinned
+                # allocation): keep the table it replaces, and the device copy made from it, alive as well
+                plan.setdefault("keepalive", []).extend([host, plan["rows_host"], plan["rows"]])
             else:
                 host = plan["rows_host"].clone()
                 host[:, 0] = src
@@ -314,7 +320,7 @@ class ArenaAllReduce:
             for p in plan["params"]:
                 plan["views"][p].copy_(p.grad * scale)
         if self.world > 1:
-            dist.all_reduce(plan["arena"], op=dist.ReduceOp.SUM)
+            dist.all_reduce(plan["arena"], op=dist.ReduceOp.SUM, group=self.group)
         return plan["views"]
 
     def finish(self, module) -> None:

@@ -12,7 +12,8 @@ SG_DEFINE_LEAK_SETTER(sg_set_leak_conv_direct)
 // fall through to the direct kernel, 0 on success, <0 / cudaError on failure.
 int sg_tc_fprop(const void* x, const void* wp, const float* bias, const void* mask_src, void* y,
                 int N, int Cin, int Cout, int D, int H, int W, float scale, int lrelu,
-                void* workspace, int64_t workspace_bytes, cudaStream_t s, int tf32);
+                void* workspace, int64_t workspace_bytes, cudaStream_t s, int tf32, void* pn_y = nullptr,
+                float pn_eps = 0.f, int pn_lrelu_after = 0, void* pool_y = nullptr, float pool_scale = 0.f);
 int sg_tc_wgrad(const void* x, const void* gy, float* gw, float* gb, int N, int Cin, int Cout,
                 int D, int H, int W, float scale, void* workspace, int64_t workspace_bytes,
                 cudaStream_t s, int tf32);
@@ -483,6 +484,41 @@ extern "C" int sg_conv3d_fprop(const void* x, const void* wp, const float* bias,
   if (impl == SG_IMPL_AUTO && small_f32_applies(dtype, N, D, H, W))
     return launch_small_f32(x, wp, bias, mask_src, y, N, Cin, Cout, D, H, W, scale, lrelu, ws, ws_bytes, s);
   SG_DISPATCH(dtype, return launch_direct_fprop<T>(x, wp, bias, mask_src, y, N, Cin, Cout, D, H, W, scale, lrelu, s););
+}
+
+// conv3d + ChannelNormalization in one kernel (generator blocks, network.py:204-216): y = [lrelu](scale*conv + bias) is
+// written for the backward, y_norm = [lrelu_after](y * rsqrt(mean_c y^2 + eps)) is what the next layer reads.  bf16
+// only, shapes for which sg_conv3d_pixelnorm_supported() is 1 (weight-resident tcgen05 kernel, one N tile).
+extern "C" int sg_conv3d_fprop_pixelnorm(const void* x, const void* wp, const float* bias, void* y, void* y_norm, int dtype,
+                                         int N, int Cin, int Cout, int D, int H, int W, float scale, int lrelu,
+                                         int lrelu_after, float eps, cudaStream_t s) {
+  SG_REQUIRE(dtype == SG_DTYPE_BF16, "sg_conv3d_fprop_pixelnorm: bf16 activations only");
+  SG_REQUIRE(y_norm != nullptr, "sg_conv3d_fprop_pixelnorm: y_norm is null");
+  if (N == 0) return 0;
+  int rc = sg_tc_fprop(x, wp, bias, nullptr, y, N, Cin, Cout, D, H, W, scale, lrelu, nullptr, 0, s, 0, y_norm, eps, lrelu_after);
+  if (rc == 1) {
+    sg_set_error("sg_conv3d_fprop_pixelnorm: shape not covered (ask sg_conv3d_pixelnorm_supported first)");
+    return -6;
+  }
+  return rc;
+}
+
+// conv3d + AvgPool3d(2) in one kernel (discriminator blocks, network.py:88-90): y = [lrelu](scale*conv + bias) is still
+// written (its sign is the LeakyReLU mask of the backward pass), y_pool = pool_scale * (2x2x2 block sums of y) is what
+// the next level reads.  bf16 only, shapes for which sg_conv3d_pool_supported() is 1.
+extern "C" int sg_conv3d_fprop_pool(const void* x, const void* wp, const float* bias, void* y, void* y_pool, int dtype, int N,
+                                    int Cin, int Cout, int D, int H, int W, float scale, int lrelu, float pool_scale,
+                                    cudaStream_t s) {
+  SG_REQUIRE(dtype == SG_DTYPE_BF16, "sg_conv3d_fprop_pool: bf16 activations only");
+  SG_REQUIRE(y_pool != nullptr, "sg_conv3d_fprop_pool: y_pool is null");
+  if (N == 0) return 0;
+  int rc = sg_tc_fprop(x, wp, bias, nullptr, y, N, Cin, Cout, D, H, W, scale, lrelu, nullptr, 0, s, 0, nullptr, 0.f, 0, y_pool,
+                       pool_scale);
+  if (rc == 1) {
+    sg_set_error("sg_conv3d_fprop_pool: shape not covered (ask sg_conv3d_pool_supported first)");
+    return -6;
+  }
+  return rc;
 }
 
 // ------------------------------------------------------------------------ direct wgrad

@@ -632,6 +632,8 @@ extern "C" void sg_tc_force_plan(int nt, int big, int td_max, int splits) {
 
 int64_t sg_tc_wgrad_workspace_bytes(int N, int Cin, int Cout, int D, int H, int W, int tf32);
 
+extern "C" int sg_conv3d_pixelnorm_supported(int N, int Cin, int Cout, int D, int H, int W);
+extern "C" int sg_conv3d_pool_supported(int N, int Cin, int Cout, int D, int H, int W);
 int sg_conv_finish_f32(const float* acc, const float* bias, const void* mask_src, void* y, int N,
                        int Cout, int64_t V, float scale, int lrelu, cudaStream_t s);
 
@@ -673,10 +675,30 @@ int sg_encode_f32_half_map(CUtensorMap* map, const void* x, int half, int N, int
   return encode_f32_half_map(map, x, half, N, CC8, D, H, W, box_w, box_h, box_d, box_c);
 }
 
-// tf32 != 0: x, y, mask_src are fp32 acts, wp is the SG_TF32 packing; the streaming kernel with kind::tf32
+// 1 when the fused conv + pixel-norm epilogue covers the shape: bf16, the weight-resident kernel with ONE N tile
+extern "C" int sg_conv3d_pixelnorm_supported(int N, int Cin, int Cout, int D, int H, int W) {
+  if (N <= 0 || Cin <= 0 || Cout <= 0 || D <= 0 || H <= 0 || W <= 0 || g_force_streaming == 1) return 0;
+  ResPlan rp = make_res_plan(N, Cin, Cout, D, H, W, g_force_streaming == 2);
+  return rp.ok && rp.NT == rp.p.CoutP ? 1 : 0;
+}
+
+// 1 when the fused conv + 2x2x2 pooling epilogue covers the shape: bf16, the weight-resident kernel with an even number
+// of planes per tile
+extern "C" int sg_conv3d_pool_supported(int N, int Cin, int Cout, int D, int H, int W) {
+  if (N <= 0 || Cin <= 0 || Cout <= 0 || D <= 0 || H <= 0 || W <= 0 || g_force_streaming == 1 || D % 2) return 0;
+  ResPlan rp = make_res_plan(N, Cin, Cout, D, H, W, g_force_streaming == 2);
+  return rp.ok && rp.p.td % 2 == 0 ? 1 : 0;
+}
+
+// tf32 != 0: x, y, mask_src are fp32 acts, wp is the SG_TF32 packing; the streaming kernel with kind::tf32.
+// pn_y != null: fused pixel-norm second output; pool_y != null: fused 2x2x2 pooling second output (bf16, resident kernel
+// only: returns 1 otherwise).
 int sg_tc_fprop(const void* x, const void* wp, const float* bias, const void* mask_src, void* y, int N, int Cin,
                 int Cout, int D, int H, int W, float scale, int lrelu, void* ws, int64_t ws_bytes, cudaStream_t s,
-                int tf32) {
+                int tf32, void* pn_y = nullptr, float pn_eps = 0.f, int pn_lrelu_after = 0, void* pool_y = nullptr,
+                float pool_scale = 0.f) {
+  if (pn_y != nullptr && (tf32 || !sg_conv3d_pixelnorm_supported(N, Cin, Cout, D, H, W) || mask_src != nullptr)) return 1;
+  if (pool_y != nullptr && (tf32 || !sg_conv3d_pool_supported(N, Cin, Cout, D, H, W) || mask_src != nullptr || pn_y)) return 1;
   if (!tf32 && g_force_streaming != 1) {
     ResPlan rp = make_res_plan(N, Cin, Cout, D, H, W, g_force_streaming == 2);
     if (rp.ok) {
@@ -687,6 +709,12 @@ int sg_tc_fprop(const void* x, const void* wp, const float* bias, const void* ma
       q.y = (__nv_bfloat16*)y;
       q.scale = scale;
       q.lrelu = lrelu;
+      q.pn_y = (__nv_bfloat16*)pn_y;
+      q.pn_eps = pn_eps;
+      q.pn_inv_c = 1.f / (float)Cout;
+      q.pn_lrelu_after = pn_lrelu_after;
+      q.pool_y = (__nv_bfloat16*)pool_y;
+      q.pool_scale = pool_scale;
       CUtensorMap rmap;
       int rc = encode_halo_map(&rmap, x, N, q.CCin, D, H, W, q.halo_w, q.halo_h, q.halo_d, 1);
       if (rc) return rc;

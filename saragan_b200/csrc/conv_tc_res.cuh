@@ -49,6 +49,18 @@ struct ResParams {
   int tmem_cols;
   float scale;
   int lrelu;
+  // fused ChannelNormalization (network.py:192-197) of the generator blocks: when pn_y is set the CTA's N tile holds
+  // ALL output channels of a voxel, the epilogue thread of that voxel normalises them and writes y (the conv / LeakyReLU
+  // output the backward needs) AND pn_y = [lrelu](y * rsqrt(mean_c y^2 + eps))
+  __nv_bfloat16* pn_y;
+  float pn_eps, pn_inv_c;
+  int pn_lrelu_after;
+  // fused AvgPool3d(2) of the discriminator blocks (network.py:88-90 conv2 -> lrelu -> avg-pool): when pool_y is set the
+  // epilogue also writes pool_y[N][CCout][D/2][H/2][W/2][8] = pool_scale * (2x2x2 block sums of y).  A CTA tile holds
+  // whole blocks (TD even, 16 lines, 8 voxels): the two planes are the same thread's, the h / w neighbours sit 8 / 1
+  // lanes away (two shuffles per value).  y itself is still written: its sign is the mask of the backward pass.
+  __nv_bfloat16* pool_y;
+  float pool_scale;
 };
 
 // NT = output-channel tile, TD = depth planes per tile (= MMA tiles per accumulator set),
@@ -267,6 +279,96 @@ k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
       }
       mbar_wait(BAR(ACC_FULL + buf), (ti >> 1) & 1);
       tc_fence_after();
+      if (p.pn_y != nullptr) {
+        // conv -> [lrelu] -> pixel-norm [-> lrelu]: this thread holds all NT channels of its voxel
+        const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * acc_cols);
+#pragma unroll 1
+        for (int sub = 0; sub < TD; ++sub) {
+          float t[NT];
+          __syncwarp();
+          tmem_ld_block<NT>(trow + (uint32_t)(sub * NT), t);
+          float ss = 0.f;
+#pragma unroll
+          for (int i = 0; i < NT; ++i) {
+            float a = fmaf(t[i], scale, s_bias[i]);
+            if (lrelu) a = lrelu02(a);
+            t[i] = a;
+            ss = fmaf(a, a, ss);
+          }
+          const float r = rsqrtf(ss * p.pn_inv_c + p.pn_eps);
+          __nv_bfloat16* y0 = yout + obase0 + sub * plane8;
+          __nv_bfloat16* y1 = p.pn_y + obase0 + sub * plane8;
+#pragma unroll
+          for (int c = 0; c < NT / 8; ++c) {
+            F8 a, b;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              a.v[j] = t[8 * c + j];
+              const float u = t[8 * c + j] * r;
+              b.v[j] = p.pn_lrelu_after ? lrelu02(u) : u;
+            }
+            st8(y0 + (int64_t)c * V * 8, a);
+            st8(y1 + (int64_t)c * V * 8, b);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(ACC_EMPTY + buf));
+        continue;
+      }
+      if constexpr (TD % 2 == 0) {
+        if (p.pool_y != nullptr) {
+          const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * acc_cols);
+          const int Hp = p.H >> 1, Wp = p.W >> 1;
+          const int64_t Vp = (int64_t)(p.D >> 1) * Hp * Wp;
+          const bool writer = (lane & 9) == 0;                       // even w (lane bit 0) and even h (lane bit 3)
+          const int64_t pbase0 = (((int64_t)n * p.CCout + co0 / 8) * Vp +
+                                  ((int64_t)(d0 >> 1) * Hp + ((h0 + (row >> 3)) >> 1)) * Wp + ((w0 + (row & 7)) >> 1)) * 8;
+#pragma unroll 1
+          for (int sub = 0; sub < TD; sub += 2) {
+#pragma unroll 1
+            for (int c0 = 0; c0 < NT; c0 += 16) {
+              float v0[16], v1[16];
+              __syncwarp();
+              tmem_ld16(trow + (uint32_t)(sub * NT + c0), v0);
+              tmem_ld16(trow + (uint32_t)((sub + 1) * NT + c0), v1);
+              float sum[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                float a = fmaf(v0[i], scale, s_bias[c0 + i]), b = fmaf(v1[i], scale, s_bias[c0 + i]);
+                if (lrelu) {
+                  a = lrelu02(a);
+                  b = lrelu02(b);
+                }
+                v0[i] = a;
+                v1[i] = b;
+                float t = a + b;
+                t += __shfl_xor_sync(0xffffffffu, t, 1);
+                t += __shfl_xor_sync(0xffffffffu, t, 8);
+                sum[i] = t * p.pool_scale;
+              }
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                F8 o0, o1, op;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  o0.v[j] = v0[half * 8 + j];
+                  o1.v[j] = v1[half * 8 + j];
+                  op.v[j] = sum[half * 8 + j];
+                }
+                const int64_t ch = (int64_t)(c0 / 8 + half);
+                st8(yout + obase0 + sub * plane8 + ch * V * 8, o0);
+                st8(yout + obase0 + (sub + 1) * plane8 + ch * V * 8, o1);
+                if (writer) st8(p.pool_y + pbase0 + (int64_t)(sub >> 1) * Hp * Wp * 8 + ch * Vp * 8, op);
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(ACC_EMPTY + buf));
+          continue;
+        }
+      }
 #pragma unroll
       for (int sub = 0; sub < TD; ++sub) {
         uint4 mn[NT / 8];      // !PREFETCH_TILE: the next plane's masks, in flight during this plane's epilogue

@@ -173,6 +173,44 @@ def conv3d_fprop(x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor]
     return y
 
 
+def conv_pixelnorm_supported(x: torch.Tensor, cin: int, cout: int) -> bool:
+    """True when conv3d_fprop_pixelnorm covers this call (bf16, weight-resident kernel, all channels in one N tile)."""
+    if x.dtype != torch.bfloat16:
+        return False
+    n, _, d, h, w, _ = x.shape
+    return bool(_lib.load().sg_conv3d_pixelnorm_supported(n, cin, cout, d, h, w))
+
+
+def conv3d_fprop_pixelnorm(x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor], cin: int, cout: int,
+                           scale: float, lrelu: bool, lrelu_after: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(y, y_norm): y = [lrelu](scale*conv(x) + bias), y_norm = [lrelu_after](pixel-norm(y)) from one kernel."""
+    n, cc, d, h, w, _ = x.shape
+    y = torch.empty((n, chunks(cout), d, h, w, 8), dtype=x.dtype, device=x.device)
+    y_norm = torch.empty_like(y)
+    call("sg_conv3d_fprop_pixelnorm", x, wp, bias, y, y_norm, _lib.dtype_code(x), n, cin, cout, d, h, w, float(scale),
+         int(lrelu), int(lrelu_after), EPS_PN)
+    return y, y_norm
+
+
+def conv_pool_supported(x: torch.Tensor, cin: int, cout: int) -> bool:
+    """True when conv3d_fprop_pool covers this call (bf16 in and out, weight-resident kernel, even planes per tile)."""
+    if x.dtype != torch.bfloat16:
+        return False
+    n, _, d, h, w, _ = x.shape
+    return bool(_lib.load().sg_conv3d_pool_supported(n, cin, cout, d, h, w))
+
+
+def conv3d_fprop_pool(x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor], cin: int, cout: int, scale: float,
+                      lrelu: bool, pool_scale: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(y, y_pool): y = [lrelu](scale*conv(x) + bias), y_pool = pool_scale * (2x2x2 block sums of y) from one kernel."""
+    n, cc, d, h, w, _ = x.shape
+    y = torch.empty((n, chunks(cout), d, h, w, 8), dtype=x.dtype, device=x.device)
+    y_pool = torch.empty((n, chunks(cout), d // 2, h // 2, w // 2, 8), dtype=x.dtype, device=x.device)
+    call("sg_conv3d_fprop_pool", x, wp, bias, y, y_pool, _lib.dtype_code(x), n, cin, cout, d, h, w, float(scale), int(lrelu),
+         float(pool_scale))
+    return y, y_pool
+
+
 def conv3d_wgrad(x: torch.Tensor, gy: torch.Tensor, cin: int, cout: int, scale: float,
                  want_bias: bool, impl: int = _lib.IMPL_AUTO
                  ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:

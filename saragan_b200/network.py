@@ -175,8 +175,16 @@ class DiscriminatorBlock(nn.Sequential, _Blocked):
         # for conv1, the avg-pool backward masks for conv2; in the gradient penalty's double backward
         # they ride in the producers' epilogues (dd_fuse, ops.Conv3x3)
         x = self.conv1(x, lrelu=True, premasked=True, mask_input_grad=input_is_lrelu and not plain, dd_fuse=True)
-        x = self.conv2(x, lrelu=True, premasked=True, mask_input_grad=True, dd_fuse=True)
-        x = ops.Down2.apply(x, 0.125, config.act_dtype(_voxels(x) // 8), True, True)
+        conv2 = self.conv2
+        if (kernels.conv_pool_supported(x, conv2.in_channels, conv2.out_channels)
+                and config.act_dtype(_voxels(x) // 8) == x.dtype):
+            # conv2 -> lrelu -> avg-pool in one kernel (the pooling rides in the convolution's epilogue)
+            if conv2._packed.weight is not conv2.weight:
+                conv2._packed = ops.PackedWeight(conv2.weight, known=conv2._packed.known)
+            x = ops.ConvPool.apply(x, conv2.weight, conv2.bias, conv2._packed, float(conv2.std), True, True)
+        else:
+            x = conv2(x, lrelu=True, premasked=True, mask_input_grad=True, dd_fuse=True)
+            x = ops.Down2.apply(x, 0.125, config.act_dtype(_voxels(x) // 8), True, True)
         return self.leave(x, self.filters_out) if plain else x
 
 
@@ -307,11 +315,23 @@ class GeneratorBlock(nn.Sequential, _Blocked):
         x = self.enter(input) if plain else input
         c = self.conv1.out_channels
         x = ops.Up2.apply(x, 1.0, config.act_dtype(_voxels(x) * 8))
-        x = self.conv1(x, lrelu=True, premasked=True)          # pixel-norm's backward applies the mask
-        x = self.cn(x, channels=c, mask_input=True)
-        x = self.conv2(x)
-        x = self.cn(x, lrelu_after=True, channels=c)
+        x = self._conv_norm(self.conv1, x, lrelu=True, lrelu_after=False)     # conv1 -> lrelu -> pixel-norm
+        x = self._conv_norm(self.conv2, x, lrelu=False, lrelu_after=True)     # conv2 -> pixel-norm -> lrelu
         return self.leave(x, c) if plain else x
+
+    def _conv_norm(self, conv, x, lrelu: bool, lrelu_after: bool):
+        """conv + ChannelNormalization (+ the LeakyReLU on either side): one fused tcgen05 kernel where the layer's
+        channels fit one N tile of the weight-resident kernel (the two top levels of the benchmarked configurations),
+        the convolution and the pixel-norm kernel otherwise."""
+        c = conv.out_channels
+        if kernels.conv_pixelnorm_supported(x, conv.in_channels, c):
+            if conv._packed.weight is not conv.weight:
+                conv._packed = ops.PackedWeight(conv.weight, known=conv._packed.known)
+            return ops.ConvPixelNorm.apply(x, conv.weight, conv.bias, conv._packed, float(conv.std), lrelu, lrelu_after)
+        if lrelu:
+            x = conv(x, lrelu=True, premasked=True)            # pixel-norm's backward applies the mask
+            return self.cn(x, channels=c, mask_input=True)
+        return self.cn(conv(x), lrelu_after=lrelu_after, channels=c)
 
 
 class ToRGB(nn.Sequential):

@@ -201,6 +201,75 @@ class ConvDgrad(Function):
         return gg, gw, None, None, None, None, None
 
 
+class ConvPool(Function):
+    """pool = 1/8 * (2x2x2 block sums of lrelu(std * conv3d(x, w) + b)): the discriminator block's conv2 -> LeakyReLU ->
+    AvgPool3d(2) (network.py:88-90) in ONE tcgen05 kernel.  The backward is exactly the graph the separate ops build with
+    the block's fusion flags -- Up2 (masked by the conv output y) -> ConvDgrad / ConvWgrad -- so the gradient penalty's
+    double backward differentiates through it like before."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, pw: Optional[PackedWeight], std: float, mask_input_grad: bool, dd_fuse: bool):
+        cout, cin = weight.shape[0], weight.shape[1]
+        pw = pw if pw is not None else PackedWeight(weight, cache=False)
+        y, y_pool = K.conv3d_fprop_pool(x, pw.get(x.dtype, False), bias, cin, cout, std, True, 0.125)
+        ctx.save_for_backward(x, weight, y)
+        ctx.pw, ctx.std, ctx.has_bias, ctx.mask_input_grad, ctx.dd_fuse = pw, std, bias is not None, mask_input_grad, dd_fuse
+        return y_pool
+
+    @staticmethod
+    def backward(ctx, gpool):
+        x, weight, y = ctx.saved_tensors
+        g = Up2.apply(_c(gpool), 0.125, y.dtype, y, ctx.dd_fuse)          # avg-pool backward with the LeakyReLU mask
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = ConvDgrad.apply(g, weight, ctx.pw, ctx.std, x if ctx.mask_input_grad else None,
+                                 y if ctx.dd_fuse else None, ctx.dd_fuse and ctx.mask_input_grad)
+        want_w = ctx.needs_input_grad[1] and _weight_grads_enabled
+        want_b = ctx.has_bias and ctx.needs_input_grad[2] and _weight_grads_enabled
+        if want_w:
+            gw, gb_ = ConvWgrad.apply(x, g, ctx.std, weight.shape[1], weight.shape[0], want_b)
+            gb = gb_ if want_b else None
+        elif want_b:
+            gb = ChanSum.apply(g, weight.shape[0])
+        return gx, gw, gb, None, None, None, None
+
+
+class ConvPixelNorm(Function):
+    """y = [lrelu_after](pixel_norm([lrelu](std * conv3d(x, w) + b))): a generator-block convolution with its
+    ChannelNormalization (and the LeakyReLU on either side, network.py:204-216) in ONE tcgen05 kernel -- the epilogue
+    thread of a voxel holds all its channels.  First order only (the generator is never differentiated twice); the
+    backward is pixel-norm backward (with the inner LeakyReLU's mask) -> dgrad / wgrad."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, pw: Optional[PackedWeight], std: float, lrelu: bool, lrelu_after: bool):
+        cout, cin = weight.shape[0], weight.shape[1]
+        pw = pw if pw is not None else PackedWeight(weight, cache=False)
+        y, y_norm = K.conv3d_fprop_pixelnorm(x, pw.get(x.dtype, False), bias, cin, cout, std, lrelu, lrelu_after)
+        ctx.save_for_backward(x, weight, y)
+        ctx.pw, ctx.std, ctx.lrelu, ctx.lrelu_after, ctx.has_bias = pw, std, lrelu, lrelu_after, bias is not None
+        return y_norm
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x, weight, y = ctx.saved_tensors
+        cout, cin = weight.shape[0], weight.shape[1]
+        # through [lrelu_after] and the normalisation, then through the conv's own LeakyReLU (mask_input: y is its output)
+        g = K.pixelnorm_bwd(y, _c(gy), cout, ctx.lrelu_after, ctx.lrelu)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            impl, kind = config.conv_route(g, cout, cin)
+            gx = K.conv3d_fprop(g, ctx.pw.get(kind, True), None, None, cout, cin, ctx.std, False, impl)
+        want_w = ctx.needs_input_grad[1] and _weight_grads_enabled
+        want_b = ctx.has_bias and ctx.needs_input_grad[2] and _weight_grads_enabled
+        if want_w:
+            gw, gb_ = K.conv3d_wgrad(x, g, cin, cout, ctx.std, want_b, config.wgrad_impl(x, cin, cout))
+            gb = gb_ if want_b else None
+        elif want_b:
+            gb = K.pw_wgrad(g, None, cout, 1.0, False, True)[1]
+        return gx, gw, gb, None, None, None, None
+
+
 class ConvWgrad(Function):
     """gw = std * sum_p g (x) x,  gb = sum_p g   (fp32)."""
 

@@ -81,6 +81,8 @@ class FusedAdam(torch.optim.Optimizer):
             host = dict(t=spare["t"][:len(rows)], bt=spare["bt"][:len(block_tensor)], bo=spare["bo"][:len(block_offset)])
             host["t"].copy_(t_rows), host["bt"].copy_(t_bt), host["bo"].copy_(t_bo)
             self._graph_keepalive.append(spare)   # must outlive the graph even if an eager step rebuilds the table
+            if gi in self._tables:                # ... and nothing pinned may be released while the stream captures
+                self._graph_keepalive.append(self._tables[gi])
         else:
             host = dict(t=t_rows.pin_memory(), bt=t_bt.pin_memory(), bo=t_bo.pin_memory())
         tab = dict(key=key, host=host, n_blocks=len(block_tensor),

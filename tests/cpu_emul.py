@@ -92,6 +92,46 @@ def conv3d_fprop(x, wp, bias, mask_src, cin, cout, scale, lrelu, impl=0):
     return out
 
 
+def conv_pixelnorm_supported(x, cin, cout):
+    """mirror of sg_conv3d_pixelnorm_supported: bf16, H % 16 == 0, W % 8 == 0, the resident weights of ONE N tile fit"""
+    n, _, d, h, w, _ = x.shape
+    coutp, ccin = 16 * ((cout + 15) // 16), chunks(cin)
+    return (x.dtype == torch.bfloat16 and h % 16 == 0 and w % 8 == 0 and coutp in (16, 32, 64)
+            and 27 * ccin * coutp * 16 <= 120 * 1024 and d >= 2 and d % 2 == 0)
+
+
+def conv3d_fprop_pixelnorm(x, wp, bias, cin, cout, scale, lrelu, lrelu_after):
+    """the fused kernel normalises the fp32 accumulator values (y itself is rounded to bf16 only when stored)"""
+    xp = act_to_plain(x, cin)
+    y = F.conv3d(xp, wp.w, None, 1, 1) * scale
+    if bias is not None:
+        y = y + bias.view(1, -1, 1, 1, 1)
+    if lrelu:
+        y = F.leaky_relu(y, LEAK)
+    yn = y * torch.rsqrt(torch.mean(y ** 2, dim=1, keepdim=True) + 1e-8)
+    if lrelu_after:
+        yn = F.leaky_relu(yn, LEAK)
+    return plain_to_act(y, x.dtype), plain_to_act(yn, x.dtype)
+
+
+def conv_pool_supported(x, cin, cout):
+    """mirror of sg_conv3d_pool_supported: like the resident kernel's coverage, even depth"""
+    return conv_pixelnorm_supported(x, cin, cout) or (
+        x.dtype == torch.bfloat16 and x.shape[3] % 16 == 0 and x.shape[4] % 8 == 0 and x.shape[2] % 2 == 0
+        and 16 * ((cout + 15) // 16) in (16, 32, 64) and 27 * chunks(cin) * 16 * ((cout + 15) // 16) * 16 <= 120 * 1024)
+
+
+def conv3d_fprop_pool(x, wp, bias, cin, cout, scale, lrelu, pool_scale):
+    """the fused kernel pools the fp32 values (y itself is rounded to bf16 only when stored)"""
+    xp = act_to_plain(x, cin)
+    y = F.conv3d(xp, wp.w, None, 1, 1) * scale
+    if bias is not None:
+        y = y + bias.view(1, -1, 1, 1, 1)
+    if lrelu:
+        y = F.leaky_relu(y, LEAK)
+    return plain_to_act(y, x.dtype), plain_to_act(F.avg_pool3d(y, 2) * (8.0 * pool_scale), x.dtype)
+
+
 def conv3d_wgrad(x, gy, cin, cout, scale, want_bias, impl=0):
     xp = act_to_plain(x, cin)
     gp = act_to_plain(gy, cout)

@@ -41,11 +41,23 @@ def reals(rank, i, dev):
     return torch.rand(B, 1, *VOL, generator=torch.Generator().manual_seed(77 * rank + i)).to(dev) * 2
 
 
+DEBUG = bool(os.environ.get("MGPU_DEBUG"))
+
+
+def _dbg(msg):
+    if DEBUG:
+        torch.cuda.synchronize()
+        print(f"[dbg rank {os.environ.get('RANK')}] {msg}", flush=True)
+
+
 def gather_equal(t):
     """True when every rank holds bit-identical `t`."""
     world = dist.get_world_size()
+    _dbg("gather_equal: enter")
     buf = [torch.empty_like(t) for _ in range(world)]
+    _dbg("gather_equal: buffers allocated")
     dist.all_gather(buf, t.contiguous())
+    _dbg("gather_equal: all_gather done")
     return all(torch.equal(buf[0], b) for b in buf[1:])
 
 
@@ -84,7 +96,8 @@ def main():
 
     # ---- 2. K steps: eager bucketed vs segmented graph; replicas bit-identical
     finals = {}
-    for mode in ("eager_bucketed", "graph_segments", "graph_arena"):
+    modes = os.environ.get("MGPU_MODES", "eager_bucketed,graph_segments,graph_arena").split(",")
+    for mode in modes:
         g, d = build()
         g_opt, d_opt = make_capturable_optimizers(g, d, world_size=world)
         if mode == "eager_bucketed":
@@ -99,13 +112,19 @@ def main():
                 graphed.draw = lambda dr=dr: [getattr(graphed, k).copy_(v) for k, v in dr.items()]   # replay the same draws
                 o = graphed(reals(rank, i, dev))
         torch.cuda.synchronize()
+        _dbg(f"{mode}: steps done")
+        if DEBUG:
+            tt = torch.ones(4, device=dev)
+            dist.all_reduce(tt)
+            _dbg(f"{mode}: small eager all_reduce ok {tt.tolist()}")
         flat = torch.cat([p.detach().reshape(-1) for p in list(g.parameters()) + list(d.parameters())])
+        _dbg(f"{mode}: flat built {flat.numel()}")
         same = gather_equal(flat)
         res[f"replicas_bit_identical.{mode}"] = same
         ok &= same
         finals[mode] = flat
         res[f"losses.{mode}"] = [float(o[k]) for k in ("d_loss", "gp", "g_loss")]
-    for other in ("graph_segments", "graph_arena"):
+    for other in [m for m in modes if m != "eager_bucketed" and "eager_bucketed" in modes]:
         diff = float((finals["eager_bucketed"] - finals[other]).abs().mean())
         res[f"mean_abs_weight_diff_eager_vs_{other}"] = diff
         # Adam with beta1 = 0 turns rounding-level gradient differences into +-lr steps: after K steps the two paths

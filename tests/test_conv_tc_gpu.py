@@ -211,3 +211,131 @@ def test_tcgen05_adjoint_property_full_size():
     lhs = float((y.double() * gy.double()).sum())
     rhs = float((x.double() * gx.double()).sum())
     assert abs(lhs - rhs) < 5e-3 * max(abs(lhs), abs(rhs)), (lhs, rhs)
+
+
+PN_SHAPES = [(2, 32, 16, 8, 32, 16), (1, 64, 32, 4, 16, 32), (2, 16, 16, 8, 16, 16), (1, 32, 64, 4, 16, 16), (3, 16, 8, 4, 16, 8)]
+
+
+@pytest.mark.parametrize("shape", PN_SHAPES)
+@pytest.mark.parametrize("lrelu,lrelu_after", [(True, False), (False, True)])
+def test_fused_conv_pixelnorm(shape, lrelu, lrelu_after):
+    """sg_conv3d_fprop_pixelnorm (conv + ChannelNormalization in one tcgen05 kernel: the generator block's conv1 ->
+    lrelu -> pixel-norm and conv2 -> pixel-norm -> lrelu) against the CPU restatement and against the two separate
+    kernels (which round y to bf16 before normalising it: 1e-2)."""
+    n, cin, cout, d, h, w = shape
+    g = torch.Generator().manual_seed(sum(shape) + 21)
+    wt = torch.randn(cout, cin, 3, 3, 3, generator=g)
+    xa = E.plain_to_act(torch.randn(n, cin, d, h, w, generator=g), BF)
+    bias = torch.randn(cout, generator=g)
+    xg, wp = xa.cuda(), K.pack_conv_weight(wt.cuda(), BF, False)
+    lib = _lib.load()
+    try:
+        lib.sg_tc_force_streaming(2)      # take the weight-resident kernel although the test shape has few tiles
+        assert K.conv_pixelnorm_supported(xg, cin, cout)
+        y, yn = K.conv3d_fprop_pixelnorm(xg, wp, bias.cuda(), cin, cout, 0.05, lrelu, lrelu_after)
+        y_sep = K.conv3d_fprop(xg, wp, bias.cuda(), None, cin, cout, 0.05, lrelu, _lib.IMPL_TCGEN05)
+        yn_sep = K.pixelnorm_fwd(y_sep, cout, lrelu_after)
+        torch.cuda.synchronize()
+    finally:
+        lib.sg_tc_force_streaming(0)
+    want_y, want_yn = E.conv3d_fprop_pixelnorm(xa, E.pack_conv_weight(wt, BF, False), bias, cin, cout, 0.05, lrelu, lrelu_after)
+    assert rel_err(y.float().cpu(), want_y.float()) < 3e-3 and rel_err(yn.float().cpu(), want_yn.float()) < 3e-3
+    assert torch.equal(y, y_sep)                                     # the conv output itself is the same kernel's
+    assert rel_err(yn.float(), yn_sep.float()) < 1e-2
+    if cout % 16:                                                    # pad channels stay exactly zero
+        cc = y.shape[1]
+        flat = yn.float().permute(0, 1, 5, 2, 3, 4).reshape(n, cc * 8, d, h, w)
+        assert float(flat[:, cout:].abs().max()) == 0.0
+
+
+def test_generator_block_fused_equals_unfused(monkeypatch):
+    """GeneratorBlock with the fused conv + pixel-norm kernels against the same block on the separate kernels: outputs
+    and every gradient (bf16 rounding of the intermediate is the only difference)."""
+    import saragan_b200 as sg
+    from saragan_b200 import kernels
+    torch.manual_seed(3)
+    blk = sg.GeneratorBlock(64, 32).cuda()
+    x = torch.randn(2, 64, 4, 16, 8, device="cuda")
+    gy = torch.randn(2, 32, 8, 32, 16, device="cuda")
+    lib = _lib.load()
+    res = {}
+    for fused in (True, False):
+        if not fused:
+            monkeypatch.setattr(kernels, "conv_pixelnorm_supported", lambda *a: False)
+        try:
+            lib.sg_tc_force_streaming(2)
+            for rep in range(2):           # the first pass also packs the weights: count the second
+                n0 = _lib.launch_count()
+                xi = x.clone().requires_grad_(True)
+                y = blk(xi)
+                grads = torch.autograd.grad(y, [xi] + list(blk.parameters()), gy)
+                torch.cuda.synchronize()
+            res[fused] = (y, grads, _lib.launch_count() - n0)
+        finally:
+            lib.sg_tc_force_streaming(0)
+    assert res[True][2] < res[False][2]                               # two kernels fewer in the forward
+    assert rel_err(res[True][0], res[False][0]) < 1e-2
+    for a, b in zip(res[True][1], res[False][1]):
+        assert rel_err(a, b) < 5e-2, rel_err(a, b)       # (the unfused arm normalises the bf16-rounded conv output)
+
+
+POOL_SHAPES = [(2, 32, 64, 8, 32, 16), (1, 16, 32, 4, 16, 32), (2, 16, 16, 8, 16, 16), (3, 32, 32, 4, 16, 8)]
+
+
+@pytest.mark.parametrize("shape", POOL_SHAPES)
+def test_fused_conv_avgpool(shape):
+    """sg_conv3d_fprop_pool (the discriminator block's conv2 -> lrelu -> AvgPool3d(2) in one tcgen05 kernel) against the
+    CPU restatement and the two separate kernels (which pool the bf16-rounded y)."""
+    n, cin, cout, d, h, w = shape
+    g = torch.Generator().manual_seed(sum(shape) + 31)
+    wt = torch.randn(cout, cin, 3, 3, 3, generator=g)
+    xa = E.plain_to_act(torch.randn(n, cin, d, h, w, generator=g), BF)
+    bias = torch.randn(cout, generator=g)
+    xg, wp = xa.cuda(), K.pack_conv_weight(wt.cuda(), BF, False)
+    lib = _lib.load()
+    try:
+        lib.sg_tc_force_streaming(2)
+        assert K.conv_pool_supported(xg, cin, cout)
+        y, yp = K.conv3d_fprop_pool(xg, wp, bias.cuda(), cin, cout, 0.05, True, 0.125)
+        y_sep = K.conv3d_fprop(xg, wp, bias.cuda(), None, cin, cout, 0.05, True, _lib.IMPL_TCGEN05)
+        yp_sep = K.down2(y_sep, 0.125)
+        torch.cuda.synchronize()
+    finally:
+        lib.sg_tc_force_streaming(0)
+    want_y, want_yp = E.conv3d_fprop_pool(xa, E.pack_conv_weight(wt, BF, False), bias, cin, cout, 0.05, True, 0.125)
+    assert torch.equal(y, y_sep)
+    assert rel_err(y.float().cpu(), want_y.float()) < 3e-3 and rel_err(yp.float().cpu(), want_yp.float()) < 3e-3
+    assert rel_err(yp.float(), yp_sep.float()) < 6e-3
+
+
+def test_discriminator_block_fused_pool_equals_unfused(monkeypatch):
+    """DiscriminatorBlock with the fused conv2 + avg-pool kernel against the same block on the separate kernels: output,
+    first-order gradients and the double backward of a gradient-penalty-like scalar."""
+    import saragan_b200 as sg
+    from saragan_b200 import kernels
+    torch.manual_seed(4)
+    blk = sg.DiscriminatorBlock(16, 32).cuda()
+    x = torch.randn(2, 16, 8, 32, 16, device="cuda")
+    lib = _lib.load()
+    res = {}
+    for fused in (True, False):
+        if not fused:
+            monkeypatch.setattr(kernels, "conv_pool_supported", lambda *a: False)
+        try:
+            lib.sg_tc_force_streaming(2)
+            for rep in range(2):           # the first pass also packs the weights: count the second
+                n0 = _lib.launch_count()
+                xi = x.clone().requires_grad_(True)
+                y = blk(xi)
+                (gx,) = torch.autograd.grad(y.float().pow(2).sum(), xi, create_graph=True)
+                gp = (gx.flatten(1).norm(dim=1) - 1).pow(2).mean()
+                gw = torch.autograd.grad(gp, list(blk.parameters()))
+                torch.cuda.synchronize()
+            res[fused] = (y, gx, gw, _lib.launch_count() - n0)
+        finally:
+            lib.sg_tc_force_streaming(0)
+    assert res[True][3] < res[False][3]
+    assert rel_err(res[True][0], res[False][0]) < 6e-3
+    assert rel_err(res[True][1], res[False][1]) < 2e-2
+    for a, b in zip(res[True][2], res[False][2]):
+        assert rel_err(a, b) < 5e-2, rel_err(a, b)
