@@ -470,6 +470,8 @@ def main():
                                               f"({t:.1f} s), fp32 torch CPU oracle"}
         print(json.dumps(line), flush=True)
     if world > 1:
+        if use_graph:
+            graphed.close()                    # NCCL work captured in the graph must go before the communicator does
         dist.destroy_process_group()
 
 

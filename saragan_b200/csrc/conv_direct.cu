@@ -365,22 +365,27 @@ __global__ void k_conv_finish(const float* __restrict__ acc, const float* __rest
     }
   }
 }
-int sg_conv_finish_bf16(const float* acc, const float* bias, const void* mask_src, void* y, int N,
-                        int Cout, int64_t V, float scale, int lrelu, cudaStream_t s) {
+// `slices` partial sums [slices][N*V][CoutP] -> the activation tensor (bias, scale, LeakyReLU / mask applied once)
+template <typename T>
+static int conv_finish_launch(const float* acc, const float* bias, const void* mask_src, void* y, int N, int Cout,
+                              int64_t V, float scale, int lrelu, int slices, cudaStream_t s) {
   int CCout = sg_chunks(Cout), CoutP = 16 * ((Cout + 15) / 16);
   int64_t total = (int64_t)N * CCout * V;
-  sg_launch((k_conv_finish<__nv_bfloat16, 1>), sg_grid(total, 256), 256, 0, s,
-      acc, bias, (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)y, N, Cout, CCout, CoutP, V, scale, lrelu, 1);
+  if (slices >= 8)
+    sg_launch((k_conv_finish<T, 8>), sg_grid(total * 8, 256), 256, 0, s, acc, bias, (const T*)mask_src, (T*)y, N, Cout,
+              CCout, CoutP, V, scale, lrelu, slices);
+  else
+    sg_launch((k_conv_finish<T, 1>), sg_grid(total, 256), 256, 0, s, acc, bias, (const T*)mask_src, (T*)y, N, Cout, CCout,
+              CoutP, V, scale, lrelu, slices);
   return sg_check_launch("sg_conv_finish");
 }
-
+int sg_conv_finish_bf16(const float* acc, const float* bias, const void* mask_src, void* y, int N,
+                        int Cout, int64_t V, float scale, int lrelu, int slices, cudaStream_t s) {
+  return conv_finish_launch<__nv_bfloat16>(acc, bias, mask_src, y, N, Cout, V, scale, lrelu, slices, s);
+}
 int sg_conv_finish_f32(const float* acc, const float* bias, const void* mask_src, void* y, int N,
-                       int Cout, int64_t V, float scale, int lrelu, cudaStream_t s) {
-  int CCout = sg_chunks(Cout), CoutP = 16 * ((Cout + 15) / 16);
-  int64_t total = (int64_t)N * CCout * V;
-  sg_launch((k_conv_finish<float, 1>), sg_grid(total, 256), 256, 0, s,
-      acc, bias, (const float*)mask_src, (float*)y, N, Cout, CCout, CoutP, V, scale, lrelu, 1);
-  return sg_check_launch("sg_conv_finish");
+                       int Cout, int64_t V, float scale, int lrelu, int slices, cudaStream_t s) {
+  return conv_finish_launch<float>(acc, bias, mask_src, y, N, Cout, V, scale, lrelu, slices, s);
 }
 
 static bool small_f32_applies(int dtype, int N, int D, int H, int W) {

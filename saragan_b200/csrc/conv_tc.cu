@@ -19,7 +19,7 @@
 //    2 KB bulk copies (the first version) capped the whole kernel at ~1300 cycles per tap;
 //  * warp roles: warp 0 = TMA/bulk producer, warp 1 = TMEM allocator + single-thread MMA
 //    issuer, warps 2-5 = epilogue (tcgen05.ld -> scale, bias, LeakyReLU, mask -> 16-byte stores,
-//    or fp32 atomics into the split-K workspace).
+//    or plain fp32 stores into this K slice's slab of the split-K workspace, summed in a fixed order by k_conv_finish).
 #include <cuda.h>
 
 #include <array>
@@ -31,7 +31,7 @@
 #include "common.cuh"
 
 int sg_conv_finish_bf16(const float* acc, const float* bias, const void* mask_src, void* y, int N,
-                        int Cout, int64_t V, float scale, int lrelu, cudaStream_t s);
+                        int Cout, int64_t V, float scale, int lrelu, int slices, cudaStream_t s);
 
 #include "tc_common.cuh"
 SG_DEFINE_LEAK_SETTER(sg_set_leak_conv_tc)
@@ -333,10 +333,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUte
         if (!valid) {
           // row lies on a halo line / column or outside the volume: computed, discarded
         } else if (p.splits > 1) {
-          float* dst = p.ws + ((int64_t)n * V + vox) * p.CoutP + co0 + c0;
-          // consecutive fp32 of one workspace row: 16-byte vector reductions instead of scalar ones
+          // split-K: every K slice owns a slab of the workspace (plain 16-byte stores, no zero-fill, and the finishing
+          // kernel adds the slabs in a fixed order: the result does not depend on the run, unlike fp32 atomics)
+          float* dst = p.ws + (((int64_t)blockIdx.z * p.N + n) * V + vox) * p.CoutP + co0 + c0;
 #pragma unroll
-          for (int q = 0; q < CB / 4; ++q) red_add_v4(dst + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          for (int q = 0; q < CB / 4; ++q)
+            *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         } else {
 #pragma unroll
           for (int j = 0; j < CB / 16; ++j) {
@@ -375,7 +377,7 @@ struct Plan {
 // cost-model constants (cycles at ~1.9 GHz)
 constexpr double kL2BytesPerCycle = 4500.0;   // sustained L2 -> SM bytes per cycle, whole chip
 constexpr double kCtaFixedCycles = 6000.0;    // launch, tensor-map fetch, first loads, epilogue
-constexpr double kSplitFixedCycles = 12000.0; // zero-fill + finishing kernel of a split-K launch
+constexpr double kSplitFixedCycles = 12000.0; // finishing kernel of a split-K launch
 constexpr double kLoadLatencyCycles = 4000.0; // TMA round trip seen by a stage whose data is not in L2 yet
 constexpr double kStageIssueCycles = 500.0;   // floor per weight stage: TMA issue + barrier round (tools/bulk_bench.cu)
 
@@ -635,7 +637,7 @@ int64_t sg_tc_wgrad_workspace_bytes(int N, int Cin, int Cout, int D, int H, int 
 extern "C" int sg_conv3d_pixelnorm_supported(int N, int Cin, int Cout, int D, int H, int W);
 extern "C" int sg_conv3d_pool_supported(int N, int Cin, int Cout, int D, int H, int W);
 int sg_conv_finish_f32(const float* acc, const float* bias, const void* mask_src, void* y, int N,
-                       int Cout, int64_t V, float scale, int lrelu, cudaStream_t s);
+                       int Cout, int64_t V, float scale, int lrelu, int slices, cudaStream_t s);
 
 int64_t sg_tc_workspace_bytes(int kind, int N, int Cin, int Cout, int D, int H, int W, int tf32) {
   if (kind == 1) return sg_tc_wgrad_workspace_bytes(N, Cin, Cout, D, H, W, tf32);
@@ -643,7 +645,7 @@ int64_t sg_tc_workspace_bytes(int kind, int N, int Cin, int Cout, int D, int H, 
   if (!tf32 && g_force_streaming != 1 && make_res_plan(N, Cin, Cout, D, H, W, g_force_streaming == 2).ok) return 0;
   Plan pl = make_plan(N, Cin, Cout, D, H, W, tf32 != 0);
   if (!pl.ok || pl.p.splits == 1) return 0;
-  return (int64_t)N * D * H * W * pl.p.CoutP * (int64_t)sizeof(float);
+  return (int64_t)pl.p.splits * N * D * H * W * pl.p.CoutP * (int64_t)sizeof(float);
 }
 
 namespace {
@@ -741,10 +743,9 @@ int sg_tc_fprop(const void* x, const void* wp, const float* bias, const void* ma
   p.scale = scale;
   p.lrelu = lrelu;
   if (p.splits > 1) {
-    int64_t need = (int64_t)N * D * H * W * p.CoutP * (int64_t)sizeof(float);
+    int64_t need = (int64_t)p.splits * N * D * H * W * p.CoutP * (int64_t)sizeof(float);
     SG_REQUIRE(ws != nullptr && ws_bytes >= need, "sg_conv3d_fprop(tcgen05): workspace too small (%lld < %lld)",
                (long long)ws_bytes, (long long)need);
-    cudaMemsetAsync(ws, 0, (size_t)need, s);
   }
   CUtensorMap map, map1;
   CUresult r;
@@ -808,8 +809,8 @@ int sg_tc_fprop(const void* x, const void* wp, const float* bias, const void* ma
   }
   if (rc) return rc;
   if (p.splits > 1)
-    return tf32 ? sg_conv_finish_f32((const float*)ws, bias, mask_src, y, N, Cout, (int64_t)D * H * W, scale, lrelu, s)
-                : sg_conv_finish_bf16((const float*)ws, bias, mask_src, y, N, Cout, (int64_t)D * H * W, scale, lrelu, s);
+    return tf32 ? sg_conv_finish_f32((const float*)ws, bias, mask_src, y, N, Cout, (int64_t)D * H * W, scale, lrelu, p.splits, s)
+                : sg_conv_finish_bf16((const float*)ws, bias, mask_src, y, N, Cout, (int64_t)D * H * W, scale, lrelu, p.splits, s);
   return 0;
 }
 
@@ -818,6 +819,13 @@ extern "C" int sg_conv3d_tf32_supported(int N, int Cin, int Cout, int D, int H, 
   if (N <= 0 || Cin <= 0 || Cout <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
   return make_plan(N, Cin, Cout, D, H, W, true).ok ? 1 : 0;
 }
+
+#ifdef SG_RES_TIMING
+// diagnostic build only (tools/res_timing.py): the per-CTA wait counters of the last resident-kernel launch
+extern "C" int sg_tc_res_timing(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_res_timing, sizeof(long long) * 148 * 8);
+}
+#endif
 
 // Introspection for tests / DESIGN.md: the tiling the tcgen05 path would use for a shape.
 // out[0..15] = ok, NT, tn, td, th, n_sub, kb_chunks, sw, splits, kblocks_per_split, grid.x, grid.y,

@@ -108,6 +108,16 @@ __device__ __forceinline__ void zs_issue_kblock(uint32_t d_tmem, uint64_t a_stag
   }
 }
 
+// -DSG_RES_TIMING (tools/res_timing.py, never in the release build): per-CTA clock64 stamps of where the three roles wait.
+//   [0] issuer: total, [1] issuer: waiting for A_FULL, [2] issuer: waiting for ACC_EMPTY, [3] producer: waiting for
+//   A_EMPTY, [4] epilogue warp 2: total, [5] epilogue: waiting for ACC_FULL, [6] tiles, [7] producer total
+#ifdef SG_RES_TIMING
+__device__ long long g_res_timing[148 * 8];
+#define RT(...) __VA_ARGS__
+#else
+#define RT(...)
+#endif
+
 template <int NT, int TD, int KBC, bool ZS>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ ResParams p) {
@@ -174,6 +184,7 @@ k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
       const uint32_t a_addr = smem_u32(a_smem);
       const uint32_t a_tx = (uint32_t)p.kb_chunks * (uint32_t)p.chunk_tx_bytes;
       int it = 0;
+      RT(long long rt_w = 0; const long long rt_p0 = clock64();)
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         int t = tile;
         const int tile_w = t % p.tiles_w; t /= p.tiles_w;
@@ -183,13 +194,16 @@ k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
         const int w0 = tile_w * 8, h0 = tile_h * p.th, d0 = tile_d * p.td;
         for (int kb = 0; kb < p.n_kblocks; ++kb, ++it) {
           const int s = it % p.stages;
+          RT(const long long rt_t = clock64();)
           mbar_wait(BAR(A_EMPTY + s), ((it / p.stages) & 1) ^ 1);
+          RT(rt_w += clock64() - rt_t;)
           mbar_expect_tx(BAR(A_FULL + s), a_tx);
           for (int c = 0; c < p.kb_chunks; ++c)
             tma_load_5d(a_addr + s * p.stage_bytes + c * p.chunk_bytes, &xmap, BAR(A_FULL + s), (w0 - 1) * 8, h0 - 1,
                         d0 - 1, kb * p.kb_chunks + c, n);
         }
       }
+      RT(g_res_timing[blockIdx.x * 8 + 3] = rt_w; g_res_timing[blockIdx.x * 8 + 7] = clock64() - rt_p0;)
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
@@ -205,13 +219,18 @@ k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
       const uint32_t wz_khw16 = (uint32_t)(p.CCin * 3 * NT);
       mbar_wait(BAR(W_FULL), 0);
       int s = 0, ph = 0, ti = 0;
+      RT(long long rt_full = 0, rt_acc = 0; const long long rt_i0 = clock64();)
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
         const int buf = ti & 1;
+        RT(const long long rt_t = clock64();)
         mbar_wait(BAR(ACC_EMPTY + buf), ((ti >> 1) & 1) ^ 1);   // epilogue has drained this set
+        RT(rt_acc += clock64() - rt_t;)
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * acc_cols;
         for (int kb = 0; kb < n_kblocks; ++kb) {
+          RT(const long long rt_u = clock64();)
           mbar_wait(BAR(A_FULL + s), ph);
+          RT(rt_full += clock64() - rt_u;)
           tc_fence_after();
           const uint64_t a_stage = a_desc0 + (uint64_t)(s * stage16);
           const uint32_t acc0 = kb != 0;
@@ -239,6 +258,12 @@ k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
         }
         tc_commit(BAR(ACC_FULL + buf), leader);
       }
+      RT(if (lane == 0) {
+        g_res_timing[blockIdx.x * 8 + 0] = clock64() - rt_i0;
+        g_res_timing[blockIdx.x * 8 + 1] = rt_full;
+        g_res_timing[blockIdx.x * 8 + 2] = rt_acc;
+        g_res_timing[blockIdx.x * 8 + 6] = ti;
+      })
     }
   } else {
     // ================================ epilogue ================================
@@ -252,6 +277,7 @@ k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
     for (int i = row; i < NT; i += 128) s_bias[i] = (p.bias && co0 + i < p.Cout) ? p.bias[co0 + i] : 0.f;
     asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
     int ti = 0;
+    RT(long long rt_e = 0; const long long rt_e0 = clock64();)
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
       int t = tile;
       const int tile_w = t % p.tiles_w; t /= p.tiles_w;
@@ -277,7 +303,9 @@ k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
           for (int c = 0; c < NT / 8; ++c)
             mk[sub][c] = __ldg(reinterpret_cast<const uint4*>(mask + obase0 + sub * plane8 + (int64_t)c * V * 8));
       }
+      RT(const long long rt_t = clock64();)
       mbar_wait(BAR(ACC_FULL + buf), (ti >> 1) & 1);
+      RT(rt_e += clock64() - rt_t;)
       tc_fence_after();
       if (p.pn_y != nullptr) {
         // conv -> [lrelu] -> pixel-norm [-> lrelu]: this thread holds all NT channels of its voxel
@@ -397,6 +425,10 @@ k_conv_tc_res(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(ACC_EMPTY + buf));
     }
+    RT(if (warp == 2 && lane == 0) {
+      g_res_timing[blockIdx.x * 8 + 4] = clock64() - rt_e0;
+      g_res_timing[blockIdx.x * 8 + 5] = rt_e;
+    })
   }
   tc_fence_before();
   __syncthreads();

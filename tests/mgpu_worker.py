@@ -67,13 +67,19 @@ def main():
     dev = torch.device("cuda", torch.cuda.current_device())
     dist.init_process_group("nccl", device_id=dev)
     res, ok = {"world": world}, True
+    if DEBUG:
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ.get("MGPU_DUMP_AFTER", "90")), exit=True)
 
-    # ---- 1. averaged gradients == mean of the per-rank gradients
+    # ---- 1. averaged gradients == mean of the per-rank gradients.  In the exact fp32 mode: two runs of the same step
+    # then agree to the order of the weight-gradient atomics (~2e-6), so the 1e-4 bound tests the exchange and nothing
+    # else (in the reduced-precision modes the GP double backward amplifies that noise, see tools/determinism_probe.py)
+    sg.set_precision("fp32")
     g, d = build()
     g_opt, d_opt = sg.make_optimizers(g, d)
     sg.train_step(reals(rank, 0, dev), g, d, g_opt, d_opt, ALPHA, apply=False, **draws(rank, 0, dev))
     worst = {}
-    for net, tag in ((d, "d"), (g, "g")):
+    for net, tag in (() if os.environ.get("MGPU_SKIP_PART1") else ((d, "d"), (g, "g"))):
         own = {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None}
         mean = {}
         for k, v in own.items():
@@ -93,6 +99,7 @@ def main():
             ok &= err < 1e-4 and same
             res[f"grads_identical_across_ranks.{tag}.{sync_name}"] = same
     res["avg_grad_vs_mean_of_rank_grads_max_rel"] = worst
+    sg.set_precision("bf16")
 
     # ---- 2. K steps: eager bucketed vs segmented graph; replicas bit-identical
     finals = {}
@@ -107,10 +114,14 @@ def main():
         else:
             dp = comm.FlatAllReduce(g, d) if mode == "graph_segments" else comm.ArenaAllReduce(g, d)
             graphed = GraphedTrainStep(g, d, g_opt, d_opt, B, VOL, ALPHA, warmup=2, seed=1, grad_sync=dp)
+            _dbg(f"{mode}: captured")
             for i in range(K):
+                _dbg(f"{mode}: replay {i}")
                 dr = draws(rank, i, dev)
                 graphed.draw = lambda dr=dr: [getattr(graphed, k).copy_(v) for k, v in dr.items()]   # replay the same draws
                 o = graphed(reals(rank, i, dev))
+            o = {k: v.clone() for k, v in o.items()}
+            graphed.close()
         torch.cuda.synchronize()
         _dbg(f"{mode}: steps done")
         if DEBUG:

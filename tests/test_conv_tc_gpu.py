@@ -315,7 +315,7 @@ def test_discriminator_block_fused_pool_equals_unfused(monkeypatch):
     from saragan_b200 import kernels
     torch.manual_seed(4)
     blk = sg.DiscriminatorBlock(16, 32).cuda()
-    x = torch.randn(2, 16, 8, 32, 16, device="cuda")
+    x = torch.randn(2, 16, 16, 32, 32, device="cuda")     # pooled level 8x16x16 > config.TF32_MAX_VOXELS: bf16 on both sides
     lib = _lib.load()
     res = {}
     for fused in (True, False):
