@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", default="cfg3")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
+    ap.add_argument("--phase", type=int, default=0, help="growth phase (default: the config's top phase); the per-phase "
+                                                         "table of a progression (cfg2) is one run per phase")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
     ap.add_argument("--alpha", type=float, default=0.5)
@@ -203,7 +205,7 @@ def parity_check(args, cfg, g, d, g_opt, d_opt, dev):
     from saragan_b200 import costmodel as C
     from saragan_b200.data import step_draws, synthetic_reals
     path = os.path.join(ROOT, "tests", "golden", f"fullsize_{args.config}_b{cfg['batch']}.json")
-    if args.network != "network" or not os.path.exists(path):
+    if args.network != "network" or args.phase or not os.path.exists(path):
         return None
     with open(path) as f:
         ref = json.load(f)
@@ -288,7 +290,7 @@ def roofline_entries(table, pk, n_passes):
         dur = float(np.mean(ms)) * 1e-3
         peak = pk["bf16_burst"] if bound == "tensor" else pk["hbm"]
         ach = work / dur / (1e12 if bound == "tensor" else 1e9)
-        key = name + ":" + ",".join(map(str, ints[:7]))
+        key = name + ("+mask" if name == "sg_up2" and len(flags) > 2 and flags[2] else "") + ":" + ",".join(map(str, ints[:7]))
         rows.append({"bound": bound, "kernel": f"{name}: {label}", "achieved": ach, "peak": peak,
                      "unit": "TFLOP/s" if bound == "tensor" else "GB/s", "frac": ach / peak,
                      "traffic": traffic.get(key, {}).get("dram_bytes"), "launches_per_step": len(ms) / n_passes,
@@ -311,6 +313,9 @@ def main():
     cfg = dict(C.CONFIGS[args.config])
     if args.batch:
         cfg["batch"] = args.batch
+    if args.phase:
+        cfg["phase"] = args.phase
+        cfg["desc"] = cfg["desc"].replace(", B=", f" [run at phase {args.phase}: {'x'.join(map(str, C.volume(args.phase)))}], B=")
     if args.impl == "reference":
         run_reference(args, cfg, rank)
         return

@@ -1,5 +1,6 @@
 """Run-time configuration of the CUDA path."""
 import contextlib
+import os
 
 import torch
 
@@ -36,7 +37,9 @@ FP32_MAX_VOXELS = 16
 # weight-stream-bound) keep fp32 storage and run their convolutions as TF32 on the tensor cores.  Their pre-activations
 # feed the deepest part of the gradient chain (and the minibatch-stddev statistics); at TF32 the whole-step parameter
 # gradients of the golden configurations sit at 1.4 % median against the fp32 reference (bf16 there: 5 %).
-TF32_MAX_VOXELS = 1024
+# (SARAGAN_TF32_MAX_VOXELS overrides it for the per-policy table of DESIGN.md / profiles/: 16 = bf16 everywhere above the
+# base level, 8192 = TF32 up to 8x32x32.)
+TF32_MAX_VOXELS = int(os.environ.get("SARAGAN_TF32_MAX_VOXELS", "1024"))
 
 
 def act_dtype(voxels: int = 1 << 30) -> torch.dtype:

@@ -69,7 +69,7 @@ struct ResParams {
 // loop costs one uniform-datapath add per MMA.
 // The MMAs of one K block of the z-stacked form.  B rows [kd = 2, 1, 0][co] of a (kh, kw, chunk): chunk stride (LBO) =
 // 3*NT rows.  PLANE-OUTER order: the 9 * KBC/2 MMAs of an input plane go to the same accumulator columns back to back.
-// FIRST (the tile's first K block): the first K step of every plane is issued tap by tap, the kd = 0 tap (first touch
+// FIRST (the tile's first K block): the first MMA of every plane is issued in two pieces, the kd = 0 tap (first touch
 // of output plane q + 1) with the accumulate flag off -- one instruction has one flag for all its columns.  Every
 // descriptor offset is a compile-time constant or a running uniform add.
 template <int NT, int TD, int KBC, bool FIRST>
@@ -95,10 +95,14 @@ __device__ __forceinline__ void zs_issue_kblock(uint32_t d_tmem, uint64_t a_stag
 #pragma unroll
       for (int kk = 0; kk < KBC / 2; ++kk) {
         const uint64_t a = a_plane + (uint64_t)(a_off + kk * KK_A);
-        if (FIRST && (khw | kk) == 0) {
-#pragma unroll
-          for (int kd = kd_lo; kd <= kd_hi; ++kd)
-            tc_mma(d_tmem + (q + 1 - kd) * NT, a, b_run + (uint64_t)((kd_hi - kd) * NT), idesc, kd != 0, leader);
+        if (FIRST && (khw | kk) == 0 && kd_lo == 0) {
+          // first touch of output plane q + 1 (tap kd = 0): overwrite; the taps kd_hi..1 before it in the same B rows
+          // accumulate into planes that earlier input planes have already touched -- one MMA for both of them
+          if (kd_hi >= 1) {
+            const uint32_t idacc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((kd_hi * NT) >> 3) << 17) | ((128u >> 4) << 24);
+            tc_mma(d_tmem + (q + 1 - kd_hi) * NT, a, b_run, idacc, 1u, leader);
+          }
+          tc_mma(d_tmem + (q + 1) * NT, a, b_run + (uint64_t)(kd_hi * NT), idesc, 0u, leader);
         } else {
           tc_mma(d_tmem + (q + 1 - kd_hi) * NT, a, b_run + (uint64_t)(kk * 2 * 3 * NT), idz, 1u, leader);
         }

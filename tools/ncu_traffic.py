@@ -17,9 +17,16 @@ KEYS = {
     "wgrad_32_64": "sg_conv3d_wgrad:0,4,32,64,32,128,128",
     "wgrad_32_32": "sg_conv3d_wgrad:0,4,32,32,32,128,128",
 }
+# tools/membound_bench.py --reps 1 under ncu (cfg3 top-level shapes): one warm-up Adam launch, then 3 launches per case in
+# this order; bench.py key of each case (pointer-flag variants carry a suffix, as in bench.roofline_entries)
+MEMBOUND_CASES = ["sg_pw_expand:0,4,32,524288,1", "sg_pw_expand_masked:0,4,32,524288,0", "sg_pw_reduce:0,4,32,524288",
+                  "sg_pw_wgrad:0,4,32,524288", "sg_pw_wgrad:0,4,64,524288", "sg_down2:0,0,8,32,32,128,128",
+                  "sg_up2+mask:0,0,8,32,16,64,64", "sg_up2:0,0,8,32,16,64,64", "sg_mask_mul:0,134217728",
+                  "sg_lincomb:0,134217728", "sg_pixelnorm_fwd:0,4,32,524288,1", "sg_pixelnorm_bwd:0,4,32,524288,1,1",
+                  "sg_adam_step:32000000"]
 COLS = [("gpu__time_duration.sum", "us", 1.0), ("sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active", "tensor %", 1.0),
         ("dram__bytes_read.sum", "rd MB", 1.0), ("dram__bytes_write.sum", "wr MB", 1.0),
-        ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram %", 1.0), ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 %", 1.0),
+        ("dram__cycles_active.avg.pct_of_peak_sustained_elapsed", "dram act %", 1.0), ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 %", 1.0),
         ("launch__registers_per_thread", "regs", 1.0), ("launch__grid_size", "grid", 1.0)]
 
 
@@ -44,6 +51,14 @@ def main():
         hdr, units = rows[0], rows[1]
         idx = {h: i for i, h in enumerate(hdr)}
         last = {}
+        body = [r for r in rows[2:] if len(r) == len(hdr)]
+        if name == "membound" and len(body) == 1 + 3 * len(MEMBOUND_CASES):
+            for ci, key in enumerate(MEMBOUND_CASES):
+                r = body[1 + 3 * ci + 2]
+                g = lambda col: to_float(r[idx[col]], units[idx[col]])      # noqa: E731
+                traffic[key] = {"dram_bytes": (g("dram__bytes_read.sum") + g("dram__bytes_write.sum")) * 1e6,
+                                "kernel": re.sub(r"\(.*", "", r[idx["Kernel Name"]]).replace("void ", ""),
+                                "ncu_us": g("gpu__time_duration.sum"), "source": os.path.basename(path)}
         for r in rows[2:]:
             if len(r) != len(hdr):
                 continue
@@ -51,7 +66,7 @@ def main():
         for kname, r in last.items():       # the last launch of every kernel: warmed up
             vals = []
             for col, _, _ in COLS:
-                vals.append(to_float(r[idx[col]], units[idx[col]]) if col in idx and r[idx[col]] not in ("", "n/a") else float("nan"))
+                vals.append(to_float(r[idx[col]], units[idx[col]]) if col in idx and r[idx[col]] not in ("", "n/a", "no data") else float("nan"))
             print(f"{name:14s} {kname[:58]:58s} " + " ".join(f"{v:9.1f}" for v in vals))
             if name in KEYS and ("k_conv_tc" in kname or "k_wgrad_tc" in kname):
                 traffic[KEYS[name]] = {"dram_bytes": (vals[2] + vals[3]) * 1e6, "kernel": kname, "tensor_pipe_pct": vals[1],
