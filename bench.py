@@ -300,7 +300,9 @@ def roofline_entries(table, pk, n_passes):
                      "timed": "CUDA events on the launching stream, eager single-stream passes after the timed region"})
     rows.sort(key=lambda r: -r["ms_per_step"])
     conv = [r for r in rows if r["bound"] == "tensor"]
-    mem = [r for r in rows if r["bound"] == "hbm"]
+    # bandwidth entries: launches that move >= 32 MB (a smaller launch is bound by launch latency, and in these eager
+    # passes its event-to-event time also holds the host's call overhead)
+    mem = [r for r in rows if r["bound"] == "hbm" and r["bytes_per_launch"] >= 32e6]
     return conv[:4] + mem[:6]
 
 
