@@ -42,9 +42,16 @@ FP32_MAX_VOXELS = 16
 TF32_MAX_VOXELS = int(os.environ.get("SARAGAN_TF32_MAX_VOXELS", "1024"))
 
 
-def act_dtype(voxels: int = 1 << 30) -> torch.dtype:
-    """Storage type of an activation / gradient tensor at a level with `voxels` = D*H*W."""
-    if _precision != "bf16" or voxels <= max(FP32_MAX_VOXELS, TF32_MAX_VOXELS):
+# The generator's own threshold (experiment knob; default = the discriminator's): its low-resolution activations do not
+# feed the minibatch-stddev statistics, only D's do.
+G_TF32_MAX_VOXELS = int(os.environ.get("SARAGAN_G_TF32_MAX_VOXELS", str(TF32_MAX_VOXELS)))
+
+
+def act_dtype(voxels: int = 1 << 30, net: str = "d") -> torch.dtype:
+    """Storage type of an activation / gradient tensor at a level with `voxels` = D*H*W (`net`: "g" inside the
+    generator, "d" elsewhere)."""
+    limit = G_TF32_MAX_VOXELS if net == "g" else TF32_MAX_VOXELS
+    if _precision != "bf16" or voxels <= max(FP32_MAX_VOXELS, limit):
         return torch.float32
     return torch.bfloat16
 
@@ -85,7 +92,7 @@ def tf32_supported(n, cin, cout, d, h, w) -> bool:
 
 def policy_key():
     """Everything that decides which storage types (hence which weight packings) a pass uses."""
-    return (_precision, FP32_MAX_VOXELS, TF32_MAX_VOXELS)
+    return (_precision, FP32_MAX_VOXELS, TF32_MAX_VOXELS, G_TF32_MAX_VOXELS)
 
 
 def describe() -> str:

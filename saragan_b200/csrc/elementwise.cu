@@ -36,11 +36,24 @@ int g_sg_pdl = 0;   // measured on cfg3 (graph replay): 17.57 ms/step with the a
 extern "C" void sg_set_pdl(int on) { g_sg_pdl = on; }
 extern "C" const char* sg_last_error(void) { return g_err; }
 SG_DEFINE_LEAK_SETTER(sg_set_leak_elementwise)
-static float g_sg_leak = 0.2f;
-extern "C" float sg_get_leaky_slope(void) { return g_sg_leak; }
+// host copy of the slope, PER DEVICE (the __constant__ copies live per device; one process per GPU is the intended use,
+// but a process that touches a second device must not believe it carries the first one's slope)
+static float* sg_leak_slot() {
+  static float slots[64];
+  static bool init = false;
+  if (!init) {
+    for (int i = 0; i < 64; ++i) slots[i] = 0.2f;
+    init = true;
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return &slots[dev & 63];
+}
+extern "C" float sg_get_leaky_slope(void) { return *sg_leak_slot(); }
 extern "C" int sg_set_leaky_slope(float slope) {
   SG_REQUIRE(slope >= 0.f && slope <= 1.f, "leaky slope %g outside [0, 1]", (double)slope);
-  if (slope == g_sg_leak) return 0;
+  float* slot = sg_leak_slot();
+  if (slope == *slot) return 0;
   // configuration call, not on the hot path: everything already enqueued keeps the old slope, everything
   // enqueued afterwards (including replays of captured graphs) sees the new one
   cudaError_t e = cudaDeviceSynchronize();
@@ -54,7 +67,7 @@ extern "C" int sg_set_leaky_slope(float slope) {
     sg_set_error("sg_set_leaky_slope: %s", cudaGetErrorString((cudaError_t)rc));
     return rc;
   }
-  g_sg_leak = slope;
+  *slot = slope;
   return 0;
 }
 extern "C" int sg_version(void) { return 200; }

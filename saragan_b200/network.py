@@ -314,7 +314,7 @@ class GeneratorBlock(nn.Sequential, _Blocked):
         plain = not self.is_act(input)
         x = self.enter(input) if plain else input
         c = self.conv1.out_channels
-        x = ops.Up2.apply(x, 1.0, config.act_dtype(_voxels(x) * 8))
+        x = ops.Up2.apply(x, 1.0, config.act_dtype(_voxels(x) * 8, "g"))
         x = self._conv_norm(self.conv1, x, lrelu=True, lrelu_after=False)     # conv1 -> lrelu -> pixel-norm
         x = self._conv_norm(self.conv2, x, lrelu=False, lrelu_after=True)     # conv2 -> pixel-norm -> lrelu
         return self.leave(x, c) if plain else x
@@ -392,7 +392,7 @@ class Generator(nn.Module):
         x = gin[0](input.to(self.device), lrelu=True)
         alpha, beta = ops.blend_coef(alpha, x.device)
         x = gin[2](x)
-        x = ops.ToAct.apply(x, config.act_dtype(_voxels(x)))
+        x = ops.ToAct.apply(x, config.act_dtype(_voxels(x), "g"))
         x = gin[3](x, lrelu=True, premasked=True)
         x = gin[5](x, channels=gin[3].out_channels, mask_input=True)
 

@@ -116,3 +116,5 @@ def test_one_capture_follows_alpha_and_lr_schedules():
     graph_vs_eager = sum(float((a - b).abs().mean()) for a, b in zip(pa, pb)) / len(pa)
     eager_vs_eager = sum(float((b - c).abs().mean()) for b, c in zip(pb, pc)) / len(pa)
     assert graph_vs_eager < 6 * eager_vs_eager + 1e-4, (graph_vs_eager, eager_vs_eager)
+    graphed.close()                        # releases the captured graph(s); the weights it trained stay
+    assert graphed.graph is None and torch.isfinite(pa[0]).all()

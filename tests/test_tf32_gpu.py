@@ -169,3 +169,24 @@ def test_tf32_packing_layout():
             pad[:r, :k] = m if not flip else m
             want[tap] = pad.reshape(rp, kc4, 4).permute(1, 0, 2)
         assert torch.equal(got.reshape(27, kc4, rp, 4), want), flip
+
+
+@pytest.mark.parametrize("shape", [(4, 512, 512, 2, 8, 8), (4, 256, 256, 4, 16, 16), (4, 64, 64, 2, 8, 8)])
+@pytest.mark.parametrize("kind", ["tf32", "bf16"])
+def test_split_k_is_run_to_run_deterministic(shape, kind):
+    """The split-K shapes of the low-resolution levels: every K slice stores to its own workspace slab and the finishing
+    kernel adds the slabs in a fixed order, so repeated launches are bit-identical (with fp32 atomics they differed in
+    the last bit, which the reduced-precision step amplified to 8e-2 on D's gradients: tools/determinism_probe.py)."""
+    n, cin, cout, d, h, w = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    dt, pk, impl = (F32, "tf32", _lib.IMPL_TF32) if kind == "tf32" else (torch.bfloat16, torch.bfloat16, _lib.IMPL_AUTO)
+    x = E.plain_to_act(torch.randn(n, cin, d, h, w, generator=g), dt).cuda()
+    wp = K.pack_conv_weight(torch.randn(cout, cin, 3, 3, 3, generator=g).cuda(), pk, False)
+    bias = torch.randn(cout, generator=g).cuda()
+    first = None
+    for _ in range(6):
+        y = K.conv3d_fprop(x, wp, bias, None, cin, cout, 0.05, True, impl)
+        torch.cuda.synchronize()
+        if first is None:
+            first = y.clone()
+        assert torch.equal(first, y)
