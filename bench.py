@@ -317,6 +317,10 @@ def main():
         cfg["batch"] = args.batch
     if args.phase:
         cfg["phase"] = args.phase
+        if not args.batch:
+            # the reference's per-phase batch rule, main.py:99 (128 // resolution), floored at 2 (a batch of 1
+            # zeroes the minibatch-stddev feature): 32, 16, 8, 4, 2 for the resolutions 4 ... 64 of the xs progression
+            cfg["batch"] = max(2, 128 // (C.BASE_SHAPE[2] * 2 ** (args.phase - 1)))
         cfg["desc"] = cfg["desc"].replace(", B=", f" [run at phase {args.phase}: {'x'.join(map(str, C.volume(args.phase)))}], B=")
     if args.impl == "reference":
         run_reference(args, cfg, rank)

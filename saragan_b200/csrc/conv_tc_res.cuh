@@ -488,6 +488,14 @@ ResPlan make_res_plan(int N, int Cin, int Cout, int D, int H, int W, bool for_te
     if (!g_res_force_td && td == 8 && NT == 32 && CCin == 2 && D % 4 == 0) continue;
     const bool this_zs = td >= 2 && g_res_zs_mode != 1;
     if (!this_zs && td > 4) continue;                 // the plain form is instantiated up to td = 4
+    // every CTA should walk >= 2 tiles (weight load amortised, both accumulator sets in use): with too few tiles at
+    // this td try a smaller one before giving the layer to the streaming kernel (32 -> 32 @16x64x64, B = 2: 128 tiles
+    // at td = 8, 512 at td = 2 -- the generic streaming kernel it used to fall to ran 28 us)
+    if (!for_test && !g_res_force_td) {
+      const int tiles = (W / 8) * (H / 16) * (D / td) * N;
+      const int ctas_td = tiles < sg_num_sms() ? tiles : sg_num_sms();
+      if (tiles < 2 * ctas_td) continue;
+    }
     for (int kb : {4, 2}) {
       if (CCin % kb) continue;
       if (g_res_force_kb && kb != g_res_force_kb) continue;
