@@ -21,14 +21,19 @@ from . import kernels as K
 from . import ops
 from .loss import compute_gradient_penalty, wasserstein_loss
 
-_side_streams: Dict[torch.device, "torch.cuda.Stream"] = {}
+import os
+
+# one-GPU step: run the G update's generator forward beside the D phase (A/B switch: SARAGAN_EARLY_G=0)
+EARLY_G_FORWARD = os.environ.get("SARAGAN_EARLY_G", "1") != "0"
+
+_side_streams: Dict[tuple, "torch.cuda.Stream"] = {}
 
 
-def _side_stream(dev) -> "torch.cuda.Stream":
-    dev = torch.device(dev)
-    if dev not in _side_streams:
-        _side_streams[dev] = torch.cuda.Stream(device=dev)
-    return _side_streams[dev]
+def _side_stream(dev, index: int = 0) -> "torch.cuda.Stream":
+    key = (torch.device(dev), index)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=key[0])
+    return _side_streams[key]
 
 
 def top_image(images) -> torch.Tensor:
@@ -136,6 +141,7 @@ def g_phase(batch: int, generator, discriminator, generator_optim, alpha, *,
     g_loss.backward()
     _set_requires_grad(generator, True)
     _set_requires_grad(discriminator, True)
+    ops.mark_packs_settled(generator)
     return {"g_loss": g_loss.detach(), "d_fake_mean": d_fake.detach().mean(), "x_fake": x_fake.detach()}
 
 
@@ -148,8 +154,32 @@ def train_step(x_real: torch.Tensor, generator, discriminator, generator_optim, 
     grad_sync: optional ``comm.DataParallel``; ``arm(module)`` is called before ``backward()``
     and ``finish(module)`` before ``optim.step()`` (the data-parallel gradient all-reduce,
     reference: hvd.DistributedOptimizer, main.py:153-160)."""
+    # The generator forward of the G update needs nothing the D update changes (the generator's weights move at the END of
+    # the step), so on one GPU it runs on its own stream beside the whole D phase: its low-resolution levels -- a chain
+    # of small kernels -- fill SMs and launch slots the D chains leave idle.  Same arithmetic, same gradients: autograd
+    # runs each backward node on its forward's stream and joins the streams itself.  (Needs every weight packing of both
+    # networks to exist already, see ops.packs_settled; with a gradient exchange the arena path below places the same
+    # forward beside the D all-reduce instead.)
+    dev = discriminator.device
+    x_fake_g = None
+    early = (grad_sync is None and overlap_gp and dev.type == "cuda" and EARLY_G_FORWARD
+             and ops.packs_settled(discriminator) and ops.packs_settled(generator))
+    if early:
+        if z_d is None:                              # keep train.py's draw order on the host generator: z (D), then z (G)
+            z_d = torch.randn(x_real.shape[0], generator.latent_dim)
+        if z_g is None:
+            z_g = torch.randn(x_real.shape[0], generator.latent_dim)
+        ops.prepack(generator)                       # on the main stream, before the fork
+        main, side_g = torch.cuda.current_stream(dev), _side_stream(dev, 1)
+        side_g.wait_stream(main)
+        generator.train()
+        _set_requires_grad(generator, True)
+        with torch.cuda.stream(side_g):
+            x_fake_g = top_image(generator(z_g, alpha))
     out = d_phase(x_real, generator, discriminator, discriminator_optim, alpha, noise=noise, z_d=z_d, eps=eps,
                   grad_sync=grad_sync, overlap_gp=overlap_gp)
+    if early:
+        torch.cuda.current_stream(dev).wait_stream(side_g)
     if hasattr(grad_sync, "reduce") and hasattr(discriminator_optim, "ema_state"):
         # gradient arena + fused Adam (comm.ArenaAllReduce): the D gradients are averaged on a second stream WHILE the
         # generator forward of the G update runs (it needs nothing the D update changes); Adam reads the arena
@@ -179,7 +209,8 @@ def train_step(x_real: torch.Tensor, generator, discriminator, generator_optim, 
             grad_sync.finish(discriminator)
         if apply:
             discriminator_optim.step()
-        g = g_phase(x_real.shape[0], generator, discriminator, generator_optim, alpha, z_g=z_g, grad_sync=grad_sync)
+        g = g_phase(x_real.shape[0], generator, discriminator, generator_optim, alpha, z_g=z_g, grad_sync=grad_sync,
+                    x_fake=x_fake_g)
         if grad_sync is not None:
             grad_sync.finish(generator)
         if apply:
