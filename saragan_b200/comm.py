@@ -20,6 +20,8 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -220,6 +222,10 @@ class FlatAllReduce:
         GradBucketer._scatter(flat, grads)
 
 
+# timing diagnosis only (tools): everything of the exchange but the collective itself -- the replicas then drift apart
+_SKIP_NCCL = os.environ.get("SARAGAN_ARENA_SKIP_NCCL", "0") == "1"
+
+
 class ArenaAllReduce:
     """Gradient averaging through ONE contiguous arena per network, capturable in a CUDA graph: a multi-tensor kernel
     gathers the (1/world-scaled) gradients of the active parameters into the arena (`sg_multi_copy_scale`, one launch),
@@ -319,7 +325,7 @@ class ArenaAllReduce:
         else:
             for p in plan["params"]:
                 plan["views"][p].copy_(p.grad * scale)
-        if self.world > 1:
+        if self.world > 1 and not _SKIP_NCCL:
             dist.all_reduce(plan["arena"], op=dist.ReduceOp.SUM, group=self.group)
         return plan["views"]
 
