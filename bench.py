@@ -354,7 +354,7 @@ def main():
         from saragan_b200.graph import make_capturable_optimizers
         g_opt, d_opt = make_capturable_optimizers(g, d, world_size=world)      # fused Adam in eager mode too
     ap_exchange = os.environ.get("SARAGAN_EXCHANGE", "arena")     # arena | flat (4 graph segments + eager NCCL) -- A/B switch
-    if world > 1:
+    if world > 1 or os.environ.get("SARAGAN_FORCE_ARENA") == "1":     # (the switch: the N > 1 step structure on one GPU, for profiling)
         dp = (comm.ArenaAllReduce(g, d) if ap_exchange == "arena" else comm.FlatAllReduce(g, d)) if use_graph else comm.DataParallel(g, d)
     else:
         dp = None

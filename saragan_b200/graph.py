@@ -1,13 +1,13 @@
 """Whole-step CUDA graph: one D update (with the WGAN-GP double backward) + one G update +
 both Adam steps captured once and replayed per batch.
 
-The step launches ~900 of our kernels plus a few hundred tiny torch ops (autograd bookkeeping,
+The step launches ~700 of our kernels plus a few hundred tiny torch ops (autograd bookkeeping,
 minibatch-stddev, Adam); issued one by one from Python they cost more host time than the GPU
 needs to execute them once the convolutions run on tcgen05.  Capturing the step removes the
 host from the loop (the north-star's "CUDA streams and graphs instead of a tracing compiler").
 
-On several GPUs the step is captured as four segments with the (eager) NCCL gradient all-reduce
-between them -- see __init__.
+On several GPUs the step is still ONE graph: with comm.ArenaAllReduce the NCCL all-reduces are captured inside it
+(comm.FlatAllReduce keeps round 1's form, four segments with an eager all-reduce between them) -- see __init__.
 
 Inputs live in static buffers: the real batch, the instance-noise draw, the two latent draws and
 the GP interpolation draw are refreshed outside the graph (`draw()`), then `replay()` runs the
