@@ -595,6 +595,7 @@ int launch_spec(const Plan& pl, const CUtensorMap& map, const CUtensorMap& map1,
 }  // namespace
 
 #include "conv_tc_res.cuh"
+#include "conv_tc_roll.cuh"
 
 namespace {
 // tests: 0 = auto, 1 = always the streaming kernel, 2 = the weight-resident kernel whenever the
@@ -602,7 +603,7 @@ namespace {
 int g_force_streaming = 0;
 
 int encode_halo_map(CUtensorMap* map, const void* x, int N, int CC, int D, int H, int W, int halo_w, int halo_h,
-                    int halo_d, int tn) {
+                    int halo_d, int tn, int box_c = 1) {
   EncodeTiledFn encode = get_encode();
   if (!encode) {
     sg_set_error("conv_tc: cuTensorMapEncodeTiled not available");
@@ -612,7 +613,7 @@ int encode_halo_map(CUtensorMap* map, const void* x, int N, int CC, int D, int H
   cuuint64_t dims[5] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)CC, (cuuint64_t)N};
   cuuint64_t strides[4] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16,
                            (cuuint64_t)CC * D * H * W * 16};
-  cuuint32_t box[5] = {(cuuint32_t)halo_w * 8, (cuuint32_t)halo_h, (cuuint32_t)halo_d, 1, (cuuint32_t)tn};
+  cuuint32_t box[5] = {(cuuint32_t)halo_w * 8, (cuuint32_t)halo_h, (cuuint32_t)halo_d, (cuuint32_t)box_c, (cuuint32_t)tn};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -701,6 +702,33 @@ int sg_tc_fprop(const void* x, const void* wp, const float* bias, const void* ma
                 float pool_scale = 0.f) {
   if (pn_y != nullptr && (tf32 || !sg_conv3d_pixelnorm_supported(N, Cin, Cout, D, H, W) || mask_src != nullptr)) return 1;
   if (pool_y != nullptr && (tf32 || !sg_conv3d_pool_supported(N, Cin, Cout, D, H, W) || mask_src != nullptr || pn_y)) return 1;
+  if (!tf32 && g_force_streaming != 1 && roll_mode()) {
+    // the rolling form of the resident kernel (conv_tc_roll.cuh): columns through the depth, per-plane pipelining
+    RollPlan rl = make_roll_plan(N, Cin, Cout, D, H, W, g_force_streaming == 2);
+    if (roll_wanted(rl) && (pn_y == nullptr || rl.NT == rl.p.CoutP)) {
+      RollParams& q = rl.p;
+      q.wp = (const __nv_bfloat16*)wp;
+      q.bias = bias;
+      q.mask = (const __nv_bfloat16*)mask_src;
+      q.y = (__nv_bfloat16*)y;
+      q.scale = scale;
+      q.lrelu = lrelu;
+      q.pn_y = (__nv_bfloat16*)pn_y;
+      q.pn_eps = pn_eps;
+      q.pn_inv_c = 1.f / (float)Cout;
+      q.pn_lrelu_after = pn_lrelu_after;
+      q.pool_y = (__nv_bfloat16*)pool_y;
+      q.pool_scale = pool_scale;
+      CUtensorMap rmap;
+      int rc = encode_halo_map(&rmap, x, N, rl.CCin, D, H, W, 10, 18, 2, 1, rl.CCin);
+      if (rc) return rc;
+      switch (rl.NT) {
+        case 16: return launch_roll<16>(rl, rmap, s);
+        case 32: return launch_roll<32>(rl, rmap, s);
+        default: return launch_roll<64>(rl, rmap, s);
+      }
+    }
+  }
   if (!tf32 && g_force_streaming != 1) {
     ResPlan rp = make_res_plan(N, Cin, Cout, D, H, W, g_force_streaming == 2);
     if (rp.ok) {
