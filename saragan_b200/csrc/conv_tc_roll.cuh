@@ -19,6 +19,19 @@
 
 namespace {
 
+// non-blocking barrier test (try_wait may suspend the thread for a while when the phase is not complete)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
 constexpr int kRollStagesMax = 8;    // plane buffers
 constexpr int kRollAccMax = 16;      // accumulator ring slots
 
@@ -178,6 +191,7 @@ k_conv_tc_roll(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
     mbar_wait(BAR(W_FULL), 0);
     uint32_t gp = 0, go = 0;   // planes consumed / output planes opened by earlier items
     uint32_t safe_upto = 0;    // output planes below this index may be opened without looking at the epilogue's barriers
+    bool next_ready = false;   // the stage about to be consumed has already been seen full
     RT(long long rt_full = 0, rt_acc = 0; int rt_items = 0; const long long rt_i0 = clock64();)
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       int n, d0, h0, w0;
@@ -187,10 +201,15 @@ k_conv_tc_roll(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
       int r_next = 0;   // next output plane of this item to be reported complete
       for (int jp = j_first; jp <= j_last; jp += 2) {
         const uint32_t s = gp & s_mask;
-        RT(const long long rt_u = clock64();)
-        mbar_wait(BAR(P_FULL + s), (gp >> s_log) & 1u);
-        RT(rt_full += clock64() - rt_u;)
+        if (!next_ready) {
+          RT(const long long rt_u = clock64();)
+          mbar_wait(BAR(P_FULL + s), (gp >> s_log) & 1u);
+          RT(rt_full += clock64() - rt_u;)
+        }
         tc_fence_after();
+        // the producer runs stages ahead: look at the NEXT stage's barrier now, without blocking -- the latency of the
+        // test hides behind this pair's MMA issue, and the (normally true) answer saves the blocking wait next time round
+        next_ready = mbar_test_wait(BAR(P_FULL + ((gp + 1u) & s_mask)), ((gp + 1u) >> s_log) & 1u);
 #pragma unroll 1
         for (int q = 0; q < 2; ++q) {
           const int j = jp + q;
